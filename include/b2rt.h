@@ -1,0 +1,171 @@
+/* b2rt.h -- C ABI of libb2rt.so: the B200 (sm_100a) replacement for the device
+ * side of Mini-OpenCL-Raytracer, i.e. everything the reference reaches through
+ * its OpenCL wrapper layer CLutils.{h,cpp} (CLContext / CLKernel, the drop-in
+ * boundary of SURVEY.md 8b) plus a ray-stream entry the reference lacks.
+ *
+ * Plain C: opaque handle, plain pointers and sizes, int status returns, no
+ * exceptions and no torch/CUDA types in any signature. One host thread per
+ * handle at a time. There is NO CPU fallback: every entry point fails with
+ * B2RT_DEVICE_NOT_FOUND when no CUDA device is usable.
+ *
+ * Citations are file:line in the reference tree (/root/reference).
+ */
+#ifndef B2RT_H
+#define B2RT_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2RT_VERSION 100
+
+/* Status codes reuse the OpenCL numbering so that the host wrappers can turn
+ * them into the same CLException text as the reference (CLutils.h:29-114). */
+enum {
+    B2RT_SUCCESS = 0,
+    B2RT_DEVICE_NOT_FOUND = -1,             /* CL_DEVICE_NOT_FOUND */
+    B2RT_MEM_OBJECT_ALLOCATION_FAILURE = -4,
+    B2RT_OUT_OF_RESOURCES = -5,             /* any CUDA runtime failure */
+    B2RT_OUT_OF_HOST_MEMORY = -6,
+    B2RT_INVALID_VALUE = -30,
+    B2RT_INVALID_CONTEXT = -34,
+    B2RT_INVALID_MEM_OBJECT = -38,
+    B2RT_INVALID_ARG_INDEX = -49,
+    B2RT_INVALID_ARG_VALUE = -50,
+    B2RT_INVALID_ARG_SIZE = -51,
+    B2RT_INVALID_KERNEL_ARGS = -52,
+    B2RT_INVALID_GLOBAL_WORK_SIZE = -63
+};
+
+/* The 14 argument slots of KernelEntry (kernel_bvh.cl:415-431), numbered like
+ * RenderKernelArgument_t (CLutils.h:11-27). */
+enum {
+    B2RT_ARG_BUFFER_OUT = 0,       /* b2rt_buffer: W*H*16 B accumulation image     */
+    B2RT_ARG_BUFFER_SCENE = 1,     /* b2rt_buffer: CLTriangle[]  (256 B each)      */
+    B2RT_ARG_BUFFER_NODE = 2,      /* b2rt_buffer: CLLinearBVHNode[] (48 B each)   */
+    B2RT_ARG_BUFFER_MATERIAL = 3,  /* b2rt_buffer: CLMaterial[]  (64 B each)       */
+    B2RT_ARG_WIDTH = 4,            /* uint32 */
+    B2RT_ARG_HEIGHT = 5,           /* uint32 */
+    B2RT_ARG_FRAME_COUNT = 6,      /* uint32 */
+    B2RT_ARG_FRAME_SEED = 7,       /* uint32, accepted and ignored like the kernel does */
+    B2RT_ARG_LIGHT_BOUNCES = 8,    /* int32  */
+    B2RT_ARG_LIGHT_TYPE = 9,       /* int32  */
+    B2RT_ARG_SKYBOX_INTENSITY = 10,/* float  */
+    B2RT_ARG_CAMERA_POS = 11,      /* 16-byte float3 (CLRaytracer.cpp:42-47 passes sizeof(float3)) */
+    B2RT_ARG_CAMERA_FRONT = 12,
+    B2RT_ARG_CAMERA_UP = 13,
+    B2RT_ARG_COUNT = 14
+};
+
+/* cl_mem_flags subset used by the reference (CLBVHnode.cpp:215, CLRaytracer.cpp:133). */
+enum {
+    B2RT_MEM_WRITE_ONLY = 1 << 1,
+    B2RT_MEM_READ_ONLY = 1 << 2,
+    B2RT_MEM_COPY_HOST_PTR = 1 << 5
+};
+
+typedef struct b2rt_context b2rt_context;   /* replaces CLContext + CLKernel (CLutils.h:116-145) */
+typedef uint64_t b2rt_buffer;               /* replaces cl::Buffer; 0 is never a valid buffer */
+
+/* Ray-stream records (new API; the reference only traces camera paths inside
+ * its megakernel). dir need not be unit length: it is normalised exactly like
+ * InitRay (kernel_bvh.cl:42-55). tmin is accepted for layout compatibility and
+ * IGNORED, because the reference's RayTriangle has no lower bound on t
+ * (kernel_bvh.cl:140); tmax seeds isect.t (the reference uses 100000). */
+typedef struct { float ox, oy, oz, tmin; float dx, dy, dz, tmax; } b2rt_ray;   /* 32 B */
+typedef struct { float t, u, v; uint32_t tri; } b2rt_hit;                       /* 16 B */
+#define B2RT_MISS 0xFFFFFFFFu
+#define B2RT_MAX_RENDER_DIST 100000.0f      /* kernel_bvh.cl:7 */
+
+typedef struct {
+    uint64_t n_triangles, n_nodes, n_materials;      /* reference-layout inputs           */
+    uint64_t n_wide_nodes, n_leaf_blocks;             /* GPU-resident compressed wide BVH  */
+    uint64_t wide_node_bytes, leaf_bytes, shading_bytes;
+    uint32_t max_depth_binary, max_depth_wide;
+    uint32_t sm_count, reserved;
+} b2rt_scene_info;
+
+typedef struct {
+    uint64_t rays;              /* rays traced by counted launches                         */
+    uint64_t wide_nodes;        /* wide-node visits                                        */
+    uint64_t leaf_blocks;       /* leaf blocks fetched                                     */
+    uint64_t leaf_gate_pass;    /* ... of which passed the exact fp32 leaf box             */
+    uint64_t tri_tests;         /* Moller-Trumbore evaluations                             */
+    uint64_t bytes_fetched;     /* algorithmic bytes: 96 B per wide node + leaf block bytes */
+} b2rt_counters;
+
+enum {
+    B2RT_OPT_TRAVERSAL = 0,     /* 0 = compressed wide BVH (default), 1 = reference-layout binary walk */
+    B2RT_OPT_COUNTERS = 1,      /* 1 = launches use the counting build of the kernels      */
+    B2RT_OPT_BLOCKS_PER_SM = 2, /* persistent grid = value * SM count (0 = default)        */
+    B2RT_OPT_RENDER_MODE = 3    /* 0 = wavefront (default), 1 = megakernel                 */
+};
+
+/* ---- lifetime ---------------------------------------------------------------------- */
+/* CLContext::CLContext + CLKernel::CLKernel (CLutils.cpp:9-35, 52-66): pick the
+ * device, create the stream (the in-order queue), load the precompiled kernels. */
+int b2rt_create(int device_id, b2rt_context** out);
+void b2rt_destroy(b2rt_context* ctx);
+/* Text of the last failure on this context (or of the last failed b2rt_create when ctx == NULL). */
+const char* b2rt_last_error(const b2rt_context* ctx);
+const char* b2rt_status_string(int status);          /* GetClErrorString (CLutils.h:29-105) */
+
+/* ---- buffers and kernel arguments ----------------------------------------------------- */
+/* cl::Buffer(context, flags, size, host_ptr, &err) (CLBVHnode.cpp:214-235,
+ * CLRaytracer.cpp:132-135). With COPY_HOST_PTR the bytes are copied before return.
+ * Buffers without host data are zero-filled: the reference never clears its
+ * accumulation buffer although frame 1 reads it (kernel_bvh.cl:454). */
+int b2rt_buffer_create(b2rt_context* ctx, uint32_t flags, size_t bytes, const void* host_ptr, b2rt_buffer* out);
+int b2rt_buffer_release(b2rt_context* ctx, b2rt_buffer buf);
+/* clSetKernelArg as used by CLKernel::SetArgument (CLutils.cpp:68-77). Slots 0-3
+ * take a pointer to a b2rt_buffer (size 8), the others the scalar / float3 sizes above. */
+int b2rt_set_arg(b2rt_context* ctx, uint32_t slot, const void* data, size_t size);
+
+/* ---- frame path: CLContext::ExecuteKernel / ReadBuffer / Finish (CLutils.cpp:37-50) ---- */
+/* Enqueue KernelEntry for gid in [0, global_work_size). Asynchronous. */
+int b2rt_execute(b2rt_context* ctx, size_t global_work_size);
+/* Same, restricted to gid in [gid_begin, gid_end): one screen shard of a multi-GPU frame. */
+int b2rt_execute_range(b2rt_context* ctx, size_t gid_begin, size_t gid_end);
+/* Non-blocking read of `bytes` from offset 0 of `buf` into host memory (CLutils.cpp:37-42). */
+int b2rt_read_buffer(b2rt_context* ctx, b2rt_buffer buf, void* dst, size_t bytes);
+int b2rt_finish(b2rt_context* ctx);
+
+/* ---- convenience wrappers over the calls above --------------------------------------- */
+/* CLBVHScene::SetupBuffers (CLBVHnode.cpp:209-236): three buffer creates + binds. */
+int b2rt_upload_scene(b2rt_context* ctx, const void* triangles, uint64_t n_triangles,
+                      const void* nodes, uint64_t n_nodes, const void* materials, uint64_t n_materials);
+/* CLRaytracer::SetupBuffers (CLRaytracer.cpp:122-137): WIDTH/HEIGHT + zeroed output buffer. */
+int b2rt_resize(b2rt_context* ctx, uint32_t width, uint32_t height);
+int b2rt_read_pixels(b2rt_context* ctx, void* dst, size_t bytes);   /* read_buffer on the bound slot 0 */
+
+/* ---- ray-stream path (new) ----------------------------------------------------------- */
+/* Host buffers: H2D copy, trace, D2H copy, synchronous on return.
+ * closest: hits[i] = {t,u,v,tri} of Intersect() (kernel_bvh.cl:171-219), tri = B2RT_MISS and
+ * t = tmax on a miss. any: occluded[i] = Intersect(tmax).hit with early exit. */
+int b2rt_trace_closest(b2rt_context* ctx, const b2rt_ray* rays, uint64_t n, b2rt_hit* hits);
+int b2rt_trace_any(b2rt_context* ctx, const b2rt_ray* rays, uint64_t n, uint32_t* occluded);
+/* Device-resident buffers (plain device pointers, e.g. torch tensor data_ptr()); enqueued on
+ * `cuda_stream` (a cudaStream_t passed as void*; NULL = the context's own stream). Asynchronous. */
+int b2rt_trace_closest_device(b2rt_context* ctx, const b2rt_ray* d_rays, uint64_t n, b2rt_hit* d_hits, void* cuda_stream);
+int b2rt_trace_any_device(b2rt_context* ctx, const b2rt_ray* d_rays, uint64_t n, uint32_t* d_occluded, void* cuda_stream);
+/* CreateRay (kernel_bvh.cl:386-403) for gid in [gid_begin, gid_end) with the currently bound
+ * WIDTH/HEIGHT/FRAME_COUNT/CAMERA_* arguments, written to device memory as b2rt_ray. */
+int b2rt_camera_rays_device(b2rt_context* ctx, size_t gid_begin, size_t gid_end, b2rt_ray* d_rays, void* cuda_stream);
+
+/* ---- introspection -------------------------------------------------------------------- */
+int b2rt_device_pointer(b2rt_context* ctx, b2rt_buffer buf, void** d_ptr, size_t* bytes);
+int b2rt_bound_buffer(b2rt_context* ctx, uint32_t slot, b2rt_buffer* out);
+int b2rt_scene_info_get(b2rt_context* ctx, b2rt_scene_info* out);
+int b2rt_set_option(b2rt_context* ctx, uint32_t option, int64_t value);
+int b2rt_get_counters(b2rt_context* ctx, b2rt_counters* out);   /* accumulated since reset */
+int b2rt_reset_counters(b2rt_context* ctx);
+/* Kernels launched by this context since creation (for bench.py's gpu_launches). */
+uint64_t b2rt_launch_count(const b2rt_context* ctx);
+int b2rt_device_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2RT_H */

@@ -1,0 +1,619 @@
+// api.cu -- the C ABI of include/b2rt.h: context, buffers, kernel-argument slots,
+// frame and ray-stream entry points. Replaces what the reference does through
+// CLContext / CLKernel (CLutils.cpp:9-77). There is no CPU path in this file: a
+// missing CUDA device makes b2rt_create fail and nothing else is reachable.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <string.h>
+#include <algorithm>
+#include <memory>
+#include <new>
+#include <string>
+#include <unordered_map>
+#include <vector>
+#include "b2rt.h"
+#include "kernels.h"
+#include "wide_bvh.h"
+
+using namespace b2rt;
+
+namespace {
+
+struct Buffer {
+    void* d_ptr = nullptr;
+    size_t bytes = 0;
+    uint32_t flags = 0;
+    std::vector<uint8_t> shadow;   // host copy of COPY_HOST_PTR data, dropped once the wide BVH is built
+};
+
+constexpr uint64_t STREAM_CHUNK = 1ull << 22;   // rays per pipelined chunk of the host-buffer entry points
+
+std::string g_create_error;
+
+}  // namespace
+
+struct b2rt_context {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr, stream_in = nullptr, stream_out = nullptr;
+    std::unordered_map<uint64_t, Buffer> buffers;
+    uint64_t next_id = 1;
+    b2rt_buffer bound[4] = { 0, 0, 0, 0 };
+    bool arg_set[B2RT_ARG_COUNT] = { false };
+    uint32_t width = 0, height = 0, frame_count = 0, frame_seed = 0;
+    int32_t bounces = 0, light_type = 0;
+    float sky = 0.0f;
+    float cam_pos[4] = { 0, 0, 0, 0 }, cam_front[4] = { 0, 0, 0, 0 }, cam_up[4] = { 0, 0, 0, 0 };
+    // derived scene
+    bool scene_dirty = true;
+    void *d_wide = nullptr, *d_leaf = nullptr, *d_shade = nullptr;
+    b2rt_scene_info info;
+    uint32_t stack_bound = 8;
+    SceneView view;
+    // scratch
+    unsigned long long* d_next = nullptr;
+    unsigned long long* d_counters = nullptr;
+    void* d_stage_rays[2] = { nullptr, nullptr };
+    void* d_stage_out[2] = { nullptr, nullptr };
+    uint64_t stage_capacity = 0;
+    cudaEvent_t ev_in[2] = { nullptr, nullptr }, ev_comp[2] = { nullptr, nullptr }, ev_out[2] = { nullptr, nullptr };
+    // options
+    int64_t opt_traversal = 0, opt_counters = 0, opt_blocks_per_sm = 0, opt_render_mode = 0;
+    int grid_closest = 0, grid_any = 0;
+    uint64_t launches = 0;
+    std::string error;
+};
+
+namespace {
+
+int fail(b2rt_context* c, int status, const std::string& msg) {
+    if (c) c->error = msg; else g_create_error = msg;
+    return status;
+}
+int cuda_fail(b2rt_context* c, cudaError_t e, const char* what) {
+    int status = (e == cudaErrorMemoryAllocation) ? B2RT_MEM_OBJECT_ALLOCATION_FAILURE : B2RT_OUT_OF_RESOURCES;
+    return fail(c, status, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CK(call)                                                         \
+    do {                                                                 \
+        cudaError_t e__ = (call);                                        \
+        if (e__ != cudaSuccess) return cuda_fail(ctx, e__, #call);       \
+    } while (0)
+
+int use_device(b2rt_context* ctx) {
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaSetDevice");
+    return B2RT_SUCCESS;
+}
+
+Buffer* find(b2rt_context* ctx, b2rt_buffer id) {
+    auto it = ctx->buffers.find(id);
+    return it == ctx->buffers.end() ? nullptr : &it->second;
+}
+
+void free_scene(b2rt_context* ctx) {
+    if (ctx->d_wide) cudaFree(ctx->d_wide);
+    if (ctx->d_leaf) cudaFree(ctx->d_leaf);
+    if (ctx->d_shade) cudaFree(ctx->d_shade);
+    ctx->d_wide = ctx->d_leaf = ctx->d_shade = nullptr;
+}
+
+// Host view of a buffer's contents: the creation-time shadow if still held, else a read-back.
+int host_view(b2rt_context* ctx, Buffer* b, std::vector<uint8_t>& tmp, const uint8_t** out) {
+    if (!b->shadow.empty() || b->bytes == 0) { *out = b->shadow.data(); return B2RT_SUCCESS; }
+    try { tmp.resize(b->bytes); } catch (const std::bad_alloc&) { return fail(ctx, B2RT_OUT_OF_HOST_MEMORY, "host read-back buffer"); }
+    CK(cudaMemcpy(tmp.data(), b->d_ptr, b->bytes, cudaMemcpyDeviceToHost));
+    *out = tmp.data();
+    return B2RT_SUCCESS;
+}
+
+// Build + upload the compressed wide BVH for the currently bound triangle/node buffers.
+int ensure_scene(b2rt_context* ctx) {
+    if (!ctx->scene_dirty) return B2RT_SUCCESS;
+    Buffer* bt = find(ctx, ctx->bound[B2RT_ARG_BUFFER_SCENE]);
+    Buffer* bn = find(ctx, ctx->bound[B2RT_ARG_BUFFER_NODE]);
+    Buffer* bm = find(ctx, ctx->bound[B2RT_ARG_BUFFER_MATERIAL]);
+    if (!bt || !bn) return fail(ctx, B2RT_INVALID_KERNEL_ARGS, "triangle (slot 1) and node (slot 2) buffers must be bound");
+    if (bt->bytes % sizeof(RefTriangle) || bn->bytes % sizeof(RefNode) || bn->bytes == 0)
+        return fail(ctx, B2RT_INVALID_ARG_VALUE, "scene buffers are not whole arrays of CLTriangle (256 B) / CLLinearBVHNode (48 B)");
+    if (bm && bm->bytes % sizeof(RefMaterial))
+        return fail(ctx, B2RT_INVALID_ARG_VALUE, "material buffer is not a whole array of CLMaterial (64 B)");
+    std::vector<uint8_t> tmp_t, tmp_n;
+    const uint8_t *ht = nullptr, *hn = nullptr;
+    int st = host_view(ctx, bt, tmp_t, &ht);
+    if (st) return st;
+    st = host_view(ctx, bn, tmp_n, &hn);
+    if (st) return st;
+    uint64_t n_tris = bt->bytes / sizeof(RefTriangle), n_nodes = bn->bytes / sizeof(RefNode);
+    WideBVH w;
+    std::string err;
+    try {
+        err = build_wide_bvh(reinterpret_cast<const RefNode*>(hn), n_nodes, reinterpret_cast<const RefTriangle*>(ht), n_tris, w);
+    } catch (const std::bad_alloc&) {
+        return fail(ctx, B2RT_OUT_OF_HOST_MEMORY, "wide BVH build ran out of host memory");
+    }
+    if (!err.empty()) return fail(ctx, B2RT_INVALID_ARG_VALUE, "invalid BVH: " + err);
+    uint32_t bound = wide_stack_bound(w);
+    if (bound > 256) return fail(ctx, B2RT_OUT_OF_RESOURCES, "BVH too deep for the traversal stack (wide depth " + std::to_string(w.max_depth_wide) + ")");
+    free_scene(ctx);
+    size_t wb = w.nodes.size() * sizeof(WideNode), lb = w.leaf.size() * sizeof(U4), sb = w.shade.size() * sizeof(ShadeTri);
+    CK(cudaMalloc(&ctx->d_wide, std::max<size_t>(wb, 96)));
+    CK(cudaMalloc(&ctx->d_leaf, std::max<size_t>(lb, 16) + 64));   // +64: visit_leaf prefetches one record past the header
+    CK(cudaMalloc(&ctx->d_shade, std::max<size_t>(sb, 48)));
+    CK(cudaMemsetAsync(static_cast<char*>(ctx->d_leaf) + std::max<size_t>(lb, 16), 0, 64, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_wide, w.nodes.data(), wb, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_leaf, w.leaf.data(), lb, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_shade, w.shade.data(), sb, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    memset(&ctx->info, 0, sizeof(ctx->info));
+    ctx->info.n_triangles = n_tris;
+    ctx->info.n_nodes = n_nodes;
+    ctx->info.n_materials = bm ? bm->bytes / sizeof(RefMaterial) : 0;
+    ctx->info.n_wide_nodes = w.nodes.size();
+    ctx->info.n_leaf_blocks = w.n_leaf_blocks;
+    ctx->info.wide_node_bytes = wb;
+    ctx->info.leaf_bytes = lb;
+    ctx->info.shading_bytes = sb;
+    ctx->info.max_depth_binary = w.max_depth_binary;
+    ctx->info.max_depth_wide = w.max_depth_wide;
+    ctx->info.sm_count = (uint32_t)ctx->sm_count;
+    ctx->stack_bound = bound;
+    ctx->view.wide = static_cast<const U4*>(ctx->d_wide);
+    ctx->view.leaf = static_cast<const U4*>(ctx->d_leaf);
+    ctx->view.shade = static_cast<const ShadeTri*>(ctx->d_shade);
+    ctx->view.mats = bm ? static_cast<const RefMaterial*>(bm->d_ptr) : nullptr;
+    ctx->view.tris = static_cast<const RefTriangle*>(bt->d_ptr);
+    ctx->view.nodes = static_cast<const RefNode*>(bn->d_ptr);
+    ctx->view.n_tris = (uint32_t)n_tris;
+    ctx->view.n_nodes = (uint32_t)n_nodes;
+    ctx->view.n_mats = (uint32_t)ctx->info.n_materials;
+    ctx->view.n_wide = (uint32_t)w.nodes.size();
+    // the 256 B/triangle host shadow is only needed for this build
+    bt->shadow.clear(); bt->shadow.shrink_to_fit();
+    bn->shadow.clear(); bn->shadow.shrink_to_fit();
+    int occ = 0;
+    CK(trace_occupancy(false, bound, &occ));
+    ctx->grid_closest = ctx->sm_count * std::max(occ, 1);
+    CK(trace_occupancy(true, bound, &occ));
+    ctx->grid_any = ctx->sm_count * std::max(occ, 1);
+    ctx->scene_dirty = false;
+    return B2RT_SUCCESS;
+}
+
+int trace_device(b2rt_context* ctx, const void* d_rays, uint64_t n, void* d_out, bool any, cudaStream_t st) {
+    if (n == 0) return B2RT_SUCCESS;
+    if (!d_rays || !d_out) return fail(ctx, B2RT_INVALID_VALUE, "null ray or output pointer");
+    if (ctx->opt_traversal == 1) {
+        CK(launch_trace_binary(ctx->view, d_rays, n, d_out, any, st));
+        ctx->launches += 1;
+        return B2RT_SUCCESS;
+    }
+    int grid = any ? ctx->grid_any : ctx->grid_closest;
+    if (ctx->opt_blocks_per_sm > 0) grid = ctx->sm_count * (int)ctx->opt_blocks_per_sm;
+    uint64_t warps_needed = (n + 31) / 32, blocks_needed = (warps_needed * 32 + trace_block_threads() - 1) / trace_block_threads();
+    if ((uint64_t)grid > blocks_needed) grid = (int)blocks_needed;
+    CK(launch_trace_wide(ctx->view, d_rays, n, d_out, any, ctx->opt_counters != 0, ctx->stack_bound, grid, ctx->d_next,
+                         ctx->d_counters, st));
+    ctx->launches += 1;
+    return B2RT_SUCCESS;
+}
+
+int ensure_staging(b2rt_context* ctx, uint64_t chunk) {
+    if (ctx->stage_capacity >= chunk) return B2RT_SUCCESS;
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->d_stage_rays[i]) cudaFree(ctx->d_stage_rays[i]);
+        if (ctx->d_stage_out[i]) cudaFree(ctx->d_stage_out[i]);
+        ctx->d_stage_rays[i] = ctx->d_stage_out[i] = nullptr;
+    }
+    ctx->stage_capacity = 0;
+    for (int i = 0; i < 2; ++i) {
+        CK(cudaMalloc(&ctx->d_stage_rays[i], chunk * sizeof(b2rt_ray)));
+        CK(cudaMalloc(&ctx->d_stage_out[i], chunk * sizeof(b2rt_hit)));
+    }
+    ctx->stage_capacity = chunk;
+    return B2RT_SUCCESS;
+}
+
+// Host-buffer ray stream: chunks are copied in, traced and copied out on three streams so
+// that PCIe transfers overlap the traversal kernels.
+int trace_host(b2rt_context* ctx, const b2rt_ray* rays, uint64_t n, void* out, bool any) {
+    int st = use_device(ctx);
+    if (st) return st;
+    st = ensure_scene(ctx);
+    if (st) return st;
+    if (n == 0) return B2RT_SUCCESS;
+    if (!rays || !out) return fail(ctx, B2RT_INVALID_VALUE, "null ray or output pointer");
+    uint64_t chunk = std::min<uint64_t>(n, STREAM_CHUNK);
+    st = ensure_staging(ctx, chunk);
+    if (st) return st;
+    const size_t out_elem = any ? sizeof(uint32_t) : sizeof(b2rt_hit);
+    uint64_t k = 0;
+    for (uint64_t off = 0; off < n; off += chunk, ++k) {
+        int s = (int)(k & 1);
+        uint64_t m = std::min<uint64_t>(chunk, n - off);
+        if (k >= 2) CK(cudaStreamWaitEvent(ctx->stream_in, ctx->ev_comp[s], 0));     // rays[s] free again
+        CK(cudaMemcpyAsync(ctx->d_stage_rays[s], rays + off, m * sizeof(b2rt_ray), cudaMemcpyHostToDevice, ctx->stream_in));
+        CK(cudaEventRecord(ctx->ev_in[s], ctx->stream_in));
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_in[s], 0));
+        if (k >= 2) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_out[s], 0));         // out[s] drained
+        st = trace_device(ctx, ctx->d_stage_rays[s], m, ctx->d_stage_out[s], any, ctx->stream);
+        if (st) return st;
+        CK(cudaEventRecord(ctx->ev_comp[s], ctx->stream));
+        CK(cudaStreamWaitEvent(ctx->stream_out, ctx->ev_comp[s], 0));
+        CK(cudaMemcpyAsync(static_cast<char*>(out) + off * out_elem, ctx->d_stage_out[s], m * out_elem,
+                           cudaMemcpyDeviceToHost, ctx->stream_out));
+        CK(cudaEventRecord(ctx->ev_out[s], ctx->stream_out));
+    }
+    CK(cudaStreamSynchronize(ctx->stream_out));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return B2RT_SUCCESS;
+}
+
+int frame_args(b2rt_context* ctx, FrameArgs& a) {
+    for (int i = 0; i < B2RT_ARG_COUNT; ++i)
+        if (!ctx->arg_set[i]) return fail(ctx, B2RT_INVALID_KERNEL_ARGS, "kernel argument " + std::to_string(i) + " was never set");
+    a.width = ctx->width; a.height = ctx->height; a.frame_count = ctx->frame_count;
+    a.bounces = ctx->bounces; a.light_type = ctx->light_type; a.sky = ctx->sky;
+    for (int k = 0; k < 3; ++k) { a.pos[k] = ctx->cam_pos[k]; a.front[k] = ctx->cam_front[k]; a.up[k] = ctx->cam_up[k]; }
+    a.angle = tanf(0.5f * (45.0f * 3.1415f / 180.0f));   // kernel_bvh.cl:392, evaluated by the host libm like the oracle
+    if (a.width == 0 || a.height == 0) return fail(ctx, B2RT_INVALID_KERNEL_ARGS, "WIDTH/HEIGHT must be non-zero");
+    return B2RT_SUCCESS;
+}
+
+}  // namespace
+
+// ---- lifetime ---------------------------------------------------------------------------
+extern "C" int b2rt_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" int b2rt_create(int device_id, b2rt_context** out) {
+    if (!out) return fail(nullptr, B2RT_INVALID_VALUE, "null output handle");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(nullptr, B2RT_DEVICE_NOT_FOUND, std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                    " (libb2rt has no CPU fallback)");
+    }
+    if (device_id < 0 || device_id >= n) return fail(nullptr, B2RT_DEVICE_NOT_FOUND, "device id out of range");
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device_id)) != cudaSuccess) return cuda_fail(nullptr, e, "cudaGetDeviceProperties");
+    if (prop.major != 10)
+        return fail(nullptr, B2RT_DEVICE_NOT_FOUND, std::string("device ") + prop.name + " is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) +
+                    "; libb2rt ships sm_100a code only");
+    b2rt_context* ctx = new (std::nothrow) b2rt_context();
+    if (!ctx) return fail(nullptr, B2RT_OUT_OF_HOST_MEMORY, "context allocation");
+    ctx->device = device_id;
+    ctx->sm_count = prop.multiProcessorCount;
+    memset(&ctx->info, 0, sizeof(ctx->info));
+    memset(&ctx->view, 0, sizeof(ctx->view));
+    auto bail = [&](cudaError_t err, const char* what) { int s = cuda_fail(nullptr, err, what); b2rt_destroy(ctx); return s; };
+    if ((e = cudaSetDevice(device_id)) != cudaSuccess) return bail(e, "cudaSetDevice");
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream_in, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream_out, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
+    for (int i = 0; i < 2; ++i) {
+        if ((e = cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
+        if ((e = cudaEventCreateWithFlags(&ctx->ev_comp[i], cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
+        if ((e = cudaEventCreateWithFlags(&ctx->ev_out[i], cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
+    }
+    if ((e = cudaMalloc(&ctx->d_next, 64)) != cudaSuccess) return bail(e, "cudaMalloc");
+    if ((e = cudaMalloc(&ctx->d_counters, 64)) != cudaSuccess) return bail(e, "cudaMalloc");
+    if ((e = cudaMemset(ctx->d_counters, 0, 64)) != cudaSuccess) return bail(e, "cudaMemset");
+    *out = ctx;
+    return B2RT_SUCCESS;
+}
+
+extern "C" void b2rt_destroy(b2rt_context* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    free_scene(ctx);
+    for (auto& kv : ctx->buffers) if (kv.second.d_ptr) cudaFree(kv.second.d_ptr);
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->d_stage_rays[i]) cudaFree(ctx->d_stage_rays[i]);
+        if (ctx->d_stage_out[i]) cudaFree(ctx->d_stage_out[i]);
+        if (ctx->ev_in[i]) cudaEventDestroy(ctx->ev_in[i]);
+        if (ctx->ev_comp[i]) cudaEventDestroy(ctx->ev_comp[i]);
+        if (ctx->ev_out[i]) cudaEventDestroy(ctx->ev_out[i]);
+    }
+    if (ctx->d_next) cudaFree(ctx->d_next);
+    if (ctx->d_counters) cudaFree(ctx->d_counters);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->stream_in) cudaStreamDestroy(ctx->stream_in);
+    if (ctx->stream_out) cudaStreamDestroy(ctx->stream_out);
+    delete ctx;
+}
+
+extern "C" const char* b2rt_last_error(const b2rt_context* ctx) { return ctx ? ctx->error.c_str() : g_create_error.c_str(); }
+
+extern "C" const char* b2rt_status_string(int status) {
+    switch (status) {   // same names as GetClErrorString (CLutils.h:29-105) for the codes this library returns
+        case B2RT_SUCCESS: return "CL_SUCCESS";
+        case B2RT_DEVICE_NOT_FOUND: return "CL_DEVICE_NOT_FOUND";
+        case B2RT_MEM_OBJECT_ALLOCATION_FAILURE: return "CL_MEM_OBJECT_ALLOCATION_FAILURE";
+        case B2RT_OUT_OF_RESOURCES: return "CL_OUT_OF_RESOURCES";
+        case B2RT_OUT_OF_HOST_MEMORY: return "CL_OUT_OF_HOST_MEMORY";
+        case B2RT_INVALID_VALUE: return "CL_INVALID_VALUE";
+        case B2RT_INVALID_CONTEXT: return "CL_INVALID_CONTEXT";
+        case B2RT_INVALID_MEM_OBJECT: return "CL_INVALID_MEM_OBJECT";
+        case B2RT_INVALID_ARG_INDEX: return "CL_INVALID_ARG_INDEX";
+        case B2RT_INVALID_ARG_VALUE: return "CL_INVALID_ARG_VALUE";
+        case B2RT_INVALID_ARG_SIZE: return "CL_INVALID_ARG_SIZE";
+        case B2RT_INVALID_KERNEL_ARGS: return "CL_INVALID_KERNEL_ARGS";
+        case B2RT_INVALID_GLOBAL_WORK_SIZE: return "CL_INVALID_GLOBAL_WORK_SIZE";
+        default: return "Unknown OpenCL error";
+    }
+}
+
+// ---- buffers and arguments --------------------------------------------------------------
+extern "C" int b2rt_buffer_create(b2rt_context* ctx, uint32_t flags, size_t bytes, const void* host_ptr, b2rt_buffer* out) {
+    if (!ctx) return B2RT_INVALID_CONTEXT;
+    if (!out) return fail(ctx, B2RT_INVALID_VALUE, "null output buffer handle");
+    *out = 0;
+    if (bytes == 0) return fail(ctx, -61 /* CL_INVALID_BUFFER_SIZE */, "zero-sized buffer");
+    bool copy = (flags & B2RT_MEM_COPY_HOST_PTR) != 0;
+    if (copy != (host_ptr != nullptr)) return fail(ctx, -37 /* CL_INVALID_HOST_PTR */, "host_ptr and COPY_HOST_PTR must be given together");
+    int st = use_device(ctx);
+    if (st) return st;
+    Buffer b;
+    b.bytes = bytes;
+    b.flags = flags;
+    CK(cudaMalloc(&b.d_ptr, bytes));
+    cudaError_t e;
+    if (copy) {
+        e = cudaMemcpyAsync(b.d_ptr, host_ptr, bytes, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e == cudaSuccess) {
+            try { b.shadow.assign(static_cast<const uint8_t*>(host_ptr), static_cast<const uint8_t*>(host_ptr) + bytes); }
+            catch (const std::bad_alloc&) { b.shadow.clear(); }   // fall back to a read-back at build time
+        }
+    } else {
+        e = cudaMemsetAsync(b.d_ptr, 0, bytes, ctx->stream);
+    }
+    if (e != cudaSuccess) { cudaFree(b.d_ptr); return cuda_fail(ctx, e, "buffer initialisation"); }
+    uint64_t id = ctx->next_id++;
+    ctx->buffers.emplace(id, std::move(b));
+    *out = id;
+    return B2RT_SUCCESS;
+}
+
+extern "C" int b2rt_buffer_release(b2rt_context* ctx, b2rt_buffer buf) {
+    if (!ctx) return B2RT_INVALID_CONTEXT;
+    Buffer* b = find(ctx, buf);
+    if (!b) return fail(ctx, B2RT_INVALID_MEM_OBJECT, "unknown buffer");
+    int st = use_device(ctx);
+    if (st) return st;
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(b->d_ptr);
+    ctx->buffers.erase(buf);
+    for (int i = 0; i < 4; ++i)
+        if (ctx->bound[i] == buf) { ctx->bound[i] = 0; ctx->arg_set[i] = false; if (i) ctx->scene_dirty = true; }
+    return B2RT_SUCCESS;
+}
+
+extern "C" int b2rt_set_arg(b2rt_context* ctx, uint32_t slot, const void* data, size_t size) {
+    if (!ctx) return B2RT_INVALID_CONTEXT;
+    if (slot >= B2RT_ARG_COUNT) return fail(ctx, B2RT_INVALID_ARG_INDEX, "argument index " + std::to_string(slot) + " out of range");
+    if (!data) return fail(ctx, B2RT_INVALID_ARG_VALUE, "null argument value");
+    static const size_t want[B2RT_ARG_COUNT] = { 8, 8, 8, 8, 4, 4, 4, 4, 4, 4, 4, 16, 16, 16 };
+    if (size != want[slot])
+        return fail(ctx, B2RT_INVALID_ARG_SIZE, "argument " + std::to_string(slot) + " expects " + std::to_string(want[slot]) + " bytes, got " + std::to_string(size));
+    switch (slot) {
+        case B2RT_ARG_BUFFER_OUT: case B2RT_ARG_BUFFER_SCENE: case B2RT_ARG_BUFFER_NODE: case B2RT_ARG_BUFFER_MATERIAL: {
+            b2rt_buffer id;
+            memcpy(&id, data, 8);
+            if (!find(ctx, id)) return fail(ctx, B2RT_INVALID_MEM_OBJECT, "argument " + std::to_string(slot) + " is not a live buffer");
+            if (ctx->bound[slot] != id && slot != B2RT_ARG_BUFFER_OUT) ctx->scene_dirty = true;
+            ctx->bound[slot] = id;
+            break;
+        }
+        case B2RT_ARG_WIDTH: memcpy(&ctx->width, data, 4); break;
+        case B2RT_ARG_HEIGHT: memcpy(&ctx->height, data, 4); break;
+        case B2RT_ARG_FRAME_COUNT: memcpy(&ctx->frame_count, data, 4); break;
+        case B2RT_ARG_FRAME_SEED: memcpy(&ctx->frame_seed, data, 4); break;   // unused by the kernel (kernel_bvh.cl:424)
+        case B2RT_ARG_LIGHT_BOUNCES: memcpy(&ctx->bounces, data, 4); break;
+        case B2RT_ARG_LIGHT_TYPE: memcpy(&ctx->light_type, data, 4); break;
+        case B2RT_ARG_SKYBOX_INTENSITY: memcpy(&ctx->sky, data, 4); break;
+        case B2RT_ARG_CAMERA_POS: memcpy(ctx->cam_pos, data, 16); break;
+        case B2RT_ARG_CAMERA_FRONT: memcpy(ctx->cam_front, data, 16); break;
+        case B2RT_ARG_CAMERA_UP: memcpy(ctx->cam_up, data, 16); break;
+    }
+    ctx->arg_set[slot] = true;
+    return B2RT_SUCCESS;
+}
+
+// ---- frame path -------------------------------------------------------------------------
+extern "C" int b2rt_execute_range(b2rt_context* ctx, size_t gid_begin, size_t gid_end) {
+    if (!ctx) return B2RT_INVALID_CONTEXT;
+    int st = use_device(ctx);
+    if (st) return st;
+    FrameArgs a;
+    st = frame_args(ctx, a);
+    if (st) return st;
+    st = ensure_scene(ctx);
+    if (st) return st;
+    Buffer* out = find(ctx, ctx->bound[B2RT_ARG_BUFFER_OUT]);
+    if (!out) return fail(ctx, B2RT_INVALID_KERNEL_ARGS, "output buffer (slot 0) is not bound");
+    if (!ctx->view.mats || ctx->view.n_mats == 0) return fail(ctx, B2RT_INVALID_KERNEL_ARGS, "material buffer (slot 3) is not bound");
+    if (gid_end < gid_begin || gid_end > 0xffffffffull || gid_end * 16 > out->bytes)
+        return fail(ctx, B2RT_INVALID_GLOBAL_WORK_SIZE, "work range [" + std::to_string(gid_begin) + "," + std::to_string(gid_end) +
+                    ") exceeds the output buffer (" + std::to_string(out->bytes / 16) + " pixels)");
+    if (gid_end == gid_begin) return B2RT_SUCCESS;
+    CK(launch_render_mega(ctx->view, a, static_cast<float*>(out->d_ptr), gid_begin, gid_end, ctx->opt_traversal == 1,
+                          ctx->stack_bound, ctx->stream));
+    ctx->launches += 1;
+    return B2RT_SUCCESS;
+}
+
+extern "C" int b2rt_execute(b2rt_context* ctx, size_t global_work_size) {
+    if (!ctx) return B2RT_INVALID_CONTEXT;
+    if (global_work_size == 0) return fail(ctx, B2RT_INVALID_GLOBAL_WORK_SIZE, "global work size is 0");
+    return b2rt_execute_range(ctx, 0, global_work_size);
+}
+
+extern "C" int b2rt_read_buffer(b2rt_context* ctx, b2rt_buffer buf, void* dst, size_t bytes) {
+    if (!ctx) return B2RT_INVALID_CONTEXT;
+    Buffer* b = find(ctx, buf);
+    if (!b) return fail(ctx, B2RT_INVALID_MEM_OBJECT, "unknown buffer");
+    if (!dst || bytes > b->bytes) return fail(ctx, B2RT_INVALID_VALUE, "read of " + std::to_string(bytes) + " bytes from a " + std::to_string(b->bytes) + "-byte buffer");
+    int st = use_device(ctx);
+    if (st) return st;
+    CK(cudaMemcpyAsync(dst, b->d_ptr, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return B2RT_SUCCESS;
+}
+
+extern "C" int b2rt_finish(b2rt_context* ctx) {
+    if (!ctx) return B2RT_INVALID_CONTEXT;
+    int st = use_device(ctx);
+    if (st) return st;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return B2RT_SUCCESS;
+}
+
+// ---- convenience --------------------------------------------------------------------------
+extern "C" int b2rt_upload_scene(b2rt_context* ctx, const void* triangles, uint64_t n_triangles, const void* nodes,
+                                 uint64_t n_nodes, const void* materials, uint64_t n_materials) {
+    if (!ctx) return B2RT_INVALID_CONTEXT;
+    if (!triangles || !nodes || !materials || !n_triangles || !n_nodes || !n_materials)
+        return fail(ctx, B2RT_INVALID_VALUE, "upload_scene needs non-empty triangle, node and material arrays");
+    const void* src[3] = { triangles, nodes, materials };
+    size_t bytes[3] = { (size_t)n_triangles * sizeof(RefTriangle), (size_t)n_nodes * sizeof(RefNode), (size_t)n_materials * sizeof(RefMaterial) };
+    for (int i = 0; i < 3; ++i) {
+        b2rt_buffer old = ctx->bound[1 + i], buf = 0;
+        int st = b2rt_buffer_create(ctx, B2RT_MEM_READ_ONLY | B2RT_MEM_COPY_HOST_PTR, bytes[i], src[i], &buf);
+        if (st) return st;
+        st = b2rt_set_arg(ctx, 1 + i, &buf, sizeof(buf));
+        if (st) return st;
+        if (old && old != buf) b2rt_buffer_release(ctx, old), ctx->bound[1 + i] = buf, ctx->arg_set[1 + i] = true;
+    }
+    return ensure_scene(ctx);
+}
+
+extern "C" int b2rt_resize(b2rt_context* ctx, uint32_t width, uint32_t height) {
+    if (!ctx) return B2RT_INVALID_CONTEXT;
+    if (!width || !height) return fail(ctx, B2RT_INVALID_VALUE, "zero frame size");
+    int st = b2rt_set_arg(ctx, B2RT_ARG_WIDTH, &width, 4);
+    if (st) return st;
+    st = b2rt_set_arg(ctx, B2RT_ARG_HEIGHT, &height, 4);
+    if (st) return st;
+    b2rt_buffer old = ctx->bound[0], buf = 0;
+    st = b2rt_buffer_create(ctx, B2RT_MEM_WRITE_ONLY, (size_t)width * height * 16, nullptr, &buf);
+    if (st) return st;
+    st = b2rt_set_arg(ctx, B2RT_ARG_BUFFER_OUT, &buf, sizeof(buf));
+    if (st) return st;
+    if (old) { b2rt_buffer_release(ctx, old); ctx->bound[0] = buf; ctx->arg_set[0] = true; }
+    return B2RT_SUCCESS;
+}
+
+extern "C" int b2rt_read_pixels(b2rt_context* ctx, void* dst, size_t bytes) {
+    if (!ctx) return B2RT_INVALID_CONTEXT;
+    if (!ctx->bound[0]) return fail(ctx, B2RT_INVALID_KERNEL_ARGS, "output buffer (slot 0) is not bound");
+    return b2rt_read_buffer(ctx, ctx->bound[0], dst, bytes);
+}
+
+// ---- ray streams -----------------------------------------------------------------------------
+extern "C" int b2rt_trace_closest(b2rt_context* ctx, const b2rt_ray* rays, uint64_t n, b2rt_hit* hits) {
+    if (!ctx) return B2RT_INVALID_CONTEXT;
+    return trace_host(ctx, rays, n, hits, false);
+}
+extern "C" int b2rt_trace_any(b2rt_context* ctx, const b2rt_ray* rays, uint64_t n, uint32_t* occluded) {
+    if (!ctx) return B2RT_INVALID_CONTEXT;
+    return trace_host(ctx, rays, n, occluded, true);
+}
+extern "C" int b2rt_trace_closest_device(b2rt_context* ctx, const b2rt_ray* d_rays, uint64_t n, b2rt_hit* d_hits, void* cuda_stream) {
+    if (!ctx) return B2RT_INVALID_CONTEXT;
+    int st = use_device(ctx);
+    if (st) return st;
+    st = ensure_scene(ctx);
+    if (st) return st;
+    return trace_device(ctx, d_rays, n, d_hits, false, cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->stream);
+}
+extern "C" int b2rt_trace_any_device(b2rt_context* ctx, const b2rt_ray* d_rays, uint64_t n, uint32_t* d_occluded, void* cuda_stream) {
+    if (!ctx) return B2RT_INVALID_CONTEXT;
+    int st = use_device(ctx);
+    if (st) return st;
+    st = ensure_scene(ctx);
+    if (st) return st;
+    return trace_device(ctx, d_rays, n, d_occluded, true, cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->stream);
+}
+extern "C" int b2rt_camera_rays_device(b2rt_context* ctx, size_t gid_begin, size_t gid_end, b2rt_ray* d_rays, void* cuda_stream) {
+    if (!ctx) return B2RT_INVALID_CONTEXT;
+    int st = use_device(ctx);
+    if (st) return st;
+    for (int i = B2RT_ARG_WIDTH; i < B2RT_ARG_COUNT; ++i) {
+        if (i == B2RT_ARG_FRAME_SEED || i == B2RT_ARG_LIGHT_BOUNCES || i == B2RT_ARG_LIGHT_TYPE || i == B2RT_ARG_SKYBOX_INTENSITY) continue;
+        if (!ctx->arg_set[i]) return fail(ctx, B2RT_INVALID_KERNEL_ARGS, "kernel argument " + std::to_string(i) + " was never set");
+    }
+    if (gid_end < gid_begin || gid_end > 0xffffffffull || !d_rays) return fail(ctx, B2RT_INVALID_VALUE, "bad camera ray range");
+    FrameArgs a;
+    memset(&a, 0, sizeof(a));
+    a.width = ctx->width; a.height = ctx->height; a.frame_count = ctx->frame_count;
+    for (int k = 0; k < 3; ++k) { a.pos[k] = ctx->cam_pos[k]; a.front[k] = ctx->cam_front[k]; a.up[k] = ctx->cam_up[k]; }
+    a.angle = tanf(0.5f * (45.0f * 3.1415f / 180.0f));
+    if (!a.width || !a.height) return fail(ctx, B2RT_INVALID_KERNEL_ARGS, "WIDTH/HEIGHT must be non-zero");
+    CK(launch_camera_rays(a, gid_begin, gid_end, d_rays, cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->stream));
+    ctx->launches += 1;
+    return B2RT_SUCCESS;
+}
+
+// ---- introspection ------------------------------------------------------------------------------
+extern "C" int b2rt_device_pointer(b2rt_context* ctx, b2rt_buffer buf, void** d_ptr, size_t* bytes) {
+    if (!ctx) return B2RT_INVALID_CONTEXT;
+    Buffer* b = find(ctx, buf);
+    if (!b) return fail(ctx, B2RT_INVALID_MEM_OBJECT, "unknown buffer");
+    if (d_ptr) *d_ptr = b->d_ptr;
+    if (bytes) *bytes = b->bytes;
+    return B2RT_SUCCESS;
+}
+extern "C" int b2rt_bound_buffer(b2rt_context* ctx, uint32_t slot, b2rt_buffer* out) {
+    if (!ctx) return B2RT_INVALID_CONTEXT;
+    if (slot > 3 || !out) return fail(ctx, B2RT_INVALID_ARG_INDEX, "slot is not a buffer argument");
+    *out = ctx->bound[slot];
+    return B2RT_SUCCESS;
+}
+extern "C" int b2rt_scene_info_get(b2rt_context* ctx, b2rt_scene_info* out) {
+    if (!ctx) return B2RT_INVALID_CONTEXT;
+    if (!out) return fail(ctx, B2RT_INVALID_VALUE, "null output");
+    int st = use_device(ctx);
+    if (st) return st;
+    st = ensure_scene(ctx);
+    if (st) return st;
+    *out = ctx->info;
+    return B2RT_SUCCESS;
+}
+extern "C" int b2rt_set_option(b2rt_context* ctx, uint32_t option, int64_t value) {
+    if (!ctx) return B2RT_INVALID_CONTEXT;
+    switch (option) {
+        case B2RT_OPT_TRAVERSAL: if (value != 0 && value != 1) return fail(ctx, B2RT_INVALID_VALUE, "traversal must be 0 or 1"); ctx->opt_traversal = value; break;
+        case B2RT_OPT_COUNTERS: ctx->opt_counters = value ? 1 : 0; break;
+        case B2RT_OPT_BLOCKS_PER_SM: if (value < 0 || value > 32) return fail(ctx, B2RT_INVALID_VALUE, "blocks per SM out of range"); ctx->opt_blocks_per_sm = value; break;
+        case B2RT_OPT_RENDER_MODE: ctx->opt_render_mode = value; break;
+        default: return fail(ctx, B2RT_INVALID_VALUE, "unknown option");
+    }
+    return B2RT_SUCCESS;
+}
+extern "C" int b2rt_get_counters(b2rt_context* ctx, b2rt_counters* out) {
+    if (!ctx) return B2RT_INVALID_CONTEXT;
+    if (!out) return fail(ctx, B2RT_INVALID_VALUE, "null output");
+    int st = use_device(ctx);
+    if (st) return st;
+    unsigned long long v[6];
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpy(v, ctx->d_counters, sizeof(v), cudaMemcpyDeviceToHost));
+    out->rays = v[0]; out->wide_nodes = v[1]; out->leaf_blocks = v[2]; out->leaf_gate_pass = v[3]; out->tri_tests = v[4];
+    out->bytes_fetched = v[5] * 16ull;
+    return B2RT_SUCCESS;
+}
+extern "C" int b2rt_reset_counters(b2rt_context* ctx) {
+    if (!ctx) return B2RT_INVALID_CONTEXT;
+    int st = use_device(ctx);
+    if (st) return st;
+    CK(cudaMemsetAsync(ctx->d_counters, 0, 64, ctx->stream));
+    return B2RT_SUCCESS;
+}
+extern "C" uint64_t b2rt_launch_count(const b2rt_context* ctx) { return ctx ? ctx->launches : 0; }

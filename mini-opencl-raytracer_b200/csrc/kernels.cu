@@ -1,0 +1,331 @@
+// kernels.cu -- hand-written sm_100a kernels behind libb2rt.so.
+//
+//  trace_persistent<ANY,COUNT,CAP>  persistent-thread while-while traversal of the
+//      compressed wide BVH for a ray stream: one grid of (SMs x blocks/SM) CTAs,
+//      every warp pulls chunks of rays from a global atomic counter into a
+//      warp-local pool, idle lanes are re-filled from the pool with ballot/popc
+//      compaction, interior-node steps and leaf steps run in separate
+//      warp-uniform loops, all node/leaf fetches are 128-bit __ldg.
+//  trace_binary_kernel<ANY>         one thread per ray over the reference's own
+//      48 B / 256 B arrays in the reference's order: the "recompiled reference
+//      kernel" baseline and an on-device cross-check of the wide path.
+//  camera_rays_kernel               CreateRay (kernel_bvh.cl:386-403) as a ray stream.
+//  render_mega_kernel               KernelEntry (kernel_bvh.cl:415-456): one thread per
+//      pixel, path loop around the same traversal primitives.
+//
+// No tensor cores: the path is pointer chasing + fp32 slab/triangle tests, not a
+// contraction (BASELINE.json north_star). Compile with -fmad=false; all
+// parity-critical arithmetic additionally uses explicit *_rn intrinsics.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "kernels.h"
+#include "shade.cuh"
+
+namespace b2rt {
+
+static constexpr unsigned FULL = 0xffffffffu;
+static constexpr int TRACE_BLOCK = 128;
+static constexpr uint32_t POOL_CHUNK = 512;     // rays a warp takes from the global counter at a time
+
+struct RayIn { float ox, oy, oz, tmin, dx, dy, dz, tmax; };
+
+__device__ __forceinline__ void load_ray(const RayIn* rays, uint64_t i, RayX& r, float& tmax) {
+    const float4* p = reinterpret_cast<const float4*>(rays + i);
+    float4 a = __ldg(p), b = __ldg(p + 1);
+    r = make_ray(a.x, a.y, a.z, b.x, b.y, b.z);
+    tmax = b.w;
+}
+
+// ---------------------------------------------------------------------------------------
+// Persistent while-while traversal.
+// ---------------------------------------------------------------------------------------
+template <bool ANY, bool COUNT, int CAP>
+__global__ void __launch_bounds__(TRACE_BLOCK)
+trace_persistent(SceneView s, const RayIn* __restrict__ rays, uint64_t n, void* __restrict__ out,
+                 unsigned long long* __restrict__ next, unsigned long long* __restrict__ counters) {
+    const unsigned lane = threadIdx.x & 31u;
+    uint32_t stack[CAP];
+    int sp = 0;
+    uint32_t cur = REF_EMPTY;
+    bool active = false;
+    uint64_t my_index = 0;
+    RayX r;
+    HitX h;
+    TravCounters tc = { 0, 0, 0, 0, 0 };
+    uint64_t pool_next = 0, pool_end = 0;    // warp-uniform
+    bool exhausted = false;                  // warp-uniform: the global counter ran past n
+    uint32_t traced = 0;
+
+    auto finish = [&]() {
+        if (ANY) reinterpret_cast<uint32_t*>(out)[my_index] = (h.tri != 0xFFFFFFFFu) ? 1u : 0u;
+        else reinterpret_cast<float4*>(out)[my_index] = make_float4(h.t, h.u, h.v, __uint_as_float(h.tri));
+        active = false;
+        cur = REF_EMPTY;
+        if (COUNT) traced++;
+    };
+    auto pop = [&]() {
+        if (sp == 0) finish();
+        else cur = stack[--sp];
+    };
+
+    for (;;) {
+        // ---- refill idle lanes from the warp pool (ballot compaction) --------------------
+        unsigned idle = __ballot_sync(FULL, !active);
+        if (idle) {
+            if (pool_next == pool_end && !exhausted) {
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(next, (unsigned long long)POOL_CHUNK);
+                base = __shfl_sync(FULL, base, 0);
+                if (base >= n) { exhausted = true; }
+                else { pool_next = base; pool_end = (base + POOL_CHUNK < n) ? base + POOL_CHUNK : n; }
+            }
+            uint64_t avail = pool_end - pool_next;
+            if (avail) {
+                unsigned rank = __popc(idle & ((1u << lane) - 1u));
+                if (!active && rank < avail) {
+                    my_index = pool_next + rank;
+                    float tmax;
+                    load_ray(rays, my_index, r, tmax);
+                    h.t = tmax; h.u = 0.0f; h.v = 0.0f; h.tri = 0xFFFFFFFFu;
+                    sp = 0;
+                    cur = 0;
+                    active = true;
+                }
+                unsigned taken = __popc(idle);
+                pool_next += (taken < avail) ? taken : avail;
+            }
+        }
+        if (!__any_sync(FULL, active)) {
+            if (exhausted && pool_next == pool_end) break;
+            continue;
+        }
+
+        // ---- loop A: interior wide nodes until every live lane holds a leaf ----------------
+        while (__any_sync(FULL, active && !(cur & REF_LEAF_BIT))) {
+            if (active && !(cur & REF_LEAF_BIT)) {
+                WideHits w = test_wide_node(s.wide, cur, r, h.t);
+                if (COUNT) { tc.wide_nodes++; tc.words += 6; }
+                uint32_t first = REF_EMPTY;
+#pragma unroll
+                for (int k = 7; k >= 0; --k) {
+                    uint32_t slot = slot_of_rank(w.flips, (uint32_t)k);
+                    if ((w.mask >> slot) & 1u) {
+                        if (first != REF_EMPTY && sp < CAP) stack[sp++] = first;
+                        first = child_ref(w, slot);
+                    }
+                }
+                if (first != REF_EMPTY) cur = first;
+                else pop();
+            }
+        }
+        // ---- loop B: one leaf per live lane --------------------------------------------------
+        if (active) {   // cur is a leaf here
+            bool got = visit_leaf<COUNT>(s.leaf, cur & ~REF_LEAF_BIT, r, h, COUNT ? &tc : nullptr);
+            if ((ANY && got) || h.t < 0.0f) finish();     // best < 0 ends the reference's walk too
+            else pop();
+        }
+    }
+
+    if (COUNT) {
+        // one atomic per counter per warp
+        unsigned long long v[6] = { traced, tc.wide_nodes, tc.leaf_blocks, tc.leaf_pass, tc.tri_tests, tc.words };
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            unsigned long long x = v[i];
+            for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(FULL, x, o);
+            if (lane == 0 && x) atomicAdd(&counters[i], x);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Reference-layout binary walk (kernel_bvh.cl:171-219 verbatim semantics).
+// ---------------------------------------------------------------------------------------
+template <bool ANY>
+__device__ __forceinline__ HitX trace_binary(const RefTriangle* __restrict__ tris, const RefNode* __restrict__ nodes,
+                                             const RayX& r, float tmax) {
+    HitX h; h.t = tmax; h.u = 0.0f; h.v = 0.0f; h.tri = 0xFFFFFFFFu;
+    uint32_t stack[64];
+    int sp = 0;
+    uint32_t cur = 0;
+    for (;;) {
+        const float4* np = reinterpret_cast<const float4*>(nodes + cur);
+        float4 lo = __ldg(np), hi = __ldg(np + 1);
+        uint4 tail = __ldg(reinterpret_cast<const uint4*>(np + 2));
+        uint32_t nprim = tail.y & 0xffffu, axis = (tail.y >> 16) & 0xffu;
+        bool descend = false;
+        if (box_gate_exact(r, lo.x, lo.y, lo.z, hi.x, hi.y, hi.z, h.t)) {
+            if (nprim > 0) {
+                for (uint32_t i = 0; i < nprim; ++i) {
+                    const float4* tp = reinterpret_cast<const float4*>(tris + tail.x + i);
+                    float4 a = __ldg(tp), b = __ldg(tp + 5), c = __ldg(tp + 10);   // positions at +0, +80, +160 B
+                    tri_test_exact(r, a.x, a.y, a.z, b.x, b.y, b.z, c.x, c.y, c.z, tail.x + i, h);
+                }
+                if (ANY && h.tri != 0xFFFFFFFFu) break;
+            } else {
+                descend = true;
+                bool second_first = (r.sign >> axis) & 1u;
+                if (sp < 64) stack[sp++] = second_first ? cur + 1u : tail.x;
+                cur = second_first ? tail.x : cur + 1u;
+            }
+        }
+        if (!descend) {
+            if (sp == 0) break;
+            cur = stack[--sp];
+        }
+    }
+    return h;
+}
+
+template <bool ANY>
+__global__ void __launch_bounds__(128)
+trace_binary_kernel(SceneView s, const RayIn* __restrict__ rays, uint64_t n, void* __restrict__ out) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    RayX r; float tmax;
+    load_ray(rays, i, r, tmax);
+    HitX h = trace_binary<ANY>(s.tris, s.nodes, r, tmax);
+    if (ANY) reinterpret_cast<uint32_t*>(out)[i] = (h.tri != 0xFFFFFFFFu) ? 1u : 0u;
+    else reinterpret_cast<float4*>(out)[i] = make_float4(h.t, h.u, h.v, __uint_as_float(h.tri));
+}
+
+// ---------------------------------------------------------------------------------------
+// Camera rays and the frame megakernel.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+camera_rays_kernel(FrameArgs a, uint64_t gid0, uint64_t gid1, RayIn* __restrict__ rays) {
+    uint64_t g = gid0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= gid1) return;
+    uint32_t gid = (uint32_t)g;
+    uint32_t seed = gid + hash_u32(a.frame_count);
+    V3 d = camera_dir(a, gid, seed);
+    // InitRay normalises once more (kernel_bvh.cl:402,44); emit that direction.
+    RayX r = make_ray(a.pos[0], a.pos[1], a.pos[2], d.x, d.y, d.z);
+    float4* p = reinterpret_cast<float4*>(rays + (g - gid0));
+    p[0] = make_float4(r.ox, r.oy, r.oz, 0.0f);
+    p[1] = make_float4(r.dx, r.dy, r.dz, 100000.0f);
+}
+
+template <bool BINARY, int CAP>
+__global__ void __launch_bounds__(128)
+render_mega_kernel(SceneView s, FrameArgs a, float* __restrict__ result, uint64_t gid0, uint64_t gid1) {
+    uint64_t g = gid0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= gid1) return;
+    uint32_t gid = (uint32_t)g;
+    uint32_t seed = gid + hash_u32(a.frame_count);                        // kernel_bvh.cl:445
+    V3 dir = camera_dir(a, gid, seed);
+    RayX r = make_ray(a.pos[0], a.pos[1], a.pos[2], dir.x, dir.y, dir.z);
+    V3 radiance = v3(0.0f, 0.0f, 0.0f), beta = v3(1.0f, 1.0f, 1.0f);
+    for (int i = 0; (uint32_t)i < (uint32_t)a.bounces; ++i) {              // Render(), kernel_bvh.cl:349-384
+        HitX h;
+        if (BINARY) h = trace_binary<false>(s.tris, s.nodes, r, 100000.0f);
+        else h = trace_wide<false, false, CAP>(s.wide, s.leaf, r, 100000.0f, nullptr, nullptr);
+        if (h.tri == 0xFFFFFFFFu) {
+            float sky = xmul(0.5f, a.sky);
+            radiance = vadd(radiance, vmul(beta, v3(sky, sky, sky)));
+            break;
+        }
+        V3 o = v3(r.ox, r.oy, r.oz), d = v3(r.dx, r.dy, r.dz);
+        V3 pos = vadd(o, vscale(d, h.t));
+        V3 normal = hit_normal(s.shade, h);
+        uint32_t mtl = s.shade[h.tri].mtl;
+        if (mtl >= s.n_mats) mtl = s.n_mats - 1u;      // the reference reads out of bounds here (usemtl miss)
+        const RefMaterial m = s.mats[mtl];
+        radiance = vadd(radiance, vscale(vmul(beta, ldv(m.emission)), 50.0f));
+        V3 wi = v3(0.0f, 0.0f, 0.0f), wo = vneg(d);
+        float pdf = 0.0f;
+        V3 f = sample_brdf(wo, wi, pdf, normal, m, seed);
+        if (pdf <= 0.0f || pdf != pdf) break;
+        beta = vmul(beta, vdiv(vscale(f, vdot(wi, normal)), pdf));
+        float lp = light_pixel(o, d, h.t, normal, a.light_type);
+        radiance = vadd(radiance, vmul(vmul(v3(lp, lp, lp), ldv(m.diffuse)), beta));
+        V3 no = vadd(pos, vscale(wi, 0.01f));
+        r = make_ray(no.x, no.y, no.z, wi.x, wi.y, wi.z);
+    }
+    radiance = v3(max_cl(radiance.x, 0.0f), max_cl(radiance.y, 0.0f), max_cl(radiance.z, 0.0f));
+    accumulate(result + 4 * g, radiance, a.frame_count);
+}
+
+// ---------------------------------------------------------------------------------------
+// Launch wrappers (host).
+// ---------------------------------------------------------------------------------------
+static int pick_cap(uint32_t bound) { return bound <= 32 ? 32 : (bound <= 64 ? 64 : (bound <= 128 ? 128 : (bound <= 256 ? 256 : 0))); }
+
+template <bool ANY, bool COUNT>
+static cudaError_t launch_persistent_cap(int cap, int grid, cudaStream_t st, const SceneView& s, const void* rays,
+                                         uint64_t n, void* out, unsigned long long* next, unsigned long long* counters) {
+    const RayIn* r = static_cast<const RayIn*>(rays);
+    switch (cap) {
+        case 32: trace_persistent<ANY, COUNT, 32><<<grid, TRACE_BLOCK, 0, st>>>(s, r, n, out, next, counters); break;
+        case 64: trace_persistent<ANY, COUNT, 64><<<grid, TRACE_BLOCK, 0, st>>>(s, r, n, out, next, counters); break;
+        case 128: trace_persistent<ANY, COUNT, 128><<<grid, TRACE_BLOCK, 0, st>>>(s, r, n, out, next, counters); break;
+        case 256: trace_persistent<ANY, COUNT, 256><<<grid, TRACE_BLOCK, 0, st>>>(s, r, n, out, next, counters); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_trace_wide(const SceneView& s, const void* d_rays, uint64_t n, void* d_out, bool any, bool count,
+                              uint32_t stack_bound, int grid_blocks, unsigned long long* d_next,
+                              unsigned long long* d_counters, cudaStream_t st) {
+    int cap = pick_cap(stack_bound);
+    if (!cap) return cudaErrorInvalidValue;
+    cudaError_t e = cudaMemsetAsync(d_next, 0, sizeof(unsigned long long), st);
+    if (e != cudaSuccess) return e;
+    if (any) return count ? launch_persistent_cap<true, true>(cap, grid_blocks, st, s, d_rays, n, d_out, d_next, d_counters)
+                          : launch_persistent_cap<true, false>(cap, grid_blocks, st, s, d_rays, n, d_out, d_next, d_counters);
+    return count ? launch_persistent_cap<false, true>(cap, grid_blocks, st, s, d_rays, n, d_out, d_next, d_counters)
+                 : launch_persistent_cap<false, false>(cap, grid_blocks, st, s, d_rays, n, d_out, d_next, d_counters);
+}
+
+cudaError_t launch_trace_binary(const SceneView& s, const void* d_rays, uint64_t n, void* d_out, bool any, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    uint64_t blocks = (n + 127) / 128;
+    if (blocks > 0x7fffffffull) return cudaErrorInvalidValue;
+    const RayIn* r = static_cast<const RayIn*>(d_rays);
+    if (any) trace_binary_kernel<true><<<(unsigned)blocks, 128, 0, st>>>(s, r, n, d_out);
+    else trace_binary_kernel<false><<<(unsigned)blocks, 128, 0, st>>>(s, r, n, d_out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_camera_rays(const FrameArgs& a, uint64_t gid0, uint64_t gid1, void* d_rays, cudaStream_t st) {
+    if (gid1 <= gid0) return cudaSuccess;
+    uint64_t blocks = (gid1 - gid0 + 255) / 256;
+    if (blocks > 0x7fffffffull) return cudaErrorInvalidValue;
+    camera_rays_kernel<<<(unsigned)blocks, 256, 0, st>>>(a, gid0, gid1, static_cast<RayIn*>(d_rays));
+    return cudaGetLastError();
+}
+
+cudaError_t launch_render_mega(const SceneView& s, const FrameArgs& a, float* d_result, uint64_t gid0, uint64_t gid1,
+                               bool binary, uint32_t stack_bound, cudaStream_t st) {
+    if (gid1 <= gid0) return cudaSuccess;
+    uint64_t blocks = (gid1 - gid0 + 127) / 128;
+    if (blocks > 0x7fffffffull) return cudaErrorInvalidValue;
+    unsigned g = (unsigned)blocks;
+    if (binary) { render_mega_kernel<true, 32><<<g, 128, 0, st>>>(s, a, d_result, gid0, gid1); return cudaGetLastError(); }
+    switch (pick_cap(stack_bound)) {
+        case 32: render_mega_kernel<false, 32><<<g, 128, 0, st>>>(s, a, d_result, gid0, gid1); break;
+        case 64: render_mega_kernel<false, 64><<<g, 128, 0, st>>>(s, a, d_result, gid0, gid1); break;
+        case 128: render_mega_kernel<false, 128><<<g, 128, 0, st>>>(s, a, d_result, gid0, gid1); break;
+        case 256: render_mega_kernel<false, 256><<<g, 128, 0, st>>>(s, a, d_result, gid0, gid1); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+int trace_block_threads() { return TRACE_BLOCK; }
+
+cudaError_t trace_occupancy(bool any, uint32_t stack_bound, int* blocks_per_sm) {
+    int cap = pick_cap(stack_bound);
+    const void* fn = nullptr;
+    switch (cap) {
+        case 32: fn = any ? (const void*)trace_persistent<true, false, 32> : (const void*)trace_persistent<false, false, 32>; break;
+        case 64: fn = any ? (const void*)trace_persistent<true, false, 64> : (const void*)trace_persistent<false, false, 64>; break;
+        case 128: fn = any ? (const void*)trace_persistent<true, false, 128> : (const void*)trace_persistent<false, false, 128>; break;
+        case 256: fn = any ? (const void*)trace_persistent<true, false, 256> : (const void*)trace_persistent<false, false, 256>; break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, fn, TRACE_BLOCK, 0);
+}
+
+}  // namespace b2rt

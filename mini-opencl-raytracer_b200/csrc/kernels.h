@@ -1,0 +1,23 @@
+// kernels.h -- host-callable launch wrappers implemented in kernels.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "b2rt_types.h"
+
+namespace b2rt {
+
+// Persistent while-while traversal of the compressed wide BVH over a device-resident ray
+// stream. d_out is b2rt_hit[n] (closest) or uint32_t[n] (any). d_next is an 8-byte scratch
+// counter (reset by the wrapper), d_counters six 64-bit accumulators (used when count).
+cudaError_t launch_trace_wide(const SceneView& s, const void* d_rays, uint64_t n, void* d_out, bool any, bool count,
+                              uint32_t stack_bound, int grid_blocks, unsigned long long* d_next,
+                              unsigned long long* d_counters, cudaStream_t st);
+// One thread per ray over the reference-layout arrays (baseline / cross-check).
+cudaError_t launch_trace_binary(const SceneView& s, const void* d_rays, uint64_t n, void* d_out, bool any, cudaStream_t st);
+cudaError_t launch_camera_rays(const FrameArgs& a, uint64_t gid0, uint64_t gid1, void* d_rays, cudaStream_t st);
+cudaError_t launch_render_mega(const SceneView& s, const FrameArgs& a, float* d_result, uint64_t gid0, uint64_t gid1,
+                               bool binary, uint32_t stack_bound, cudaStream_t st);
+int trace_block_threads();
+cudaError_t trace_occupancy(bool any, uint32_t stack_bound, int* blocks_per_sm);
+
+}  // namespace b2rt

@@ -1,0 +1,32 @@
+// wide_bvh.h -- host-side construction of the GPU-resident compressed wide BVH
+// from the reference's host-built arrays (CLBVHScene::m_Nodes / m_Triangles,
+// produced by CLBVHnode.cpp:185-207). Pure C++ (no CUDA) so that it can also be
+// unit-tested without a GPU.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+#include "b2rt_types.h"
+
+namespace b2rt {
+
+struct WideBVH {
+    std::vector<WideNode> nodes;      // nodes[0] = root
+    std::vector<U4> leaf;             // leaf blocks, 16-byte words
+    std::vector<ShadeTri> shade;      // one per reference triangle
+    uint64_t n_leaf_blocks = 0;
+    uint32_t max_depth_binary = 0;    // deepest binary node (root = 0)
+    uint32_t max_depth_wide = 0;      // deepest wide node (root = 0)
+    uint32_t max_leaf_records = 0;
+    uint64_t n_children = 0;          // occupied child slots, for fill statistics
+};
+
+// Returns an empty string on success, else a description of why the input
+// arrays are not a valid flattened BVH (out-of-range offsets, cycles, ...).
+std::string build_wide_bvh(const RefNode* nodes, uint64_t n_nodes, const RefTriangle* tris, uint64_t n_tris,
+                           WideBVH& out);
+
+// Worst-case traversal stack entries for this tree (see trace_wide).
+inline uint32_t wide_stack_bound(const WideBVH& b) { return 7u * (b.max_depth_wide + 1u) + 1u; }
+
+}  // namespace b2rt
