@@ -1,0 +1,250 @@
+"""ctypes view of libb2rt.so (include/b2rt.h). No compute happens in Python and there is
+no fallback: a missing library or CUDA device raises."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from .layouts import HIT_DTYPE, MAT_BYTES, NODE_BYTES, RAY_DTYPE, TRI_BYTES
+
+MISS = 0xFFFFFFFF
+HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+ARG_BUFFER_OUT, ARG_BUFFER_SCENE, ARG_BUFFER_NODE, ARG_BUFFER_MATERIAL = 0, 1, 2, 3
+ARG_WIDTH, ARG_HEIGHT, ARG_FRAME_COUNT, ARG_FRAME_SEED = 4, 5, 6, 7
+ARG_LIGHT_BOUNCES, ARG_LIGHT_TYPE, ARG_SKYBOX_INTENSITY = 8, 9, 10
+ARG_CAMERA_POS, ARG_CAMERA_FRONT, ARG_CAMERA_UP = 11, 12, 13
+OPT_TRAVERSAL, OPT_COUNTERS, OPT_BLOCKS_PER_SM, OPT_RENDER_MODE = 0, 1, 2, 3
+MEM_WRITE_ONLY, MEM_READ_ONLY, MEM_COPY_HOST_PTR = 1 << 1, 1 << 2, 1 << 5
+
+# every symbol include/b2rt.h declares (tests/test_abi.py checks the header against this list)
+SYMBOLS = [
+    "b2rt_create", "b2rt_destroy", "b2rt_last_error", "b2rt_status_string", "b2rt_buffer_create",
+    "b2rt_buffer_release", "b2rt_set_arg", "b2rt_execute", "b2rt_execute_range", "b2rt_read_buffer",
+    "b2rt_finish", "b2rt_upload_scene", "b2rt_resize", "b2rt_read_pixels", "b2rt_trace_closest",
+    "b2rt_trace_any", "b2rt_trace_closest_device", "b2rt_trace_any_device", "b2rt_camera_rays_device",
+    "b2rt_device_pointer", "b2rt_bound_buffer", "b2rt_scene_info_get", "b2rt_set_option",
+    "b2rt_get_counters", "b2rt_reset_counters", "b2rt_launch_count", "b2rt_device_count",
+]
+
+
+class SceneInfo(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("n_triangles", "n_nodes", "n_materials", "n_wide_nodes", "n_leaf_blocks",
+                                          "wide_node_bytes", "leaf_bytes", "shading_bytes")] + \
+               [(n, C.c_uint32) for n in ("max_depth_binary", "max_depth_wide", "sm_count", "reserved")]
+
+
+class Counters(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("rays", "wide_nodes", "leaf_blocks", "leaf_gate_pass", "tri_tests",
+                                          "bytes_fetched")]
+
+    def as_dict(self):
+        return {n: int(getattr(self, n)) for n, _ in self._fields_}
+
+
+class B2RTError(RuntimeError):
+    def __init__(self, status, text):
+        super().__init__("b2rt status %d (%s): %s" % (status, _status_name(status), text))
+        self.status = status
+
+
+def lib_path():
+    return os.path.join(HERE, "libb2rt.so")
+
+
+def lib():
+    """Load libb2rt.so. Fails loudly when it has not been built (no fallback exists)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    p = lib_path()
+    if not os.path.exists(p):
+        raise ImportError("%s is missing: run `python mini-opencl-raytracer_b200/build.py` "
+                          "(there is no CPU or PyTorch fallback for the traversal kernels)" % p)
+    L = C.CDLL(p, mode=C.RTLD_GLOBAL)
+    vp, u64, u32, sz = C.c_void_p, C.c_uint64, C.c_uint32, C.c_size_t
+    sig = {
+        "b2rt_create": (C.c_int, [C.c_int, C.POINTER(vp)]),
+        "b2rt_destroy": (None, [vp]),
+        "b2rt_last_error": (C.c_char_p, [vp]),
+        "b2rt_status_string": (C.c_char_p, [C.c_int]),
+        "b2rt_buffer_create": (C.c_int, [vp, u32, sz, vp, C.POINTER(u64)]),
+        "b2rt_buffer_release": (C.c_int, [vp, u64]),
+        "b2rt_set_arg": (C.c_int, [vp, u32, vp, sz]),
+        "b2rt_execute": (C.c_int, [vp, sz]),
+        "b2rt_execute_range": (C.c_int, [vp, sz, sz]),
+        "b2rt_read_buffer": (C.c_int, [vp, u64, vp, sz]),
+        "b2rt_finish": (C.c_int, [vp]),
+        "b2rt_upload_scene": (C.c_int, [vp, vp, u64, vp, u64, vp, u64]),
+        "b2rt_resize": (C.c_int, [vp, u32, u32]),
+        "b2rt_read_pixels": (C.c_int, [vp, vp, sz]),
+        "b2rt_trace_closest": (C.c_int, [vp, vp, u64, vp]),
+        "b2rt_trace_any": (C.c_int, [vp, vp, u64, vp]),
+        "b2rt_trace_closest_device": (C.c_int, [vp, vp, u64, vp, vp]),
+        "b2rt_trace_any_device": (C.c_int, [vp, vp, u64, vp, vp]),
+        "b2rt_camera_rays_device": (C.c_int, [vp, sz, sz, vp, vp]),
+        "b2rt_device_pointer": (C.c_int, [vp, u64, C.POINTER(vp), C.POINTER(sz)]),
+        "b2rt_bound_buffer": (C.c_int, [vp, u32, C.POINTER(u64)]),
+        "b2rt_scene_info_get": (C.c_int, [vp, C.POINTER(SceneInfo)]),
+        "b2rt_set_option": (C.c_int, [vp, u32, C.c_int64]),
+        "b2rt_get_counters": (C.c_int, [vp, C.POINTER(Counters)]),
+        "b2rt_reset_counters": (C.c_int, [vp]),
+        "b2rt_launch_count": (u64, [vp]),
+        "b2rt_device_count": (C.c_int, []),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)
+        fn.restype, fn.argtypes = res, args
+    _LIB = L
+    return L
+
+
+def _status_name(status):
+    try:
+        return lib().b2rt_status_string(status).decode()
+    except Exception:  # noqa: BLE001
+        return "?"
+
+
+def device_count():
+    return int(lib().b2rt_device_count())
+
+
+def _ptr(a):
+    return C.c_void_p(a.ctypes.data) if isinstance(a, np.ndarray) else C.c_void_p(int(a))
+
+
+def _raw(a, itemsize, what):
+    a = np.ascontiguousarray(a)
+    if a.nbytes % itemsize:
+        raise ValueError("%s: %d bytes is not a whole number of %d-byte records" % (what, a.nbytes, itemsize))
+    return a, a.nbytes // itemsize
+
+
+class Context:
+    """b2rt_context: what the reference reaches through CLContext + CLKernel (CLutils.h:116-145)."""
+
+    def __init__(self, device=0):
+        self._L = lib()
+        h = C.c_void_p()
+        st = self._L.b2rt_create(int(device), C.byref(h))
+        if st:
+            raise B2RTError(st, self._L.b2rt_last_error(None).decode())
+        self._h = h
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.b2rt_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _ck(self, st):
+        if st:
+            raise B2RTError(st, self._L.b2rt_last_error(self._h).decode())
+
+    # ---- scene / arguments -------------------------------------------------------------
+    def upload_scene(self, tris, nodes, mats):
+        t, nt = _raw(tris, TRI_BYTES, "triangles")
+        n, nn = _raw(nodes, NODE_BYTES, "nodes")
+        m, nm = _raw(mats, MAT_BYTES, "materials")
+        self._ck(self._L.b2rt_upload_scene(self._h, _ptr(t), nt, _ptr(n), nn, _ptr(m), nm))
+
+    def resize(self, width, height):
+        self._ck(self._L.b2rt_resize(self._h, int(width), int(height)))
+        self.width, self.height = int(width), int(height)
+
+    def set_arg(self, slot, value):
+        v = np.ascontiguousarray(value)
+        self._ck(self._L.b2rt_set_arg(self._h, int(slot), _ptr(v), v.nbytes))
+
+    def set_frame(self, frame_count, bounces, light_type=0, sky=1.0, pos=(0.0, -25.0, 8.5), front=(0.0, 1.0, 0.0),
+                  up=(0.0, 0.0, 1.0), seed=0):
+        """The eight per-frame SetUniform calls of CLRaytracer::RenderFrame (CLRaytracer.cpp:36-47)."""
+        self.set_arg(ARG_FRAME_COUNT, np.uint32(frame_count))
+        self.set_arg(ARG_FRAME_SEED, np.uint32(seed))
+        self.set_arg(ARG_LIGHT_BOUNCES, np.int32(bounces))
+        self.set_arg(ARG_LIGHT_TYPE, np.int32(light_type))
+        self.set_arg(ARG_SKYBOX_INTENSITY, np.float32(sky))
+        for slot, v in ((ARG_CAMERA_POS, pos), (ARG_CAMERA_FRONT, front), (ARG_CAMERA_UP, up)):
+            self.set_arg(slot, np.array([v[0], v[1], v[2], 0.0], dtype=np.float32))
+
+    def set_option(self, option, value):
+        self._ck(self._L.b2rt_set_option(self._h, int(option), int(value)))
+
+    # ---- frame path -------------------------------------------------------------------------
+    def execute(self, work_size):
+        self._ck(self._L.b2rt_execute(self._h, int(work_size)))
+
+    def execute_range(self, gid0, gid1):
+        self._ck(self._L.b2rt_execute_range(self._h, int(gid0), int(gid1)))
+
+    def finish(self):
+        self._ck(self._L.b2rt_finish(self._h))
+
+    def read_pixels(self, out=None):
+        n = self.width * self.height
+        if out is None:
+            out = np.empty((n, 4), dtype=np.float32)
+        self._ck(self._L.b2rt_read_pixels(self._h, _ptr(out), out.nbytes))
+        self.finish()
+        return out
+
+    def output_device_pointer(self):
+        buf = C.c_uint64()
+        self._ck(self._L.b2rt_bound_buffer(self._h, 0, C.byref(buf)))
+        p, n = C.c_void_p(), C.c_size_t()
+        self._ck(self._L.b2rt_device_pointer(self._h, buf.value, C.byref(p), C.byref(n)))
+        return int(p.value), int(n.value)
+
+    # ---- ray streams ------------------------------------------------------------------------
+    def trace_closest(self, rays, hits=None):
+        rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)
+        if hits is None:
+            hits = np.empty(rays.shape[0], dtype=HIT_DTYPE)
+        self._ck(self._L.b2rt_trace_closest(self._h, _ptr(rays), rays.shape[0], _ptr(hits)))
+        return hits
+
+    def trace_any(self, rays, occluded=None):
+        rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)
+        if occluded is None:
+            occluded = np.empty(rays.shape[0], dtype=np.uint32)
+        self._ck(self._L.b2rt_trace_any(self._h, _ptr(rays), rays.shape[0], _ptr(occluded)))
+        return occluded
+
+    def trace_closest_device(self, d_rays, n, d_hits, stream=0):
+        self._ck(self._L.b2rt_trace_closest_device(self._h, C.c_void_p(int(d_rays)), int(n), C.c_void_p(int(d_hits)),
+                                                   C.c_void_p(int(stream))))
+
+    def trace_any_device(self, d_rays, n, d_occ, stream=0):
+        self._ck(self._L.b2rt_trace_any_device(self._h, C.c_void_p(int(d_rays)), int(n), C.c_void_p(int(d_occ)),
+                                               C.c_void_p(int(stream))))
+
+    def camera_rays_device(self, gid0, gid1, d_rays, stream=0):
+        self._ck(self._L.b2rt_camera_rays_device(self._h, int(gid0), int(gid1), C.c_void_p(int(d_rays)),
+                                                 C.c_void_p(int(stream))))
+
+    # ---- introspection ------------------------------------------------------------------------
+    def scene_info(self):
+        s = SceneInfo()
+        self._ck(self._L.b2rt_scene_info_get(self._h, C.byref(s)))
+        return {n: int(getattr(s, n)) for n, _ in SceneInfo._fields_}
+
+    def counters(self):
+        c = Counters()
+        self._ck(self._L.b2rt_get_counters(self._h, C.byref(c)))
+        return c.as_dict()
+
+    def reset_counters(self):
+        self._ck(self._L.b2rt_reset_counters(self._h))
+
+    def launch_count(self):
+        return int(self._L.b2rt_launch_count(self._h))

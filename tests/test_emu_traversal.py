@@ -1,0 +1,76 @@
+"""CPU checks of the PRODUCT's traversal logic: csrc/traverse.cuh and csrc/wide_bvh.cpp compile
+as plain C++ (tests/emu/, test only), so the compressed wide BVH + reference-order walk can be
+compared with the oracle without a GPU. The CUDA build of the same text is what the -m gpu tests
+exercise through the C ABI."""
+import numpy as np
+
+import oracle_lib as ol
+import scenes
+
+MISS = 0xFFFFFFFF
+
+
+def _same(e, h):
+    assert np.array_equal(e["tri"], h["tri"])
+    assert np.array_equal(e["t"].view(np.uint32), h["t"].view(np.uint32))
+    m = h["tri"] != MISS
+    assert np.array_equal(e["u"][m].view(np.uint32), h["u"][m].view(np.uint32))
+    assert np.array_equal(e["v"][m].view(np.uint32), h["v"][m].view(np.uint32))
+
+
+def test_cornell_camera_and_shell(cornell_ref):
+    tris, nodes, _ = cornell_ref
+    st = ol.emu_build(tris, nodes)
+    assert st.n_leaf_blocks == 20 and st.max_depth_binary >= 5
+    rays = np.concatenate([ol.oracle_camera_rays(160, 120, 1),
+                           scenes.shell_rays(20000, 12.0, seed=5, centre=(0.0, 7.0, 8.0)),
+                           scenes.box_rays(20000, (-9, -2, -1), (9, 16, 17), seed=6),
+                           scenes.axis_rays((-9, -2, -1), (9, 16, 17), 100, seed=7)])
+    st2 = ol.EmuStats()
+    _same(ol.emu_trace(rays, stats=st2), ol.oracle_closest(tris, nodes, rays))
+    assert st2.overflow == 0
+    assert np.array_equal(ol.emu_trace(rays, any_hit=True) != 0, ol.oracle_any(tris, nodes, rays) != 0)
+
+
+def test_bumpy_primary_bounce_and_any(bumpy_ref):
+    tris, nodes, _ = bumpy_ref
+    st = ol.emu_build(tris, nodes)
+    assert st.n_wide < nodes.shape[0] / 3
+    rays = scenes.shell_rays(40000, 10.0, seed=41)
+    h = ol.oracle_closest(tris, nodes, rays)
+    _same(ol.emu_trace(rays), h)
+    b = scenes.bounce_rays(rays, h, scenes.tri_normals(tris, h), seed=42)
+    hb = ol.oracle_closest(tris, nodes, b)
+    assert (hb["t"] < 0).mean() > 0.01
+    _same(ol.emu_trace(b), hb)                               # negative-t trap: order-faithful walk
+    short = b.copy()
+    short["tmax"] = 3.0
+    _same(ol.emu_trace(short), ol.oracle_closest(tris, nodes, short))
+    assert np.array_equal(ol.emu_trace(short, any_hit=True) != 0, ol.oracle_any(tris, nodes, short) != 0)
+    inside = scenes.box_rays(20000, (-5, -5, -5), (5, 5, 5), seed=43)   # culling: mostly misses from inside
+    _same(ol.emu_trace(inside), ol.oracle_closest(tris, nodes, inside))
+
+
+def test_wide_nodes_fetch_fewer_bytes_than_reference_layout(bumpy_ref):
+    tris, nodes, _ = bumpy_ref
+    ol.emu_build(tris, nodes)
+    rays = scenes.shell_rays(5000, 10.0, seed=44)
+    st = ol.EmuStats()
+    ol.emu_trace(rays, stats=st)
+    _, cnt = ol.oracle_closest(tris, nodes, rays, want_counters=True)
+    ref_bytes = cnt["nodes_visited"] * 48 + cnt["tris_tested"] * 256
+    assert st.words * 16 < 0.5 * ref_bytes
+    assert st.tri_tests == cnt["tris_tested"]               # identical set of exact triangle tests
+
+
+def test_degenerate_scenes(tmp_scene_dir):
+    import os
+    # one triangle (root is a leaf) and a quad face (the loader fans it into 3 overlapping triangles)
+    p = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [1, 1, 0]], dtype=np.float32)
+    n = np.tile(np.array([[0, 0, 1]], dtype=np.float32), (4, 1))
+    for name, faces, quads in (("one.obj", [[0, 1, 2]], None), ("quad.obj", [[0, 1, 2]], [[0, 1, 3, 2]])):
+        path = scenes.write_obj(os.path.join(tmp_scene_dir, name), p, n, np.array(faces), quads)
+        tris, nodes, _ = ol.ref_load_scene(path, 4)
+        ol.emu_build(tris, nodes)
+        rays = scenes.box_rays(4000, (-1, -1, 0.5), (2, 2, 3), seed=45)
+        _same(ol.emu_trace(rays), ol.oracle_closest(tris, nodes, rays))
