@@ -14,3 +14,4 @@ The directory name contains hyphens, so load it with ``importlib`` (see
 from .capi import (B2RTError, Context, HIT_DTYPE, MISS, RAY_DTYPE, device_count, lib, lib_path)  # noqa: F401
 from .build import build_all  # noqa: F401
 from . import layouts  # noqa: F401
+from . import host  # noqa: F401

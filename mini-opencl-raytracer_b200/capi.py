@@ -125,8 +125,19 @@ def _raw(a, itemsize, what):
 class Context:
     """b2rt_context: what the reference reaches through CLContext + CLKernel (CLutils.h:116-145)."""
 
+    @classmethod
+    def borrow(cls, handle, device=0):
+        """Wrap a b2rt_context owned by someone else (e.g. the C++ CLContext of host.Engine)."""
+        self = cls.__new__(cls)
+        self._L = lib()
+        self._h = C.c_void_p(handle)
+        self._borrowed = True
+        self.device = int(device)
+        return self
+
     def __init__(self, device=0):
         self._L = lib()
+        self._borrowed = False
         h = C.c_void_p()
         st = self._L.b2rt_create(int(device), C.byref(h))
         if st:
@@ -136,7 +147,8 @@ class Context:
 
     def close(self):
         if getattr(self, "_h", None):
-            self._L.b2rt_destroy(self._h)
+            if not getattr(self, "_borrowed", False):
+                self._L.b2rt_destroy(self._h)
             self._h = None
 
     __del__ = close

@@ -1,0 +1,178 @@
+// obj_loader.cpp -- CLOBJloader: the OBJ/MTL dialect the reference accepts (CLOBJloader.cpp:10-176),
+// parsed from an in-memory copy of the file with a small cursor instead of fscanf/fgets/strtok.
+//
+// Behaviour kept from the reference, because it defines the triangle array and therefore hit IDs:
+//   * the stream is a sequence of whitespace-separated words; only `v`, `vt`, `vn`, `usemtl`, `f`
+//     (OBJ) and `newmtl`, `Kd`, `Ks`, `Ke`, `Ns`, `Ni` (MTL) are acted on, every other word --
+//     comments included -- is skipped one word at a time (CLOBJloader.cpp:39-46, 140-147);
+//   * numbers are read the way scanf("%f") reads them (strtof after skipping white space; a field
+//     that does not parse leaves the value unchanged and the cursor in place);
+//   * an `f` record is the rest of its line, at most 127 characters, split on SPACES only; words of
+//     length <= 1 are ignored; each word must be `v/vt/vn` (CLOBJloader.cpp:79-100);
+//   * an n-vertex face yields triangles (i, i+1, i+2) for i = 0..n-3 and then (n-2, n-1, 0): a
+//     triangular face therefore appears TWICE, the second copy with rotated vertices
+//     (CLOBJloader.cpp:102-126);
+//   * `usemtl` with an unknown name keeps the previous material index; the index starts at
+//     0xFFFFFFFF (CLOBJloader.cpp:37, 66-77);
+//   * the material file is the scene path with its last four characters replaced by ".mtl".
+// Deliberate differences: malformed input that makes the reference read out of bounds (missing
+// v/vt/vn fields, indices outside the arrays, a material statement before any `newmtl`, paths longer
+// than its 80-byte buffer) raises CLException here instead.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include "glaze3d.h"
+
+namespace Glaze3D
+{
+    namespace
+    {
+        struct Cursor
+        {
+            const char* p;
+            const char* end;
+            static bool space(char c) { return c == ' ' || c == '\t' || c == '\n' || c == '\r' || c == '\v' || c == '\f'; }
+            void skipSpace() { while (p < end && space(*p)) ++p; }
+            // scanf("%s") with a width limit: next run of non-space characters
+            bool word(std::string& out, size_t limit = 127)
+            {
+                skipSpace();
+                if (p >= end) return false;
+                const char* s = p;
+                while (p < end && !space(*p) && (size_t)(p - s) < limit) ++p;
+                out.assign(s, p);
+                return true;
+            }
+            // scanf("%f"): on failure nothing is consumed beyond the leading white space
+            bool number(float& out)
+            {
+                skipSpace();
+                if (p >= end) return false;
+                char* stop = nullptr;
+                float v = std::strtof(p, &stop);
+                if (stop == p) return false;
+                out = v;
+                p = stop;
+                return true;
+            }
+            void numbers(float* dst, int n) { for (int i = 0; i < n; ++i) if (!number(dst[i])) return; }
+            // fgets(buf, 128): up to 127 characters, through the newline
+            std::string restOfLine()
+            {
+                const char* s = p;
+                while (p < end && (p - s) < 127) { if (*p++ == '\n') break; }
+                return std::string(s, p);
+            }
+        };
+
+        std::string slurp(const std::string& path, const char* what)
+        {
+            FILE* f = std::fopen(path.c_str(), "rb");
+            if (!f) throw CLException(std::string("Failed to open ") + what + " file '" + path + "'", B2RT_INVALID_VALUE);
+            std::string data;
+            char buf[1 << 16];
+            size_t n;
+            while ((n = std::fread(buf, 1, sizeof(buf), f)) > 0) data.append(buf, n);
+            std::fclose(f);
+            data.push_back('\0');     // strtof needs a terminator
+            return data;
+        }
+
+        void loadMaterials(CLBVHScene& scene, const std::string& path)
+        {
+            std::string data = slurp(path, "material");
+            Cursor c{ data.data(), data.data() + data.size() - 1 };
+            std::string w;
+            auto current = [&]() -> CLMaterial& {
+                if (scene.m_Materials.empty()) throw CLException("Material statement before any newmtl in '" + path + "'", B2RT_INVALID_VALUE);
+                return scene.m_Materials.back();
+            };
+            while (c.word(w))
+            {
+                if (w == "newmtl")
+                {
+                    std::string name;
+                    c.word(name, 79);
+                    scene.m_MaterialNames.push_back(name);
+                    scene.m_Materials.push_back(CLMaterial());
+                }
+                else if (w == "Kd") c.numbers(&current().diffuse.x, 3);
+                else if (w == "Ks") c.numbers(&current().specular.x, 3);
+                else if (w == "Ke") c.numbers(&current().emission.x, 3);
+                else if (w == "Ns") c.numbers(&current().roughness, 1);
+                else if (w == "Ni") c.numbers(&current().ior, 1);
+            }
+        }
+    }
+
+    void CLOBJloader::LoadInto(CLBVHScene& scene, const char* filename)
+    {
+        std::string path(filename ? filename : "");
+        if (path.size() < 5 || path.size() > 75) throw CLException("Scene path must be 5..75 characters and end in a 4-character extension", B2RT_INVALID_VALUE);
+        loadMaterials(scene, path.substr(0, path.size() - 4) + ".mtl");
+
+        std::string data = slurp(path, "scene");
+        Cursor c{ data.data(), data.data() + data.size() - 1 };
+        std::vector<float3> positions, normals;
+        std::vector<float2> texcoords;
+        unsigned int materialIndex = 0xFFFFFFFFu;
+        std::string w;
+        std::vector<unsigned int> iv, it, in;
+
+        auto vertex = [&](size_t k) {
+            unsigned int a = iv[k] - 1, b = it[k] - 1, n = in[k] - 1;     // 0 (missing field) wraps to 0xFFFFFFFF
+            if (a >= positions.size() || b >= texcoords.size() || n >= normals.size())
+                throw CLException("Face references v/vt/vn " + std::to_string(iv[k]) + "/" + std::to_string(it[k]) + "/" + std::to_string(in[k]) +
+                                  " outside the arrays read so far (faces must be v/vt/vn triplets with positive indices)", B2RT_INVALID_VALUE);
+            return CLVertex(positions[a], texcoords[b], normals[n]);
+        };
+
+        while (c.word(w))
+        {
+            if (w == "v") { float3 p; c.numbers(&p.x, 3); positions.push_back(p); }
+            else if (w == "vt") { float2 t; c.numbers(&t.x, 2); texcoords.push_back(t); }
+            else if (w == "vn") { float3 n; c.numbers(&n.x, 3); normals.push_back(n); }
+            else if (w == "usemtl")
+            {
+                std::string name;
+                c.word(name, 79);
+                for (unsigned int i = 0; i < scene.m_MaterialNames.size(); ++i)
+                    if (scene.m_MaterialNames[i] == name) { materialIndex = i; break; }
+            }
+            else if (w == "f")
+            {
+                std::string line = c.restOfLine();
+                iv.clear(); it.clear(); in.clear();
+                size_t pos = 0;
+                while (pos < line.size())
+                {
+                    size_t stop = line.find(' ', pos);
+                    if (stop == std::string::npos) stop = line.size();
+                    if (stop - pos > 1)
+                    {
+                        unsigned int a = 0, b = 0, n = 0;
+                        std::sscanf(line.substr(pos, stop - pos).c_str(), "%d/%d/%d", (int*)&a, (int*)&b, (int*)&n);
+                        iv.push_back(a); it.push_back(b); in.push_back(n);
+                    }
+                    pos = stop + 1;
+                }
+                if (iv.size() < 2)
+                {
+                    if (iv.empty()) continue;
+                    throw CLException("Face with a single vertex", B2RT_INVALID_VALUE);
+                }
+                for (size_t i = 0; i + 2 < iv.size(); ++i)
+                    scene.m_Triangles.push_back(CLTriangle(vertex(i), vertex(i + 1), vertex(i + 2), materialIndex));
+                scene.m_Triangles.push_back(CLTriangle(vertex(iv.size() - 2), vertex(iv.size() - 1), vertex(0), materialIndex));
+            }
+        }
+    }
+
+    void CLOBJloader::Load(const char* filename, unsigned int maxPrimitivesInNode)
+    {
+        if (!eng || !eng->render || !eng->render->m_Scene)
+            throw CLException("CLOBJloader::Load needs eng->render->m_Scene (the reference writes into the global engine)", B2RT_INVALID_CONTEXT);
+        eng->render->m_Scene->m_MaxPrimitivesInNode = maxPrimitivesInNode;
+        LoadInto(*eng->render->m_Scene, filename);
+    }
+}

@@ -1,0 +1,256 @@
+// scene_build.cpp -- CLBounds3 helpers and CLBVHScene: the SAH BVH build + flattening that defines
+// triangle order (= hit IDs) and the CLLinearBVHNode array the device consumes.
+//
+// Behavioural contract (reference CLBVHnode.cpp:7-207, CLmathlib.hpp:120-204): PBRT-style recursive
+// build -- leaf when one primitive is left or all centroids coincide on the widest centroid axis;
+// median split (std::nth_element) for two primitives; otherwise 12 centroid buckets, SAH cost
+// 1 + (n0*A0 + n1*A1)/A, split (std::partition) when n > maxPrimitivesInNode or the best cost beats
+// the leaf cost n. The arrays must come out IDENTICAL to the reference's (tests compare them with
+// the verbatim reference build), because hit IDs are indices into the re-ordered triangle array. Two
+// details of the reference matter for that and are reproduced on purpose:
+//   * all arithmetic is fp32 in the reference's expression order (bucket index = int(12 * offset),
+//     cost accumulation with int*float products, NaN costs from empty buckets never win `<`);
+//   * the reference builds its two children inside one call expression,
+//     InitInterior(dim, RecursiveBuild(first...), RecursiveBuild(second...)) (CLBVHnode.cpp:150-154);
+//     g++ evaluates those arguments right to left, so the SECOND child's subtree is built -- and its
+//     triangles appended to the ordered array -- before the first child's. Node numbering is still
+//     pre-order with the first child at index+1 (CLBVHnode.cpp:161-183).
+// Here the build writes an index-linked node pool with an explicit work stack (no per-node `new`,
+// no recursion), then numbers it in pre-order.
+#include <algorithm>
+#include <cassert>
+#include <cmath>
+#include <limits>
+#include "glaze3d.h"
+
+namespace Glaze3D
+{
+    // ---- CLBounds3 -----------------------------------------------------------------------------
+    CLBounds3::CLBounds3()
+    {
+        const float hi = std::numeric_limits<float>::max(), lo = std::numeric_limits<float>::lowest();
+        min = float3(hi, hi, hi);
+        max = float3(lo, lo, lo);
+    }
+    static inline float3 lower(const float3& a, const float3& b) { return float3(std::min(a.x, b.x), std::min(a.y, b.y), std::min(a.z, b.z)); }
+    static inline float3 upper(const float3& a, const float3& b) { return float3(std::max(a.x, b.x), std::max(a.y, b.y), std::max(a.z, b.z)); }
+    CLBounds3::CLBounds3(const float3& a, const float3& b) : min(lower(a, b)), max(upper(a, b)) {}
+    CLBounds3 Union(const CLBounds3& b, const float3& p) { CLBounds3 r; r.min = lower(b.min, p); r.max = upper(b.max, p); return r; }
+    CLBounds3 Union(const CLBounds3& a, const CLBounds3& b) { CLBounds3 r; r.min = lower(a.min, b.min); r.max = upper(a.max, b.max); return r; }
+    unsigned int CLBounds3::MaximumExtent() const
+    {
+        float3 d = Diagonal();
+        if (d.x > d.y && d.x > d.z) return 0;
+        return d.y > d.z ? 1 : 2;
+    }
+    float3 CLBounds3::Offset(const float3& p) const
+    {
+        float3 o = p - min;
+        if (max.x > min.x) o.x /= max.x - min.x;
+        if (max.y > min.y) o.y /= max.y - min.y;
+        if (max.z > min.z) o.z /= max.z - min.z;
+        return o;
+    }
+
+    void CLCamera::Update()
+    {
+        // CLcamera.h:15-21: `right` is refreshed from the OLD front before front is recomputed.
+        right = vec3(front.y * up.z - front.z * up.y, front.z * up.x - front.x * up.z, front.x * up.y - front.y * up.x);
+        front = vec3(std::cos(yaw) * std::sin(pitch), std::sin(yaw) * std::sin(pitch), std::cos(pitch));
+    }
+
+    // ---- BVH build ---------------------------------------------------------------------------------
+    namespace
+    {
+        struct PrimInfo { unsigned int prim; CLBounds3 bounds; float3 centroid; };
+        struct BuildNode { CLBounds3 bounds; int child[2]; int axis; unsigned int firstPrim, nPrims; };
+        struct Bucket { int count = 0; CLBounds3 bounds; };
+        constexpr unsigned int kBuckets = 12;
+
+        struct Builder
+        {
+            std::vector<PrimInfo> info;
+            std::vector<BuildNode> pool;
+            std::vector<unsigned int> order;      // order[k] = original index of the k-th triangle of the new array
+            unsigned int maxPrims = 0;
+
+            int bucketOf(const CLBounds3& cb, unsigned int dim, const float3& centroid) const
+            {
+                int b = kBuckets * cb.Offset(centroid)[dim];     // unsigned * float -> float -> int, as in the reference
+                if (b == (int)kBuckets) b = kBuckets - 1;
+                assert(b >= 0 && b < (int)kBuckets);
+                return b;
+            }
+
+            void makeLeaf(BuildNode& n, unsigned int start, unsigned int end, const CLBounds3& bounds)
+            {
+                n.firstPrim = (unsigned int)order.size();
+                n.nPrims = end - start;
+                n.bounds = bounds;
+                n.child[0] = n.child[1] = -1;
+                for (unsigned int i = start; i < end; ++i) order.push_back(info[i].prim);
+            }
+
+            // Decides what node `id` over info[start,end) is. Returns true and sets mid/dim for an interior node.
+            bool split(int id, unsigned int start, unsigned int end, unsigned int& mid, unsigned int& dim)
+            {
+                CLBounds3 bounds;
+                for (unsigned int i = start; i < end; ++i) bounds = Union(bounds, info[i].bounds);
+                const unsigned int n = end - start;
+                if (n == 1) { makeLeaf(pool[id], start, end, bounds); return false; }
+                CLBounds3 cb;
+                for (unsigned int i = start; i < end; ++i) cb = Union(cb, info[i].centroid);
+                dim = cb.MaximumExtent();
+                mid = (start + end) / 2;
+                if (cb.max[dim] == cb.min[dim]) { makeLeaf(pool[id], start, end, bounds); return false; }
+                if (n <= 2)
+                {
+                    const unsigned int d = dim;
+                    std::nth_element(&info[start], &info[mid], &info[end - 1] + 1,
+                                     [d](const PrimInfo& a, const PrimInfo& b) { return a.centroid[d] < b.centroid[d]; });
+                }
+                else
+                {
+                    Bucket buckets[kBuckets];
+                    for (unsigned int i = start; i < end; ++i)
+                    {
+                        int b = bucketOf(cb, dim, info[i].centroid);
+                        buckets[b].count++;
+                        buckets[b].bounds = Union(buckets[b].bounds, info[i].bounds);
+                    }
+                    float cost[kBuckets - 1];
+                    for (unsigned int i = 0; i < kBuckets - 1; ++i)
+                    {
+                        CLBounds3 b0, b1;
+                        int c0 = 0, c1 = 0;
+                        for (unsigned int j = 0; j <= i; ++j) { b0 = Union(b0, buckets[j].bounds); c0 += buckets[j].count; }
+                        for (unsigned int j = i + 1; j < kBuckets; ++j) { b1 = Union(b1, buckets[j].bounds); c1 += buckets[j].count; }
+                        cost[i] = 1.0f + (c0 * b0.SurfaceArea() + c1 * b1.SurfaceArea()) / bounds.SurfaceArea();
+                    }
+                    float best = cost[0];
+                    unsigned int bestBucket = 0;
+                    for (unsigned int i = 1; i < kBuckets - 1; ++i)
+                        if (cost[i] < best) { best = cost[i]; bestBucket = i; }
+                    if (!(n > maxPrims || best < float(n))) { makeLeaf(pool[id], start, end, bounds); return false; }
+                    const CLBounds3 cbv = cb;
+                    const unsigned int d = dim;
+                    PrimInfo* p = std::partition(&info[start], &info[end - 1] + 1, [=](const PrimInfo& pi) {
+                        int b = kBuckets * cbv.Offset(pi.centroid)[d];
+                        if (b == (int)kBuckets) b = kBuckets - 1;
+                        return (unsigned int)b <= bestBucket;
+                    });
+                    mid = (unsigned int)(p - &info[0]);
+                }
+                return true;
+            }
+
+            int build(unsigned int nTris)
+            {
+                struct Task { int id; unsigned int start, end; };
+                std::vector<Task> todo;
+                pool.reserve(2 * (size_t)nTris);
+                order.reserve(nTris);
+                pool.push_back(BuildNode());
+                todo.push_back(Task{ 0, 0u, nTris });
+                while (!todo.empty())
+                {
+                    Task t = todo.back();
+                    todo.pop_back();
+                    unsigned int mid = 0, dim = 0;
+                    if (!split(t.id, t.start, t.end, mid, dim)) continue;
+                    int first = (int)pool.size();
+                    pool.push_back(BuildNode());
+                    pool.push_back(BuildNode());
+                    BuildNode& n = pool[t.id];
+                    n.child[0] = first; n.child[1] = first + 1; n.axis = (int)dim; n.nPrims = 0; n.firstPrim = 0;
+                    // LIFO: the second child's whole subtree is processed before the first child's (see header).
+                    todo.push_back(Task{ first, t.start, mid });
+                    todo.push_back(Task{ first + 1, mid, t.end });
+                }
+                // interior bounds = union of the children, bottom-up (children always have larger pool ids)
+                for (size_t i = pool.size(); i-- > 0;)
+                    if (pool[i].child[0] >= 0) pool[i].bounds = Union(pool[pool[i].child[0]].bounds, pool[pool[i].child[1]].bounds);
+                return 0;
+            }
+        };
+    }
+
+    void CLBVHScene::BuildOnly(unsigned int maxPrimitivesInNode)
+    {
+        m_MaxPrimitivesInNode = maxPrimitivesInNode;
+        m_Nodes.clear();
+        if (m_Triangles.empty()) throw CLException("Cannot build a BVH over an empty scene", B2RT_INVALID_VALUE);
+        if (m_Triangles.size() >= 0xfffffffeull) throw CLException("Scene too large", B2RT_INVALID_VALUE);
+        Builder b;
+        b.maxPrims = maxPrimitivesInNode;
+        b.info.resize(m_Triangles.size());
+        for (unsigned int i = 0; i < m_Triangles.size(); ++i)
+        {
+            CLBounds3 tb = m_Triangles[i].GetBounds();
+            b.info[i] = PrimInfo{ i, tb, tb.min * 0.5f + tb.max * 0.5f };
+        }
+        b.build((unsigned int)m_Triangles.size());
+        std::vector<PrimInfo>().swap(b.info);
+
+        // re-order the triangles
+        {
+            std::vector<CLTriangle> ordered;
+            ordered.reserve(b.order.size());
+            for (unsigned int src : b.order) ordered.push_back(m_Triangles[src]);
+            m_Triangles.swap(ordered);
+        }
+        // pre-order numbering, first child at index + 1
+        m_Nodes.resize(b.pool.size());
+        struct Visit { int pool; int parent; };     // parent: linear index whose `offset` must point at this node, or -1
+        std::vector<Visit> stack;
+        stack.push_back(Visit{ 0, -1 });
+        unsigned int next = 0;
+        while (!stack.empty())
+        {
+            Visit v = stack.back();
+            stack.pop_back();
+            const BuildNode& n = b.pool[v.pool];
+            unsigned int me = next++;
+            if (v.parent >= 0) m_Nodes[v.parent].offset = me;
+            CLLinearBVHNode& out = m_Nodes[me];
+            out.bounds = n.bounds;
+            if (n.child[0] < 0)
+            {
+                if (n.nPrims >= 65536) throw CLException("Leaf with more than 65535 primitives", B2RT_INVALID_VALUE);
+                out.offset = n.firstPrim;
+                out.nPrimitives = (unsigned short)n.nPrims;
+            }
+            else
+            {
+                out.axis = (unsigned char)n.axis;
+                out.nPrimitives = 0;
+                stack.push_back(Visit{ n.child[1], (int)me });   // numbered after the whole first subtree
+                stack.push_back(Visit{ n.child[0], -1 });        // numbered next: index me + 1
+            }
+        }
+        assert(next == m_Nodes.size());
+    }
+
+    void CLBVHScene::CreateBVHTrees(unsigned int maxPrimitivesInNode)
+    {
+        BuildOnly(maxPrimitivesInNode);
+        if (eng && eng->render && eng->render->m_CLContext) SetupBuffers();
+    }
+
+    void CLBVHScene::SetupBuffers()
+    {
+        if (!eng || !eng->render || !eng->render->m_CLContext)
+            throw CLException("CLBVHScene::SetupBuffers needs eng->render->m_CLContext", B2RT_INVALID_CONTEXT);
+        const CLContext& ctx = *eng->render->m_CLContext;
+        int err = 0;
+        m_TriangleBuffer = CLBuffer(ctx, B2RT_MEM_READ_ONLY | B2RT_MEM_COPY_HOST_PTR, m_Triangles.size() * sizeof(CLTriangle), m_Triangles.data(), &err);
+        if (err) throw CLException("Failed to create scene buffer", err);
+        eng->render->SetUniform<CLBuffer>((int)RenderKernelArgument_t::BUFFER_SCENE, m_TriangleBuffer);
+        m_NodeBuffer = CLBuffer(ctx, B2RT_MEM_READ_ONLY | B2RT_MEM_COPY_HOST_PTR, m_Nodes.size() * sizeof(CLLinearBVHNode), m_Nodes.data(), &err);
+        if (err) throw CLException("Failed to create BVH node buffer", err);
+        eng->render->SetUniform<CLBuffer>((int)RenderKernelArgument_t::BUFFER_NODE, m_NodeBuffer);
+        m_MaterialBuffer = CLBuffer(ctx, B2RT_MEM_READ_ONLY | B2RT_MEM_COPY_HOST_PTR, m_Materials.size() * sizeof(CLMaterial), m_Materials.data(), &err);
+        if (err) throw CLException("Failed to create material buffer", err);
+        eng->render->SetUniform<CLBuffer>((int)RenderKernelArgument_t::BUFFER_MATERIAL, m_MaterialBuffer);
+    }
+}

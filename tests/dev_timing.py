@@ -30,7 +30,9 @@ rays = scenes.shell_rays(nrays, 10.0, seed=1)
 d_rays = torch.from_numpy(rays.view(np.float32).reshape(-1, 8)).cuda()
 d_hits = torch.empty((nrays, 4), dtype=torch.float32, device="cuda")
 d_occ = torch.empty((nrays,), dtype=torch.int32, device="cuda")
-st = torch.cuda.current_stream().cuda_stream
+stream = torch.cuda.Stream()
+torch.cuda.set_stream(stream)
+st = stream.cuda_stream
 
 
 def timeit(fn, reps=5):

@@ -1,0 +1,95 @@
+"""The product's host mirror (CLOBJloader + CLBVHScene in host/*.cpp, written from scratch) must
+produce the SAME triangle order and node array as the reference's own loader + builder (oracle/_ref,
+compiled verbatim), because hit IDs are indices into that array."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+import scenes
+from conftest import load_product
+
+pytestmark = pytest.mark.skipif(ol.ref() is None, reason="oracle/_ref not built")
+
+TRI_FLOATS = [0, 1, 2, 4, 5, 6, 8, 9, 10, 20, 21, 22, 24, 25, 26, 28, 29, 30, 40, 41, 42, 44, 45, 46, 48, 49, 50]
+
+
+def _same_scene(a, b):
+    (ta, na, ma), (tb, nb, mb) = a, b
+    assert ta.shape == tb.shape and na.shape == nb.shape and ma.shape == mb.shape
+    fa, fb = ta.view(np.float32).reshape(-1, 64), tb.view(np.float32).reshape(-1, 64)
+    assert np.array_equal(fa[:, TRI_FLOATS].view(np.uint32), fb[:, TRI_FLOATS].view(np.uint32))     # positions, uvs, normals
+    assert np.array_equal(ta.view(np.uint32).reshape(-1, 64)[:, 60], tb.view(np.uint32).reshape(-1, 64)[:, 60])   # mtlIndex
+    ba, bb = na.view(np.float32).reshape(-1, 12), nb.view(np.float32).reshape(-1, 12)
+    assert np.array_equal(ba[:, [0, 1, 2, 4, 5, 6]].view(np.uint32), bb[:, [0, 1, 2, 4, 5, 6]].view(np.uint32))
+    assert np.array_equal(na.view(np.uint32).reshape(-1, 12)[:, 8], nb.view(np.uint32).reshape(-1, 12)[:, 8])      # offset
+    pa, pb = na.view(np.uint16).reshape(-1, 24)[:, 18], nb.view(np.uint16).reshape(-1, 24)[:, 18]
+    assert np.array_equal(pa, pb)                                                                                     # nPrimitives
+    interior = pa == 0
+    assert np.array_equal(na[interior, 38], nb[interior, 38])                                                        # axis (garbage in leaves)
+    fm, gm = ma.view(np.float32).reshape(-1, 16), mb.view(np.float32).reshape(-1, 16)
+    assert np.array_equal(fm[:, [0, 1, 2, 4, 5, 6, 8, 9, 10, 13, 14]].view(np.uint32), gm[:, [0, 1, 2, 4, 5, 6, 8, 9, 10, 13, 14]].view(np.uint32))
+
+
+def test_cornell_matches_reference_and_golden(cornell_ref):
+    prod = load_product()
+    mine = prod.host.load_scene(scenes.CORNELL, 4)
+    _same_scene(mine, cornell_ref)
+    g = np.load(os.path.join(scenes.GOLDEN, "cornell_scene.npz"))
+    assert np.array_equal(mine[1].view(np.uint32).reshape(-1, 12)[:, 8], g["node_offset"])
+    assert np.array_equal(mine[0].view(np.uint32).reshape(-1, 64)[:, 60], g["tri_mtl"])
+
+
+@pytest.mark.parametrize("max_prims", [1, 4, 16])
+def test_bumpy_sphere_matches_reference(tmp_scene_dir, max_prims):
+    prod = load_product()
+    p, n, f = scenes.displaced_sphere(4, amplitude=0.3)
+    quads = np.array([[0, 1, 2, 3], [10, 11, 12, 13]])
+    path = scenes.write_obj(os.path.join(tmp_scene_dir, "hs%d.obj" % max_prims), p, n, f, quads)
+    _same_scene(prod.host.load_scene(path, max_prims), ol.ref_load_scene(path, max_prims))
+
+
+def test_scattered_and_generated_scenes_match_reference(tmp_scene_dir):
+    prod = load_product()
+    path = os.path.join(tmp_scene_dir, "scatter.obj")
+    assert prod.host.write_scattered_obj(path, 20000, seed=3) == 20000
+    a = prod.host.load_scene(path, 4)
+    assert a[0].shape[0] == 40000
+    _same_scene(a, ol.ref_load_scene(path, 4))
+    path = os.path.join(tmp_scene_dir, "geo.obj")
+    assert prod.host.write_icosphere_obj(path, 24, amplitude=0.1) == 20 * 24 * 24
+    a = prod.host.load_scene(path, 4)
+    _same_scene(a, ol.ref_load_scene(path, 4))
+    # closed, outward-facing mesh: every outside-in ray hits a front face
+    rays = scenes.shell_rays(4000, 8.0, seed=9)
+    h = ol.oracle_closest(a[0], a[1], rays)
+    assert (h["tri"] != 0xFFFFFFFF).mean() > 0.99
+
+
+def test_loader_quirks(tmp_scene_dir):
+    """Comment words, unknown usemtl, ignored one-character tokens, malformed faces."""
+    prod = load_product()
+    base = os.path.join(tmp_scene_dir, "quirk")
+    with open(base + ".mtl", "w") as f:
+        f.write("# comment\nnewmtl a\n# Kd 9 9 9 (comment words are parsed like statements)\nKd 1 0 0\nNs 10\nnewmtl b\nKe 2 2 2\nNi 1.5\n")
+    with open(base + ".obj", "w") as f:
+        f.write("# a comment\nmtllib quirk.mtl\no thing\nv 0 0 0\nv 1 0 0\nv 0 1 0\nv 1 1 0\nvt 0 0\nvn 0 0 1\ns off\n"
+                "usemtl b\nf 1/1/1 2/1/1 3/1/1 \nusemtl nosuch\nf 2/1/1 4/1/1 3/1/1\n")
+    mine = prod.host.load_scene(base + ".obj", 4)
+    _same_scene(mine, ol.ref_load_scene(base + ".obj", 4))
+    assert mine[0].shape[0] == 4 and set(mine[0].view(np.uint32).reshape(-1, 64)[:, 60]) == {1}
+    with open(base + "2.mtl", "w") as f:
+        f.write("newmtl a\n")
+    with open(base + "2.obj", "w") as f:
+        f.write("v 0 0 0\nv 1 0 0\nv 0 1 0\nvt 0 0\nvn 0 0 1\nf 1 2 3\n")      # no v/vt/vn triplets
+    with pytest.raises(prod.host.HostError):
+        prod.host.load_scene(base + "2.obj", 4)                                  # one-character tokens are ignored -> no faces
+    with open(base + "3.obj", "w") as f:
+        f.write("v 0 0 0\nv 1 0 0\nv 0 1 0\nvt 0 0\nvn 0 0 1\nf 1//1 2//1 9//1\n")
+    with open(base + "3.mtl", "w") as f:
+        f.write("newmtl a\n")
+    with pytest.raises(prod.host.HostError):
+        prod.host.load_scene(base + "3.obj", 4)                                  # the reference reads out of bounds here
+    with pytest.raises(prod.host.HostError):
+        prod.host.load_scene(os.path.join(tmp_scene_dir, "missing.obj"), 4)
