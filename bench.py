@@ -1,0 +1,351 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the hot path (BVH traversal + ray/triangle intersection).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[2]/[4]): synthetic displaced geodesic icosphere, 1 003 520 OBJ faces ->
+2 007 040 CLTriangle after the loader's duplication, built by the product's own CLOBJloader + CLBVHScene
+mirror; one step = one closest-hit pass over a seeded stream of 2^24 incoherent rays per GPU (origins on
+a sphere of radius 3R, targets in the ball of radius R). Multi-GPU: BVH replicated, the ray stream is
+sharded by rank (weak scaling), no data-path collective.
+
+One JSON line on stdout (rank 0): value = whole-job Mrays/s with rays resident in HBM; e2e = the same
+metric through b2rt_trace_closest with pinned HOST buffers (H2D + D2H inside the timed region);
+roofline = algorithmic bytes (48 B/ray stream + counted node/leaf bytes) / kernel time vs the measured
+HBM peak; cpu_baseline = the reference's own Intersect() (oracle/_ref) on the host cores, bounded sample.
+"""
+import argparse
+import importlib.util
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "mini-opencl-raytracer_b200")
+SCENE_DIR = os.environ.get("B2RT_SCENE_DIR", "/tmp/b2rt_scenes")
+RADIUS = 10.0
+
+
+def product():
+    if "mor_b200" in sys.modules:
+        return sys.modules["mor_b200"]
+    spec = importlib.util.spec_from_file_location("mor_b200", os.path.join(PKG, "__init__.py"), submodule_search_locations=[PKG])
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules["mor_b200"] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def checkers():
+    """The CPU checkers (oracle/): used ONLY for the cpu_baseline leg and --impl reference."""
+    tests = os.path.join(ROOT, "tests")
+    if tests not in sys.path:
+        sys.path.insert(0, tests)
+    import oracle_lib
+    return oracle_lib
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+def ensure_scene(prod, frequency, rank, world, barrier):
+    os.makedirs(SCENE_DIR, exist_ok=True)
+    path = os.path.join(SCENE_DIR, "ico_f%d.obj" % frequency)
+    done = path + ".done"
+    if rank == 0 and not os.path.exists(done):
+        t0 = time.time()
+        faces = prod.host.write_icosphere_obj(path, frequency, radius=RADIUS, amplitude=0.08, seed=7)
+        with open(done, "w") as f:
+            f.write(str(faces))
+        log("[bench] wrote %s: %d faces (%.1f s)" % (path, faces, time.time() - t0))
+    barrier()
+    return path
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100", "-i", str(gpu)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 7 and r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def cpu_baseline(ol, kind_pref, tris, nodes, rays, seconds, threads):
+    """Reference Intersect() on the host cores over a bounded sample of the same ray stream."""
+    kind = "reference" if (kind_pref == "reference" and ol.ref() is not None) else "port"
+    fn = (lambda r: ol.ref_closest(tris, nodes, r, threads)) if kind == "reference" else (lambda r: ol.oracle_closest(tris, nodes, r, threads))
+    probe = rays[:20000 * max(threads, 1)]
+    t0 = time.perf_counter()
+    fn(probe)
+    dt = time.perf_counter() - t0
+    rate = probe.shape[0] / dt
+    n = int(min(rays.shape[0], max(probe.shape[0], rate * seconds)))
+    t0 = time.perf_counter()
+    fn(rays[:n])
+    dt = time.perf_counter() - t0
+    return {"value": n / dt / 1e6, "unit": "Mrays/s", "cores": threads, "kind": kind,
+            "sample": "%d rays of the same stream, closest-hit, %.1f s on %d host threads (%s)" % (
+                n, dt, threads, "reference kernel_bvh.cl Intersect() compiled as C++; PoCL unavailable" if kind == "reference" else "oracle/rt_oracle.c port")}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path on the host cores."""
+    if rank != 0:
+        return
+    prod = product()
+    ol = checkers()
+    path = ensure_scene(prod, args.frequency, 0, 1, lambda: None)
+    tris, nodes, mats = prod.host.load_scene(path, 4)
+    threads = os.cpu_count() or 1
+    n = args.ref_rays
+    rays = prod.workloads.shell_rays(n * (args.steps + args.warmup), RADIUS, seed=1000)
+    kind = "reference" if ol.ref() is not None else "port"
+    fn = (lambda r: ol.ref_closest(tris, nodes, r, threads)) if kind == "reference" else (lambda r: ol.oracle_closest(tris, nodes, r, threads))
+    for w in range(args.warmup):
+        fn(rays[w * n:(w + 1) * n])
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        fn(rays[(args.warmup + s) * n:(args.warmup + s + 1) * n])
+    dt = time.perf_counter() - t0
+    value = n * args.steps / dt / 1e6
+    print(json.dumps({
+        "impl": "reference", "metric": "closest_hit_ray_throughput", "value": value, "unit": "Mrays/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args, tris.shape[0]), "rays_per_step": n, "note": "bounded sample of the workload per step"},
+        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": threads, "kind": kind,
+                         "sample": "%d rays per step, %d steps, %d host threads" % (n, args.steps, threads)},
+        "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+def workload_name(args, n_tris):
+    return "displaced icosphere f=%d: %d OBJ faces -> %d CLTriangle; incoherent ray stream (origins on sphere 3R, targets in ball R), closest-hit" % (
+        args.frequency, 20 * args.frequency ** 2, n_tris)
+
+
+def run_b200(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    prod = product()
+    if prod.device_count() < 1:
+        raise RuntimeError("bench.py needs a CUDA device: the product has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    path = ensure_scene(prod, args.frequency, rank, world, barrier)
+    t0 = time.time()
+    eng = prod.host.Engine(1920, 1080, device=local_rank)        # CLEngineBase + CLRaytracer::Init on this GPU
+    eng.load_scene(path, 4)                                      # CLOBJloader::Load + CreateBVHTrees (+ upload)
+    ctx = prod.Context.borrow(eng.context_handle(), local_rank)
+    info = ctx.scene_info()
+    log("[bench r%d] scene ready in %.1f s: %s" % (rank, time.time() - t0, info))
+
+    n = args.rays
+    stream = torch.cuda.Stream()
+    host_rays = torch.empty((n, 8), dtype=torch.float32, pin_memory=True)
+    rays_np = host_rays.numpy().view(prod.RAY_DTYPE).reshape(-1)
+    prod.workloads.shell_rays(n, RADIUS, seed=1000 + rank, out=rays_np)
+    d_rays = host_rays.to("cuda", non_blocking=False)
+    d_hits = torch.empty((n, 4), dtype=torch.float32, device="cuda")
+    d_occ = torch.empty((n,), dtype=torch.int32, device="cuda")
+    host_hits = torch.empty((n, 4), dtype=torch.float32, pin_memory=True)
+    hits_np = host_hits.numpy().view(prod.HIT_DTYPE).reshape(-1)
+
+    def timed(fn, steps, warmup):
+        """W untimed steps, then K steps between barrier+synchronize, per-step CUDA events on the launch stream."""
+        with torch.cuda.stream(stream):
+            for _ in range(warmup):
+                fn()
+        torch.cuda.synchronize()
+        barrier()
+        torch.cuda.synchronize()
+        l0 = ctx.launch_count()
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        with torch.cuda.stream(stream):
+            evs[0].record()
+            for i in range(steps):
+                fn()
+                evs[i + 1].record()
+        torch.cuda.synchronize()
+        barrier()
+        total_ms = evs[0].elapsed_time(evs[-1])
+        per = [evs[i].elapsed_time(evs[i + 1]) for i in range(steps)]
+        if world > 1:
+            t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            total_ms = float(t.item())
+        return total_ms, per, ctx.launch_count() - l0
+
+    # ---- counted pass (outside the timed region): algorithmic bytes per ray -------------------------
+    ctx.set_option(prod.capi.OPT_COUNTERS, 1)
+    ctx.reset_counters()
+    ctx.finish()
+    ctx.trace_closest_device(d_rays.data_ptr(), n, d_hits.data_ptr(), stream.cuda_stream)
+    torch.cuda.synchronize()
+    cnt = ctx.counters()
+    ctx.set_option(prod.capi.OPT_COUNTERS, 0)
+    trav_bytes = cnt["bytes_fetched"] / max(cnt["rays"], 1)
+    bytes_per_ray = 48.0 + trav_bytes
+
+    # ---- device-resident headline ------------------------------------------------------------------------
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    total_ms, per, launches = timed(lambda: ctx.trace_closest_device(d_rays.data_ptr(), n, d_hits.data_ptr(), stream.cuda_stream),
+                          args.steps, args.warmup)
+    clocks = sampler.stop() if sampler else None
+    value = world * n * args.steps / (total_ms * 1e-3) / 1e6
+    kernel_ms = statistics.mean(per)
+
+    # ---- any-hit on the same stream ---------------------------------------------------------------------------
+    any_ms, _, _ = timed(lambda: ctx.trace_any_device(d_rays.data_ptr(), n, d_occ.data_ptr(), stream.cuda_stream), args.steps, args.warmup)
+    any_value = world * n * args.steps / (any_ms * 1e-3) / 1e6
+
+    # ---- end to end through the C ABI with host buffers -----------------------------------------------------------
+    def e2e_step():
+        ctx.trace_closest(rays_np, hits_np)      # H2D 32 B/ray, traversal, D2H 16 B/ray; synchronous
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = world * n * args.steps / e2e_s / 1e6
+    dev_hits = d_hits.cpu().numpy().view(prod.HIT_DTYPE).reshape(-1)
+    assert np.array_equal(dev_hits["tri"], hits_np["tri"]), "host-buffer and device-resident paths disagree"
+
+    # ---- cornell 1920x1080, 4 bounces, 16 frames accumulated (configs[1]) --------------------------------------------
+    extra = {}
+    if rank == 0 and not args.skip_frames:
+        cornell = os.path.join(ROOT, "tests", "golden", "cornell.obj")
+        with prod.host.Engine(1920, 1080, device=local_rank) as ce:
+            ce.load_scene(cornell, 4)
+            ce.set_render(frame_count=1, bounces=4)
+            ce.render_frame()                                    # warm-up frame (also frame 1 of the accumulation)
+            t0 = time.perf_counter()
+            for _ in range(15):
+                ce.render_frame()                                # RenderFrame: args, kernel, full read-back, finish
+            extra["cornell_1080p_4bounce_frame_ms"] = (time.perf_counter() - t0) / 15 * 1e3
+
+    # ---- CPU baseline (rank 0, N=1 only) ------------------------------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.skip_cpu:
+        ol = checkers()
+        tris, nodes, _ = eng.scene_arrays()
+        cpu = cpu_baseline(ol, "reference", tris, nodes, rays_np, args.cpu_seconds, os.cpu_count() or 1)
+        # parity spot check of the timed output against the checker (not timed)
+        want = ol.oracle_closest(tris, nodes, rays_np[:100000])
+        same = float((want["tri"] == hits_np["tri"][:100000]).mean())
+        extra["parity_ids_identical_frac_100k"] = same
+        extra["parity_t_bit_identical_frac_100k"] = float((want["t"] == hits_np["t"][:100000]).mean())
+
+    if rank == 0:
+        peaks, which = measured_peaks()
+        achieved = n * bytes_per_ray / (kernel_ms * 1e-3) / 1e9
+        out = {
+            "metric": "closest_hit_ray_throughput", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(args, info["n_triangles"]), "rays_per_gpu_per_step": n,
+                       "bvh": "replicated per GPU; %d wide nodes (%.1f MB) + %d leaf blocks (%.1f MB)" % (
+                           info["n_wide_nodes"], info["wide_node_bytes"] / 1e6, info["n_leaf_blocks"], info["leaf_bytes"] / 1e6),
+                       "parallelism": "ray stream sharded by rank, no data-path collective" if world > 1 else "single GPU",
+                       "l2": "ray + hit streams (%.0f MB per step) exceed the 126 MB L2; the BVH is re-used from L2 across steps by design" % (n * 48 / 1e6)},
+            "any_hit": {"value": any_value, "unit": "Mrays/s"},
+            "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": n * 32, "d2h_bytes_per_step": n * 16,
+                    "api": "b2rt_trace_closest (pinned host buffers, chunked H2D/kernel/D2H pipeline)"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+                         "traffic": None, "peak_source": which + " copy bandwidth (MEASURED_PEAKS.json)" if which == "measured" else "fallback",
+                         "kernel": "trace_persistent<closest>", "kernel_ms": kernel_ms,
+                         "bytes_per_ray": bytes_per_ray, "traversal_bytes_per_ray": trav_bytes,
+                         "per_ray": {k: v / max(cnt["rays"], 1) for k, v in cnt.items() if k != "rays"}},
+            "cpu_baseline": cpu,
+            "clocks": clocks,
+        }
+        out.update(extra)
+        print(json.dumps(out), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=6)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--rays", type=int, default=1 << 24, help="rays per GPU per step")
+    ap.add_argument("--frequency", type=int, default=224, help="geodesic frequency: 20*f^2 OBJ faces")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--ref-rays", type=int, default=1 << 19, help="--impl reference: rays per step (bounded sample)")
+    ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-frames", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        log("[bench] note: --warmup %d < 3; the timing rules ask for >= 3" % args.warmup)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_b200(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -15,3 +15,4 @@ from .capi import (B2RTError, Context, HIT_DTYPE, MISS, RAY_DTYPE, device_count,
 from .build import build_all  # noqa: F401
 from . import layouts  # noqa: F401
 from . import host  # noqa: F401
+from . import workloads  # noqa: F401
