@@ -93,14 +93,15 @@ typedef struct {
     uint64_t leaf_blocks;       /* leaf blocks fetched                                     */
     uint64_t leaf_gate_pass;    /* ... of which passed the exact fp32 leaf box             */
     uint64_t tri_tests;         /* Moller-Trumbore evaluations                             */
-    uint64_t bytes_fetched;     /* algorithmic bytes: 96 B per wide node + leaf block bytes */
+    uint64_t bytes_fetched;     /* algorithmic bytes: 112 B per wide node + leaf block bytes */
 } b2rt_counters;
 
 enum {
     B2RT_OPT_TRAVERSAL = 0,     /* 0 = compressed wide BVH (default), 1 = reference-layout binary walk */
     B2RT_OPT_COUNTERS = 1,      /* 1 = launches use the counting build of the kernels      */
     B2RT_OPT_BLOCKS_PER_SM = 2, /* persistent grid = value * SM count (0 = default)        */
-    B2RT_OPT_RENDER_MODE = 3    /* 0 = wavefront (default), 1 = megakernel                 */
+    B2RT_OPT_RENDER_MODE = 3,   /* 0 = wavefront (default), 1 = megakernel                 */
+    B2RT_OPT_REFILL_MIN = 4     /* idle lanes of a warp that trigger a ray refill (1..32, default 8) */
 };
 
 /* ---- lifetime ---------------------------------------------------------------------- */

@@ -58,7 +58,7 @@ struct b2rt_context {
     uint64_t stage_capacity = 0;
     cudaEvent_t ev_in[2] = { nullptr, nullptr }, ev_comp[2] = { nullptr, nullptr }, ev_out[2] = { nullptr, nullptr };
     // options
-    int64_t opt_traversal = 0, opt_counters = 0, opt_blocks_per_sm = 0, opt_render_mode = 0;
+    int64_t opt_traversal = 0, opt_counters = 0, opt_blocks_per_sm = 0, opt_render_mode = 0, opt_refill_min = 8;
     int grid_closest = 0, grid_any = 0;
     uint64_t launches = 0;
     std::string error;
@@ -137,7 +137,7 @@ int ensure_scene(b2rt_context* ctx) {
     if (bound > 256) return fail(ctx, B2RT_OUT_OF_RESOURCES, "BVH too deep for the traversal stack (wide depth " + std::to_string(w.max_depth_wide) + ")");
     free_scene(ctx);
     size_t wb = w.nodes.size() * sizeof(WideNode), lb = w.leaf.size() * sizeof(U4), sb = w.shade.size() * sizeof(ShadeTri);
-    CK(cudaMalloc(&ctx->d_wide, std::max<size_t>(wb, 96)));
+    CK(cudaMalloc(&ctx->d_wide, std::max<size_t>(wb, sizeof(WideNode))));
     CK(cudaMalloc(&ctx->d_leaf, std::max<size_t>(lb, 16) + 64));   // +64: visit_leaf prefetches one record past the header
     CK(cudaMalloc(&ctx->d_shade, std::max<size_t>(sb, 48)));
     CK(cudaMemsetAsync(static_cast<char*>(ctx->d_leaf) + std::max<size_t>(lb, 16), 0, 64, ctx->stream));
@@ -193,7 +193,7 @@ int trace_device(b2rt_context* ctx, const void* d_rays, uint64_t n, void* d_out,
     uint64_t warps_needed = (n + 31) / 32, blocks_needed = (warps_needed * 32 + trace_block_threads() - 1) / trace_block_threads();
     if ((uint64_t)grid > blocks_needed) grid = (int)blocks_needed;
     CK(launch_trace_wide(ctx->view, d_rays, n, d_out, any, ctx->opt_counters != 0, ctx->stack_bound, grid, ctx->d_next,
-                         ctx->d_counters, st));
+                         ctx->d_counters, (uint32_t)ctx->opt_refill_min, st));
     ctx->launches += 1;
     return B2RT_SUCCESS;
 }
@@ -593,6 +593,7 @@ extern "C" int b2rt_set_option(b2rt_context* ctx, uint32_t option, int64_t value
         case B2RT_OPT_COUNTERS: ctx->opt_counters = value ? 1 : 0; break;
         case B2RT_OPT_BLOCKS_PER_SM: if (value < 0 || value > 32) return fail(ctx, B2RT_INVALID_VALUE, "blocks per SM out of range"); ctx->opt_blocks_per_sm = value; break;
         case B2RT_OPT_RENDER_MODE: ctx->opt_render_mode = value; break;
+        case B2RT_OPT_REFILL_MIN: if (value < 1 || value > 32) return fail(ctx, B2RT_INVALID_VALUE, "refill threshold must be 1..32"); ctx->opt_refill_min = value; break;
         default: return fail(ctx, B2RT_INVALID_VALUE, "unknown option");
     }
     return B2RT_SUCCESS;
@@ -603,7 +604,7 @@ extern "C" int b2rt_get_counters(b2rt_context* ctx, b2rt_counters* out) {
     int st = use_device(ctx);
     if (st) return st;
     unsigned long long v[6];
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaDeviceSynchronize());     // counted launches may sit on caller-provided streams
     CK(cudaMemcpy(v, ctx->d_counters, sizeof(v), cudaMemcpyDeviceToHost));
     out->rays = v[0]; out->wide_nodes = v[1]; out->leaf_blocks = v[2]; out->leaf_gate_pass = v[3]; out->tri_tests = v[4];
     out->bytes_fetched = v[5] * 16ull;

@@ -4,9 +4,9 @@
 // Inputs keep the reference's byte layouts (CLshared_structs.hpp:13-88):
 //   CLTriangle 256 B, CLLinearBVHNode 48 B, CLMaterial 64 B.
 // Derived, traversal-only layout built at upload time:
-//   WideNode   96 B  8-wide node = a binary node of the host BVH collapsed with
-//                    its children and grandchildren (a depth<=3 treelet); child
-//                    boxes quantised to 8 bits per plane, conservatively.
+//   WideNode  112 B  up-to-8-wide node = a treelet of the host's binary BVH; child
+//                    boxes quantised to 8 bits per plane, conservatively; the
+//                    reference's visiting order stored per ray-sign octant.
 //   leaf block 32 B header (the leaf's exact fp32 box, first triangle id, counts)
 //                    + 48 B per stored triangle record (positions only).
 //   ShadeTri   48 B  the three vertex normals + material index of a triangle.
@@ -26,27 +26,40 @@ static_assert(sizeof(RefNode) == 48, "CLLinearBVHNode layout (CLshared_structs.h
 static_assert(sizeof(RefMaterial) == 64, "CLMaterial layout (CLshared_structs.hpp:13-26)");
 
 // ---- compressed wide BVH -----------------------------------------------------------
-// Child slot c in 0..7 is the 3-bit path from the treelet root: bit2 = first
-// split (0 = first child `index+1`, 1 = second child `offset`), bit1 = second
-// split, bit0 = third. A binary leaf met above depth 3 keeps the remaining path
-// bits zero. The treelet's (up to) 7 binary interior nodes are numbered heap
-// style: 0 = root, 1+b2 = depth 1, 3+(b2<<1|b1) = depth 2; their split axes are
-// stored as three 7-bit masks so that the reference's near-child-first order
-// (kernel_bvh.cl:200-207) can be replayed exactly for any ray sign octant.
-struct alignas(32) WideNode {
-    float base[3];          //  0  quantisation origin (min corner of the union of the child boxes)
-    uint8_t exp[3];         // 12  biased exponents: plane = base + q * 2^(exp-127)
-    uint8_t imask;          // 15  bit c: slot c holds an interior child (another WideNode)
-    uint32_t child_base;    // 16  index of the first interior child; child of slot c = child_base + popc(imask & ((1<<c)-1))
-    uint32_t leaf_base;     // 20  offset (16-byte units) of this node's first leaf block in the leaf buffer
-    uint32_t axes;          // 24  mx | my<<8 | mz<<16 | valid<<24 (bit j of m*: treelet node j splits on that axis)
-    uint32_t reserved;      // 28
-    uint8_t meta[8];        // 32  leaf child: block offset relative to leaf_base in 16-byte units
-    uint8_t qlo[3][8];      // 40  quantised min planes: qlo[axis][slot]
-    uint8_t qhi[3][8];      // 64  quantised max planes
-    uint8_t spare[8];       // 88
+// A wide node is a treelet of the host's binary BVH: starting from a binary node, the
+// interior child with the largest surface area is opened repeatedly until 8 children
+// are reached (or only leaves remain). Child slot c (0..n-1) is the child's position in
+// the treelet's depth-first order with the FIRST binary child (`index+1`) before the
+// second (`offset`) -- the order the reference walks for a ray whose direction is
+// positive on every split axis. For the other seven sign octants the reference swaps
+// the two sub-ranges under every treelet node whose split axis has a negative direction
+// (kernel_bvh.cl:200-207); the resulting visiting order is precomputed per octant as
+// eight 4-bit slot numbers (`order[octant]`, nibble k = slot visited k-th), so the
+// kernels can replay the reference's leaf order exactly for any treelet shape.
+//
+//   word0 = { base.x, base.y, base.z, exp_x | exp_y<<8 | exp_z<<16 | n_children<<24 }
+//   word1 = { child_base, leaf_base, meta[0..3], meta[4..7] }
+//   word2 = { qlo_x[0..3], qlo_x[4..7], qlo_y[0..3], qlo_y[4..7] }
+//   word3 = { qlo_z[0..3], qlo_z[4..7], qhi_x[0..3], qhi_x[4..7] }
+//   word4 = { qhi_y[0..3], qhi_y[4..7], qhi_z[0..3], qhi_z[4..7] }
+//   word5 = { order[0..3] }   word6 = { order[4..7] }
+// plane(axis, q) = base[axis] + q * 2^(exp[axis]-127); child boxes are quantised outward
+// (qlo rounded down, qhi rounded up). meta[c]: bit 7 set = interior child, wide node
+// index child_base + (meta & 0x7f); clear = leaf block at leaf_base + meta (16-byte
+// units). Ranks >= n_children of an order word name an empty slot.
+struct alignas(16) WideNode {
+    float base[3];          //  0
+    uint8_t exp[3];         // 12
+    uint8_t n_children;     // 15
+    uint32_t child_base;    // 16
+    uint32_t leaf_base;     // 20
+    uint8_t meta[8];        // 24
+    uint8_t qlo[3][8];      // 32  qlo[axis][slot]
+    uint8_t qhi[3][8];      // 56
+    uint32_t order[8];      // 80  order[sign octant: sx | sy<<1 | sz<<2]
 };
-static_assert(sizeof(WideNode) == 96, "WideNode must be 96 B (three 32-byte sectors)");
+static_assert(sizeof(WideNode) == 112, "WideNode must be 112 B (seven 16-byte words)");
+enum { WIDE_NODE_WORDS = 7, META_INTERIOR = 0x80, META_MAX_LEAF_OFFSET = 0x7f };
 
 // Leaf block header, two 16-byte words followed by n_records * 3 words.
 //   word0 = { bmin.x, bmin.y, bmin.z, first_tri }
@@ -71,7 +84,7 @@ enum : uint32_t { REF_LEAF_BIT = 0x80000000u, REF_EMPTY = 0xFFFFFFFFu };
 struct alignas(16) U4 { uint32_t x, y, z, w; };   // one 128-bit load
 
 struct SceneView {                 // plain device pointers handed to kernels
-    const U4* wide;                // WideNode[] viewed as 6 x U4 each; node 0 is the root
+    const U4* wide;                // WideNode[] viewed as 7 x U4 each; node 0 is the root
     const U4* leaf;                // leaf blocks
     const ShadeTri* shade;         // per reference triangle
     const RefMaterial* mats;

@@ -25,7 +25,6 @@ namespace b2rt {
 
 static constexpr unsigned FULL = 0xffffffffu;
 static constexpr int TRACE_BLOCK = 128;
-static constexpr uint32_t POOL_CHUNK = 512;     // rays a warp takes from the global counter at a time
 
 struct RayIn { float ox, oy, oz, tmin, dx, dy, dz, tmax; };
 
@@ -37,98 +36,78 @@ __device__ __forceinline__ void load_ray(const RayIn* rays, uint64_t i, RayX& r,
 }
 
 // ---------------------------------------------------------------------------------------
-// Persistent while-while traversal.
+// Persistent speculative while-while traversal.
+//
+// Every lane owns one ray (Lane<> in traverse.cuh). Per iteration the warp votes: lanes whose
+// next action is a wide-node test vs lanes holding a queued leaf. The majority action runs for
+// the lanes that want it (a lane with a queued leaf AND a node to test can join either), so most
+// issued instructions have many active lanes even though rays are incoherent. Finished lanes are
+// re-filled from a warp-local pool of ray indices (ballot + popc compaction) that is topped up
+// from one global atomic counter, `chunk` rays at a time.
 // ---------------------------------------------------------------------------------------
 template <bool ANY, bool COUNT, int CAP>
 __global__ void __launch_bounds__(TRACE_BLOCK)
 trace_persistent(SceneView s, const RayIn* __restrict__ rays, uint64_t n, void* __restrict__ out,
-                 unsigned long long* __restrict__ next, unsigned long long* __restrict__ counters) {
+                 unsigned long long* __restrict__ next, unsigned long long* __restrict__ counters, uint32_t chunk,
+                 uint32_t refill_min) {
     const unsigned lane = threadIdx.x & 31u;
-    uint32_t stack[CAP];
-    int sp = 0;
-    uint32_t cur = REF_EMPTY;
+    Lane<ANY, COUNT, CAP> L;
+    L.clear();
+    L.overflow = false;
+    L.tc.wide_nodes = L.tc.leaf_blocks = L.tc.leaf_pass = L.tc.tri_tests = L.tc.words = 0;
     bool active = false;
     uint64_t my_index = 0;
-    RayX r;
-    HitX h;
-    TravCounters tc = { 0, 0, 0, 0, 0 };
     uint64_t pool_next = 0, pool_end = 0;    // warp-uniform
     bool exhausted = false;                  // warp-uniform: the global counter ran past n
     uint32_t traced = 0;
 
-    auto finish = [&]() {
-        if (ANY) reinterpret_cast<uint32_t*>(out)[my_index] = (h.tri != 0xFFFFFFFFu) ? 1u : 0u;
-        else reinterpret_cast<float4*>(out)[my_index] = make_float4(h.t, h.u, h.v, __uint_as_float(h.tri));
-        active = false;
-        cur = REF_EMPTY;
-        if (COUNT) traced++;
-    };
-    auto pop = [&]() {
-        if (sp == 0) finish();
-        else cur = stack[--sp];
-    };
-
     for (;;) {
-        // ---- refill idle lanes from the warp pool (ballot compaction) --------------------
-        unsigned idle = __ballot_sync(FULL, !active);
-        if (idle) {
-            if (pool_next == pool_end && !exhausted) {
+        const unsigned idle = __ballot_sync(FULL, !active);
+        const unsigned vn = __ballot_sync(FULL, active && L.wants_node());
+        const unsigned vl = __ballot_sync(FULL, active && L.wants_leaf());
+        const bool pool_dry = exhausted && pool_next == pool_end;
+        if (idle && !pool_dry && ((unsigned)__popc(idle) >= refill_min || (vn | vl) == 0u)) {
+            // ---- refill idle lanes from the warp pool -------------------------------------------
+            if (pool_next == pool_end) {
                 unsigned long long base = 0;
-                if (lane == 0) base = atomicAdd(next, (unsigned long long)POOL_CHUNK);
+                if (lane == 0) base = atomicAdd(next, (unsigned long long)chunk);
                 base = __shfl_sync(FULL, base, 0);
-                if (base >= n) { exhausted = true; }
-                else { pool_next = base; pool_end = (base + POOL_CHUNK < n) ? base + POOL_CHUNK : n; }
+                if (base >= n) exhausted = true;
+                else { pool_next = base; pool_end = (base + chunk < n) ? base + chunk : n; }
             }
-            uint64_t avail = pool_end - pool_next;
+            const uint64_t avail = pool_end - pool_next;
             if (avail) {
-                unsigned rank = __popc(idle & ((1u << lane) - 1u));
+                const unsigned rank = __popc(idle & ((1u << lane) - 1u));
                 if (!active && rank < avail) {
                     my_index = pool_next + rank;
-                    float tmax;
+                    RayX r; float tmax;
                     load_ray(rays, my_index, r, tmax);
-                    h.t = tmax; h.u = 0.0f; h.v = 0.0f; h.tri = 0xFFFFFFFFu;
-                    sp = 0;
-                    cur = 0;
+                    L.start(r, tmax);
                     active = true;
                 }
-                unsigned taken = __popc(idle);
+                const unsigned taken = __popc(idle);
                 pool_next += (taken < avail) ? taken : avail;
             }
-        }
-        if (!__any_sync(FULL, active)) {
-            if (exhausted && pool_next == pool_end) break;
             continue;
         }
+        if ((vn | vl) == 0u) break;          // nothing in flight and nothing left to fetch
 
-        // ---- loop A: interior wide nodes until every live lane holds a leaf ----------------
-        while (__any_sync(FULL, active && !(cur & REF_LEAF_BIT))) {
-            if (active && !(cur & REF_LEAF_BIT)) {
-                WideHits w = test_wide_node(s.wide, cur, r, h.t);
-                if (COUNT) { tc.wide_nodes++; tc.words += 6; }
-                uint32_t first = REF_EMPTY;
-#pragma unroll
-                for (int k = 7; k >= 0; --k) {
-                    uint32_t slot = slot_of_rank(w.flips, (uint32_t)k);
-                    if ((w.mask >> slot) & 1u) {
-                        if (first != REF_EMPTY && sp < CAP) stack[sp++] = first;
-                        first = child_ref(w, slot);
-                    }
-                }
-                if (first != REF_EMPTY) cur = first;
-                else pop();
-            }
+        if (__popc(vn) >= __popc(vl)) {
+            if (active && L.wants_node()) L.node_step(s.wide);
+        } else {
+            if (active && L.wants_leaf()) L.leaf_step(s.leaf);
         }
-        // ---- loop B: one leaf per live lane --------------------------------------------------
-        if (active) {   // cur is a leaf here
-            bool got = visit_leaf<COUNT>(s.leaf, cur & ~REF_LEAF_BIT, r, h, COUNT ? &tc : nullptr);
-            if ((ANY && got) || h.t < 0.0f) finish();     // best < 0 ends the reference's walk too
-            else pop();
+        if (active && L.done()) {
+            if (ANY) reinterpret_cast<uint32_t*>(out)[my_index] = (L.h.tri != 0xFFFFFFFFu) ? 1u : 0u;
+            else reinterpret_cast<float4*>(out)[my_index] = make_float4(L.h.t, L.h.u, L.h.v, __uint_as_float(L.h.tri));
+            active = false;
+            if (COUNT) traced++;
         }
     }
 
     if (COUNT) {
         // one atomic per counter per warp
-        unsigned long long v[6] = { traced, tc.wide_nodes, tc.leaf_blocks, tc.leaf_pass, tc.tri_tests, tc.words };
+        unsigned long long v[6] = { traced, L.tc.wide_nodes, L.tc.leaf_blocks, L.tc.leaf_pass, L.tc.tri_tests, L.tc.words };
 #pragma unroll
         for (int i = 0; i < 6; ++i) {
             unsigned long long x = v[i];
@@ -253,13 +232,18 @@ static int pick_cap(uint32_t bound) { return bound <= 32 ? 32 : (bound <= 64 ? 6
 
 template <bool ANY, bool COUNT>
 static cudaError_t launch_persistent_cap(int cap, int grid, cudaStream_t st, const SceneView& s, const void* rays,
-                                         uint64_t n, void* out, unsigned long long* next, unsigned long long* counters) {
+                                         uint64_t n, void* out, unsigned long long* next, unsigned long long* counters,
+                                         uint32_t refill_min) {
     const RayIn* r = static_cast<const RayIn*>(rays);
+    // rays per pool top-up: about 1/8 of a warp's fair share, a multiple of 32 in [32, 512]
+    uint64_t warps = (uint64_t)grid * (TRACE_BLOCK / 32);
+    uint64_t c = n / (warps * 8u + 1u);
+    uint32_t chunk = (uint32_t)(c < 32 ? 32 : (c > 512 ? 512 : (c & ~31ull)));
     switch (cap) {
-        case 32: trace_persistent<ANY, COUNT, 32><<<grid, TRACE_BLOCK, 0, st>>>(s, r, n, out, next, counters); break;
-        case 64: trace_persistent<ANY, COUNT, 64><<<grid, TRACE_BLOCK, 0, st>>>(s, r, n, out, next, counters); break;
-        case 128: trace_persistent<ANY, COUNT, 128><<<grid, TRACE_BLOCK, 0, st>>>(s, r, n, out, next, counters); break;
-        case 256: trace_persistent<ANY, COUNT, 256><<<grid, TRACE_BLOCK, 0, st>>>(s, r, n, out, next, counters); break;
+        case 32: trace_persistent<ANY, COUNT, 32><<<grid, TRACE_BLOCK, 0, st>>>(s, r, n, out, next, counters, chunk, refill_min); break;
+        case 64: trace_persistent<ANY, COUNT, 64><<<grid, TRACE_BLOCK, 0, st>>>(s, r, n, out, next, counters, chunk, refill_min); break;
+        case 128: trace_persistent<ANY, COUNT, 128><<<grid, TRACE_BLOCK, 0, st>>>(s, r, n, out, next, counters, chunk, refill_min); break;
+        case 256: trace_persistent<ANY, COUNT, 256><<<grid, TRACE_BLOCK, 0, st>>>(s, r, n, out, next, counters, chunk, refill_min); break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
@@ -267,15 +251,16 @@ static cudaError_t launch_persistent_cap(int cap, int grid, cudaStream_t st, con
 
 cudaError_t launch_trace_wide(const SceneView& s, const void* d_rays, uint64_t n, void* d_out, bool any, bool count,
                               uint32_t stack_bound, int grid_blocks, unsigned long long* d_next,
-                              unsigned long long* d_counters, cudaStream_t st) {
+                              unsigned long long* d_counters, uint32_t refill_min, cudaStream_t st) {
     int cap = pick_cap(stack_bound);
     if (!cap) return cudaErrorInvalidValue;
     cudaError_t e = cudaMemsetAsync(d_next, 0, sizeof(unsigned long long), st);
     if (e != cudaSuccess) return e;
-    if (any) return count ? launch_persistent_cap<true, true>(cap, grid_blocks, st, s, d_rays, n, d_out, d_next, d_counters)
-                          : launch_persistent_cap<true, false>(cap, grid_blocks, st, s, d_rays, n, d_out, d_next, d_counters);
-    return count ? launch_persistent_cap<false, true>(cap, grid_blocks, st, s, d_rays, n, d_out, d_next, d_counters)
-                 : launch_persistent_cap<false, false>(cap, grid_blocks, st, s, d_rays, n, d_out, d_next, d_counters);
+    if (refill_min < 1 || refill_min > 32) refill_min = 8;
+    if (any) return count ? launch_persistent_cap<true, true>(cap, grid_blocks, st, s, d_rays, n, d_out, d_next, d_counters, refill_min)
+                          : launch_persistent_cap<true, false>(cap, grid_blocks, st, s, d_rays, n, d_out, d_next, d_counters, refill_min);
+    return count ? launch_persistent_cap<false, true>(cap, grid_blocks, st, s, d_rays, n, d_out, d_next, d_counters, refill_min)
+                 : launch_persistent_cap<false, false>(cap, grid_blocks, st, s, d_rays, n, d_out, d_next, d_counters, refill_min);
 }
 
 cudaError_t launch_trace_binary(const SceneView& s, const void* d_rays, uint64_t n, void* d_out, bool any, cudaStream_t st) {

@@ -17,7 +17,10 @@
 //    box contains its children and fp32 subtraction/multiplication by a fixed
 //    operand are monotone, that is equivalent to the reference's rule "every
 //    ancestor passed when it was visited", so interior culling may be anything
-//    conservative: here 8-bit quantised boxes evaluated with directed rounding.
+//    conservative: here 8-bit quantised boxes evaluated with one FMA per plane and an
+//    explicit error margin (see test_wide_node). For the same reason interior nodes may
+//    be tested AHEAD of pending leaves with a stale (larger) `best` -- the Lane state
+//    machine below keeps up to two leaves queued in order while it walks on.
 #pragma once
 #include "b2rt_types.h"
 
@@ -48,6 +51,9 @@ B2_HD float mul_ru(float a, float b) { return __fmul_ru(a, b); }
 B2_HD float max_nn(float a, float b) { return fmaxf(a, b); }   // NaN-ignoring
 B2_HD float min_nn(float a, float b) { return fminf(a, b); }
 B2_HD float u2f(uint32_t v) { return __uint2float_rn(v); }
+B2_HD float fma_rn(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+B2_HD uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) { return __byte_perm(a, b, sel); }
+B2_HD uint32_t top_bit(uint32_t v) { return 31u - (uint32_t)__clz((int)v); }
 B2_HD uint32_t byte_of(uint32_t w, uint32_t i) { return __byte_perm(w, 0, 0x4440u + i); }
 B2_HD uint32_t popc32(uint32_t v) { return __popc(v); }
 B2_HD float bits2f(uint32_t v) { return __uint_as_float(v); }
@@ -56,6 +62,7 @@ B2_HD U4 ld128(const U4* p) {
     uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
     U4 r; r.x = v.x; r.y = v.y; r.z = v.z; r.w = v.w; return r;
 }
+B2_HD uint32_t ld32(const uint32_t* p) { return __ldg(p); }
 #else
 // Host emulation (tests only). Built with -ffp-contract=off -frounding-math.
 B2_HD float xadd(float a, float b) { volatile float r = a + b; return r; }
@@ -75,11 +82,20 @@ B2_HD float mul_ru(float a, float b) { return with_round(FE_UPWARD, [&] { volati
 B2_HD float max_nn(float a, float b) { return std::fmax(a, b); }
 B2_HD float min_nn(float a, float b) { return std::fmin(a, b); }
 B2_HD float u2f(uint32_t v) { return (float)v; }
+B2_HD float fma_rn(float a, float b, float c) { return std::fmaf(a, b, c); }
+B2_HD uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {   // PTX prmt.b32, default mode, selector nibbles 0..7
+    uint64_t src = ((uint64_t)b << 32) | a;
+    uint32_t r = 0;
+    for (int i = 0; i < 4; ++i) r |= (uint32_t)((src >> (8 * ((sel >> (4 * i)) & 7u))) & 0xffu) << (8 * i);
+    return r;
+}
+B2_HD uint32_t top_bit(uint32_t v) { return 31u - (uint32_t)__builtin_clz(v); }
 B2_HD uint32_t byte_of(uint32_t w, uint32_t i) { return (w >> (8 * i)) & 0xffu; }
 B2_HD uint32_t popc32(uint32_t v) { return (uint32_t)__builtin_popcount(v); }
 B2_HD float bits2f(uint32_t v) { float f; std::memcpy(&f, &v, 4); return f; }
 B2_HD uint32_t f2bits(float v) { uint32_t u; std::memcpy(&u, &v, 4); return u; }
 B2_HD U4 ld128(const U4* p) { return *p; }
+B2_HD uint32_t ld32(const uint32_t* p) { return *p; }
 #endif
 
 // OpenCL max()/min() as worded by the spec ("y if x < y, otherwise x"), the
@@ -190,115 +206,164 @@ B2_HD bool visit_leaf(const U4* leaf, uint32_t offset, const RayX& r, HitX& h, T
 
 // ---- wide node ------------------------------------------------------------------------
 struct WideHits {
-    uint32_t mask;         // bit c: child slot c may intersect [0,best] (conservative)
-    uint32_t flips;        // 7 bits: treelet node j is visited second-child-first for this ray
-    uint32_t imask, child_base, leaf_base, meta_lo, meta_hi;
+    uint32_t mask;                // bit k: the child visited k-th (reference order) may intersect [0,best]
+    uint32_t meta_lo, meta_hi;    // meta bytes permuted into visiting order
+    uint32_t child_base, leaf_base;
 };
 
-// Child reference of slot c (interior: wide node index, leaf: REF_LEAF_BIT | block offset).
-B2_HD uint32_t child_ref(const WideHits& w, uint32_t c) {
-    if ((w.imask >> c) & 1u) return w.child_base + popc32(w.imask & ((1u << c) - 1u));
-    uint32_t m = byte_of(c < 4 ? w.meta_lo : w.meta_hi, c & 3u);
-    return REF_LEAF_BIT | (w.leaf_base + m);
+// Child reference of the child visited k-th: wide node index, or REF_LEAF_BIT | block offset.
+B2_HD uint32_t child_ref(const WideHits& w, uint32_t k) {
+    uint32_t m = prmt(w.meta_lo, w.meta_hi, k) & 0xffu;
+    return (m & META_INTERIOR) ? w.child_base + (m & 0x7fu) : (REF_LEAF_BIT | (w.leaf_base + m));
 }
 
-// Slot visited k-th (k = 0 first) when the treelet is walked in the reference's order.
-B2_HD uint32_t slot_of_rank(uint32_t flips, uint32_t k) {
-    uint32_t c2 = ((k >> 2) & 1u) ^ (flips & 1u);
-    uint32_t c1 = ((k >> 1) & 1u) ^ ((flips >> (1u + c2)) & 1u);
-    uint32_t c0 = (k & 1u) ^ ((flips >> (3u + 2u * c2 + c1)) & 1u);
-    return (c2 << 2) | (c1 << 1) | c0;
-}
+// float 1 + q * 2^-15 from byte i of w: the byte lands in mantissa bits 8..15 of 1.0f.
+#define B2_PLANE_V(w, i) bits2f(prmt((w), 0x3F800000u, 0x7604u | ((i) << 4)))
 
-// Conservative slab test of the 8 quantised child boxes against [0, best].
-// For every axis the ray is mirrored so that it travels in +direction:
-//   near plane lower bound  n = RD( RD(q_near * S + A_rd) * |inv| )
-//   far  plane upper bound  f = RU( RU(q_far  * S + A_ru) * |inv| )
-// with S = +-2^e and A = +-(base - o) rounded toward the safe side, so that
-// n <= fl((plane_near - o) * inv) and f >= fl((plane_far - o) * inv) of the exact
-// test for any exact plane inside the quantised one (monotonicity of fl()).
+// Conservative slab test of the (up to) 8 quantised child boxes against [0, best], evaluated in
+// the reference's visiting order for this ray's sign octant.
+//
+// With S = 2^(exp-127), plane(q) = base + q*S and v = 1 + q*2^-15, the reference's slab value for an
+// exact plane P is R(P) = fl(fl(P - o) * inv) (kernel_bvh.cl:158-167). Here one FMA per plane gives
+//     t(q) = fl(v*K + B),  K = 2^15*S*inv (exact), B = fl(A - K) -+ slack, A = fl(fl(base - o) * inv)
+// whose real-arithmetic value is (plane(q) - o)*inv. Rounding of A, B and the FMA, plus the two
+// roundings inside R, differ from that by less than 1.5 * 2^-22 * (|A| + |K|); slack =
+// 2^-20 * (|A| + |K|) + 1e-35 therefore makes t_near(q_near) <= R(P) for every exact plane P on the
+// far side of the quantised near plane (R is monotone in P), and likewise t_far >= R(P). NaNs
+// (inv = +-inf or NaN, overflow) drop out of fminf/fmaxf, i.e. that axis does not constrain: the
+// test can only pass more children than the reference's, never fewer.
 B2_HD WideHits test_wide_node(const U4* wide, uint32_t index, const RayX& r, float best) {
-    const U4* p = wide + 6u * index;
-    U4 w0 = ld128(p), w1 = ld128(p + 1), w2 = ld128(p + 2), w3 = ld128(p + 3), w4 = ld128(p + 4), w5 = ld128(p + 5);
+    const U4* p = wide + (uint32_t)WIDE_NODE_WORDS * index;
+    U4 w0 = ld128(p), w1 = ld128(p + 1), w2 = ld128(p + 2), w3 = ld128(p + 3), w4 = ld128(p + 4);
+    const uint32_t order = ld32(reinterpret_cast<const uint32_t*>(p + 5) + r.sign);
     WideHits out;
-    out.imask = w0.w >> 24;
     out.child_base = w1.x;
     out.leaf_base = w1.y;
-    out.meta_lo = w2.x;
-    out.meta_hi = w2.y;
-    uint32_t axes = w1.z;
-    uint32_t rm = ((r.sign & 1u) ? 0x7fu : 0u) | ((r.sign & 2u) ? 0x7f00u : 0u) | ((r.sign & 4u) ? 0x7f0000u : 0u);
-    uint32_t t = axes & rm;
-    out.flips = (t | (t >> 8) | (t >> 16)) & 0x7fu;
+    const uint32_t sel_lo = order, sel_hi = order >> 16;      // prmt reads the low four nibbles only
+    out.meta_lo = prmt(w1.z, w1.w, sel_lo);
+    out.meta_hi = prmt(w1.z, w1.w, sel_hi);
 
-    float S[3], Ard[3], Aru[3], IA[3];
-    uint32_t qn_lo[3], qn_hi[3], qf_lo[3], qf_hi[3];
     const float o[3] = { r.ox, r.oy, r.oz };
     const float inv[3] = { r.ix, r.iy, r.iz };
     const float base[3] = { bits2f(w0.x), bits2f(w0.y), bits2f(w0.z) };
-    const uint32_t lo_lo[3] = { w2.z, w3.x, w3.z }, lo_hi[3] = { w2.w, w3.y, w3.w };
-    const uint32_t hi_lo[3] = { w4.x, w4.z, w5.x }, hi_hi[3] = { w4.y, w4.w, w5.y };
+    const uint32_t qlo_a[3] = { w2.x, w2.z, w3.x }, qlo_b[3] = { w2.y, w2.w, w3.y };   // slots 0..3 / 4..7
+    const uint32_t qhi_a[3] = { w3.z, w4.x, w4.z }, qhi_b[3] = { w3.w, w4.y, w4.w };
+    float K[3], Bn[3], Bf[3];
+    uint32_t near_lo[3], near_hi[3], far_lo[3], far_hi[3];      // plane bytes in visiting order, ranks 0..3 / 4..7
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
-        float s = bits2f(((w0.w >> (8 * a)) & 0xffu) << 23);
-        float d_rd = sub_rd(base[a], o[a]), d_ru = sub_ru(base[a], o[a]);
-        bool neg = (r.sign >> a) & 1u;
-        S[a] = neg ? -s : s;
-        Ard[a] = neg ? -d_ru : d_rd;
-        Aru[a] = neg ? -d_rd : d_ru;
-        IA[a] = fabsf(inv[a]);
-        qn_lo[a] = neg ? hi_lo[a] : lo_lo[a]; qn_hi[a] = neg ? hi_hi[a] : lo_hi[a];
-        qf_lo[a] = neg ? lo_lo[a] : hi_lo[a]; qf_hi[a] = neg ? lo_hi[a] : hi_hi[a];
+        const uint32_t e = (w0.w >> (8 * a)) & 0xffu;
+        K[a] = xmul(bits2f((e + 15u) << 23), inv[a]);
+        const float A = xmul(xsub(base[a], o[a]), inv[a]);
+        const float B = xsub(A, K[a]);
+        const float slack = fma_rn(xadd(fabsf(A), fabsf(K[a])), 9.5367431640625e-7f, 1.0e-35f);
+        Bn[a] = xsub(B, slack);
+        Bf[a] = xadd(B, slack);
+        const bool neg = (r.sign >> a) & 1u;
+        const uint32_t na = neg ? qhi_a[a] : qlo_a[a], nb = neg ? qhi_b[a] : qlo_b[a];
+        const uint32_t fa = neg ? qlo_a[a] : qhi_a[a], fb = neg ? qlo_b[a] : qhi_b[a];
+        near_lo[a] = prmt(na, nb, sel_lo); near_hi[a] = prmt(na, nb, sel_hi);
+        far_lo[a] = prmt(fa, fb, sel_lo);  far_hi[a] = prmt(fa, fb, sel_hi);
     }
     uint32_t mask = 0;
 #pragma unroll
-    for (uint32_t c = 0; c < 8; ++c) {
-        float t0 = 0.0f, t1 = best;
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-            float qn = u2f(byte_of(c < 4 ? qn_lo[a] : qn_hi[a], c & 3u));
-            float qf = u2f(byte_of(c < 4 ? qf_lo[a] : qf_hi[a], c & 3u));
-            float n = mul_rd(fma_rd(qn, S[a], Ard[a]), IA[a]);
-            float f = mul_ru(fma_ru(qf, S[a], Aru[a]), IA[a]);
-            t0 = max_nn(t0, n);
-            t1 = min_nn(t1, f);
-        }
-        if (t1 >= t0) mask |= 1u << c;
+    for (uint32_t k = 0; k < 8; ++k) {
+        const uint32_t i = k & 3u;
+        float n0 = fma_rn(B2_PLANE_V(k < 4 ? near_lo[0] : near_hi[0], i), K[0], Bn[0]);
+        float n1 = fma_rn(B2_PLANE_V(k < 4 ? near_lo[1] : near_hi[1], i), K[1], Bn[1]);
+        float n2 = fma_rn(B2_PLANE_V(k < 4 ? near_lo[2] : near_hi[2], i), K[2], Bn[2]);
+        float f0 = fma_rn(B2_PLANE_V(k < 4 ? far_lo[0] : far_hi[0], i), K[0], Bf[0]);
+        float f1 = fma_rn(B2_PLANE_V(k < 4 ? far_lo[1] : far_hi[1], i), K[1], Bf[1]);
+        float f2 = fma_rn(B2_PLANE_V(k < 4 ? far_lo[2] : far_hi[2], i), K[2], Bf[2]);
+        float t0 = max_nn(max_nn(max_nn(n0, n1), n2), 0.0f);
+        float t1 = min_nn(min_nn(min_nn(f0, f1), f2), best);
+        if (t1 >= t0) mask |= 1u << k;
     }
-    out.mask = mask & (axes >> 24);
+    out.mask = mask & ((1u << (w0.w >> 24)) - 1u);
     return out;
 }
 
-// ---- simple per-ray driver (one thread = one ray; also the host emulation) -------------
-// ANY: stop at the first accepted triangle (occlusion query). The persistent
-// kernels in kernels.cu re-implement this loop warp-synchronously with the same
-// primitives; this form is used by the render megakernel and by tests/emu.
-template <bool ANY, bool COUNT, int STACK_CAP>
-B2_HD HitX trace_wide(const U4* wide, const U4* leaf, const RayX& r, float tmax, TravCounters* c, bool* overflow) {
-    HitX h; h.t = tmax; h.u = 0.0f; h.v = 0.0f; h.tri = 0xFFFFFFFFu;
-    uint32_t stack[STACK_CAP];
-    int sp = 0;
-    uint32_t cur = 0;   // root wide node
-    for (;;) {
-        if (cur & REF_LEAF_BIT) {
-            bool got = visit_leaf<COUNT>(leaf, cur & ~REF_LEAF_BIT, r, h, c);
-            if ((ANY && got) || h.t < 0.0f) break;   // best < 0: every later box test fails (A-5)
-        } else {
-            WideHits w = test_wide_node(wide, cur, r, h.t);
-            if (COUNT) { c->wide_nodes++; c->words += 6; }
-            // push far -> near so that the nearest child in reference order pops first
-            for (int k = 7; k >= 0; --k) {
-                uint32_t s = slot_of_rank(w.flips, (uint32_t)k);
-                if ((w.mask >> s) & 1u) {
-                    if (sp == STACK_CAP) { if (overflow) *overflow = true; break; }
-                    stack[sp++] = child_ref(w, s);
-                }
-            }
-        }
-        if (sp == 0) break;
-        cur = stack[--sp];
+// ---- one ray's traversal state ------------------------------------------------------------
+// node_step() tests the current wide node and walks on; leaves met on the way are queued (two
+// slots, FIFO) and consumed in order by leaf_step(). Any interleaving of the two calls that the
+// wants_*() predicates allow gives the reference's result; the kernels pick per warp, by vote,
+// whichever step more lanes are waiting for.
+template <bool ANY, bool COUNT, int CAP>
+struct Lane {
+    RayX r;
+    HitX h;
+    uint32_t cur;          // wide node to test next, a leaf waiting for a queue slot, or REF_EMPTY
+    uint32_t leaf0, leaf1; // queued leaves, leaf0 first
+    int sp;
+    bool overflow;
+    TravCounters tc;
+    uint32_t stack[CAP];
+
+    B2_HD void start(const RayX& ray, float tmax) {
+        r = ray;
+        h.t = tmax; h.u = 0.0f; h.v = 0.0f; h.tri = 0xFFFFFFFFu;
+        cur = 0; leaf0 = leaf1 = REF_EMPTY; sp = 0; overflow = false;
     }
-    return h;
+    B2_HD void clear() { cur = leaf0 = leaf1 = REF_EMPTY; sp = 0; }
+    B2_HD bool done() const { return cur == REF_EMPTY && leaf0 == REF_EMPTY; }
+    B2_HD bool wants_node() const { return cur != REF_EMPTY && !(cur & REF_LEAF_BIT); }
+    B2_HD bool wants_leaf() const { return leaf0 != REF_EMPTY; }
+
+    B2_HD uint32_t pop() { return sp > 0 ? stack[--sp] : REF_EMPTY; }
+    // Move leaves from `cur` into the queue while there is room.
+    B2_HD void settle() {
+        while (cur != REF_EMPTY && (cur & REF_LEAF_BIT) && leaf1 == REF_EMPTY) {
+            if (leaf0 == REF_EMPTY) leaf0 = cur; else leaf1 = cur;
+            cur = pop();
+        }
+    }
+    B2_HD void node_step(const U4* wide) {
+        WideHits w = test_wide_node(wide, cur, r, h.t);
+        if (COUNT) { tc.wide_nodes++; tc.words += WIDE_NODE_WORDS; }
+        uint32_t m = w.mask;
+        if (m == 0) { cur = pop(); }
+        else {
+            while (m & (m - 1u)) {                       // more than one: push the farthest
+                uint32_t k = top_bit(m);
+                m ^= 1u << k;
+                if (sp < CAP) stack[sp++] = child_ref(w, k); else overflow = true;
+            }
+            cur = child_ref(w, top_bit(m));
+        }
+        settle();
+    }
+    // Returns true when the ray is finished by this leaf (any-hit accept, or best < 0: every later
+    // box test of the reference fails).
+    B2_HD bool leaf_step(const U4* leaf) {
+        bool got = visit_leaf<COUNT>(leaf, leaf0 & ~REF_LEAF_BIT, r, h, COUNT ? &tc : nullptr);
+        leaf0 = leaf1; leaf1 = REF_EMPTY;
+        if ((ANY && got) || h.t < 0.0f) { clear(); return true; }
+        settle();
+        return false;
+    }
+};
+
+// ---- simple per-ray driver (one thread = one ray; also the host emulation) -------------
+// `schedule` != 0 makes the emulation pick node/leaf steps pseudo-randomly whenever both are
+// allowed, to exercise every interleaving the warp-vote kernels can produce.
+template <bool ANY, bool COUNT, int CAP>
+B2_HD HitX trace_wide(const U4* wide, const U4* leaf, const RayX& r, float tmax, TravCounters* c, bool* overflow,
+                      uint32_t schedule = 0) {
+    Lane<ANY, COUNT, CAP> L;
+    L.overflow = false;
+    L.tc.wide_nodes = L.tc.leaf_blocks = L.tc.leaf_pass = L.tc.tri_tests = L.tc.words = 0;
+    L.start(r, tmax);
+    L.settle();
+    while (!L.done()) {
+        const bool node = L.wants_node(), lf = L.wants_leaf();
+        bool do_leaf = lf;                                  // default: consume pending leaves first (no speculation)
+        if (node && lf && schedule) { schedule = schedule * 1664525u + 1013904223u; do_leaf = (schedule >> 16) & 1u; }
+        if (do_leaf) { if (L.leaf_step(leaf)) break; }
+        else L.node_step(wide);
+    }
+    if (COUNT && c) *c = L.tc;
+    if (overflow) *overflow = L.overflow;
+    return L.h;
 }
 
 }  // namespace b2rt

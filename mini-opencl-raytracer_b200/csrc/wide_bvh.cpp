@@ -1,8 +1,9 @@
 // wide_bvh.cpp -- collapse the reference's flattened binary BVH (CLLinearBVHNode[],
 // DFS order: first child = index+1, second child = offset, leaf iff nPrimitives>0;
-// CLBVHnode.cpp:161-183) into 8-wide nodes with 8-bit conservative child boxes, and
-// re-pack leaf triangles as position-only records. See b2rt_types.h for the layout
-// and traverse.cuh for why this keeps results identical to the reference's walk.
+// CLBVHnode.cpp:161-183) into up-to-8-wide treelet nodes with 8-bit conservative child
+// boxes and per-octant visiting orders, and re-pack leaf triangles as position-only
+// records. See b2rt_types.h for the layout and traverse.cuh for why this keeps results
+// identical to the reference's walk.
 #include "wide_bvh.h"
 #include <algorithm>
 #include <cmath>
@@ -79,6 +80,85 @@ int quant_ceil(float base, float s, float hi) {
 
 }  // namespace
 
+namespace {
+
+// Treelet under construction: a small binary tree whose terminals become the child slots.
+struct TNode { int left = -1, right = -1; uint32_t bin = 0; uint32_t depth = 0; uint8_t axis = 0; int slot = -1; };
+
+inline float half_area(const RefNode& n) {
+    float dx = n.bmax.x - n.bmin.x, dy = n.bmax.y - n.bmin.y, dz = n.bmax.z - n.bmin.z;
+    return dx * dy + dx * dz + dy * dz;
+}
+
+// Optimal treelet cuts (surface-area heuristic, after Ylitie et al. 2017, restricted to the host's
+// fixed binary topology and atomic leaves): the expected number of wide-node visits of a random
+// ray is proportional to the summed surface area of the binary nodes at which wide nodes are
+// rooted. dist(n,k) = least such sum for the subtree of n when it may occupy at most k child slots
+// of its parent wide node:
+//   leaf:      dist(n,k) = 0
+//   interior:  dist(n,1) = own(n) = area(n) + min_i dist(first,i) + dist(second,8-i)      (n roots a wide node)
+//              dist(n,k) = min(dist(n,k-1), min_i dist(first,i) + dist(second,k-i))       (n is opened in place)
+// Children follow their parent in the flattened array, so one reverse sweep fills the table.
+struct CutPlan {
+    std::vector<float> dist;         // [node*8 + (k-1)]
+    std::vector<uint8_t> split;      // [node*8 + (k-1)]: slots given to the first child when n is opened with k slots, 0 = closed
+    std::vector<uint8_t> open_root;  // [node]: slots given to the first child when n roots a wide node
+    uint32_t split_of(uint32_t n, uint32_t k) const { return split[(size_t)n * 8 + (k - 1)]; }
+};
+
+void plan_cuts(const RefNode* nodes, uint64_t n_nodes, CutPlan& plan) {
+    plan.dist.assign((size_t)n_nodes * 8, 0.0f);
+    plan.split.assign((size_t)n_nodes * 8, 0);
+    plan.open_root.assign((size_t)n_nodes, 0);
+    for (uint64_t idx = n_nodes; idx-- > 0;) {
+        const RefNode& n = nodes[idx];
+        if (n.nPrimitives > 0) continue;
+        const float* a = &plan.dist[(size_t)(idx + 1) * 8];
+        const float* b = &plan.dist[(size_t)n.offset * 8];
+        float* d = &plan.dist[(size_t)idx * 8];
+        uint8_t* sp = &plan.split[(size_t)idx * 8];
+        float area = half_area(n);
+        if (!(area >= 0.0f)) area = 0.0f;
+        // best way to spend k slots on the two children, k = 2..8
+        float open_cost[9];
+        uint8_t open_split[9];
+        for (uint32_t k = 2; k <= 8; ++k) {
+            float best = INFINITY;
+            uint8_t arg = 1;
+            for (uint32_t i = 1; i < k; ++i) {
+                float c = a[i - 1] + b[k - i - 1];
+                if (c < best) { best = c; arg = (uint8_t)i; }
+            }
+            open_cost[k] = best;
+            open_split[k] = arg;
+        }
+        plan.open_root[idx] = open_split[8];
+        d[0] = area + open_cost[8];
+        sp[0] = 0;
+        for (uint32_t k = 2; k <= 8; ++k) {
+            if (open_cost[k] < d[k - 2]) { d[k - 1] = open_cost[k]; sp[k - 1] = open_split[k]; }
+            else { d[k - 1] = d[k - 2]; sp[k - 1] = sp[k - 2]; }
+        }
+    }
+}
+
+// Visiting order of the terminals under t for sign octant `oct` (kernel_bvh.cl:200-207):
+// second child first iff the ray direction is negative on the node's split axis.
+void visit_order(const TNode* t, int i, uint32_t oct, uint32_t& word, int& rank) {
+    if (t[i].left < 0) { word |= (uint32_t)t[i].slot << (4 * rank++); return; }
+    bool flip = (oct >> t[i].axis) & 1u;
+    visit_order(t, flip ? t[i].right : t[i].left, oct, word, rank);
+    visit_order(t, flip ? t[i].left : t[i].right, oct, word, rank);
+}
+
+void number_slots(TNode* t, int i, int& next) {
+    if (t[i].left < 0) { t[i].slot = next++; return; }
+    number_slots(t, t[i].left, next);
+    number_slots(t, t[i].right, next);
+}
+
+}  // namespace
+
 std::string build_wide_bvh(const RefNode* nodes, uint64_t n_nodes, const RefTriangle* tris, uint64_t n_tris,
                            WideBVH& out) {
     out = WideBVH();
@@ -107,8 +187,10 @@ std::string build_wide_bvh(const RefNode* nodes, uint64_t n_nodes, const RefTria
         s.n3[0] = t.v3.normal.x; s.n3[1] = t.v3.normal.y; s.n3[2] = t.v3.normal.z; s.pad1 = 0;
     }
 
-    out.nodes.reserve(n_nodes / 3 + 16);
+    out.nodes.reserve(n_nodes / 5 + 16);
     out.leaf.reserve((size_t)n_tris * 3 + 16);
+    CutPlan plan;
+    plan_cuts(nodes, n_nodes, plan);
     std::deque<Work> queue;
     out.nodes.emplace_back();
     queue.push_back(Work{ 0u, 0u, 0u, 0u });
@@ -118,41 +200,55 @@ std::string build_wide_bvh(const RefNode* nodes, uint64_t n_nodes, const RefTria
         queue.pop_front();
         out.max_depth_wide = std::max(out.max_depth_wide, w.depth_wide);
 
-        // ---- gather the depth<=3 treelet under binary node w.bin ----------------------------
-        Slot slots[8];
-        uint8_t axis_of[7] = { 3, 3, 3, 3, 3, 3, 3 };   // 3 = treelet node absent
-        struct Item { uint32_t bin, level, path; };
-        Item todo[16];
-        int n_todo = 0;
-        todo[n_todo++] = Item{ w.bin, 0u, 0u };
-        while (n_todo) {
-            Item it = todo[--n_todo];
-            const RefNode& n = nodes[it.bin];
-            bool is_leaf = n.nPrimitives > 0;
-            out.max_depth_binary = std::max(out.max_depth_binary, w.depth_bin + it.level);
-            if (is_leaf || it.level == 3) {
-                Slot& s = slots[it.path << (3 - it.level)];
-                s.kind = is_leaf ? Slot::LEAF : Slot::INTERIOR;
-                s.bin = it.bin;
-                s.depth = w.depth_bin + it.level;
-                continue;
+        // ---- cut the treelet under binary node w.bin along the optimal partition (see plan_cuts) ---
+        TNode t[15];
+        int n_t = 1;
+        t[0].bin = w.bin; t[0].depth = w.depth_bin;
+        if (nodes[w.bin].nPrimitives == 0) {
+            struct Open { int t; uint32_t slots; };
+            Open todo[16];
+            int n_todo = 0;
+            todo[n_todo++] = Open{ 0, 8u };
+            bool root = true;
+            while (n_todo) {
+                Open o = todo[--n_todo];
+                const RefNode& n = nodes[t[o.t].bin];
+                if (n.nPrimitives > 0) continue;                          // binary leaf: a leaf slot
+                uint32_t give_first = root ? plan.open_root[t[o.t].bin] : plan.split_of(t[o.t].bin, o.slots);
+                root = false;
+                if (give_first == 0) continue;                             // stays closed: becomes its own wide node
+                t[o.t].axis = n.axis;
+                t[o.t].left = n_t; t[o.t].right = n_t + 1;
+                t[n_t].bin = t[o.t].bin + 1u; t[n_t].depth = t[o.t].depth + 1u;
+                t[n_t + 1].bin = n.offset; t[n_t + 1].depth = t[o.t].depth + 1u;
+                todo[n_todo++] = Open{ n_t, give_first };
+                todo[n_todo++] = Open{ n_t + 1, o.slots - give_first };
+                n_t += 2;
             }
-            uint32_t heap = it.level == 0 ? 0u : (it.level == 1 ? 1u + it.path : 3u + it.path);
-            axis_of[heap] = n.axis;
-            todo[n_todo++] = Item{ it.bin + 1u, it.level + 1u, (it.path << 1) | 0u };
-            todo[n_todo++] = Item{ n.offset, it.level + 1u, (it.path << 1) | 1u };
         }
+        int next_slot = 0;
+        number_slots(t, 0, next_slot);
+        Slot slots[8];
+        for (int i = 0; i < n_t; ++i) {
+            out.max_depth_binary = std::max(out.max_depth_binary, t[i].depth);
+            if (t[i].left >= 0) continue;
+            Slot& s = slots[t[i].slot];
+            s.kind = nodes[t[i].bin].nPrimitives > 0 ? Slot::LEAF : Slot::INTERIOR;
+            s.bin = t[i].bin;
+            s.depth = t[i].depth;
+        }
+        const int n_children = next_slot;
 
         // ---- quantisation frame -----------------------------------------------------------
         float lo[3] = { INFINITY, INFINITY, INFINITY }, hi[3] = { -INFINITY, -INFINITY, -INFINITY };
-        for (const Slot& s : slots) {
-            if (s.kind == Slot::EMPTY) continue;
-            const RefNode& n = nodes[s.bin];
+        for (int c = 0; c < n_children; ++c) {
+            const RefNode& n = nodes[slots[c].bin];
             const float bl[3] = { n.bmin.x, n.bmin.y, n.bmin.z }, bh[3] = { n.bmax.x, n.bmax.y, n.bmax.z };
             for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], bl[a]); hi[a] = std::max(hi[a], bh[a]); }
         }
         WideNode wn;
         std::memset(&wn, 0, sizeof(wn));
+        wn.n_children = (uint8_t)n_children;
         for (int a = 0; a < 3; ++a) {
             if (!(lo[a] <= hi[a]) || !std::isfinite(lo[a]) || !std::isfinite(hi[a]))
                 return "non-finite or inverted bounds under node " + std::to_string(w.bin);
@@ -165,13 +261,13 @@ std::string build_wide_bvh(const RefNode* nodes, uint64_t n_nodes, const RefTria
                 e = std::min(std::max(k + 127, 1), 254);
             }
             for (;; ++e) {
-                if (e > 254) return "bounds too large to quantise under node " + std::to_string(w.bin);
+                if (e > 230) return "bounds too large to quantise under node " + std::to_string(w.bin);
                 float s;
                 uint32_t sb = (uint32_t)e << 23;
                 std::memcpy(&s, &sb, 4);
                 bool ok = true;
                 for (int c = 0; c < 8 && ok; ++c) {
-                    if (slots[c].kind == Slot::EMPTY) { wn.qlo[a][c] = 255; wn.qhi[a][c] = 0; continue; }
+                    if (c >= n_children) { wn.qlo[a][c] = 255; wn.qhi[a][c] = 0; continue; }
                     const RefNode& n = nodes[slots[c].bin];
                     float bl = a == 0 ? n.bmin.x : (a == 1 ? n.bmin.y : n.bmin.z);
                     float bh = a == 0 ? n.bmax.x : (a == 1 ? n.bmax.y : n.bmax.z);
@@ -184,39 +280,40 @@ std::string build_wide_bvh(const RefNode* nodes, uint64_t n_nodes, const RefTria
             }
         }
 
-        // ---- children -----------------------------------------------------------------------
-        uint32_t mx = 0, my = 0, mz = 0, valid = 0;
-        for (int j = 0; j < 7; ++j) {
-            if (axis_of[j] == 0) mx |= 1u << j;
-            else if (axis_of[j] == 1) my |= 1u << j;
-            else if (axis_of[j] == 2) mz |= 1u << j;
+        // ---- visiting order per sign octant ------------------------------------------------------
+        for (uint32_t oct = 0; oct < 8; ++oct) {
+            uint32_t word = 0;
+            int rank = 0;
+            visit_order(t, 0, oct, word, rank);
+            // unused ranks name an empty slot (7 is empty whenever n_children < 8)
+            for (; rank < 8; ++rank) word |= 7u << (4 * rank);
+            wn.order[oct] = word;
         }
+
+        // ---- children -----------------------------------------------------------------------
         wn.leaf_base = (uint32_t)out.leaf.size();
         if (out.leaf.size() >= 0x7fffff00ull) return "leaf buffer exceeds 31-bit word offsets";
         bool wrap[8] = { false };
-        for (int c = 0; c < 8; ++c) {
-            if (slots[c].kind == Slot::EMPTY) continue;
-            valid |= 1u << c;
+        for (int c = 0; c < n_children; ++c) {
             out.n_children++;
             if (slots[c].kind != Slot::LEAF) continue;
             size_t rel = out.leaf.size() - wn.leaf_base;
-            // The root treelet may itself be a single leaf (w.bin is a leaf): it must be emitted here.
-            if (rel > 255 && !(nodes[w.bin].nPrimitives > 0)) { wrap[c] = true; continue; }
+            // A treelet that is a single binary leaf (w.bin itself) must emit it here (rel == 0).
+            if (rel > META_MAX_LEAF_OFFSET && n_children > 1) { wrap[c] = true; continue; }
+            if (rel > META_MAX_LEAF_OFFSET) return "internal error: lone leaf not at offset 0";
             wn.meta[c] = (uint8_t)rel;
             emit_leaf(nodes[slots[c].bin], tris, out);
         }
         wn.child_base = (uint32_t)out.nodes.size();
-        uint32_t imask = 0;
-        for (int c = 0; c < 8; ++c) {
+        uint32_t n_interior = 0;
+        for (int c = 0; c < n_children; ++c) {
             if (slots[c].kind == Slot::INTERIOR || wrap[c]) {
-                imask |= 1u << c;
+                wn.meta[c] = (uint8_t)(META_INTERIOR | n_interior++);
                 uint32_t idx = (uint32_t)out.nodes.size();
                 out.nodes.emplace_back();
                 queue.push_back(Work{ slots[c].bin, idx, slots[c].depth, w.depth_wide + 1u });
             }
         }
-        wn.imask = (uint8_t)imask;
-        wn.axes = mx | (my << 8) | (mz << 16) | (valid << 24);
         out.nodes[w.wide] = wn;
     }
     return std::string();

@@ -52,6 +52,11 @@ for bps in (0, 4, 8, 12, 16):
     ms = timeit(lambda: ctx.trace_closest_device(d_rays.data_ptr(), nrays, d_hits.data_ptr(), st))
     print("wide closest  blocks/SM=%2d  %.3f ms  %.1f Mrays/s" % (bps, ms, nrays / ms / 1e3), flush=True)
 ctx.set_option(prod.capi.OPT_BLOCKS_PER_SM, 0)
+for rm in (1, 4, 8, 16, 24):
+    ctx.set_option(prod.capi.OPT_REFILL_MIN, rm)
+    ms = timeit(lambda: ctx.trace_closest_device(d_rays.data_ptr(), nrays, d_hits.data_ptr(), st))
+    print("wide closest  refill_min=%2d  %.3f ms  %.1f Mrays/s" % (rm, ms, nrays / ms / 1e3), flush=True)
+ctx.set_option(prod.capi.OPT_REFILL_MIN, 8)
 ms = timeit(lambda: ctx.trace_any_device(d_rays.data_ptr(), nrays, d_occ.data_ptr(), st))
 print("wide any      %.3f ms  %.1f Mrays/s" % (ms, nrays / ms / 1e3))
 ctx.set_option(prod.capi.OPT_TRAVERSAL, 1)

@@ -34,7 +34,7 @@ extern "C" const char* emu_build(const void* nodes, uint64_t n_nodes, const void
     return nullptr;
 }
 
-extern "C" void emu_trace(const EmuRay* rays, uint64_t n, EmuHit* hits, uint32_t* occluded, int any, EmuStats* st) {
+extern "C" void emu_trace(const EmuRay* rays, uint64_t n, EmuHit* hits, uint32_t* occluded, int any, EmuStats* st, uint32_t schedule) {
     const U4* wide = reinterpret_cast<const U4*>(g_bvh.nodes.data());
     const U4* leaf = g_bvh.leaf.data();
     TravCounters total = { 0, 0, 0, 0, 0 };
@@ -43,8 +43,9 @@ extern "C" void emu_trace(const EmuRay* rays, uint64_t n, EmuHit* hits, uint32_t
         RayX r = make_ray(rays[i].ox, rays[i].oy, rays[i].oz, rays[i].dx, rays[i].dy, rays[i].dz);
         TravCounters c = { 0, 0, 0, 0, 0 };
         bool overflow = false;
-        HitX h = any ? trace_wide<true, true, 256>(wide, leaf, r, rays[i].tmax, &c, &overflow)
-                     : trace_wide<false, true, 256>(wide, leaf, r, rays[i].tmax, &c, &overflow);
+        uint32_t sched = schedule ? schedule + (uint32_t)i * 2654435761u : 0u;   // 0 = leaves first; else a per-ray pseudo-random interleaving
+        HitX h = any ? trace_wide<true, true, 256>(wide, leaf, r, rays[i].tmax, &c, &overflow, sched)
+                     : trace_wide<false, true, 256>(wide, leaf, r, rays[i].tmax, &c, &overflow, sched);
         if (overflow) st->overflow++;
         if (any) occluded[i] = h.tri != 0xFFFFFFFFu;
         else { hits[i].t = h.t; hits[i].u = h.u; hits[i].v = h.v; hits[i].tri = h.tri; }

@@ -123,7 +123,7 @@ def emu():
         L.emu_build.restype = C.c_char_p
         L.emu_build.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(EmuStats)]
         L.emu_trace.restype = None
-        L.emu_trace.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(EmuStats)]
+        L.emu_trace.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(EmuStats), C.c_uint32]
         _cache["emu"] = L
     return _cache["emu"]
 
@@ -226,13 +226,15 @@ def emu_build(tris, nodes):
     return st
 
 
-def emu_trace(rays, any_hit=False, stats=None):
+def emu_trace(rays, any_hit=False, stats=None, schedule=0):
+    """schedule = 0: leaves are consumed as soon as they are queued; != 0: node and leaf steps are
+    interleaved pseudo-randomly per ray (what the warp-vote scheduling of the kernels can produce)."""
     rays = np.ascontiguousarray(rays)
     st = stats if stats is not None else EmuStats()
     if any_hit:
         occ = np.empty(rays.shape[0], dtype=np.uint32)
-        emu().emu_trace(_p(rays), rays.shape[0], None, _p(occ), 1, C.byref(st))
+        emu().emu_trace(_p(rays), rays.shape[0], None, _p(occ), 1, C.byref(st), schedule)
         return occ
     hits = np.empty(rays.shape[0], dtype=HIT)
-    emu().emu_trace(_p(rays), rays.shape[0], _p(hits), None, 0, C.byref(st))
+    emu().emu_trace(_p(rays), rays.shape[0], _p(hits), None, 0, C.byref(st), schedule)
     return hits
