@@ -94,6 +94,8 @@ typedef struct {
     uint64_t leaf_gate_pass;    /* ... of which passed the exact fp32 leaf box             */
     uint64_t tri_tests;         /* Moller-Trumbore evaluations                             */
     uint64_t bytes_fetched;     /* algorithmic bytes: 112 B per wide node + leaf block bytes */
+    /* warp scheduling of the persistent kernels: phases run and lanes that took part in them */
+    uint64_t node_phases, node_phase_lanes, leaf_phases, leaf_phase_lanes, refills, refill_lanes;
 } b2rt_counters;
 
 enum {
@@ -101,7 +103,8 @@ enum {
     B2RT_OPT_COUNTERS = 1,      /* 1 = launches use the counting build of the kernels      */
     B2RT_OPT_BLOCKS_PER_SM = 2, /* persistent grid = value * SM count (0 = default)        */
     B2RT_OPT_RENDER_MODE = 3,   /* 0 = wavefront (default), 1 = megakernel                 */
-    B2RT_OPT_REFILL_MIN = 4     /* idle lanes of a warp that trigger a ray refill (1..32, default 8) */
+    B2RT_OPT_REFILL_MIN = 4,    /* idle lanes of a warp that trigger a ray refill (1..32, default 8) */
+    B2RT_OPT_LEAF_BIAS = 5      /* weight of the leaf vote in sixteenths (16 = plain majority, default 28) */
 };
 
 /* ---- lifetime ---------------------------------------------------------------------- */

@@ -58,7 +58,7 @@ struct b2rt_context {
     uint64_t stage_capacity = 0;
     cudaEvent_t ev_in[2] = { nullptr, nullptr }, ev_comp[2] = { nullptr, nullptr }, ev_out[2] = { nullptr, nullptr };
     // options
-    int64_t opt_traversal = 0, opt_counters = 0, opt_blocks_per_sm = 0, opt_render_mode = 0, opt_refill_min = 8;
+    int64_t opt_traversal = 0, opt_counters = 0, opt_blocks_per_sm = 0, opt_render_mode = 0, opt_refill_min = 8, opt_leaf_bias = 28;
     int grid_closest = 0, grid_any = 0;
     uint64_t launches = 0;
     std::string error;
@@ -168,6 +168,7 @@ int ensure_scene(b2rt_context* ctx) {
     ctx->view.n_nodes = (uint32_t)n_nodes;
     ctx->view.n_mats = (uint32_t)ctx->info.n_materials;
     ctx->view.n_wide = (uint32_t)w.nodes.size();
+    ctx->view.one_bits = 0x3F800000u;
     // the 256 B/triangle host shadow is only needed for this build
     bt->shadow.clear(); bt->shadow.shrink_to_fit();
     bn->shadow.clear(); bn->shadow.shrink_to_fit();
@@ -193,7 +194,7 @@ int trace_device(b2rt_context* ctx, const void* d_rays, uint64_t n, void* d_out,
     uint64_t warps_needed = (n + 31) / 32, blocks_needed = (warps_needed * 32 + trace_block_threads() - 1) / trace_block_threads();
     if ((uint64_t)grid > blocks_needed) grid = (int)blocks_needed;
     CK(launch_trace_wide(ctx->view, d_rays, n, d_out, any, ctx->opt_counters != 0, ctx->stack_bound, grid, ctx->d_next,
-                         ctx->d_counters, (uint32_t)ctx->opt_refill_min, st));
+                         ctx->d_counters, (uint32_t)ctx->opt_refill_min, (uint32_t)ctx->opt_leaf_bias, st));
     ctx->launches += 1;
     return B2RT_SUCCESS;
 }
@@ -302,8 +303,8 @@ extern "C" int b2rt_create(int device_id, b2rt_context** out) {
         if ((e = cudaEventCreateWithFlags(&ctx->ev_out[i], cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
     }
     if ((e = cudaMalloc(&ctx->d_next, 64)) != cudaSuccess) return bail(e, "cudaMalloc");
-    if ((e = cudaMalloc(&ctx->d_counters, 64)) != cudaSuccess) return bail(e, "cudaMalloc");
-    if ((e = cudaMemset(ctx->d_counters, 0, 64)) != cudaSuccess) return bail(e, "cudaMemset");
+    if ((e = cudaMalloc(&ctx->d_counters, 128)) != cudaSuccess) return bail(e, "cudaMalloc");
+    if ((e = cudaMemset(ctx->d_counters, 0, 128)) != cudaSuccess) return bail(e, "cudaMemset");
     *out = ctx;
     return B2RT_SUCCESS;
 }
@@ -593,6 +594,7 @@ extern "C" int b2rt_set_option(b2rt_context* ctx, uint32_t option, int64_t value
         case B2RT_OPT_COUNTERS: ctx->opt_counters = value ? 1 : 0; break;
         case B2RT_OPT_BLOCKS_PER_SM: if (value < 0 || value > 32) return fail(ctx, B2RT_INVALID_VALUE, "blocks per SM out of range"); ctx->opt_blocks_per_sm = value; break;
         case B2RT_OPT_RENDER_MODE: ctx->opt_render_mode = value; break;
+        case B2RT_OPT_LEAF_BIAS: if (value < 1 || value > 512) return fail(ctx, B2RT_INVALID_VALUE, "leaf bias must be 1..512 (sixteenths)"); ctx->opt_leaf_bias = value; break;
         case B2RT_OPT_REFILL_MIN: if (value < 1 || value > 32) return fail(ctx, B2RT_INVALID_VALUE, "refill threshold must be 1..32"); ctx->opt_refill_min = value; break;
         default: return fail(ctx, B2RT_INVALID_VALUE, "unknown option");
     }
@@ -603,18 +605,20 @@ extern "C" int b2rt_get_counters(b2rt_context* ctx, b2rt_counters* out) {
     if (!out) return fail(ctx, B2RT_INVALID_VALUE, "null output");
     int st = use_device(ctx);
     if (st) return st;
-    unsigned long long v[6];
+    unsigned long long v[12];
     CK(cudaDeviceSynchronize());     // counted launches may sit on caller-provided streams
     CK(cudaMemcpy(v, ctx->d_counters, sizeof(v), cudaMemcpyDeviceToHost));
     out->rays = v[0]; out->wide_nodes = v[1]; out->leaf_blocks = v[2]; out->leaf_gate_pass = v[3]; out->tri_tests = v[4];
     out->bytes_fetched = v[5] * 16ull;
+    out->node_phases = v[6]; out->node_phase_lanes = v[7]; out->leaf_phases = v[8]; out->leaf_phase_lanes = v[9];
+    out->refills = v[10]; out->refill_lanes = v[11];
     return B2RT_SUCCESS;
 }
 extern "C" int b2rt_reset_counters(b2rt_context* ctx) {
     if (!ctx) return B2RT_INVALID_CONTEXT;
     int st = use_device(ctx);
     if (st) return st;
-    CK(cudaMemsetAsync(ctx->d_counters, 0, 64, ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_counters, 0, 128, ctx->stream));
     return B2RT_SUCCESS;
 }
 extern "C" uint64_t b2rt_launch_count(const b2rt_context* ctx) { return ctx ? ctx->launches : 0; }

@@ -91,6 +91,7 @@ struct SceneView {                 // plain device pointers handed to kernels
     const RefTriangle* tris;       // reference-layout copies (binary-walk kernels only)
     const RefNode* nodes;
     uint32_t n_tris, n_nodes, n_mats, n_wide;
+    uint32_t one_bits;             // 0x3F800000 as run-time data (see Lane::node_step)
 };
 
 // Scalar arguments of KernelEntry (kernel_bvh.cl:421-430) as the kernels receive them.

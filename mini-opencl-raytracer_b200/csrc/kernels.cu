@@ -23,7 +23,14 @@
 
 namespace b2rt {
 
+#ifndef B2_PREFETCH
+#define B2_PREFETCH 0
+#endif
+#ifndef B2_MIN_BLOCKS
+#define B2_MIN_BLOCKS 10
+#endif
 static constexpr unsigned FULL = 0xffffffffu;
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 static constexpr int TRACE_BLOCK = 128;
 
 struct RayIn { float ox, oy, oz, tmin, dx, dy, dz, tmax; };
@@ -46,10 +53,10 @@ __device__ __forceinline__ void load_ray(const RayIn* rays, uint64_t i, RayX& r,
 // from one global atomic counter, `chunk` rays at a time.
 // ---------------------------------------------------------------------------------------
 template <bool ANY, bool COUNT, int CAP>
-__global__ void __launch_bounds__(TRACE_BLOCK)
+__global__ void __launch_bounds__(TRACE_BLOCK, B2_MIN_BLOCKS)
 trace_persistent(SceneView s, const RayIn* __restrict__ rays, uint64_t n, void* __restrict__ out,
                  unsigned long long* __restrict__ next, unsigned long long* __restrict__ counters, uint32_t chunk,
-                 uint32_t refill_min) {
+                 uint32_t refill_min, uint32_t leaf_bias) {
     const unsigned lane = threadIdx.x & 31u;
     Lane<ANY, COUNT, CAP> L;
     L.clear();
@@ -60,6 +67,7 @@ trace_persistent(SceneView s, const RayIn* __restrict__ rays, uint64_t n, void* 
     uint64_t pool_next = 0, pool_end = 0;    // warp-uniform
     bool exhausted = false;                  // warp-uniform: the global counter ran past n
     uint32_t traced = 0;
+    uint32_t ph_node = 0, ph_node_lanes = 0, ph_leaf = 0, ph_leaf_lanes = 0, ph_refill = 0, ph_refill_lanes = 0;   // COUNT only, warp-uniform
 
     for (;;) {
         const unsigned idle = __ballot_sync(FULL, !active);
@@ -86,17 +94,27 @@ trace_persistent(SceneView s, const RayIn* __restrict__ rays, uint64_t n, void* 
                     active = true;
                 }
                 const unsigned taken = __popc(idle);
+                if (COUNT) { ph_refill++; ph_refill_lanes += (taken < avail) ? taken : (unsigned)avail; }
                 pool_next += (taken < avail) ? taken : avail;
             }
             continue;
         }
         if ((vn | vl) == 0u) break;          // nothing in flight and nothing left to fetch
 
-        if (__popc(vn) >= __popc(vl)) {
-            if (active && L.wants_node()) L.node_step(s.wide);
+        // leaf_bias/16 weighs the leaf vote: > 1 consumes queued leaves earlier (less speculation)
+        if (__popc(vn) * 16u >= __popc(vl) * leaf_bias) {
+            if (COUNT) { ph_node++; ph_node_lanes += __popc(vn); }
+            if (active && L.wants_node()) L.node_step(s.wide, s.one_bits);
         } else {
+            if (COUNT) { ph_leaf++; ph_leaf_lanes += __popc(vl); }
             if (active && L.wants_leaf()) L.leaf_step(s.leaf);
         }
+#if B2_PREFETCH
+        if (active) {
+            if (L.wants_node()) prefetch_l1(s.wide + (uint32_t)WIDE_NODE_WORDS * L.cur);
+            if (L.wants_leaf()) prefetch_l1(s.leaf + (L.leaf0 & ~REF_LEAF_BIT));
+        }
+#endif
         if (active && L.done()) {
             if (ANY) reinterpret_cast<uint32_t*>(out)[my_index] = (L.h.tri != 0xFFFFFFFFu) ? 1u : 0u;
             else reinterpret_cast<float4*>(out)[my_index] = make_float4(L.h.t, L.h.u, L.h.v, __uint_as_float(L.h.tri));
@@ -113,6 +131,10 @@ trace_persistent(SceneView s, const RayIn* __restrict__ rays, uint64_t n, void* 
             unsigned long long x = v[i];
             for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(FULL, x, o);
             if (lane == 0 && x) atomicAdd(&counters[i], x);
+        }
+        if (lane == 0) {
+            const unsigned long long ph[6] = { ph_node, ph_node_lanes, ph_leaf, ph_leaf_lanes, ph_refill, ph_refill_lanes };
+            for (int i = 0; i < 6; ++i) if (ph[i]) atomicAdd(&counters[6 + i], ph[i]);
         }
     }
 }
@@ -198,7 +220,7 @@ render_mega_kernel(SceneView s, FrameArgs a, float* __restrict__ result, uint64_
     for (int i = 0; (uint32_t)i < (uint32_t)a.bounces; ++i) {              // Render(), kernel_bvh.cl:349-384
         HitX h;
         if (BINARY) h = trace_binary<false>(s.tris, s.nodes, r, 100000.0f);
-        else h = trace_wide<false, false, CAP>(s.wide, s.leaf, r, 100000.0f, nullptr, nullptr);
+        else h = trace_wide<false, false, CAP>(s.wide, s.leaf, r, 100000.0f, nullptr, nullptr, s.one_bits);
         if (h.tri == 0xFFFFFFFFu) {
             float sky = xmul(0.5f, a.sky);
             radiance = vadd(radiance, vmul(beta, v3(sky, sky, sky)));
@@ -233,17 +255,17 @@ static int pick_cap(uint32_t bound) { return bound <= 32 ? 32 : (bound <= 64 ? 6
 template <bool ANY, bool COUNT>
 static cudaError_t launch_persistent_cap(int cap, int grid, cudaStream_t st, const SceneView& s, const void* rays,
                                          uint64_t n, void* out, unsigned long long* next, unsigned long long* counters,
-                                         uint32_t refill_min) {
+                                         uint32_t refill_min, uint32_t leaf_bias) {
     const RayIn* r = static_cast<const RayIn*>(rays);
     // rays per pool top-up: about 1/8 of a warp's fair share, a multiple of 32 in [32, 512]
     uint64_t warps = (uint64_t)grid * (TRACE_BLOCK / 32);
     uint64_t c = n / (warps * 8u + 1u);
     uint32_t chunk = (uint32_t)(c < 32 ? 32 : (c > 512 ? 512 : (c & ~31ull)));
     switch (cap) {
-        case 32: trace_persistent<ANY, COUNT, 32><<<grid, TRACE_BLOCK, 0, st>>>(s, r, n, out, next, counters, chunk, refill_min); break;
-        case 64: trace_persistent<ANY, COUNT, 64><<<grid, TRACE_BLOCK, 0, st>>>(s, r, n, out, next, counters, chunk, refill_min); break;
-        case 128: trace_persistent<ANY, COUNT, 128><<<grid, TRACE_BLOCK, 0, st>>>(s, r, n, out, next, counters, chunk, refill_min); break;
-        case 256: trace_persistent<ANY, COUNT, 256><<<grid, TRACE_BLOCK, 0, st>>>(s, r, n, out, next, counters, chunk, refill_min); break;
+        case 32: trace_persistent<ANY, COUNT, 32><<<grid, TRACE_BLOCK, 0, st>>>(s, r, n, out, next, counters, chunk, refill_min, leaf_bias); break;
+        case 64: trace_persistent<ANY, COUNT, 64><<<grid, TRACE_BLOCK, 0, st>>>(s, r, n, out, next, counters, chunk, refill_min, leaf_bias); break;
+        case 128: trace_persistent<ANY, COUNT, 128><<<grid, TRACE_BLOCK, 0, st>>>(s, r, n, out, next, counters, chunk, refill_min, leaf_bias); break;
+        case 256: trace_persistent<ANY, COUNT, 256><<<grid, TRACE_BLOCK, 0, st>>>(s, r, n, out, next, counters, chunk, refill_min, leaf_bias); break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
@@ -251,16 +273,17 @@ static cudaError_t launch_persistent_cap(int cap, int grid, cudaStream_t st, con
 
 cudaError_t launch_trace_wide(const SceneView& s, const void* d_rays, uint64_t n, void* d_out, bool any, bool count,
                               uint32_t stack_bound, int grid_blocks, unsigned long long* d_next,
-                              unsigned long long* d_counters, uint32_t refill_min, cudaStream_t st) {
+                              unsigned long long* d_counters, uint32_t refill_min, uint32_t leaf_bias, cudaStream_t st) {
     int cap = pick_cap(stack_bound);
     if (!cap) return cudaErrorInvalidValue;
     cudaError_t e = cudaMemsetAsync(d_next, 0, sizeof(unsigned long long), st);
     if (e != cudaSuccess) return e;
     if (refill_min < 1 || refill_min > 32) refill_min = 8;
-    if (any) return count ? launch_persistent_cap<true, true>(cap, grid_blocks, st, s, d_rays, n, d_out, d_next, d_counters, refill_min)
-                          : launch_persistent_cap<true, false>(cap, grid_blocks, st, s, d_rays, n, d_out, d_next, d_counters, refill_min);
-    return count ? launch_persistent_cap<false, true>(cap, grid_blocks, st, s, d_rays, n, d_out, d_next, d_counters, refill_min)
-                 : launch_persistent_cap<false, false>(cap, grid_blocks, st, s, d_rays, n, d_out, d_next, d_counters, refill_min);
+    if (leaf_bias < 1 || leaf_bias > 512) leaf_bias = 16;
+    if (any) return count ? launch_persistent_cap<true, true>(cap, grid_blocks, st, s, d_rays, n, d_out, d_next, d_counters, refill_min, leaf_bias)
+                          : launch_persistent_cap<true, false>(cap, grid_blocks, st, s, d_rays, n, d_out, d_next, d_counters, refill_min, leaf_bias);
+    return count ? launch_persistent_cap<false, true>(cap, grid_blocks, st, s, d_rays, n, d_out, d_next, d_counters, refill_min, leaf_bias)
+                 : launch_persistent_cap<false, false>(cap, grid_blocks, st, s, d_rays, n, d_out, d_next, d_counters, refill_min, leaf_bias);
 }
 
 cudaError_t launch_trace_binary(const SceneView& s, const void* d_rays, uint64_t n, void* d_out, bool any, cudaStream_t st) {

@@ -11,7 +11,7 @@ namespace b2rt {
 // counter (reset by the wrapper), d_counters six 64-bit accumulators (used when count).
 cudaError_t launch_trace_wide(const SceneView& s, const void* d_rays, uint64_t n, void* d_out, bool any, bool count,
                               uint32_t stack_bound, int grid_blocks, unsigned long long* d_next,
-                              unsigned long long* d_counters, uint32_t refill_min, cudaStream_t st);
+                              unsigned long long* d_counters, uint32_t refill_min, uint32_t leaf_bias, cudaStream_t st);
 // One thread per ray over the reference-layout arrays (baseline / cross-check).
 cudaError_t launch_trace_binary(const SceneView& s, const void* d_rays, uint64_t n, void* d_out, bool any, cudaStream_t st);
 cudaError_t launch_camera_rays(const FrameArgs& a, uint64_t gid0, uint64_t gid1, void* d_rays, cudaStream_t st);

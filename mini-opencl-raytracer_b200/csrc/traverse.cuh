@@ -52,7 +52,9 @@ B2_HD float max_nn(float a, float b) { return fmaxf(a, b); }   // NaN-ignoring
 B2_HD float min_nn(float a, float b) { return fminf(a, b); }
 B2_HD float u2f(uint32_t v) { return __uint2float_rn(v); }
 B2_HD float fma_rn(float a, float b, float c) { return __fmaf_rn(a, b, c); }
-B2_HD uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) { return __byte_perm(a, b, sel); }
+// prmt.b32 without __byte_perm's selector masking; selectors used here never set a nibble's bit 3.
+B2_HD uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) { uint32_t d; asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel)); return d; }
+
 B2_HD uint32_t top_bit(uint32_t v) { return 31u - (uint32_t)__clz((int)v); }
 B2_HD uint32_t byte_of(uint32_t w, uint32_t i) { return __byte_perm(w, 0, 0x4440u + i); }
 B2_HD uint32_t popc32(uint32_t v) { return __popc(v); }
@@ -218,7 +220,7 @@ B2_HD uint32_t child_ref(const WideHits& w, uint32_t k) {
 }
 
 // float 1 + q * 2^-15 from byte i of w: the byte lands in mantissa bits 8..15 of 1.0f.
-#define B2_PLANE_V(w, i) bits2f(prmt((w), 0x3F800000u, 0x7604u | ((i) << 4)))
+#define B2_PLANE_V(w, i) bits2f(prmt((w), one, 0x7604u | ((i) << 4)))
 
 // Conservative slab test of the (up to) 8 quantised child boxes against [0, best], evaluated in
 // the reference's visiting order for this ray's sign octant.
@@ -232,7 +234,7 @@ B2_HD uint32_t child_ref(const WideHits& w, uint32_t k) {
 // far side of the quantised near plane (R is monotone in P), and likewise t_far >= R(P). NaNs
 // (inv = +-inf or NaN, overflow) drop out of fminf/fmaxf, i.e. that axis does not constrain: the
 // test can only pass more children than the reference's, never fewer.
-B2_HD WideHits test_wide_node(const U4* wide, uint32_t index, const RayX& r, float best) {
+B2_HD WideHits test_wide_node(const U4* wide, uint32_t index, const RayX& r, float best, uint32_t one) {
     const U4* p = wide + (uint32_t)WIDE_NODE_WORDS * index;
     U4 w0 = ld128(p), w1 = ld128(p + 1), w2 = ld128(p + 2), w3 = ld128(p + 3), w4 = ld128(p + 4);
     const uint32_t order = ld32(reinterpret_cast<const uint32_t*>(p + 5) + r.sign);
@@ -317,8 +319,10 @@ struct Lane {
             cur = pop();
         }
     }
-    B2_HD void node_step(const U4* wide) {
-        WideHits w = test_wide_node(wide, cur, r, h.t);
+    // `one` must be 0x3F800000, passed as run-time data: held in one register it lets the constant
+    // byte selectors of B2_PLANE_V be instruction immediates (ptxas otherwise keeps four selector registers).
+    B2_HD void node_step(const U4* wide, uint32_t one) {
+        WideHits w = test_wide_node(wide, cur, r, h.t, one);
         if (COUNT) { tc.wide_nodes++; tc.words += WIDE_NODE_WORDS; }
         uint32_t m = w.mask;
         if (m == 0) { cur = pop(); }
@@ -348,7 +352,7 @@ struct Lane {
 // allowed, to exercise every interleaving the warp-vote kernels can produce.
 template <bool ANY, bool COUNT, int CAP>
 B2_HD HitX trace_wide(const U4* wide, const U4* leaf, const RayX& r, float tmax, TravCounters* c, bool* overflow,
-                      uint32_t schedule = 0) {
+                      uint32_t one, uint32_t schedule = 0) {
     Lane<ANY, COUNT, CAP> L;
     L.overflow = false;
     L.tc.wide_nodes = L.tc.leaf_blocks = L.tc.leaf_pass = L.tc.tri_tests = L.tc.words = 0;
@@ -359,7 +363,7 @@ B2_HD HitX trace_wide(const U4* wide, const U4* leaf, const RayX& r, float tmax,
         bool do_leaf = lf;                                  // default: consume pending leaves first (no speculation)
         if (node && lf && schedule) { schedule = schedule * 1664525u + 1013904223u; do_leaf = (schedule >> 16) & 1u; }
         if (do_leaf) { if (L.leaf_step(leaf)) break; }
-        else L.node_step(wide);
+        else L.node_step(wide, one);
     }
     if (COUNT && c) *c = L.tc;
     if (overflow) *overflow = L.overflow;

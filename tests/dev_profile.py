@@ -37,4 +37,12 @@ with torch.cuda.stream(stream):
             ctx.trace_closest_device(d_rays.data_ptr(), nrays, d_out.data_ptr(), stream.cuda_stream)
     e1.record()
 torch.cuda.synchronize()
+if os.environ.get("B2_COUNT"):
+    ctx.set_option(prod.capi.OPT_COUNTERS, 1)
+    ctx.reset_counters()
+    ctx.finish()
+    ctx.trace_closest_device(d_rays.data_ptr(), nrays, d_out.data_ptr(), stream.cuda_stream)
+    torch.cuda.synchronize()
+    c = ctx.counters()
+    print({k: v / c["rays"] for k, v in c.items()})
 print("last launch %.3f ms, %.1f Mrays/s" % (e0.elapsed_time(e1), nrays / e0.elapsed_time(e1) / 1e3))

@@ -57,6 +57,11 @@ for rm in (1, 4, 8, 16, 24):
     ms = timeit(lambda: ctx.trace_closest_device(d_rays.data_ptr(), nrays, d_hits.data_ptr(), st))
     print("wide closest  refill_min=%2d  %.3f ms  %.1f Mrays/s" % (rm, ms, nrays / ms / 1e3), flush=True)
 ctx.set_option(prod.capi.OPT_REFILL_MIN, 8)
+for lb in (8, 12, 16, 24, 32, 64):
+    ctx.set_option(prod.capi.OPT_LEAF_BIAS, lb)
+    ms = timeit(lambda: ctx.trace_closest_device(d_rays.data_ptr(), nrays, d_hits.data_ptr(), st))
+    print("wide closest  leaf_bias=%2d/16  %.3f ms  %.1f Mrays/s" % (lb, ms, nrays / ms / 1e3), flush=True)
+ctx.set_option(prod.capi.OPT_LEAF_BIAS, 16)
 ms = timeit(lambda: ctx.trace_any_device(d_rays.data_ptr(), nrays, d_occ.data_ptr(), st))
 print("wide any      %.3f ms  %.1f Mrays/s" % (ms, nrays / ms / 1e3))
 ctx.set_option(prod.capi.OPT_TRAVERSAL, 1)

@@ -44,8 +44,8 @@ extern "C" void emu_trace(const EmuRay* rays, uint64_t n, EmuHit* hits, uint32_t
         TravCounters c = { 0, 0, 0, 0, 0 };
         bool overflow = false;
         uint32_t sched = schedule ? schedule + (uint32_t)i * 2654435761u : 0u;   // 0 = leaves first; else a per-ray pseudo-random interleaving
-        HitX h = any ? trace_wide<true, true, 256>(wide, leaf, r, rays[i].tmax, &c, &overflow, sched)
-                     : trace_wide<false, true, 256>(wide, leaf, r, rays[i].tmax, &c, &overflow, sched);
+        HitX h = any ? trace_wide<true, true, 256>(wide, leaf, r, rays[i].tmax, &c, &overflow, 0x3F800000u, sched)
+                     : trace_wide<false, true, 256>(wide, leaf, r, rays[i].tmax, &c, &overflow, 0x3F800000u, sched);
         if (overflow) st->overflow++;
         if (any) occluded[i] = h.tri != 0xFFFFFFFFu;
         else { hits[i].t = h.t; hits[i].u = h.u; hits[i].v = h.v; hits[i].tri = h.tri; }
