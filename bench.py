@@ -6,7 +6,7 @@
 
 Workload (BASELINE.json configs[2]/[4]): synthetic displaced geodesic icosphere, 1 003 520 OBJ faces ->
 2 007 040 CLTriangle after the loader's duplication, built by the product's own CLOBJloader + CLBVHScene
-mirror; one step = one closest-hit pass over a seeded stream of 2^24 incoherent rays per GPU (origins on
+mirror; one step = one closest-hit pass over a seeded stream of 100 M incoherent rays per GPU (origins on
 a sphere of radius 3R, targets in the ball of radius R). Multi-GPU: BVH replicated, the ray stream is
 sharded by rank (weak scaling), no data-path collective.
 
@@ -152,7 +152,7 @@ def run_reference(args, rank, world):
         fn(rays[(args.warmup + s) * n:(args.warmup + s + 1) * n])
     dt = time.perf_counter() - t0
     value = n * args.steps / dt / 1e6
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": "closest_hit_ray_throughput", "value": value, "unit": "Mrays/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -160,7 +160,7 @@ def run_reference(args, rank, world):
         "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": threads, "kind": kind,
                          "sample": "%d rays per step, %d steps, %d host threads" % (n, args.steps, threads)},
         "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }), flush=True)
+    })
 
 
 def workload_name(args, n_tris):
@@ -194,7 +194,7 @@ def run_b200(args, rank, world, local_rank):
     stream = torch.cuda.Stream()
     host_rays = torch.empty((n, 8), dtype=torch.float32, pin_memory=True)
     rays_np = host_rays.numpy().view(prod.RAY_DTYPE).reshape(-1)
-    prod.workloads.shell_rays(n, RADIUS, seed=1000 + rank, out=rays_np)
+    prod.workloads.shell_rays(n, RADIUS, seed=1000 + (rank if not os.environ.get("B2RT_SAME_SEED") else 0), out=rays_np)
     d_rays = host_rays.to("cuda", non_blocking=False)
     d_hits = torch.empty((n, 4), dtype=torch.float32, device="cuda")
     d_occ = torch.empty((n,), dtype=torch.int32, device="cuda")
@@ -244,6 +244,7 @@ def run_b200(args, rank, world, local_rank):
     clocks = sampler.stop() if sampler else None
     value = world * n * args.steps / (total_ms * 1e-3) / 1e6
     kernel_ms = statistics.mean(per)
+    log("[bench r%d] closest-hit per-step ms: %s" % (rank, " ".join("%.3f" % x for x in per)))
 
     # ---- any-hit on the same stream ---------------------------------------------------------------------------
     any_ms, _, _ = timed(lambda: ctx.trace_any_device(d_rays.data_ptr(), n, d_occ.data_ptr(), stream.cuda_stream), args.steps, args.warmup)
@@ -279,6 +280,50 @@ def run_b200(args, rank, world, local_rank):
             for _ in range(15):
                 ce.render_frame()                                # RenderFrame: args, kernel, full read-back, finish
             extra["cornell_1080p_4bounce_frame_ms"] = (time.perf_counter() - t0) / 15 * 1e3
+
+    # ---- N>1: one 4K cornell frame split into row bands over the ranks + NCCL all_gather of the framebuffer ----
+    if world > 1 and not args.skip_frames:
+        W, H, frames = 3840, 2160, 8
+        cornell = os.path.join(ROOT, "tests", "golden", "cornell.obj")
+        tris_c, nodes_c, mats_c = prod.host.load_scene(cornell, 4)
+        plan = prod.sharding.BandPlan(W, H, world, band_rows=8)
+        with prod.Context(local_rank) as fc:
+            fc.upload_scene(tris_c, nodes_c, mats_c)
+            fc.resize(W, H)
+            ptr, nbytes = fc.output_device_pointer()
+            frame = prod.sharding.as_tensor(ptr, nbytes, torch.device("cuda", local_rank)).view(-1, 4)
+
+            def tiled_frame(frame_count):
+                fc.set_frame(frame_count, 4)
+                for lo, hi in plan.gid_ranges(rank):
+                    fc.execute_range(lo, hi)
+                fc.finish()
+                return prod.sharding.gather_frame(plan, frame, rank)
+
+            tiled_frame(1)
+            torch.cuda.synchronize()
+            barrier()
+            t0 = time.perf_counter()
+            for f in range(frames):
+                full = tiled_frame(2 + f)
+            torch.cuda.synchronize()
+            barrier()
+            ms = (time.perf_counter() - t0) / frames * 1e3
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            if rank == 0:
+                # the gathered frame must equal what one GPU renders alone, bit for bit
+                with prod.Context(local_rank) as one:
+                    one.upload_scene(tris_c, nodes_c, mats_c)
+                    one.resize(W, H)
+                    for k in range(1, 2 + frames):
+                        one.set_frame(k, 4)
+                        one.execute(W * H)
+                    alone = one.read_pixels()
+                extra["tiled_frame_4k"] = {"scene": "cornell.obj 3840x2160, 4 bounces", "ms_per_frame": float(t.item()),
+                                           "bands": "8-row bands round-robin over %d ranks, ncclAllGather of %.1f MB shards" % (
+                                               world, plan.rounds * plan.band_pixels * 16 / 1e6),
+                                           "bit_identical_to_single_gpu": bool(np.array_equal(full.cpu().numpy().view(np.uint32), alone.view(np.uint32)))}
 
     # ---- CPU baseline (rank 0, N=1 only) ------------------------------------------------------------------------------
     cpu = None
@@ -317,19 +362,37 @@ def run_b200(args, rank, world, local_rank):
             "clocks": clocks,
         }
         out.update(extra)
-        print(json.dumps(out), flush=True)
+        emit(out)
     eng.close()
     if world > 1:
         dist.destroy_process_group()
 
 
+_JSON_FD = None
+
+
+def emit(obj):
+    """The ONE JSON line goes to the process's original stdout; everything else (NCCL banners, library
+    chatter) was re-pointed at stderr in main()."""
+    line = json.dumps(obj) + "\n"
+    if _JSON_FD is None:
+        sys.stdout.write(line)
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, line.encode())
+
+
 def main():
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=6)
+    ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--rays", type=int, default=1 << 24, help="rays per GPU per step")
+    ap.add_argument("--rays", type=int, default=100_000_000, help="rays per GPU per step (BASELINE.json configs[4]: 100M random rays)")
     ap.add_argument("--frequency", type=int, default=224, help="geodesic frequency: 20*f^2 OBJ faces")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--ref-rays", type=int, default=1 << 19, help="--impl reference: rays per step (bounded sample)")

@@ -96,6 +96,7 @@ typedef struct {
     uint64_t bytes_fetched;     /* algorithmic bytes: 112 B per wide node + leaf block bytes */
     /* warp scheduling of the persistent kernels: phases run and lanes that took part in them */
     uint64_t node_phases, node_phase_lanes, leaf_phases, leaf_phase_lanes, refills, refill_lanes;
+    uint64_t max_steps_per_ray; /* node + leaf steps of the most expensive ray (tail detector) */
 } b2rt_counters;
 
 enum {

@@ -16,3 +16,11 @@ from .build import build_all  # noqa: F401
 from . import layouts  # noqa: F401
 from . import host  # noqa: F401
 from . import workloads  # noqa: F401
+
+
+def __getattr__(name):
+    # torch is only needed by the multi-GPU helpers: import them on first use
+    if name == "sharding":
+        import importlib
+        return importlib.import_module(".sharding", __name__)
+    raise AttributeError(name)

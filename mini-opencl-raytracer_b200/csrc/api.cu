@@ -605,13 +605,13 @@ extern "C" int b2rt_get_counters(b2rt_context* ctx, b2rt_counters* out) {
     if (!out) return fail(ctx, B2RT_INVALID_VALUE, "null output");
     int st = use_device(ctx);
     if (st) return st;
-    unsigned long long v[12];
+    unsigned long long v[13];
     CK(cudaDeviceSynchronize());     // counted launches may sit on caller-provided streams
     CK(cudaMemcpy(v, ctx->d_counters, sizeof(v), cudaMemcpyDeviceToHost));
     out->rays = v[0]; out->wide_nodes = v[1]; out->leaf_blocks = v[2]; out->leaf_gate_pass = v[3]; out->tri_tests = v[4];
     out->bytes_fetched = v[5] * 16ull;
     out->node_phases = v[6]; out->node_phase_lanes = v[7]; out->leaf_phases = v[8]; out->leaf_phase_lanes = v[9];
-    out->refills = v[10]; out->refill_lanes = v[11];
+    out->refills = v[10]; out->refill_lanes = v[11]; out->max_steps_per_ray = v[12];
     return B2RT_SUCCESS;
 }
 extern "C" int b2rt_reset_counters(b2rt_context* ctx) {

@@ -67,6 +67,7 @@ trace_persistent(SceneView s, const RayIn* __restrict__ rays, uint64_t n, void* 
     uint64_t pool_next = 0, pool_end = 0;    // warp-uniform
     bool exhausted = false;                  // warp-uniform: the global counter ran past n
     uint32_t traced = 0;
+    uint32_t ray_steps = 0, max_ray_steps = 0;   // COUNT only: node + leaf steps of the current ray / the worst ray of this lane
     uint32_t ph_node = 0, ph_node_lanes = 0, ph_leaf = 0, ph_leaf_lanes = 0, ph_refill = 0, ph_refill_lanes = 0;   // COUNT only, warp-uniform
 
     for (;;) {
@@ -104,10 +105,10 @@ trace_persistent(SceneView s, const RayIn* __restrict__ rays, uint64_t n, void* 
         // leaf_bias/16 weighs the leaf vote: > 1 consumes queued leaves earlier (less speculation)
         if (__popc(vn) * 16u >= __popc(vl) * leaf_bias) {
             if (COUNT) { ph_node++; ph_node_lanes += __popc(vn); }
-            if (active && L.wants_node()) L.node_step(s.wide, s.one_bits);
+            if (active && L.wants_node()) { L.node_step(s.wide, s.one_bits); if (COUNT) ray_steps++; }
         } else {
             if (COUNT) { ph_leaf++; ph_leaf_lanes += __popc(vl); }
-            if (active && L.wants_leaf()) L.leaf_step(s.leaf);
+            if (active && L.wants_leaf()) { L.leaf_step(s.leaf); if (COUNT) ray_steps++; }
         }
 #if B2_PREFETCH
         if (active) {
@@ -119,7 +120,7 @@ trace_persistent(SceneView s, const RayIn* __restrict__ rays, uint64_t n, void* 
             if (ANY) reinterpret_cast<uint32_t*>(out)[my_index] = (L.h.tri != 0xFFFFFFFFu) ? 1u : 0u;
             else reinterpret_cast<float4*>(out)[my_index] = make_float4(L.h.t, L.h.u, L.h.v, __uint_as_float(L.h.tri));
             active = false;
-            if (COUNT) traced++;
+            if (COUNT) { traced++; max_ray_steps = max_ray_steps > ray_steps ? max_ray_steps : ray_steps; ray_steps = 0; }
         }
     }
 
@@ -132,6 +133,7 @@ trace_persistent(SceneView s, const RayIn* __restrict__ rays, uint64_t n, void* 
             for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(FULL, x, o);
             if (lane == 0 && x) atomicAdd(&counters[i], x);
         }
+        atomicMax(&counters[12], (unsigned long long)max_ray_steps);
         if (lane == 0) {
             const unsigned long long ph[6] = { ph_node, ph_node_lanes, ph_leaf, ph_leaf_lanes, ph_refill, ph_refill_lanes };
             for (int i = 0; i < 6; ++i) if (ph[i]) atomicAdd(&counters[6 + i], ph[i]);

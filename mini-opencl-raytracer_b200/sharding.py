@@ -1,0 +1,80 @@
+"""Multi-GPU partition of the path: one process per GPU, the scene replicated, work units
+sharded, results gathered with a torch.distributed collective (NCCL over NVLink on GPUs, gloo on CPU in
+the tests). Rays/pixels are independent, so the only exchange step is the gather of the framebuffer.
+
+  ray streams ...... contiguous equal index ranges per rank, no collective (each rank keeps its hits)
+  frames ........... `gid = y*W + x` (kernel_bvh.cl:394-395) split into bands of `band_rows` image rows dealt
+                     round-robin to the ranks (sky and geometry rows interleave, so ranks finish together);
+                     every rank renders its bands with b2rt_execute_range, then one all_gather of equal
+                     contiguous shards + a de-interleave copy rebuilds the W*H*16-byte image on every rank.
+"""
+import torch
+import torch.distributed as dist
+
+
+def stream_range(n_items, world, rank):
+    """Contiguous [lo, hi) of a ray stream for `rank` (sizes differ by at most one)."""
+    lo = n_items * rank // world
+    hi = n_items * (rank + 1) // world
+    return lo, hi
+
+
+class BandPlan:
+    """Round-robin bands of image rows. The frame is padded (virtually) to a whole number of band rounds;
+    padded rows are never rendered and are cut off after the gather."""
+
+    def __init__(self, width, height, world, band_rows=8):
+        if width <= 0 or height <= 0 or world <= 0 or band_rows <= 0:
+            raise ValueError("width, height, world and band_rows must be positive")
+        self.width, self.height, self.world, self.band_rows = width, height, world, band_rows
+        self.n_bands = -(-height // band_rows)
+        self.rounds = -(-self.n_bands // world)               # bands per rank (last round may be partly empty)
+        self.band_pixels = band_rows * width
+
+    def bands_of(self, rank):
+        return [b for b in range(rank, self.n_bands, self.world)]
+
+    def gid_ranges(self, rank):
+        """[(gid_begin, gid_end)] this rank renders, clipped to the real frame."""
+        n = self.width * self.height
+        out = []
+        for b in self.bands_of(rank):
+            lo = b * self.band_pixels
+            out.append((lo, min(lo + self.band_pixels, n)))
+        return out
+
+    def pack(self, frame, rank):
+        """Own bands of a (W*H, C) frame as one contiguous (rounds*band_pixels, C) shard (zero padded)."""
+        c = frame.shape[1]
+        shard = torch.zeros((self.rounds * self.band_pixels, c), dtype=frame.dtype, device=frame.device)
+        for i, (lo, hi) in enumerate(self.gid_ranges(rank)):
+            shard[i * self.band_pixels:i * self.band_pixels + (hi - lo)] = frame[lo:hi]
+        return shard
+
+    def unpack(self, gathered):
+        """(world*rounds*band_pixels, C) all-gather result -> (W*H, C) frame."""
+        c = gathered.shape[1]
+        g = gathered.view(self.world, self.rounds, self.band_pixels, c).permute(1, 0, 2, 3)   # band index = round*world + rank
+        return g.reshape(-1, c)[: self.width * self.height]
+
+
+def gather_frame(plan, frame, rank, group=None):
+    """All ranks end up with the complete frame. `frame` is this rank's (W*H, C) buffer in which only its own
+    bands are valid. One collective: all_gather of equal contiguous shards."""
+    shard = plan.pack(frame, rank)
+    if plan.world == 1:
+        return plan.unpack(shard)
+    out = torch.empty((plan.world * shard.shape[0], shard.shape[1]), dtype=shard.dtype, device=shard.device)
+    dist.all_gather_into_tensor(out, shard, group=group)
+    return plan.unpack(out)
+
+
+class DeviceBuffer:
+    """A torch view of device memory owned by libb2rt (e.g. the bound output buffer), no copy."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes // 4,), "typestr": "<f4", "data": (int(ptr), False), "version": 3, "strides": None}
+
+
+def as_tensor(ptr, nbytes, device):
+    return torch.as_tensor(DeviceBuffer(ptr, nbytes), device=device)
