@@ -357,7 +357,8 @@ def run_b200(args, rank, world, local_rank):
                          "traffic": None, "peak_source": which + " copy bandwidth (MEASURED_PEAKS.json)" if which == "measured" else "fallback",
                          "kernel": "trace_persistent<closest>", "kernel_ms": kernel_ms,
                          "bytes_per_ray": bytes_per_ray, "traversal_bytes_per_ray": trav_bytes,
-                         "per_ray": {k: v / max(cnt["rays"], 1) for k, v in cnt.items() if k != "rays"}},
+                         "per_ray": {k: v / max(cnt["rays"], 1) for k, v in cnt.items() if k not in ("rays", "max_steps_per_ray")},
+                         "max_steps_of_one_ray": cnt["max_steps_per_ray"]},
             "cpu_baseline": cpu,
             "clocks": clocks,
         }
