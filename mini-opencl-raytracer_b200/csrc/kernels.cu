@@ -27,7 +27,7 @@ namespace b2rt {
 #define B2_PREFETCH 0
 #endif
 #ifndef B2_MIN_BLOCKS
-#define B2_MIN_BLOCKS 10
+#define B2_MIN_BLOCKS 8
 #endif
 static constexpr unsigned FULL = 0xffffffffu;
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
@@ -59,10 +59,10 @@ trace_persistent(SceneView s, const RayIn* __restrict__ rays, uint64_t n, void* 
                  uint32_t refill_min, uint32_t leaf_bias) {
     const unsigned lane = threadIdx.x & 31u;
     Lane<ANY, COUNT, CAP> L;
+    uint32_t stack[CAP];
     L.clear();
     L.overflow = false;
     L.tc.wide_nodes = L.tc.leaf_blocks = L.tc.leaf_pass = L.tc.tri_tests = L.tc.words = 0;
-    bool active = false;
     uint64_t my_index = 0;
     uint64_t pool_next = 0, pool_end = 0;    // warp-uniform
     bool exhausted = false;                  // warp-uniform: the global counter ran past n
@@ -70,10 +70,11 @@ trace_persistent(SceneView s, const RayIn* __restrict__ rays, uint64_t n, void* 
     uint32_t ray_steps = 0, max_ray_steps = 0;   // COUNT only: node + leaf steps of the current ray / the worst ray of this lane
     uint32_t ph_node = 0, ph_node_lanes = 0, ph_leaf = 0, ph_leaf_lanes = 0, ph_refill = 0, ph_refill_lanes = 0;   // COUNT only, warp-uniform
 
+    // A lane is idle exactly when its Lane is done(): a live ray always wants a node or a leaf step.
     for (;;) {
-        const unsigned idle = __ballot_sync(FULL, !active);
-        const unsigned vn = __ballot_sync(FULL, active && L.wants_node());
-        const unsigned vl = __ballot_sync(FULL, active && L.wants_leaf());
+        const unsigned vn = __ballot_sync(FULL, L.wants_node());
+        const unsigned vl = __ballot_sync(FULL, L.wants_leaf());
+        const unsigned idle = ~(vn | vl);
         const bool pool_dry = exhausted && pool_next == pool_end;
         if (idle && !pool_dry && ((unsigned)__popc(idle) >= refill_min || (vn | vl) == 0u)) {
             // ---- refill idle lanes from the warp pool -------------------------------------------
@@ -87,12 +88,11 @@ trace_persistent(SceneView s, const RayIn* __restrict__ rays, uint64_t n, void* 
             const uint64_t avail = pool_end - pool_next;
             if (avail) {
                 const unsigned rank = __popc(idle & ((1u << lane) - 1u));
-                if (!active && rank < avail) {
+                if (((idle >> lane) & 1u) && rank < avail) {
                     my_index = pool_next + rank;
                     RayX r; float tmax;
                     load_ray(rays, my_index, r, tmax);
                     L.start(r, tmax);
-                    active = true;
                 }
                 const unsigned taken = __popc(idle);
                 if (COUNT) { ph_refill++; ph_refill_lanes += (taken < avail) ? taken : (unsigned)avail; }
@@ -103,23 +103,20 @@ trace_persistent(SceneView s, const RayIn* __restrict__ rays, uint64_t n, void* 
         if ((vn | vl) == 0u) break;          // nothing in flight and nothing left to fetch
 
         // leaf_bias/16 weighs the leaf vote: > 1 consumes queued leaves earlier (less speculation)
+        bool stepped;
         if (__popc(vn) * 16u >= __popc(vl) * leaf_bias) {
             if (COUNT) { ph_node++; ph_node_lanes += __popc(vn); }
-            if (active && L.wants_node()) { L.node_step(s.wide, s.one_bits); if (COUNT) ray_steps++; }
+            stepped = L.wants_node();
+            if (stepped) L.node_step(s.wide, stack, s.one_bits);
         } else {
             if (COUNT) { ph_leaf++; ph_leaf_lanes += __popc(vl); }
-            if (active && L.wants_leaf()) { L.leaf_step(s.leaf); if (COUNT) ray_steps++; }
+            stepped = L.wants_leaf();
+            if (stepped) L.leaf_step(s.leaf, stack);
         }
-#if B2_PREFETCH
-        if (active) {
-            if (L.wants_node()) prefetch_l1(s.wide + (uint32_t)WIDE_NODE_WORDS * L.cur);
-            if (L.wants_leaf()) prefetch_l1(s.leaf + (L.leaf0 & ~REF_LEAF_BIT));
-        }
-#endif
-        if (active && L.done()) {
+        if (COUNT && stepped) ray_steps++;
+        if (stepped && L.done()) {
             if (ANY) reinterpret_cast<uint32_t*>(out)[my_index] = (L.h.tri != 0xFFFFFFFFu) ? 1u : 0u;
             else reinterpret_cast<float4*>(out)[my_index] = make_float4(L.h.t, L.h.u, L.h.v, __uint_as_float(L.h.tri));
-            active = false;
             if (COUNT) { traced++; max_ray_steps = max_ray_steps > ray_steps ? max_ray_steps : ray_steps; ray_steps = 0; }
         }
     }

@@ -210,13 +210,15 @@ B2_HD bool visit_leaf(const U4* leaf, uint32_t offset, const RayX& r, HitX& h, T
 struct WideHits {
     uint32_t mask;                // bit k: the child visited k-th (reference order) may intersect [0,best]
     uint32_t meta_lo, meta_hi;    // meta bytes permuted into visiting order
-    uint32_t child_base, leaf_base;
+    uint32_t add_interior;        // child_base - META_INTERIOR
+    uint32_t add_leaf;            // REF_LEAF_BIT | leaf_base
 };
 
 // Child reference of the child visited k-th: wide node index, or REF_LEAF_BIT | block offset.
+// meta = 0x80 | index for interior children, block offset (< 0x80) for leaves, so ref = meta + addend.
 B2_HD uint32_t child_ref(const WideHits& w, uint32_t k) {
     uint32_t m = prmt(w.meta_lo, w.meta_hi, k) & 0xffu;
-    return (m & META_INTERIOR) ? w.child_base + (m & 0x7fu) : (REF_LEAF_BIT | (w.leaf_base + m));
+    return m + ((m & META_INTERIOR) ? w.add_interior : w.add_leaf);
 }
 
 // float 1 + q * 2^-15 from byte i of w: the byte lands in mantissa bits 8..15 of 1.0f.
@@ -239,8 +241,8 @@ B2_HD WideHits test_wide_node(const U4* wide, uint32_t index, const RayX& r, flo
     U4 w0 = ld128(p), w1 = ld128(p + 1), w2 = ld128(p + 2), w3 = ld128(p + 3), w4 = ld128(p + 4);
     const uint32_t order = ld32(reinterpret_cast<const uint32_t*>(p + 5) + r.sign);
     WideHits out;
-    out.child_base = w1.x;
-    out.leaf_base = w1.y;
+    out.add_interior = w1.x - (uint32_t)META_INTERIOR;
+    out.add_leaf = REF_LEAF_BIT | w1.y;
     const uint32_t sel_lo = order, sel_hi = order >> 16;      // prmt reads the low four nibbles only
     out.meta_lo = prmt(w1.z, w1.w, sel_lo);
     out.meta_hi = prmt(w1.z, w1.w, sel_hi);
@@ -290,6 +292,8 @@ B2_HD WideHits test_wide_node(const U4* wide, uint32_t index, const RayX& r, flo
 // slots, FIFO) and consumed in order by leaf_step(). Any interleaving of the two calls that the
 // wants_*() predicates allow gives the reference's result; the kernels pick per warp, by vote,
 // whichever step more lanes are waiting for.
+// The short stack of child references lives OUTSIDE this struct (a plain local array owned by the
+// caller): with the array inside, the compiler keeps every scalar of the struct in local memory too.
 template <bool ANY, bool COUNT, int CAP>
 struct Lane {
     RayX r;
@@ -299,7 +303,6 @@ struct Lane {
     int sp;
     bool overflow;
     TravCounters tc;
-    uint32_t stack[CAP];
 
     B2_HD void start(const RayX& ray, float tmax) {
         r = ray;
@@ -311,21 +314,21 @@ struct Lane {
     B2_HD bool wants_node() const { return cur != REF_EMPTY && !(cur & REF_LEAF_BIT); }
     B2_HD bool wants_leaf() const { return leaf0 != REF_EMPTY; }
 
-    B2_HD uint32_t pop() { return sp > 0 ? stack[--sp] : REF_EMPTY; }
+    B2_HD uint32_t pop(const uint32_t* stack) { return sp > 0 ? stack[--sp] : REF_EMPTY; }
     // Move leaves from `cur` into the queue while there is room.
-    B2_HD void settle() {
+    B2_HD void settle(const uint32_t* stack) {
         while (cur != REF_EMPTY && (cur & REF_LEAF_BIT) && leaf1 == REF_EMPTY) {
             if (leaf0 == REF_EMPTY) leaf0 = cur; else leaf1 = cur;
-            cur = pop();
+            cur = pop(stack);
         }
     }
     // `one` must be 0x3F800000, passed as run-time data: held in one register it lets the constant
     // byte selectors of B2_PLANE_V be instruction immediates (ptxas otherwise keeps four selector registers).
-    B2_HD void node_step(const U4* wide, uint32_t one) {
+    B2_HD void node_step(const U4* wide, uint32_t* stack, uint32_t one) {
         WideHits w = test_wide_node(wide, cur, r, h.t, one);
         if (COUNT) { tc.wide_nodes++; tc.words += WIDE_NODE_WORDS; }
         uint32_t m = w.mask;
-        if (m == 0) { cur = pop(); }
+        if (m == 0) { cur = pop(stack); }
         else {
             while (m & (m - 1u)) {                       // more than one: push the farthest
                 uint32_t k = top_bit(m);
@@ -334,15 +337,15 @@ struct Lane {
             }
             cur = child_ref(w, top_bit(m));
         }
-        settle();
+        settle(stack);
     }
     // Returns true when the ray is finished by this leaf (any-hit accept, or best < 0: every later
     // box test of the reference fails).
-    B2_HD bool leaf_step(const U4* leaf) {
+    B2_HD bool leaf_step(const U4* leaf, const uint32_t* stack) {
         bool got = visit_leaf<COUNT>(leaf, leaf0 & ~REF_LEAF_BIT, r, h, COUNT ? &tc : nullptr);
         leaf0 = leaf1; leaf1 = REF_EMPTY;
         if ((ANY && got) || h.t < 0.0f) { clear(); return true; }
-        settle();
+        settle(stack);
         return false;
     }
 };
@@ -354,16 +357,15 @@ template <bool ANY, bool COUNT, int CAP>
 B2_HD HitX trace_wide(const U4* wide, const U4* leaf, const RayX& r, float tmax, TravCounters* c, bool* overflow,
                       uint32_t one, uint32_t schedule = 0) {
     Lane<ANY, COUNT, CAP> L;
-    L.overflow = false;
+    uint32_t stack[CAP];
     L.tc.wide_nodes = L.tc.leaf_blocks = L.tc.leaf_pass = L.tc.tri_tests = L.tc.words = 0;
     L.start(r, tmax);
-    L.settle();
     while (!L.done()) {
         const bool node = L.wants_node(), lf = L.wants_leaf();
         bool do_leaf = lf;                                  // default: consume pending leaves first (no speculation)
         if (node && lf && schedule) { schedule = schedule * 1664525u + 1013904223u; do_leaf = (schedule >> 16) & 1u; }
-        if (do_leaf) { if (L.leaf_step(leaf)) break; }
-        else L.node_step(wide, one);
+        if (do_leaf) { if (L.leaf_step(leaf, stack)) break; }
+        else L.node_step(wide, stack, one);
     }
     if (COUNT && c) *c = L.tc;
     if (overflow) *overflow = L.overflow;
