@@ -23,14 +23,16 @@
 
 namespace b2rt {
 
-#ifndef B2_PREFETCH
-#define B2_PREFETCH 0
-#endif
 #ifndef B2_MIN_BLOCKS
 #define B2_MIN_BLOCKS 8
 #endif
 static constexpr unsigned FULL = 0xffffffffu;
-__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+#ifndef B2_TOUCH
+#define B2_TOUCH 0
+#endif
+// "Touch" prefetch: an ordinary cached load whose result is never read, issued as soon as the next
+// node / leaf of a lane is known so that the line is (on its way) in L1 when the step runs.
+__device__ __forceinline__ void touch(const void* p) { unsigned d; asm volatile("ld.global.nc.b32 %0, [%1];" : "=r"(d) : "l"(p)); }
 static constexpr int TRACE_BLOCK = 128;
 
 struct RayIn { float ox, oy, oz, tmin, dx, dy, dz, tmax; };
@@ -113,6 +115,12 @@ trace_persistent(SceneView s, const RayIn* __restrict__ rays, uint64_t n, void* 
             stepped = L.wants_leaf();
             if (stepped) L.leaf_step(s.leaf, stack);
         }
+#if B2_TOUCH
+        if (stepped) {
+            if (L.wants_node()) { touch(s.wide + (uint32_t)WIDE_NODE_WORDS * L.cur); if (B2_TOUCH > 1) touch(s.wide + (uint32_t)WIDE_NODE_WORDS * L.cur + 6); }
+            if (L.wants_leaf()) touch(s.leaf + (L.leaf0 & ~REF_LEAF_BIT));
+        }
+#endif
         if (COUNT && stepped) ray_steps++;
         if (stepped && L.done()) {
             if (ANY) reinterpret_cast<uint32_t*>(out)[my_index] = (L.h.tri != 0xFFFFFFFFu) ? 1u : 0u;

@@ -147,6 +147,9 @@ B2_HD bool box_gate_exact(const RayX& r, float lox, float loy, float loz, float 
 
 // RayTriangle, kernel_bvh.cl:98-153, for triangle (a,b,c) = (v1,v2,v3) with id `tri`.
 // Accepts iff det >= 1e-8, 0<=u<=1, v>=0, u+v<=1 and t < best (no lower bound on t).
+// Branch-free: the reference's early returns only skip work, so evaluating every comparison
+// of the sequence and AND-ing them gives the same decision (NaN/inf operands included -- each
+// comparison is the negation the reference tests, in its order) without divergent exits.
 B2_HD void tri_test_exact(const RayX& r, float ax, float ay, float az, float bx, float by, float bz,
                           float cx, float cy, float cz, uint32_t tri, HitX& h) {
     float e1x = xsub(bx, ax), e1y = xsub(by, ay), e1z = xsub(bz, az);
@@ -155,18 +158,18 @@ B2_HD void tri_test_exact(const RayX& r, float ax, float ay, float az, float bx,
     float py = xsub(xmul(r.dz, e2x), xmul(r.dx, e2z));
     float pz = xsub(xmul(r.dx, e2y), xmul(r.dy, e2x));
     float det = xadd(xadd(xmul(e1x, px), xmul(e1y, py)), xmul(e1z, pz));
-    if (det < 1.0e-8f || -det > 1.0e-8f) return;
+    bool ok = !(det < 1.0e-8f) && !(-det > 1.0e-8f);                                   // :116
     float inv = xdiv(1.0f, det);
     float tx = xsub(r.ox, ax), ty = xsub(r.oy, ay), tz = xsub(r.oz, az);
     float u = xmul(xadd(xadd(xmul(tx, px), xmul(ty, py)), xmul(tz, pz)), inv);
-    if (u < 0.0f || u > 1.0f) return;
+    ok = ok && !(u < 0.0f) && !(u > 1.0f);                                             // :125
     float qx = xsub(xmul(ty, e1z), xmul(tz, e1y));
     float qy = xsub(xmul(tz, e1x), xmul(tx, e1z));
     float qz = xsub(xmul(tx, e1y), xmul(ty, e1x));
     float v = xmul(xadd(xadd(xmul(r.dx, qx), xmul(r.dy, qy)), xmul(r.dz, qz)), inv);
-    if (v < 0.0f || xadd(u, v) > 1.0f) return;
+    ok = ok && !(v < 0.0f) && !(xadd(u, v) > 1.0f);                                    // :132
     float t = xmul(xadd(xadd(xmul(e2x, qx), xmul(e2y, qy)), xmul(e2z, qz)), inv);
-    if (t < h.t) { h.t = t; h.u = u; h.v = v; h.tri = tri; }
+    if (ok && t < h.t) { h.t = t; h.u = u; h.v = v; h.tri = tri; }                      // :140
 }
 
 // ---- leaf block ----------------------------------------------------------------------
@@ -191,11 +194,12 @@ B2_HD bool visit_leaf(const U4* leaf, uint32_t offset, const RayX& r, HitX& h, T
         uint32_t flags = a.w;
         tri_test_exact(r, v1x, v1y, v1z, v2x, v2y, v2z, v3x, v3y, v3z, id, h);
         if (COUNT) c->tri_tests++;
-        if (flags == REC_ROT_LEFT) {
-            tri_test_exact(r, v2x, v2y, v2z, v3x, v3y, v3z, v1x, v1y, v1z, id + 1, h);
-            if (COUNT) c->tri_tests++;
-        } else if (flags == REC_ROT_RIGHT) {
-            tri_test_exact(r, v3x, v3y, v3z, v1x, v1y, v1z, v2x, v2y, v2z, id + 1, h);
+        if (flags) {
+            // the loader's second copy of the same triangle, rotated left (v2,v3,v1) or right (v3,v1,v2)
+            const bool left = flags == REC_ROT_LEFT;
+            tri_test_exact(r, left ? v2x : v3x, left ? v2y : v3y, left ? v2z : v3z,
+                           left ? v3x : v1x, left ? v3y : v1y, left ? v3z : v1z,
+                           left ? v1x : v2x, left ? v1y : v2y, left ? v1z : v2z, id + 1, h);
             if (COUNT) c->tri_tests++;
         }
         id += flags ? 2u : 1u;
@@ -300,21 +304,32 @@ struct Lane {
     HitX h;
     uint32_t cur;          // wide node to test next, a leaf waiting for a queue slot, or REF_EMPTY
     uint32_t leaf0, leaf1; // queued leaves, leaf0 first
-    int sp;
+    uint32_t top;          // most recently pushed child reference, kept in a register (REF_EMPTY = stack empty)
+    int sp;                // entries below `top`, in the caller's local array
     bool overflow;
     TravCounters tc;
 
     B2_HD void start(const RayX& ray, float tmax) {
         r = ray;
         h.t = tmax; h.u = 0.0f; h.v = 0.0f; h.tri = 0xFFFFFFFFu;
-        cur = 0; leaf0 = leaf1 = REF_EMPTY; sp = 0; overflow = false;
+        cur = 0; leaf0 = leaf1 = top = REF_EMPTY; sp = 0; overflow = false;
     }
-    B2_HD void clear() { cur = leaf0 = leaf1 = REF_EMPTY; sp = 0; }
+    B2_HD void clear() { cur = leaf0 = leaf1 = top = REF_EMPTY; sp = 0; }
     B2_HD bool done() const { return cur == REF_EMPTY && leaf0 == REF_EMPTY; }
     B2_HD bool wants_node() const { return cur != REF_EMPTY && !(cur & REF_LEAF_BIT); }
     B2_HD bool wants_leaf() const { return leaf0 != REF_EMPTY; }
 
-    B2_HD uint32_t pop(const uint32_t* stack) { return sp > 0 ? stack[--sp] : REF_EMPTY; }
+    // The top of the stack sits in a register: a pop answers at once and the load that refills the
+    // register from local memory is only waited for by the NEXT pop.
+    B2_HD void push(uint32_t* stack, uint32_t ref) {
+        if (top != REF_EMPTY) { if (sp < CAP) stack[sp++] = top; else overflow = true; }
+        top = ref;
+    }
+    B2_HD uint32_t pop(const uint32_t* stack) {
+        uint32_t ref = top;
+        top = sp > 0 ? stack[--sp] : REF_EMPTY;
+        return ref;
+    }
     // Move leaves from `cur` into the queue while there is room.
     B2_HD void settle(const uint32_t* stack) {
         while (cur != REF_EMPTY && (cur & REF_LEAF_BIT) && leaf1 == REF_EMPTY) {
@@ -333,7 +348,7 @@ struct Lane {
             while (m & (m - 1u)) {                       // more than one: push the farthest
                 uint32_t k = top_bit(m);
                 m ^= 1u << k;
-                if (sp < CAP) stack[sp++] = child_ref(w, k); else overflow = true;
+                push(stack, child_ref(w, k));
             }
             cur = child_ref(w, top_bit(m));
         }
