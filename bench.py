@@ -64,6 +64,20 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0}, "fallback"
 
 
+def measured_traffic(frequency, rays):
+    """dram__bytes_{read,write}.sum of one launch of the dominant kernel from the committed ncu --set full
+    capture, when that capture was taken on this exact workload; else None."""
+    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if not os.path.exists(p):
+        return None
+    with open(p) as f:
+        t = json.load(f)
+    w = t.get("workload", {})
+    if w.get("frequency") == frequency and w.get("rays_per_launch") == rays:
+        return t["dram_bytes_per_launch"] / 1e9
+    return None
+
+
 def ensure_scene(prod, frequency, rank, world, barrier):
     os.makedirs(SCENE_DIR, exist_ok=True)
     path = os.path.join(SCENE_DIR, "ico_f%d.obj" % frequency)
@@ -354,7 +368,8 @@ def run_b200(args, rank, world, local_rank):
                     "api": "b2rt_trace_closest (pinned host buffers, chunked H2D/kernel/D2H pipeline)"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-                         "traffic": None, "peak_source": which + " copy bandwidth (MEASURED_PEAKS.json)" if which == "measured" else "fallback",
+                         "traffic": measured_traffic(args.frequency, n), "traffic_unit": "GB per launch (ncu dram bytes, profiles/r1_traffic.json)",
+                         "algorithmic_gb_per_launch": n * bytes_per_ray / 1e9, "peak_source": which + " copy bandwidth (MEASURED_PEAKS.json)" if which == "measured" else "fallback",
                          "kernel": "trace_persistent<closest>", "kernel_ms": kernel_ms,
                          "bytes_per_ray": bytes_per_ray, "traversal_bytes_per_ray": trav_bytes,
                          "per_ray": {k: v / max(cnt["rays"], 1) for k, v in cnt.items() if k not in ("rays", "max_steps_per_ray")},
