@@ -282,18 +282,29 @@ def run_b200(args, rank, world, local_rank):
     dev_hits = d_hits.cpu().numpy().view(prod.HIT_DTYPE).reshape(-1)
     assert np.array_equal(dev_hits["tri"], hits_np["tri"]), "host-buffer and device-resident paths disagree"
 
-    # ---- cornell 1920x1080, 4 bounces, 16 frames accumulated (configs[1]) --------------------------------------------
+    # ---- cornell 1920x1080, 4 bounces, 16 frames accumulated = 16 spp (configs[1]) -------------------------------------
     extra = {}
+    cornell_img = None
     if rank == 0 and not args.skip_frames:
         cornell = os.path.join(ROOT, "tests", "golden", "cornell.obj")
         with prod.host.Engine(1920, 1080, device=local_rank) as ce:
             ce.load_scene(cornell, 4)
             ce.set_render(frame_count=1, bounces=4)
-            ce.render_frame()                                    # warm-up frame (also frame 1 of the accumulation)
+            ce.render_frame()                                    # frame 1 of the accumulation doubles as warm-up
             t0 = time.perf_counter()
             for _ in range(15):
-                ce.render_frame()                                # RenderFrame: args, kernel, full read-back, finish
-            extra["cornell_1080p_4bounce_frame_ms"] = (time.perf_counter() - t0) / 15 * 1e3
+                ce.render_frame()                                # RenderFrame: 8 args, kernel, full 33 MB read-back, finish
+            frame_ms = (time.perf_counter() - t0) / 15 * 1e3
+            cornell_img = ce.pixels().copy()
+            cctx = prod.Context.borrow(ce.context_handle(), local_rank)
+            t0 = time.perf_counter()
+            for f in range(17, 33):
+                cctx.set_frame(f, 4)
+                cctx.execute(1920 * 1080)
+            cctx.finish()
+            cornell_kernel_ms = (time.perf_counter() - t0) / 16 * 1e3
+        extra["cornell_1080p_4bounce"] = {"frame_ms": frame_ms, "kernel_only_frame_ms": cornell_kernel_ms, "spp": 16,
+                                          "api": "CLRaytracer::RenderFrame (args + KernelEntry + 33 MB read-back + finish)"}
 
     # ---- N>1: one 4K cornell frame split into row bands over the ranks + NCCL all_gather of the framebuffer ----
     if world > 1 and not args.skip_frames:
@@ -350,6 +361,21 @@ def run_b200(args, rank, world, local_rank):
         same = float((want["tri"] == hits_np["tri"][:100000]).mean())
         extra["parity_ids_identical_frac_100k"] = same
         extra["parity_t_bit_identical_frac_100k"] = float((want["t"] == hits_np["t"][:100000]).mean())
+        if cornell_img is not None:
+            # the same 16 accumulated frames by the reference's KernelEntry on the host cores
+            ct, cn, cm = prod.host.load_scene(os.path.join(ROOT, "tests", "golden", "cornell.obj"), 4)
+            ref_img = np.zeros((1920 * 1080, 4), dtype=np.float32)
+            render = ol.ref_render if ol.ref() is not None else ol.oracle_render
+            t0 = time.perf_counter()
+            for fc in range(1, 17):
+                render(ct, cn, cm, ref_img, 1920, 1080, fc, 4, threads=os.cpu_count() or 1)
+            cpu_ms = (time.perf_counter() - t0) / 16 * 1e3
+            a = np.clip(np.nan_to_num(cornell_img[:, :3].astype(np.float64)), 0, 1)
+            b = np.clip(np.nan_to_num(ref_img[:, :3].astype(np.float64)), 0, 1)
+            mse = float(np.mean((a - b) ** 2))
+            extra["cornell_1080p_4bounce"].update({"cpu_reference_frame_ms": cpu_ms, "cpu_threads": os.cpu_count() or 1,
+                                                   "psnr_vs_reference_db": (10 * np.log10(1.0 / mse)) if mse > 0 else 999.0,
+                                                   "pixels_bit_identical_frac": float((cornell_img[:, :3] == ref_img[:, :3]).all(axis=1).mean())})
 
     if rank == 0:
         peaks, which = measured_peaks()

@@ -136,6 +136,11 @@ int b2rt_execute_range(b2rt_context* ctx, size_t gid_begin, size_t gid_end);
 /* Non-blocking read of `bytes` from offset 0 of `buf` into host memory (CLutils.cpp:37-42). */
 int b2rt_read_buffer(b2rt_context* ctx, b2rt_buffer buf, void* dst, size_t bytes);
 int b2rt_finish(b2rt_context* ctx);
+/* Optional: page-lock a host range that b2rt_read_buffer / the ray-stream calls will be given repeatedly
+ * (e.g. CLRaytracer::pixels, CLRaytracer.cpp:127), so that the copies run at full PCIe speed and truly
+ * asynchronously. The reference's OpenCL runtime pins its staging memory itself; here it is explicit. */
+int b2rt_host_register(b2rt_context* ctx, void* ptr, size_t bytes);
+int b2rt_host_unregister(b2rt_context* ctx, void* ptr);
 
 /* ---- convenience wrappers over the calls above --------------------------------------- */
 /* CLBVHScene::SetupBuffers (CLBVHnode.cpp:209-236): three buffer creates + binds. */

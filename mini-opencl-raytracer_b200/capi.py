@@ -22,7 +22,7 @@ MEM_WRITE_ONLY, MEM_READ_ONLY, MEM_COPY_HOST_PTR = 1 << 1, 1 << 2, 1 << 5
 SYMBOLS = [
     "b2rt_create", "b2rt_destroy", "b2rt_last_error", "b2rt_status_string", "b2rt_buffer_create",
     "b2rt_buffer_release", "b2rt_set_arg", "b2rt_execute", "b2rt_execute_range", "b2rt_read_buffer",
-    "b2rt_finish", "b2rt_upload_scene", "b2rt_resize", "b2rt_read_pixels", "b2rt_trace_closest",
+    "b2rt_finish", "b2rt_host_register", "b2rt_host_unregister", "b2rt_upload_scene", "b2rt_resize", "b2rt_read_pixels", "b2rt_trace_closest",
     "b2rt_trace_any", "b2rt_trace_closest_device", "b2rt_trace_any_device", "b2rt_camera_rays_device",
     "b2rt_device_pointer", "b2rt_bound_buffer", "b2rt_scene_info_get", "b2rt_set_option",
     "b2rt_get_counters", "b2rt_reset_counters", "b2rt_launch_count", "b2rt_device_count",
@@ -78,6 +78,8 @@ def lib():
         "b2rt_execute_range": (C.c_int, [vp, sz, sz]),
         "b2rt_read_buffer": (C.c_int, [vp, u64, vp, sz]),
         "b2rt_finish": (C.c_int, [vp]),
+        "b2rt_host_register": (C.c_int, [vp, vp, sz]),
+        "b2rt_host_unregister": (C.c_int, [vp, vp]),
         "b2rt_upload_scene": (C.c_int, [vp, vp, u64, vp, u64, vp, u64]),
         "b2rt_resize": (C.c_int, [vp, u32, u32]),
         "b2rt_read_pixels": (C.c_int, [vp, vp, sz]),
@@ -203,6 +205,12 @@ class Context:
 
     def finish(self):
         self._ck(self._L.b2rt_finish(self._h))
+
+    def host_register(self, array):
+        self._ck(self._L.b2rt_host_register(self._h, _ptr(array), array.nbytes))
+
+    def host_unregister(self, array):
+        self._ck(self._L.b2rt_host_unregister(self._h, _ptr(array)))
 
     def read_pixels(self, out=None):
         n = self.width * self.height

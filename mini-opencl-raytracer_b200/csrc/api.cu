@@ -476,6 +476,28 @@ extern "C" int b2rt_finish(b2rt_context* ctx) {
     return B2RT_SUCCESS;
 }
 
+extern "C" int b2rt_host_register(b2rt_context* ctx, void* ptr, size_t bytes) {
+    if (!ctx) return B2RT_INVALID_CONTEXT;
+    if (!ptr || !bytes) return fail(ctx, B2RT_INVALID_VALUE, "null or empty host range");
+    int st = use_device(ctx);
+    if (st) return st;
+    cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterDefault);
+    if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return B2RT_SUCCESS; }
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaHostRegister");
+    return B2RT_SUCCESS;
+}
+extern "C" int b2rt_host_unregister(b2rt_context* ctx, void* ptr) {
+    if (!ctx) return B2RT_INVALID_CONTEXT;
+    if (!ptr) return fail(ctx, B2RT_INVALID_VALUE, "null host pointer");
+    int st = use_device(ctx);
+    if (st) return st;
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaError_t e = cudaHostUnregister(ptr);
+    if (e == cudaErrorHostMemoryNotRegistered) { cudaGetLastError(); return B2RT_SUCCESS; }
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaHostUnregister");
+    return B2RT_SUCCESS;
+}
+
 // ---- convenience --------------------------------------------------------------------------
 extern "C" int b2rt_upload_scene(b2rt_context* ctx, const void* triangles, uint64_t n_triangles, const void* nodes,
                                  uint64_t n_nodes, const void* materials, uint64_t n_materials) {

@@ -215,6 +215,7 @@ namespace Glaze3D
     class CLRaytracer
     {
     public:
+        ~CLRaytracer();
         void Init();
         void RenderFrame();
         template <class T> bool SetUniform(int i, T& val);

@@ -74,6 +74,11 @@ namespace Glaze3D
     template bool CLRaytracer::SetUniform<int>(int, int&);
     template bool CLRaytracer::SetUniform<unsigned int>(int, unsigned int&);
 
+    CLRaytracer::~CLRaytracer()
+    {
+        if (m_CLContext && !pixels.empty()) b2rt_host_unregister(m_CLContext->GetContext(), pixels.data());
+    }
+
     void CLRaytracer::Init()
     {
         m_CLContext = std::make_shared<CLContext>(device);
@@ -87,7 +92,10 @@ namespace Glaze3D
         int w = eng->ui->window_width, h = eng->ui->window_height;
         SetUniform<int>((int)RenderKernelArgument_t::WIDTH, w);
         SetUniform<int>((int)RenderKernelArgument_t::HEIGHT, h);
+        if (!pixels.empty()) b2rt_host_unregister(m_CLContext->GetContext(), pixels.data());
         pixels.resize((size_t)w * h);
+        // page-lock the read-back target: RenderFrame copies the whole frame into it every frame
+        b2rt_host_register(m_CLContext->GetContext(), pixels.data(), pixels.size() * sizeof(float3));
         int err = 0;
         // Zero-filled by the library: the reference never clears it although frame 1 reads it (kernel_bvh.cl:454).
         m_OutputBuffer = CLBuffer(*m_CLContext, B2RT_MEM_WRITE_ONLY, (size_t)w * h * sizeof(float3), nullptr, &err);
