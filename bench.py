@@ -320,8 +320,7 @@ def run_b200(args, rank, world, local_rank):
 
             def tiled_frame(frame_count):
                 fc.set_frame(frame_count, 4)
-                for lo, hi in plan.gid_ranges(rank):
-                    fc.execute_range(lo, hi)
+                plan.render(fc, rank)                          # b2rt_execute_bands: every world-th 8-row band, one launch sequence
                 fc.finish()
                 return prod.sharding.gather_frame(plan, frame, rank)
 

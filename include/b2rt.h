@@ -103,7 +103,8 @@ enum {
     B2RT_OPT_TRAVERSAL = 0,     /* 0 = compressed wide BVH (default), 1 = reference-layout binary walk */
     B2RT_OPT_COUNTERS = 1,      /* 1 = launches use the counting build of the kernels      */
     B2RT_OPT_BLOCKS_PER_SM = 2, /* persistent grid = value * SM count (0 = default)        */
-    B2RT_OPT_RENDER_MODE = 3,   /* 0 = wavefront (default), 1 = megakernel                 */
+    B2RT_OPT_RENDER_MODE = 3,   /* frame path: 0 = wavefront (generate, then trace + shade/compact per bounce; default),
+                                   1 = megakernel (one thread per pixel, like KernelEntry); bit-identical frames */
     B2RT_OPT_REFILL_MIN = 4,    /* idle lanes of a warp that trigger a ray refill (1..32, default 8) */
     B2RT_OPT_LEAF_BIAS = 5      /* weight of the leaf vote in sixteenths (16 = plain majority, default 28) */
 };
@@ -133,6 +134,10 @@ int b2rt_set_arg(b2rt_context* ctx, uint32_t slot, const void* data, size_t size
 int b2rt_execute(b2rt_context* ctx, size_t global_work_size);
 /* Same, restricted to gid in [gid_begin, gid_end): one screen shard of a multi-GPU frame. */
 int b2rt_execute_range(b2rt_context* ctx, size_t gid_begin, size_t gid_end);
+/* Same, for n_bands bands of band_pixels consecutive gids whose starts are stride_pixels apart, beginning at
+ * gid_begin: everything one rank of a multi-GPU frame draws (e.g. every world-th 8-row band), as ONE launch
+ * sequence instead of one per band. */
+int b2rt_execute_bands(b2rt_context* ctx, size_t gid_begin, uint32_t band_pixels, uint32_t stride_pixels, uint32_t n_bands);
 /* Non-blocking read of `bytes` from offset 0 of `buf` into host memory (CLutils.cpp:37-42). */
 int b2rt_read_buffer(b2rt_context* ctx, b2rt_buffer buf, void* dst, size_t bytes);
 int b2rt_finish(b2rt_context* ctx);
@@ -149,6 +154,11 @@ int b2rt_upload_scene(b2rt_context* ctx, const void* triangles, uint64_t n_trian
 /* CLRaytracer::SetupBuffers (CLRaytracer.cpp:122-137): WIDTH/HEIGHT + zeroed output buffer. */
 int b2rt_resize(b2rt_context* ctx, uint32_t width, uint32_t height);
 int b2rt_read_pixels(b2rt_context* ctx, void* dst, size_t bytes);   /* read_buffer on the bound slot 0 */
+/* Display read-back: the first bytes/4 pixels of the bound output image clamped to [0,1] and quantised to 8-bit
+ * RGBA (alpha 255) on the device, then copied (non-blocking, finish with b2rt_finish). 4 B/pixel over PCIe instead
+ * of the 16 B/pixel the reference reads back and hands to glTexImage2D(GL_RGBA, GL_FLOAT) (CLRaytracer.cpp:55,64-67).
+ * The accumulation image itself is not modified. */
+int b2rt_read_pixels_rgba8(b2rt_context* ctx, void* dst, size_t bytes);
 
 /* ---- ray-stream path (new) ----------------------------------------------------------- */
 /* Host buffers: H2D copy, trace, D2H copy, synchronous on return.

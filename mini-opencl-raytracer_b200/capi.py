@@ -21,8 +21,8 @@ MEM_WRITE_ONLY, MEM_READ_ONLY, MEM_COPY_HOST_PTR = 1 << 1, 1 << 2, 1 << 5
 # every symbol include/b2rt.h declares (tests/test_abi.py checks the header against this list)
 SYMBOLS = [
     "b2rt_create", "b2rt_destroy", "b2rt_last_error", "b2rt_status_string", "b2rt_buffer_create",
-    "b2rt_buffer_release", "b2rt_set_arg", "b2rt_execute", "b2rt_execute_range", "b2rt_read_buffer",
-    "b2rt_finish", "b2rt_host_register", "b2rt_host_unregister", "b2rt_upload_scene", "b2rt_resize", "b2rt_read_pixels", "b2rt_trace_closest",
+    "b2rt_buffer_release", "b2rt_set_arg", "b2rt_execute", "b2rt_execute_range", "b2rt_execute_bands", "b2rt_read_buffer",
+    "b2rt_finish", "b2rt_host_register", "b2rt_host_unregister", "b2rt_upload_scene", "b2rt_resize", "b2rt_read_pixels", "b2rt_read_pixels_rgba8", "b2rt_trace_closest",
     "b2rt_trace_any", "b2rt_trace_closest_device", "b2rt_trace_any_device", "b2rt_camera_rays_device",
     "b2rt_device_pointer", "b2rt_bound_buffer", "b2rt_scene_info_get", "b2rt_set_option",
     "b2rt_get_counters", "b2rt_reset_counters", "b2rt_launch_count", "b2rt_device_count",
@@ -76,6 +76,7 @@ def lib():
         "b2rt_set_arg": (C.c_int, [vp, u32, vp, sz]),
         "b2rt_execute": (C.c_int, [vp, sz]),
         "b2rt_execute_range": (C.c_int, [vp, sz, sz]),
+        "b2rt_execute_bands": (C.c_int, [vp, sz, C.c_uint32, C.c_uint32, C.c_uint32]),
         "b2rt_read_buffer": (C.c_int, [vp, u64, vp, sz]),
         "b2rt_finish": (C.c_int, [vp]),
         "b2rt_host_register": (C.c_int, [vp, vp, sz]),
@@ -83,6 +84,7 @@ def lib():
         "b2rt_upload_scene": (C.c_int, [vp, vp, u64, vp, u64, vp, u64]),
         "b2rt_resize": (C.c_int, [vp, u32, u32]),
         "b2rt_read_pixels": (C.c_int, [vp, vp, sz]),
+        "b2rt_read_pixels_rgba8": (C.c_int, [vp, vp, sz]),
         "b2rt_trace_closest": (C.c_int, [vp, vp, u64, vp]),
         "b2rt_trace_any": (C.c_int, [vp, vp, u64, vp]),
         "b2rt_trace_closest_device": (C.c_int, [vp, vp, u64, vp, vp]),
@@ -203,6 +205,10 @@ class Context:
     def execute_range(self, gid0, gid1):
         self._ck(self._L.b2rt_execute_range(self._h, int(gid0), int(gid1)))
 
+    def execute_bands(self, gid0, band_pixels, stride_pixels, n_bands):
+        """n_bands bands of band_pixels gids, band starts stride_pixels apart: one rank's share of a frame."""
+        self._ck(self._L.b2rt_execute_bands(self._h, int(gid0), int(band_pixels), int(stride_pixels), int(n_bands)))
+
     def finish(self):
         self._ck(self._L.b2rt_finish(self._h))
 
@@ -217,6 +223,15 @@ class Context:
         if out is None:
             out = np.empty((n, 4), dtype=np.float32)
         self._ck(self._L.b2rt_read_pixels(self._h, _ptr(out), out.nbytes))
+        self.finish()
+        return out
+
+    def read_pixels_rgba8(self, out=None):
+        """Clamped 8-bit RGBA view of the accumulation image, quantised on the device (4 B/pixel read-back)."""
+        n = self.width * self.height
+        if out is None:
+            out = np.empty((n, 4), dtype=np.uint8)
+        self._ck(self._L.b2rt_read_pixels_rgba8(self._h, _ptr(out), out.nbytes))
         self.finish()
         return out
 

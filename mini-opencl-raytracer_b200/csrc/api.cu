@@ -56,6 +56,13 @@ struct b2rt_context {
     void* d_stage_rays[2] = { nullptr, nullptr };
     void* d_stage_out[2] = { nullptr, nullptr };
     uint64_t stage_capacity = 0;
+    // wavefront frame path: two ray queues, hits, per-path state, three rotating queue counters
+    void* d_wf_rays[2] = { nullptr, nullptr };
+    void *d_wf_hits = nullptr, *d_wf_state = nullptr;
+    unsigned long long* d_wf_count = nullptr;
+    uint64_t wf_capacity = 0;
+    void* d_rgba8 = nullptr;            // 8-bit read-back staging
+    uint64_t rgba8_capacity = 0;
     cudaEvent_t ev_in[2] = { nullptr, nullptr }, ev_comp[2] = { nullptr, nullptr }, ev_out[2] = { nullptr, nullptr };
     // options
     int64_t opt_traversal = 0, opt_counters = 0, opt_blocks_per_sm = 0, opt_render_mode = 0, opt_refill_min = 8, opt_leaf_bias = 28;
@@ -250,6 +257,117 @@ int trace_host(b2rt_context* ctx, const b2rt_ray* rays, uint64_t n, void* out, b
     return B2RT_SUCCESS;
 }
 
+int frame_args(b2rt_context* ctx, FrameArgs& a);
+
+constexpr uint32_t WF_MAX_PATHS = 1u << 24;   // paths per wavefront pass (1.9 GB of queues); larger frames take several passes
+
+void free_wavefront(b2rt_context* ctx) {
+    for (int i = 0; i < 2; ++i) { if (ctx->d_wf_rays[i]) cudaFree(ctx->d_wf_rays[i]); ctx->d_wf_rays[i] = nullptr; }
+    if (ctx->d_wf_hits) cudaFree(ctx->d_wf_hits);
+    if (ctx->d_wf_state) cudaFree(ctx->d_wf_state);
+    ctx->d_wf_hits = ctx->d_wf_state = nullptr;
+    ctx->wf_capacity = 0;
+}
+
+int ensure_wavefront(b2rt_context* ctx, uint64_t paths) {
+    if (!ctx->d_wf_count) CK(cudaMalloc(&ctx->d_wf_count, 64));
+    if (ctx->wf_capacity >= paths) return B2RT_SUCCESS;
+    CK(cudaStreamSynchronize(ctx->stream));
+    free_wavefront(ctx);
+    for (int i = 0; i < 2; ++i) CK(cudaMalloc(&ctx->d_wf_rays[i], paths * sizeof(b2rt_ray)));
+    CK(cudaMalloc(&ctx->d_wf_hits, paths * sizeof(b2rt_hit)));
+    CK(cudaMalloc(&ctx->d_wf_state, paths * 32));
+    ctx->wf_capacity = paths;
+    return B2RT_SUCCESS;
+}
+
+// KernelEntry for work items [0, n) of `map` as a wavefront: generate, then per bounce one persistent
+// traversal launch over the live ray queue and one shade/compact launch. Queue lengths stay on the device.
+int render_wavefront(b2rt_context* ctx, const FrameArgs& a, float* d_result, const GidMap& map, uint32_t n) {
+    int st = ensure_wavefront(ctx, n);
+    if (st) return st;
+    cudaStream_t s = ctx->stream;
+    unsigned long long* cnt = ctx->d_wf_count;
+    CK(cudaMemsetAsync(cnt, 0, 3 * sizeof(unsigned long long), s));
+    if (a.bounces <= 0) {
+        // Render() never enters its loop: radiance 0 for every pixel. One shade launch over an all-miss...
+        // simpler and exact: the megakernel does precisely that without tracing.
+        CK(launch_render_mega(ctx->view, a, d_result, map, n, false, ctx->stack_bound, s));
+        ctx->launches += 1;
+        return B2RT_SUCCESS;
+    }
+    CK(launch_wf_generate(a, map, n, ctx->d_wf_rays[0], ctx->d_wf_state, cnt, s));
+    ctx->launches += 1;
+    int grid = ctx->grid_closest;
+    if (ctx->opt_blocks_per_sm > 0) grid = ctx->sm_count * (int)ctx->opt_blocks_per_sm;
+    uint64_t blocks_needed = ((uint64_t)n + trace_block_threads() - 1) / trace_block_threads();
+    if ((uint64_t)grid > blocks_needed) grid = (int)blocks_needed;
+    for (int b = 0; b < a.bounces; ++b) {
+        const int in = b & 1, out = in ^ 1;
+        unsigned long long *n_in = cnt + (b % 3), *n_out = cnt + ((b + 1) % 3), *n_clear = cnt + ((b + 2) % 3);
+        CK(launch_trace_wide(ctx->view, ctx->d_wf_rays[in], n, ctx->d_wf_hits, false, ctx->opt_counters != 0, ctx->stack_bound, grid,
+                             ctx->d_next, ctx->d_counters, (uint32_t)ctx->opt_refill_min, (uint32_t)ctx->opt_leaf_bias, s, n_in));
+        CK(cudaMemsetAsync(n_clear, 0, sizeof(unsigned long long), s));   // the counter the NEXT shade stage appends to
+        CK(launch_wf_shade(ctx->view, a, map, n, ctx->d_wf_rays[in], ctx->d_wf_hits, n_in, ctx->d_wf_rays[out], n_out,
+                           ctx->d_wf_state, d_result, b == a.bounces - 1, s));
+        ctx->launches += 2;
+    }
+    return B2RT_SUCCESS;
+}
+
+// Validates and draws the work items of `map` (n of them) into the bound output buffer.
+int render_items(b2rt_context* ctx, const GidMap& map, uint64_t n) {
+    int st = use_device(ctx);
+    if (st) return st;
+    FrameArgs a;
+    st = frame_args(ctx, a);
+    if (st) return st;
+    st = ensure_scene(ctx);
+    if (st) return st;
+    Buffer* out = find(ctx, ctx->bound[B2RT_ARG_BUFFER_OUT]);
+    if (!out) return fail(ctx, B2RT_INVALID_KERNEL_ARGS, "output buffer (slot 0) is not bound");
+    if (!ctx->view.mats || ctx->view.n_mats == 0) return fail(ctx, B2RT_INVALID_KERNEL_ARGS, "material buffer (slot 3) is not bound");
+    if (n == 0) return B2RT_SUCCESS;
+    if (n > 0xffffffffull || map.band == 0) return fail(ctx, B2RT_INVALID_GLOBAL_WORK_SIZE, "work size out of range");
+    const uint64_t last = map.gid((uint32_t)(n - 1));
+    if (last > 0xfffffffeull || (last + 1) * 16 > out->bytes)
+        return fail(ctx, B2RT_INVALID_GLOBAL_WORK_SIZE, "work items up to gid " + std::to_string(last) + " exceed the output buffer (" +
+                    std::to_string(out->bytes / 16) + " pixels)");
+    float* result = static_cast<float*>(out->d_ptr);
+    if (ctx->opt_traversal == 1 || ctx->opt_render_mode == 1) {
+        CK(launch_render_mega(ctx->view, a, result, map, (uint32_t)n, ctx->opt_traversal == 1, ctx->stack_bound, ctx->stream));
+        ctx->launches += 1;
+        return B2RT_SUCCESS;
+    }
+    // wavefront passes of at most WF_MAX_PATHS work items, each of them a GidMap again
+    auto contiguous = [&](uint64_t first_gid, uint64_t count) -> int {
+        for (uint64_t off = 0; off < count; off += WF_MAX_PATHS) {
+            GidMap sub;
+            const uint32_t m = (uint32_t)std::min<uint64_t>(WF_MAX_PATHS, count - off);
+            sub.begin = first_gid + off; sub.band = sub.stride = m;
+            int rc = render_wavefront(ctx, a, result, sub, m);
+            if (rc) return rc;
+        }
+        return B2RT_SUCCESS;
+    };
+    if (map.band == map.stride) return contiguous(map.begin, n);
+    if (map.band >= WF_MAX_PATHS) {
+        for (uint64_t k = 0; k * map.band < n; ++k) {
+            st = contiguous(map.begin + k * map.stride, std::min<uint64_t>(map.band, n - k * map.band));
+            if (st) return st;
+        }
+        return B2RT_SUCCESS;
+    }
+    const uint64_t per_pass = WF_MAX_PATHS - WF_MAX_PATHS % map.band;      // whole bands
+    for (uint64_t off = 0; off < n; off += per_pass) {
+        GidMap sub = map;
+        sub.begin = map.begin + (off / map.band) * map.stride;
+        st = render_wavefront(ctx, a, result, sub, (uint32_t)std::min<uint64_t>(per_pass, n - off));
+        if (st) return st;
+    }
+    return B2RT_SUCCESS;
+}
+
 int frame_args(b2rt_context* ctx, FrameArgs& a) {
     for (int i = 0; i < B2RT_ARG_COUNT; ++i)
         if (!ctx->arg_set[i]) return fail(ctx, B2RT_INVALID_KERNEL_ARGS, "kernel argument " + std::to_string(i) + " was never set");
@@ -324,6 +442,9 @@ extern "C" void b2rt_destroy(b2rt_context* ctx) {
     }
     if (ctx->d_next) cudaFree(ctx->d_next);
     if (ctx->d_counters) cudaFree(ctx->d_counters);
+    free_wavefront(ctx);
+    if (ctx->d_wf_count) cudaFree(ctx->d_wf_count);
+    if (ctx->d_rgba8) cudaFree(ctx->d_rgba8);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->stream_in) cudaStreamDestroy(ctx->stream_in);
     if (ctx->stream_out) cudaStreamDestroy(ctx->stream_out);
@@ -431,24 +552,23 @@ extern "C" int b2rt_set_arg(b2rt_context* ctx, uint32_t slot, const void* data, 
 // ---- frame path -------------------------------------------------------------------------
 extern "C" int b2rt_execute_range(b2rt_context* ctx, size_t gid_begin, size_t gid_end) {
     if (!ctx) return B2RT_INVALID_CONTEXT;
-    int st = use_device(ctx);
-    if (st) return st;
-    FrameArgs a;
-    st = frame_args(ctx, a);
-    if (st) return st;
-    st = ensure_scene(ctx);
-    if (st) return st;
-    Buffer* out = find(ctx, ctx->bound[B2RT_ARG_BUFFER_OUT]);
-    if (!out) return fail(ctx, B2RT_INVALID_KERNEL_ARGS, "output buffer (slot 0) is not bound");
-    if (!ctx->view.mats || ctx->view.n_mats == 0) return fail(ctx, B2RT_INVALID_KERNEL_ARGS, "material buffer (slot 3) is not bound");
-    if (gid_end < gid_begin || gid_end > 0xffffffffull || gid_end * 16 > out->bytes)
-        return fail(ctx, B2RT_INVALID_GLOBAL_WORK_SIZE, "work range [" + std::to_string(gid_begin) + "," + std::to_string(gid_end) +
-                    ") exceeds the output buffer (" + std::to_string(out->bytes / 16) + " pixels)");
-    if (gid_end == gid_begin) return B2RT_SUCCESS;
-    CK(launch_render_mega(ctx->view, a, static_cast<float*>(out->d_ptr), gid_begin, gid_end, ctx->opt_traversal == 1,
-                          ctx->stack_bound, ctx->stream));
-    ctx->launches += 1;
-    return B2RT_SUCCESS;
+    if (gid_end < gid_begin || gid_end > 0xffffffffull)
+        return fail(ctx, B2RT_INVALID_GLOBAL_WORK_SIZE, "bad work range [" + std::to_string(gid_begin) + "," + std::to_string(gid_end) + ")");
+    const uint64_t n = gid_end - gid_begin;
+    GidMap map;
+    map.begin = gid_begin;
+    map.band = map.stride = (uint32_t)std::max<uint64_t>(n, 1);
+    return render_items(ctx, map, n);
+}
+
+extern "C" int b2rt_execute_bands(b2rt_context* ctx, size_t gid_begin, uint32_t band_pixels, uint32_t stride_pixels, uint32_t n_bands) {
+    if (!ctx) return B2RT_INVALID_CONTEXT;
+    if (band_pixels == 0 || stride_pixels < band_pixels) return fail(ctx, B2RT_INVALID_GLOBAL_WORK_SIZE, "band must be non-empty and stride >= band");
+    GidMap map;
+    map.begin = gid_begin;
+    map.band = band_pixels;
+    map.stride = stride_pixels;
+    return render_items(ctx, map, (uint64_t)band_pixels * n_bands);
 }
 
 extern "C" int b2rt_execute(b2rt_context* ctx, size_t global_work_size) {
@@ -539,6 +659,29 @@ extern "C" int b2rt_read_pixels(b2rt_context* ctx, void* dst, size_t bytes) {
     return b2rt_read_buffer(ctx, ctx->bound[0], dst, bytes);
 }
 
+extern "C" int b2rt_read_pixels_rgba8(b2rt_context* ctx, void* dst, size_t bytes) {
+    if (!ctx) return B2RT_INVALID_CONTEXT;
+    Buffer* b = find(ctx, ctx->bound[0]);
+    if (!b) return fail(ctx, B2RT_INVALID_KERNEL_ARGS, "output buffer (slot 0) is not bound");
+    if (!dst || bytes % 4 || bytes / 4 > b->bytes / 16)
+        return fail(ctx, B2RT_INVALID_VALUE, "8-bit read of " + std::to_string(bytes / 4) + " pixels from a " + std::to_string(b->bytes / 16) + "-pixel image");
+    int st = use_device(ctx);
+    if (st) return st;
+    const uint64_t n = bytes / 4;
+    if (n == 0) return B2RT_SUCCESS;
+    if (ctx->rgba8_capacity < n) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (ctx->d_rgba8) cudaFree(ctx->d_rgba8);
+        ctx->d_rgba8 = nullptr; ctx->rgba8_capacity = 0;
+        CK(cudaMalloc(&ctx->d_rgba8, n * 4));
+        ctx->rgba8_capacity = n;
+    }
+    CK(launch_tonemap_rgba8(b->d_ptr, ctx->d_rgba8, n, ctx->stream));
+    ctx->launches += 1;
+    CK(cudaMemcpyAsync(dst, ctx->d_rgba8, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return B2RT_SUCCESS;
+}
+
 // ---- ray streams -----------------------------------------------------------------------------
 extern "C" int b2rt_trace_closest(b2rt_context* ctx, const b2rt_ray* rays, uint64_t n, b2rt_hit* hits) {
     if (!ctx) return B2RT_INVALID_CONTEXT;
@@ -615,7 +758,7 @@ extern "C" int b2rt_set_option(b2rt_context* ctx, uint32_t option, int64_t value
         case B2RT_OPT_TRAVERSAL: if (value != 0 && value != 1) return fail(ctx, B2RT_INVALID_VALUE, "traversal must be 0 or 1"); ctx->opt_traversal = value; break;
         case B2RT_OPT_COUNTERS: ctx->opt_counters = value ? 1 : 0; break;
         case B2RT_OPT_BLOCKS_PER_SM: if (value < 0 || value > 32) return fail(ctx, B2RT_INVALID_VALUE, "blocks per SM out of range"); ctx->opt_blocks_per_sm = value; break;
-        case B2RT_OPT_RENDER_MODE: ctx->opt_render_mode = value; break;
+        case B2RT_OPT_RENDER_MODE: if (value != 0 && value != 1) return fail(ctx, B2RT_INVALID_VALUE, "render mode must be 0 (wavefront) or 1 (megakernel)"); ctx->opt_render_mode = value; break;
         case B2RT_OPT_LEAF_BIAS: if (value < 1 || value > 512) return fail(ctx, B2RT_INVALID_VALUE, "leaf bias must be 1..512 (sixteenths)"); ctx->opt_leaf_bias = value; break;
         case B2RT_OPT_REFILL_MIN: if (value < 1 || value > 32) return fail(ctx, B2RT_INVALID_VALUE, "refill threshold must be 1..32"); ctx->opt_refill_min = value; break;
         default: return fail(ctx, B2RT_INVALID_VALUE, "unknown option");

@@ -94,6 +94,18 @@ struct SceneView {                 // plain device pointers handed to kernels
     uint32_t one_bits;             // 0x3F800000 as run-time data (see Lane::node_step)
 };
 
+// Which pixels (global ids, gid = y*W + x, kernel_bvh.cl:394-395) a frame launch draws: work item i of
+// the launch is gid = begin + (i / band) * stride + i % band. A contiguous range has stride == band; a
+// multi-GPU rank's share of a frame is every world-th band of `band` pixels.
+struct GidMap {
+    uint64_t begin;
+    uint32_t band, stride;
+#if defined(__CUDACC__)
+    __host__ __device__
+#endif
+    uint64_t gid(uint32_t i) const { return begin + (uint64_t)(i / band) * stride + i % band; }
+};
+
 // Scalar arguments of KernelEntry (kernel_bvh.cl:421-430) as the kernels receive them.
 struct FrameArgs {
     uint32_t width, height, frame_count;

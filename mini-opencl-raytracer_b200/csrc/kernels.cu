@@ -58,8 +58,15 @@ template <bool ANY, bool COUNT, int CAP>
 __global__ void __launch_bounds__(TRACE_BLOCK, B2_MIN_BLOCKS)
 trace_persistent(SceneView s, const RayIn* __restrict__ rays, uint64_t n, void* __restrict__ out,
                  unsigned long long* __restrict__ next, unsigned long long* __restrict__ counters, uint32_t chunk,
-                 uint32_t refill_min, uint32_t leaf_bias) {
+                 uint32_t refill_min, uint32_t leaf_bias, const unsigned long long* __restrict__ n_dev) {
     const unsigned lane = threadIdx.x & 31u;
+    if (n_dev) {
+        // wavefront stages: the ray count is the previous stage's queue counter, never seen by the host
+        n = *n_dev;
+        if (n == 0) return;
+        const uint64_t c = n / ((uint64_t)gridDim.x * (TRACE_BLOCK / 32) * 8u + 1u);
+        chunk = (uint32_t)(c < 32 ? 32 : (c > 512 ? 512 : (c & ~31ull)));
+    }
     Lane<ANY, COUNT, CAP> L;
     uint32_t stack[CAP];
     L.clear();
@@ -214,44 +221,144 @@ camera_rays_kernel(FrameArgs a, uint64_t gid0, uint64_t gid1, RayIn* __restrict_
     p[1] = make_float4(r.dx, r.dy, r.dz, 100000.0f);
 }
 
+// One iteration of Render()'s loop after Intersect() returned `h` for ray `r` (kernel_bvh.cl:356-382).
+// Returns true when the path goes on; (next_o, next_d) are then the arguments of the reference's InitRay for
+// the next ray (direction NOT yet normalised by InitRay). Shared by the megakernel and the wavefront shade
+// stage so that both replay exactly the same arithmetic.
+__device__ __forceinline__ bool path_step(const SceneView& s, const FrameArgs& a, const RayX& r, const HitX& h, V3& radiance,
+                                          V3& beta, uint32_t& seed, V3& next_o, V3& next_d) {
+    if (h.tri == 0xFFFFFFFFu) {
+        float sky = xmul(0.5f, a.sky);
+        radiance = vadd(radiance, vmul(beta, v3(sky, sky, sky)));
+        return false;
+    }
+    V3 o = v3(r.ox, r.oy, r.oz), d = v3(r.dx, r.dy, r.dz);
+    V3 pos = vadd(o, vscale(d, h.t));
+    V3 normal = hit_normal(s.shade, h);
+    uint32_t mtl = s.shade[h.tri].mtl;
+    if (mtl >= s.n_mats) mtl = s.n_mats - 1u;      // the reference reads out of bounds here (usemtl miss)
+    const RefMaterial m = s.mats[mtl];
+    radiance = vadd(radiance, vscale(vmul(beta, ldv(m.emission)), 50.0f));
+    V3 wi = v3(0.0f, 0.0f, 0.0f), wo = vneg(d);
+    float pdf = 0.0f;
+    V3 f = sample_brdf(wo, wi, pdf, normal, m, seed);
+    if (pdf <= 0.0f || pdf != pdf) return false;
+    beta = vmul(beta, vdiv(vscale(f, vdot(wi, normal)), pdf));
+    float lp = light_pixel(o, d, h.t, normal, a.light_type);
+    radiance = vadd(radiance, vmul(vmul(v3(lp, lp, lp), ldv(m.diffuse)), beta));
+    next_o = vadd(pos, vscale(wi, 0.01f));                                // kernel_bvh.cl:380
+    next_d = wi;
+    return true;
+}
+
 template <bool BINARY, int CAP>
 __global__ void __launch_bounds__(128)
-render_mega_kernel(SceneView s, FrameArgs a, float* __restrict__ result, uint64_t gid0, uint64_t gid1) {
-    uint64_t g = gid0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= gid1) return;
+render_mega_kernel(SceneView s, FrameArgs a, float* __restrict__ result, GidMap map, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t g = map.gid(i);
     uint32_t gid = (uint32_t)g;
     uint32_t seed = gid + hash_u32(a.frame_count);                        // kernel_bvh.cl:445
     V3 dir = camera_dir(a, gid, seed);
     RayX r = make_ray(a.pos[0], a.pos[1], a.pos[2], dir.x, dir.y, dir.z);
     V3 radiance = v3(0.0f, 0.0f, 0.0f), beta = v3(1.0f, 1.0f, 1.0f);
-    for (int i = 0; (uint32_t)i < (uint32_t)a.bounces; ++i) {              // Render(), kernel_bvh.cl:349-384
+    for (int b = 0; (uint32_t)b < (uint32_t)a.bounces; ++b) {              // Render(), kernel_bvh.cl:349-384
         HitX h;
         if (BINARY) h = trace_binary<false>(s.tris, s.nodes, r, 100000.0f);
         else h = trace_wide<false, false, CAP>(s.wide, s.leaf, r, 100000.0f, nullptr, nullptr, s.one_bits);
-        if (h.tri == 0xFFFFFFFFu) {
-            float sky = xmul(0.5f, a.sky);
-            radiance = vadd(radiance, vmul(beta, v3(sky, sky, sky)));
-            break;
-        }
-        V3 o = v3(r.ox, r.oy, r.oz), d = v3(r.dx, r.dy, r.dz);
-        V3 pos = vadd(o, vscale(d, h.t));
-        V3 normal = hit_normal(s.shade, h);
-        uint32_t mtl = s.shade[h.tri].mtl;
-        if (mtl >= s.n_mats) mtl = s.n_mats - 1u;      // the reference reads out of bounds here (usemtl miss)
-        const RefMaterial m = s.mats[mtl];
-        radiance = vadd(radiance, vscale(vmul(beta, ldv(m.emission)), 50.0f));
-        V3 wi = v3(0.0f, 0.0f, 0.0f), wo = vneg(d);
-        float pdf = 0.0f;
-        V3 f = sample_brdf(wo, wi, pdf, normal, m, seed);
-        if (pdf <= 0.0f || pdf != pdf) break;
-        beta = vmul(beta, vdiv(vscale(f, vdot(wi, normal)), pdf));
-        float lp = light_pixel(o, d, h.t, normal, a.light_type);
-        radiance = vadd(radiance, vmul(vmul(v3(lp, lp, lp), ldv(m.diffuse)), beta));
-        V3 no = vadd(pos, vscale(wi, 0.01f));
-        r = make_ray(no.x, no.y, no.z, wi.x, wi.y, wi.z);
+        V3 no, nd;
+        if (!path_step(s, a, r, h, radiance, beta, seed, no, nd)) break;
+        r = make_ray(no.x, no.y, no.z, nd.x, nd.y, nd.z);
     }
     radiance = v3(max_cl(radiance.x, 0.0f), max_cl(radiance.y, 0.0f), max_cl(radiance.z, 0.0f));
     accumulate(result + 4 * g, radiance, a.frame_count);
+}
+
+// ---------------------------------------------------------------------------------------
+// Wavefront frame path: generate -> { trace_persistent -> shade } x lightBounces.
+//
+// Path i of the shard keeps {radiance, seed | beta} in state[2i], state[2i+1]; the ray queues hold
+// b2rt_ray records whose (ignored) tmin slot carries i, so only the 32-byte ray is compacted between
+// bounces. Hits are written by trace_persistent at the ray's queue position. Every path runs the same
+// arithmetic in the same order as KernelEntry, so frames are bit-identical to the megakernel's.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+wf_generate_kernel(FrameArgs a, GidMap map, uint32_t n, RayIn* __restrict__ rays, float4* __restrict__ state,
+                   unsigned long long* __restrict__ queue_count) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) *queue_count = n;
+    if (i >= n) return;
+    uint32_t gid = (uint32_t)map.gid(i);
+    uint32_t seed = gid + hash_u32(a.frame_count);                        // kernel_bvh.cl:445
+    V3 d = camera_dir(a, gid, seed);
+    float4* p = reinterpret_cast<float4*>(rays + i);
+    p[0] = make_float4(a.pos[0], a.pos[1], a.pos[2], __uint_as_float(i));
+    p[1] = make_float4(d.x, d.y, d.z, 100000.0f);                         // InitRay normalises again inside the trace stage
+    state[2 * (size_t)i] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(seed));
+    state[2 * (size_t)i + 1] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
+}
+
+__global__ void __launch_bounds__(256)
+wf_shade_kernel(SceneView s, FrameArgs a, GidMap map, const RayIn* __restrict__ rays_in, const float4* __restrict__ hits,
+                const unsigned long long* __restrict__ n_in, RayIn* __restrict__ rays_out,
+                unsigned long long* __restrict__ n_out, float4* __restrict__ state, float* __restrict__ result, int last) {
+    const uint64_t n = *n_in;
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if ((j & ~31ull) >= n) return;                      // whole warp beyond the queue
+    const unsigned lane = threadIdx.x & 31u;
+    bool go_on = false;
+    uint32_t i = 0;
+    RayX r;
+    V3 radiance, beta, no, nd;
+    uint32_t seed = 0;
+    if (j < n) {
+        const float4* p = reinterpret_cast<const float4*>(rays_in + j);
+        float4 q0 = __ldg(p), q1 = __ldg(p + 1);
+        i = __float_as_uint(q0.w);
+        r = make_ray(q0.x, q0.y, q0.z, q1.x, q1.y, q1.z);
+        float4 hv = __ldg(hits + j);
+        HitX h; h.t = hv.x; h.u = hv.y; h.v = hv.z; h.tri = __float_as_uint(hv.w);
+        float4 s0 = state[2 * (size_t)i], s1 = state[2 * (size_t)i + 1];
+        radiance = v3(s0.x, s0.y, s0.z); seed = __float_as_uint(s0.w);
+        beta = v3(s1.x, s1.y, s1.z);
+        go_on = path_step(s, a, r, h, radiance, beta, seed, no, nd) && !last;
+        if (!go_on) {
+            radiance = v3(max_cl(radiance.x, 0.0f), max_cl(radiance.y, 0.0f), max_cl(radiance.z, 0.0f));
+            accumulate(result + 4 * map.gid(i), radiance, a.frame_count);
+        }
+    }
+    // append the surviving rays to the next queue: one atomic per warp
+    const unsigned m = __ballot_sync(FULL, go_on);
+    if (m == 0u) return;
+    unsigned long long base = 0;
+    const unsigned leader = __ffs(m) - 1;
+    if (lane == leader) base = atomicAdd(n_out, (unsigned long long)__popc(m));
+    base = __shfl_sync(FULL, base, leader);
+    if (go_on) {
+        const uint64_t slot = base + __popc(m & ((1u << lane) - 1u));
+        float4* p = reinterpret_cast<float4*>(rays_out + slot);
+        // the queue carries InitRay's arguments; the trace stage (and the next shade stage) normalise them
+        // exactly once, like the megakernel's make_ray(no, wi)
+        p[0] = make_float4(no.x, no.y, no.z, __uint_as_float(i));
+        p[1] = make_float4(nd.x, nd.y, nd.z, 100000.0f);
+        state[2 * (size_t)i] = make_float4(radiance.x, radiance.y, radiance.z, __uint_as_float(seed));
+        state[2 * (size_t)i + 1] = make_float4(beta.x, beta.y, beta.z, 0.0f);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Output path: the accumulation image already holds display-referred (gamma 1/2.2) values
+// (kernel_bvh.cl:449-455) which the reference reads back as 16 B/pixel and re-uploads to GL as GL_RGBA/GL_FLOAT
+// (CLRaytracer.cpp:55,64-67), i.e. GL clamps them to [0,1] for an 8-bit target. This kernel does that clamp and
+// the 8-bit quantisation on the device so that only 4 B/pixel cross PCIe. NaN -> 0 (saturate), alpha = 255.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+tonemap_rgba8_kernel(const float4* __restrict__ image, uchar4* __restrict__ out, uint64_t n) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 p = image[i];
+    out[i] = make_uchar4((unsigned char)__float2uint_rn(__saturatef(p.x) * 255.0f), (unsigned char)__float2uint_rn(__saturatef(p.y) * 255.0f),
+                         (unsigned char)__float2uint_rn(__saturatef(p.z) * 255.0f), 255);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -262,17 +369,17 @@ static int pick_cap(uint32_t bound) { return bound <= 32 ? 32 : (bound <= 64 ? 6
 template <bool ANY, bool COUNT>
 static cudaError_t launch_persistent_cap(int cap, int grid, cudaStream_t st, const SceneView& s, const void* rays,
                                          uint64_t n, void* out, unsigned long long* next, unsigned long long* counters,
-                                         uint32_t refill_min, uint32_t leaf_bias) {
+                                         uint32_t refill_min, uint32_t leaf_bias, const unsigned long long* n_dev) {
     const RayIn* r = static_cast<const RayIn*>(rays);
     // rays per pool top-up: about 1/8 of a warp's fair share, a multiple of 32 in [32, 512]
     uint64_t warps = (uint64_t)grid * (TRACE_BLOCK / 32);
     uint64_t c = n / (warps * 8u + 1u);
     uint32_t chunk = (uint32_t)(c < 32 ? 32 : (c > 512 ? 512 : (c & ~31ull)));
     switch (cap) {
-        case 32: trace_persistent<ANY, COUNT, 32><<<grid, TRACE_BLOCK, 0, st>>>(s, r, n, out, next, counters, chunk, refill_min, leaf_bias); break;
-        case 64: trace_persistent<ANY, COUNT, 64><<<grid, TRACE_BLOCK, 0, st>>>(s, r, n, out, next, counters, chunk, refill_min, leaf_bias); break;
-        case 128: trace_persistent<ANY, COUNT, 128><<<grid, TRACE_BLOCK, 0, st>>>(s, r, n, out, next, counters, chunk, refill_min, leaf_bias); break;
-        case 256: trace_persistent<ANY, COUNT, 256><<<grid, TRACE_BLOCK, 0, st>>>(s, r, n, out, next, counters, chunk, refill_min, leaf_bias); break;
+        case 32: trace_persistent<ANY, COUNT, 32><<<grid, TRACE_BLOCK, 0, st>>>(s, r, n, out, next, counters, chunk, refill_min, leaf_bias, n_dev); break;
+        case 64: trace_persistent<ANY, COUNT, 64><<<grid, TRACE_BLOCK, 0, st>>>(s, r, n, out, next, counters, chunk, refill_min, leaf_bias, n_dev); break;
+        case 128: trace_persistent<ANY, COUNT, 128><<<grid, TRACE_BLOCK, 0, st>>>(s, r, n, out, next, counters, chunk, refill_min, leaf_bias, n_dev); break;
+        case 256: trace_persistent<ANY, COUNT, 256><<<grid, TRACE_BLOCK, 0, st>>>(s, r, n, out, next, counters, chunk, refill_min, leaf_bias, n_dev); break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
@@ -280,17 +387,18 @@ static cudaError_t launch_persistent_cap(int cap, int grid, cudaStream_t st, con
 
 cudaError_t launch_trace_wide(const SceneView& s, const void* d_rays, uint64_t n, void* d_out, bool any, bool count,
                               uint32_t stack_bound, int grid_blocks, unsigned long long* d_next,
-                              unsigned long long* d_counters, uint32_t refill_min, uint32_t leaf_bias, cudaStream_t st) {
+                              unsigned long long* d_counters, uint32_t refill_min, uint32_t leaf_bias, cudaStream_t st,
+                              const unsigned long long* d_n) {
     int cap = pick_cap(stack_bound);
     if (!cap) return cudaErrorInvalidValue;
     cudaError_t e = cudaMemsetAsync(d_next, 0, sizeof(unsigned long long), st);
     if (e != cudaSuccess) return e;
     if (refill_min < 1 || refill_min > 32) refill_min = 8;
     if (leaf_bias < 1 || leaf_bias > 512) leaf_bias = 16;
-    if (any) return count ? launch_persistent_cap<true, true>(cap, grid_blocks, st, s, d_rays, n, d_out, d_next, d_counters, refill_min, leaf_bias)
-                          : launch_persistent_cap<true, false>(cap, grid_blocks, st, s, d_rays, n, d_out, d_next, d_counters, refill_min, leaf_bias);
-    return count ? launch_persistent_cap<false, true>(cap, grid_blocks, st, s, d_rays, n, d_out, d_next, d_counters, refill_min, leaf_bias)
-                 : launch_persistent_cap<false, false>(cap, grid_blocks, st, s, d_rays, n, d_out, d_next, d_counters, refill_min, leaf_bias);
+    if (any) return count ? launch_persistent_cap<true, true>(cap, grid_blocks, st, s, d_rays, n, d_out, d_next, d_counters, refill_min, leaf_bias, d_n)
+                          : launch_persistent_cap<true, false>(cap, grid_blocks, st, s, d_rays, n, d_out, d_next, d_counters, refill_min, leaf_bias, d_n);
+    return count ? launch_persistent_cap<false, true>(cap, grid_blocks, st, s, d_rays, n, d_out, d_next, d_counters, refill_min, leaf_bias, d_n)
+                 : launch_persistent_cap<false, false>(cap, grid_blocks, st, s, d_rays, n, d_out, d_next, d_counters, refill_min, leaf_bias, d_n);
 }
 
 cudaError_t launch_trace_binary(const SceneView& s, const void* d_rays, uint64_t n, void* d_out, bool any, cudaStream_t st) {
@@ -311,20 +419,43 @@ cudaError_t launch_camera_rays(const FrameArgs& a, uint64_t gid0, uint64_t gid1,
     return cudaGetLastError();
 }
 
-cudaError_t launch_render_mega(const SceneView& s, const FrameArgs& a, float* d_result, uint64_t gid0, uint64_t gid1,
+cudaError_t launch_render_mega(const SceneView& s, const FrameArgs& a, float* d_result, const GidMap& map, uint32_t n,
                                bool binary, uint32_t stack_bound, cudaStream_t st) {
-    if (gid1 <= gid0) return cudaSuccess;
-    uint64_t blocks = (gid1 - gid0 + 127) / 128;
-    if (blocks > 0x7fffffffull) return cudaErrorInvalidValue;
-    unsigned g = (unsigned)blocks;
-    if (binary) { render_mega_kernel<true, 32><<<g, 128, 0, st>>>(s, a, d_result, gid0, gid1); return cudaGetLastError(); }
+    if (n == 0) return cudaSuccess;
+    unsigned g = (n + 127u) / 128u;
+    if (binary) { render_mega_kernel<true, 32><<<g, 128, 0, st>>>(s, a, d_result, map, n); return cudaGetLastError(); }
     switch (pick_cap(stack_bound)) {
-        case 32: render_mega_kernel<false, 32><<<g, 128, 0, st>>>(s, a, d_result, gid0, gid1); break;
-        case 64: render_mega_kernel<false, 64><<<g, 128, 0, st>>>(s, a, d_result, gid0, gid1); break;
-        case 128: render_mega_kernel<false, 128><<<g, 128, 0, st>>>(s, a, d_result, gid0, gid1); break;
-        case 256: render_mega_kernel<false, 256><<<g, 128, 0, st>>>(s, a, d_result, gid0, gid1); break;
+        case 32: render_mega_kernel<false, 32><<<g, 128, 0, st>>>(s, a, d_result, map, n); break;
+        case 64: render_mega_kernel<false, 64><<<g, 128, 0, st>>>(s, a, d_result, map, n); break;
+        case 128: render_mega_kernel<false, 128><<<g, 128, 0, st>>>(s, a, d_result, map, n); break;
+        case 256: render_mega_kernel<false, 256><<<g, 128, 0, st>>>(s, a, d_result, map, n); break;
         default: return cudaErrorInvalidValue;
     }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_wf_generate(const FrameArgs& a, const GidMap& map, uint32_t n, void* d_rays, void* d_state,
+                               unsigned long long* d_queue_count, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    wf_generate_kernel<<<(n + 255u) / 256u, 256, 0, st>>>(a, map, n, static_cast<RayIn*>(d_rays), static_cast<float4*>(d_state), d_queue_count);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_wf_shade(const SceneView& s, const FrameArgs& a, const GidMap& map, uint32_t n_max, const void* d_rays_in,
+                            const void* d_hits, const unsigned long long* d_n_in, void* d_rays_out, unsigned long long* d_n_out,
+                            void* d_state, float* d_result, bool last, cudaStream_t st) {
+    if (n_max == 0) return cudaSuccess;
+    wf_shade_kernel<<<(n_max + 255u) / 256u, 256, 0, st>>>(s, a, map, static_cast<const RayIn*>(d_rays_in), static_cast<const float4*>(d_hits),
+                                                           d_n_in, static_cast<RayIn*>(d_rays_out), d_n_out, static_cast<float4*>(d_state),
+                                                           d_result, last ? 1 : 0);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_tonemap_rgba8(const void* d_image, void* d_out, uint64_t n, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    uint64_t blocks = (n + 255) / 256;
+    if (blocks > 0x7fffffffull) return cudaErrorInvalidValue;
+    tonemap_rgba8_kernel<<<(unsigned)blocks, 256, 0, st>>>(static_cast<const float4*>(d_image), static_cast<uchar4*>(d_out), n);
     return cudaGetLastError();
 }
 

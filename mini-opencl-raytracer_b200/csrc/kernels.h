@@ -11,12 +11,22 @@ namespace b2rt {
 // counter (reset by the wrapper), d_counters six 64-bit accumulators (used when count).
 cudaError_t launch_trace_wide(const SceneView& s, const void* d_rays, uint64_t n, void* d_out, bool any, bool count,
                               uint32_t stack_bound, int grid_blocks, unsigned long long* d_next,
-                              unsigned long long* d_counters, uint32_t refill_min, uint32_t leaf_bias, cudaStream_t st);
+                              unsigned long long* d_counters, uint32_t refill_min, uint32_t leaf_bias, cudaStream_t st,
+                              const unsigned long long* d_n = nullptr);   // d_n != null: ray count read on the device (n = upper bound)
 // One thread per ray over the reference-layout arrays (baseline / cross-check).
 cudaError_t launch_trace_binary(const SceneView& s, const void* d_rays, uint64_t n, void* d_out, bool any, cudaStream_t st);
 cudaError_t launch_camera_rays(const FrameArgs& a, uint64_t gid0, uint64_t gid1, void* d_rays, cudaStream_t st);
-cudaError_t launch_render_mega(const SceneView& s, const FrameArgs& a, float* d_result, uint64_t gid0, uint64_t gid1,
+// KernelEntry for the n pixels map.gid(0..n-1), one thread per pixel.
+cudaError_t launch_render_mega(const SceneView& s, const FrameArgs& a, float* d_result, const GidMap& map, uint32_t n,
                                bool binary, uint32_t stack_bound, cudaStream_t st);
+// Wavefront stages of the same frame (kernels.cu): camera rays + path state, and the per-bounce shade/compact stage.
+cudaError_t launch_wf_generate(const FrameArgs& a, const GidMap& map, uint32_t n, void* d_rays, void* d_state,
+                               unsigned long long* d_queue_count, cudaStream_t st);
+cudaError_t launch_wf_shade(const SceneView& s, const FrameArgs& a, const GidMap& map, uint32_t n_max, const void* d_rays_in,
+                            const void* d_hits, const unsigned long long* d_n_in, void* d_rays_out, unsigned long long* d_n_out,
+                            void* d_state, float* d_result, bool last, cudaStream_t st);
+// float4 accumulation image -> clamped 8-bit RGBA (alpha 255), n pixels.
+cudaError_t launch_tonemap_rgba8(const void* d_image, void* d_out, uint64_t n, cudaStream_t st);
 int trace_block_threads();
 cudaError_t trace_occupancy(bool any, uint32_t stack_bound, int* blocks_per_sm);
 

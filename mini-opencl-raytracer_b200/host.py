@@ -33,6 +33,8 @@ def lib():
     vp, u64, cs, sz = C.c_void_p, C.c_uint64, C.c_char_p, C.c_size_t
     sig = {
         "g3d_scene_load": (vp, [cs, C.c_uint, cs, sz]),
+        "g3d_scene_load_cached": (vp, [cs, C.c_uint, cs, C.POINTER(C.c_int), cs, sz]),
+        "g3d_engine_load_scene_cached": (C.c_int, [vp, cs, C.c_uint, cs, C.POINTER(C.c_int), cs, sz]),
         "g3d_scene_from_triangles": (vp, [vp, u64, vp, u64, C.c_uint, cs, sz]),
         "g3d_scene_free": (None, [vp]),
         "g3d_scene_count": (u64, [vp, C.c_int]),
@@ -46,6 +48,8 @@ def lib():
         "g3d_engine_set_shard": (None, [vp, u64, u64]),
         "g3d_engine_render_frame": (C.c_int, [vp, cs, sz]),
         "g3d_engine_pixels": (vp, [vp]),
+        "g3d_engine_set_display_readback": (None, [vp, C.c_int]),
+        "g3d_engine_pixels8": (vp, [vp]),
         "g3d_engine_frame_count": (C.c_uint, [vp]),
         "g3d_engine_context": (vp, [vp]),
         "g3d_engine_scene": (vp, [vp]),
@@ -77,10 +81,21 @@ def _arrays(L, handle):
     return tuple(out)
 
 
-def load_scene(obj_path, max_prims=4):
-    """CLOBJloader::Load + CLBVHScene build (no device): (tris, nodes, mats) as uint8 record arrays."""
+def load_scene(obj_path, max_prims=4, cache=None):
+    """CLOBJloader::Load + CLBVHScene build (no device): (tris, nodes, mats) as uint8 record arrays.
+    cache: None = parse + build like the reference; True = binary scene cache beside the .obj; a path = that cache file.
+    With a cache the return value gains a fourth element: whether the cache was hit."""
     L = lib()
     e = _err()
+    if cache:
+        hit = C.c_int(0)
+        h = L.g3d_scene_load_cached(os.fsencode(obj_path), max_prims, None if cache is True else os.fsencode(cache), C.byref(hit), e, len(e))
+        if not h:
+            raise HostError(e.value.decode())
+        try:
+            return _arrays(L, h) + (bool(hit.value),)
+        finally:
+            L.g3d_scene_free(h)
     h = L.g3d_scene_load(os.fsencode(obj_path), max_prims, e, len(e))
     if not h:
         raise HostError(e.value.decode())
@@ -147,9 +162,17 @@ class Engine:
         if rc:
             raise HostError(e.value.decode())
 
-    def load_scene(self, obj_path, max_prims=4):
+    def load_scene(self, obj_path, max_prims=4, cache=None):
+        """CLEngineBase.cpp:172-179 (new scene, Load, CreateBVHTrees + upload). cache as in host.load_scene; returns
+        True when the binary scene cache was hit."""
         e = _err()
+        if cache:
+            hit = C.c_int(0)
+            self._ck(self._L.g3d_engine_load_scene_cached(self._h, os.fsencode(obj_path), max_prims,
+                                                          None if cache is True else os.fsencode(cache), C.byref(hit), e, len(e)), e)
+            return bool(hit.value)
         self._ck(self._L.g3d_engine_load_scene(self._h, os.fsencode(obj_path), max_prims, e, len(e)), e)
+        return False
 
     def scene_arrays(self):
         h = self._L.g3d_engine_scene(self._h)
@@ -177,6 +200,14 @@ class Engine:
         """View of CLRaytracer::pixels (W*H float3 = 4 floats each), valid until the engine is resized/closed."""
         buf = (C.c_float * (self.width * self.height * 4)).from_address(self._L.g3d_engine_pixels(self._h))
         return np.frombuffer(buf, dtype=np.float32).reshape(-1, 4)
+
+    def set_display_readback(self, on=True):
+        """RenderFrame reads back clamped 8-bit RGBA (pixels8) instead of the float image (pixels)."""
+        self._L.g3d_engine_set_display_readback(self._h, 1 if on else 0)
+
+    def pixels8(self):
+        buf = (C.c_uint8 * (self.width * self.height * 4)).from_address(self._L.g3d_engine_pixels8(self._h))
+        return np.frombuffer(buf, dtype=np.uint8).reshape(-1, 4)
 
     def context_handle(self):
         return self._L.g3d_engine_context(self._h)

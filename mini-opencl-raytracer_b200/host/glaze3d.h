@@ -198,6 +198,12 @@ namespace Glaze3D
         void BuildOnly(unsigned int maxPrimitivesInNode);                 // build + flatten, no upload
         const std::vector<CLLinearBVHNode>& Nodes() const { return m_Nodes; }
         void SetupBuffers();                                              // CLBVHnode.cpp:209-236
+
+        // Binary cache of the post-loader, post-build arrays (scene_cache.cpp): a hit restores m_Triangles (in their
+        // post-build order, i.e. identical hit IDs), the node array, materials and names without parsing or building.
+        static std::string CachePathFor(const char* objPath, unsigned int maxPrimitivesInNode);
+        void SaveCache(const char* cachePath, const char* objPath) const;
+        bool LoadCache(const char* cachePath, const char* objPath, unsigned int maxPrimitivesInNode);   // false = missing / stale / corrupt
     private:
         std::vector<CLLinearBVHNode> m_Nodes;
         CLBuffer m_TriangleBuffer, m_NodeBuffer, m_MaterialBuffer;
@@ -209,6 +215,9 @@ namespace Glaze3D
         CLOBJloader() {}
         void Load(const char* filename, unsigned int maxPrimitivesInNode);            // into eng->render->m_Scene
         static void LoadInto(CLBVHScene& scene, const char* filename);                 // same parser, explicit target
+        // Load + build through the binary cache (cachePath null/empty = beside the .obj). Returns true on a cache hit;
+        // on a miss the scene is parsed and built as usual and the cache is (re)written.
+        static bool LoadCached(CLBVHScene& scene, const char* filename, unsigned int maxPrimitivesInNode, const char* cachePath = nullptr);
     };
 
     // ---- renderer -------------------------------------------------------------------------------
@@ -236,6 +245,11 @@ namespace Glaze3D
         float skyboxIntensity = 1.0f;
 
         std::vector<float3> pixels;
+        // Display read-back (new): when set, RenderFrame fetches the frame as clamped 8-bit RGBA quantised on the device
+        // (4 B/pixel) into pixels8 instead of the 16 B/pixel float image into `pixels` -- what the reference's
+        // glTexImage2D(GL_RGBA, GL_FLOAT) upload of `pixels` displays (CLRaytracer.cpp:64-67).
+        bool displayReadback = false;
+        std::vector<uint32_t> pixels8;
         CLBuffer m_OutputBuffer;
         int device = 0;                 // which GPU Init() opens
         size_t shardBegin = 0, shardEnd = 0;   // [begin,end) of gids this renderer draws; 0,0 = whole frame
@@ -263,6 +277,7 @@ namespace Glaze3D
 
         bool isInitialized = false;
         bool windowClose = false;
+        bool sceneCache = false;                        // renderLoop loads scenes through CLOBJloader::LoadCached
         float FPS = 0;
         std::shared_ptr<CLRaytracer> render = nullptr;
         std::shared_ptr<CLui> ui = nullptr;

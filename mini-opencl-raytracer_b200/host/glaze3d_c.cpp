@@ -33,6 +33,16 @@ extern "C" void* g3d_scene_load(const char* objPath, unsigned maxPrims, char* er
     return new SceneBox{ s };
     G3D_CATCH(nullptr)
 }
+// Same through the binary scene cache; *hit (optional) reports whether the cache was used.
+extern "C" void* g3d_scene_load_cached(const char* objPath, unsigned maxPrims, const char* cachePath, int* hit, char* err, size_t errLen)
+{
+    G3D_TRY
+    auto s = std::make_shared<CLBVHScene>();
+    bool h = CLOBJloader::LoadCached(*s, objPath, maxPrims, cachePath);
+    if (hit) *hit = h ? 1 : 0;
+    return new SceneBox{ s };
+    G3D_CATCH(nullptr)
+}
 extern "C" void* g3d_scene_from_triangles(const void* tris, uint64_t nTris, const void* mats, uint64_t nMats, unsigned maxPrims, char* err, size_t errLen)
 {
     G3D_TRY
@@ -92,6 +102,18 @@ extern "C" int g3d_engine_load_scene(void* engine, const char* objPath, unsigned
     return 0;
     G3D_CATCH(-1)
 }
+extern "C" int g3d_engine_load_scene_cached(void* engine, const char* objPath, unsigned maxPrims, const char* cachePath, int* hit, char* err, size_t errLen)
+{
+    G3D_TRY
+    auto& e = static_cast<EngineBox*>(engine)->engine;
+    eng = e;
+    e->render->m_Scene = std::make_shared<CLBVHScene>();
+    bool h = CLOBJloader::LoadCached(*e->render->m_Scene, objPath, maxPrims, cachePath);
+    if (hit) *hit = h ? 1 : 0;
+    e->render->m_Scene->SetupBuffers();
+    return 0;
+    G3D_CATCH(-1)
+}
 extern "C" int g3d_engine_adopt_scene(void* engine, void* scene, char* err, size_t errLen)
 {
     G3D_TRY
@@ -133,6 +155,8 @@ extern "C" int g3d_engine_render_frame(void* engine, char* err, size_t errLen)
     G3D_CATCH(-1)
 }
 extern "C" const float* g3d_engine_pixels(void* engine) { return &static_cast<EngineBox*>(engine)->engine->render->pixels[0].x; }
+extern "C" void g3d_engine_set_display_readback(void* engine, int on) { static_cast<EngineBox*>(engine)->engine->render->displayReadback = on != 0; }
+extern "C" const uint32_t* g3d_engine_pixels8(void* engine) { return static_cast<EngineBox*>(engine)->engine->render->pixels8.data(); }
 extern "C" unsigned g3d_engine_frame_count(void* engine) { return static_cast<EngineBox*>(engine)->engine->render->m_FrameCount; }
 extern "C" void* g3d_engine_context(void* engine) { return static_cast<EngineBox*>(engine)->engine->render->m_CLContext->GetContext(); }
 extern "C" void* g3d_engine_scene(void* engine)

@@ -77,6 +77,7 @@ namespace Glaze3D
     CLRaytracer::~CLRaytracer()
     {
         if (m_CLContext && !pixels.empty()) b2rt_host_unregister(m_CLContext->GetContext(), pixels.data());
+        if (m_CLContext && !pixels8.empty()) b2rt_host_unregister(m_CLContext->GetContext(), pixels8.data());
     }
 
     void CLRaytracer::Init()
@@ -96,6 +97,9 @@ namespace Glaze3D
         pixels.resize((size_t)w * h);
         // page-lock the read-back target: RenderFrame copies the whole frame into it every frame
         b2rt_host_register(m_CLContext->GetContext(), pixels.data(), pixels.size() * sizeof(float3));
+        if (!pixels8.empty()) b2rt_host_unregister(m_CLContext->GetContext(), pixels8.data());
+        pixels8.assign((size_t)w * h, 0u);
+        b2rt_host_register(m_CLContext->GetContext(), pixels8.data(), pixels8.size() * sizeof(uint32_t));
         int err = 0;
         // Zero-filled by the library: the reference never clears it although frame 1 reads it (kernel_bvh.cl:454).
         m_OutputBuffer = CLBuffer(*m_CLContext, B2RT_MEM_WRITE_ONLY, (size_t)w * h * sizeof(float3), nullptr, &err);
@@ -124,7 +128,12 @@ namespace Glaze3D
             size_t globalWorksize = (size_t)eng->ui->window_width * eng->ui->window_height;
             if (shardEnd > shardBegin) m_CLContext->ExecuteKernelRange(m_RenderKernel, shardBegin, shardEnd);
             else m_CLContext->ExecuteKernel(m_RenderKernel, globalWorksize);
-            m_CLContext->ReadBuffer(m_OutputBuffer, pixels.data(), sizeof(float3) * globalWorksize);
+            if (displayReadback)
+            {
+                int st = b2rt_read_pixels_rgba8(m_CLContext->GetContext(), pixels8.data(), sizeof(uint32_t) * globalWorksize);
+                if (st) throw CLException(std::string("Failed to read display buffer: ") + b2rt_last_error(m_CLContext->GetContext()), st);
+            }
+            else m_CLContext->ReadBuffer(m_OutputBuffer, pixels.data(), sizeof(float3) * globalWorksize);
             m_CLContext->Finish();
         }
         eng->ui->firstRun = false;
@@ -155,9 +164,17 @@ namespace Glaze3D
         if (!isInitialized) init();
         render->Init();
         render->m_Scene = std::make_shared<CLBVHScene>();
-        CLOBJloader loader;
-        loader.Load(scene.c_str(), maxPrimitives);
-        render->m_Scene->CreateBVHTrees(maxPrimitives);
+        if (sceneCache)
+        {
+            CLOBJloader::LoadCached(*render->m_Scene, scene.c_str(), maxPrimitives);
+            render->m_Scene->SetupBuffers();
+        }
+        else
+        {
+            CLOBJloader loader;
+            loader.Load(scene.c_str(), maxPrimitives);
+            render->m_Scene->CreateBVHTrees(maxPrimitives);
+        }
         for (unsigned int f = 0; f < frames && !windowClose; ++f)
         {
             auto t0 = std::chrono::steady_clock::now();

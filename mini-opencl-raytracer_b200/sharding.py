@@ -5,7 +5,7 @@ the tests). Rays/pixels are independent, so the only exchange step is the gather
   ray streams ...... contiguous equal index ranges per rank, no collective (each rank keeps its hits)
   frames ........... `gid = y*W + x` (kernel_bvh.cl:394-395) split into bands of `band_rows` image rows dealt
                      round-robin to the ranks (sky and geometry rows interleave, so ranks finish together);
-                     every rank renders its bands with b2rt_execute_range, then one all_gather of equal
+                     every rank renders its bands with one b2rt_execute_bands, then one all_gather of equal
                      contiguous shards + a de-interleave copy rebuilds the W*H*16-byte image on every rank.
 """
 import torch
@@ -42,6 +42,22 @@ class BandPlan:
             lo = b * self.band_pixels
             out.append((lo, min(lo + self.band_pixels, n)))
         return out
+
+    def band_launch(self, rank):
+        """This rank's share as (gid_begin, band_pixels, stride_pixels, n_full_bands, tail) for b2rt_execute_bands;
+        `tail` is the (gid_begin, gid_end) of a last band clipped by the frame's bottom edge, or None."""
+        ranges = self.gid_ranges(rank)
+        full = [r for r in ranges if r[1] - r[0] == self.band_pixels]
+        tail = [r for r in ranges if r[1] - r[0] != self.band_pixels]
+        return rank * self.band_pixels, self.band_pixels, self.world * self.band_pixels, len(full), (tail[0] if tail else None)
+
+    def render(self, ctx, rank):
+        """Enqueue this rank's bands on a capi.Context: one strided launch sequence (+ one for a clipped last band)."""
+        gid0, band, stride, n_full, tail = self.band_launch(rank)
+        if n_full:
+            ctx.execute_bands(gid0, band, stride, n_full)
+        if tail:
+            ctx.execute_range(*tail)
 
     def pack(self, frame, rank):
         """Own bands of a (W*H, C) frame as one contiguous (rounds*band_pixels, C) shard (zero padded)."""

@@ -192,6 +192,49 @@ def test_cornell_512_frame_and_sharded_execute(product, cornell_ctx, cornell_ref
         cornell_ctx.set_option(product.capi.OPT_TRAVERSAL, 0)
 
 
+def test_wavefront_and_megakernel_frames_are_bit_identical(product, cornell_ctx, bumpy_ctx):
+    """B2RT_OPT_RENDER_MODE: 0 = generate / trace / shade+compact stages, 1 = one thread per pixel. Same arithmetic
+    per path, so every pixel must agree bit for bit, including bounces = 0 / 1 and a rank's strided bands."""
+    W, H = 333, 211                                             # ragged: not a multiple of the warp or band size
+    cam_b = dict(pos=(0.0, -30.0, 4.0), front=(0.0, 1.0, 0.0), up=(0.0, 0.0, 1.0))
+    for ctx, cam, bounces in ((cornell_ctx, {}, 4), (cornell_ctx, {}, 1), (cornell_ctx, {}, 0), (bumpy_ctx, cam_b, 6)):
+        imgs = []
+        for mode in (0, 1):
+            ctx.set_option(product.capi.OPT_RENDER_MODE, mode)
+            imgs.append(_render(ctx, W, H, (1, 2, 3), bounces, **cam))
+        ctx.set_option(product.capi.OPT_RENDER_MODE, 0)
+        assert np.array_equal(imgs[0].view(np.uint32), imgs[1].view(np.uint32)), bounces
+        # the same frames drawn as three ranks' band sets (b2rt_execute_bands) into one buffer
+        plan = product.sharding.BandPlan(W, H, 3, band_rows=8)
+        ctx.resize(W, H)
+        for fc in (1, 2, 3):
+            ctx.set_frame(fc, bounces, **cam)
+            for r in range(3):
+                plan.render(ctx, r)
+        assert np.array_equal(ctx.read_pixels().view(np.uint32), imgs[0].view(np.uint32)), bounces
+    with pytest.raises(product.B2RTError) as e:
+        cornell_ctx.execute_bands(0, W * 8, W * 24, 100)        # runs past the output buffer
+    assert e.value.status == -63                                 # CL_INVALID_GLOBAL_WORK_SIZE
+
+
+def test_display_readback_rgba8(product, cornell_ctx):
+    """b2rt_read_pixels_rgba8: clamp to [0,1] and round(x*255) on the device must equal the same on the float read-back."""
+    W, H = 320, 200
+    img = _render(cornell_ctx, W, H, (1, 2), 4)
+    got = cornell_ctx.read_pixels_rgba8()
+    x = np.clip(np.nan_to_num(img[:, :3], nan=0.0), 0.0, 1.0) * np.float32(255.0)
+    assert np.array_equal(got[:, :3], np.rint(x).astype(np.uint8))
+    assert (got[:, 3] == 255).all() and got[:, :3].max() > 200 and got[:, :3].min() < 50
+    assert np.array_equal(cornell_ctx.read_pixels().view(np.uint32), img.view(np.uint32))          # accumulation image untouched
+    with product.host.Engine(W, H, device=0) as eng:                                                # through CLRaytracer::RenderFrame
+        eng.load_scene(scenes.CORNELL, 4)
+        eng.set_render(frame_count=1, bounces=4)
+        eng.set_display_readback(True)
+        eng.render_frame()
+        eng.render_frame()
+        assert np.array_equal(eng.pixels8(), got)
+
+
 def test_bumpy_frame(bumpy_ctx, bumpy_ref):
     tris, nodes, mats = bumpy_ref
     W, H = 320, 240

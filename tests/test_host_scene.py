@@ -93,3 +93,44 @@ def test_loader_quirks(tmp_scene_dir):
         prod.host.load_scene(base + "3.obj", 4)                                  # the reference reads out of bounds here
     with pytest.raises(prod.host.HostError):
         prod.host.load_scene(os.path.join(tmp_scene_dir, "missing.obj"), 4)
+
+
+def test_scene_cache_round_trip_and_invalidation(tmp_scene_dir):
+    """the binary cache must return byte-identical arrays (same triangle order = same hit IDs) and must
+    be ignored when the source, maxPrimitivesInNode or the file itself changed."""
+    import shutil
+    import time
+    prod = load_product()
+    p, n, f = scenes.displaced_sphere(4, amplitude=0.3)
+    path = scenes.write_obj(os.path.join(tmp_scene_dir, "cache.obj"), p, n, f)
+    plain = prod.host.load_scene(path, 4)
+    t1, n1, m1, hit = prod.host.load_scene(path, 4, cache=True)
+    assert not hit and os.path.exists(path + ".p4.b2rtscn")
+    t2, n2, m2, hit = prod.host.load_scene(path, 4, cache=True)
+    assert hit
+    for a, b in ((plain[0], t2), (plain[1], n2), (plain[2], m2), (t1, t2), (n1, n2)):
+        assert np.array_equal(a, b)                                        # whole records, padding included
+    _same_scene((t2, n2, m2), ol.ref_load_scene(path, 4))
+    # another maxPrimitivesInNode is another cache file; an explicit cache path works too
+    assert not prod.host.load_scene(path, 2, cache=True)[3]
+    other = os.path.join(tmp_scene_dir, "elsewhere.bin")
+    assert not prod.host.load_scene(path, 4, cache=other)[3]
+    assert prod.host.load_scene(path, 4, cache=other)[3]
+    # corrupt payload -> checksum mismatch -> miss (and the cache is rewritten)
+    with open(other, "r+b") as fh:
+        fh.seek(4096)
+        fh.write(b"\xff\xff\xff\xff")
+    assert not prod.host.load_scene(path, 4, cache=other)[3]
+    assert prod.host.load_scene(path, 4, cache=other)[3]
+    # truncated file -> miss
+    with open(other, "r+b") as fh:
+        fh.truncate(os.path.getsize(other) - 16)
+    assert not prod.host.load_scene(path, 4, cache=other)[3]
+    # the source changes (new mtime) -> stale -> miss, and the new content is what comes back
+    time.sleep(0.01)
+    p2 = p * np.float32(1.5)
+    scenes.write_obj(path, p2, n, f)
+    t3, n3, m3, hit = prod.host.load_scene(path, 4, cache=True)
+    assert not hit and not np.array_equal(t3, t2)
+    assert prod.host.load_scene(path, 4, cache=True)[3]
+    shutil.rmtree(tmp_scene_dir, ignore_errors=True)

@@ -71,6 +71,15 @@ def test_band_plan_covers_every_pixel_once():
             for lo, hi in plan.gid_ranges(r):
                 seen[lo:hi] += 1
         assert (seen == 1).all()
+        # the strided description handed to b2rt_execute_bands names exactly the same pixels
+        seen[:] = 0
+        for r in range(world):
+            gid0, band, stride, n_full, tail = plan.band_launch(r)
+            for k in range(n_full):
+                seen[gid0 + k * stride:gid0 + k * stride + band] += 1
+            if tail:
+                seen[tail[0]:tail[1]] += 1
+        assert (seen == 1).all()
         # pack/unpack round trip without a process group
         frames = [torch.zeros((W * H, 4)) for _ in range(world)]
         ref = torch.arange(W * H * 4, dtype=torch.float32).view(-1, 4)
