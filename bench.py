@@ -199,10 +199,16 @@ def run_b200(args, rank, world, local_rank):
     path = ensure_scene(prod, args.frequency, rank, world, barrier)
     t0 = time.time()
     eng = prod.host.Engine(1920, 1080, device=local_rank)        # CLEngineBase + CLRaytracer::Init on this GPU
-    eng.load_scene(path, 4)                                      # CLOBJloader::Load + CreateBVHTrees (+ upload)
+    # CLOBJloader::Load + CreateBVHTrees (+ upload). Rank 0 parses + builds and leaves the binary scene cache behind;
+    # the other ranks wait for it and restore the identical arrays from the cache instead of repeating the build.
+    if rank == 0:
+        cache_hit = eng.load_scene(path, 4, cache=True)
+    barrier()
+    if rank != 0:
+        cache_hit = eng.load_scene(path, 4, cache=True)
     ctx = prod.Context.borrow(eng.context_handle(), local_rank)
     info = ctx.scene_info()
-    log("[bench r%d] scene ready in %.1f s: %s" % (rank, time.time() - t0, info))
+    log("[bench r%d] scene ready in %.1f s (scene cache %s): %s" % (rank, time.time() - t0, "hit" if cache_hit else "miss", info))
 
     n = args.rays
     stream = torch.cuda.Stream()
@@ -264,6 +270,32 @@ def run_b200(args, rank, world, local_rank):
     any_ms, _, _ = timed(lambda: ctx.trace_any_device(d_rays.data_ptr(), n, d_occ.data_ptr(), stream.cuda_stream), args.steps, args.warmup)
     any_value = world * n * args.steps / (any_ms * 1e-3) / 1e6
 
+    # ---- configs[2]: 4K camera rays from outside the mesh -> primary hits -> one diffuse bounce ray per hit; closest-hit on
+    # the (incoherent) bounce batch. Rank 0 only; the batch is built on the host from the product's own primary hits.
+    extra = {}
+    if rank == 0 and not args.skip_frames:
+        W4, H4 = 3840, 2160
+        ctx.set_arg(prod.capi.ARG_WIDTH, np.uint32(W4))           # CreateRay only needs the scalar arguments, no 4K output buffer
+        ctx.set_arg(prod.capi.ARG_HEIGHT, np.uint32(H4))
+        ctx.set_frame(1, 1, pos=(0.0, -25.0, 8.5), front=(0.0, 1.0, -0.3), up=(0.0, 0.0, 1.0))
+        d_cam = torch.empty((W4 * H4, 8), dtype=torch.float32, device="cuda")
+        d_camhits = torch.empty((W4 * H4, 4), dtype=torch.float32, device="cuda")
+        ctx.camera_rays_device(0, W4 * H4, d_cam.data_ptr(), stream.cuda_stream)
+        prim_ms, _, _ = timed(lambda: ctx.trace_closest_device(d_cam.data_ptr(), W4 * H4, d_camhits.data_ptr(), stream.cuda_stream), args.steps, args.warmup)
+        cam_np = d_cam.cpu().numpy().view(prod.RAY_DTYPE).reshape(-1)
+        camhits_np = d_camhits.cpu().numpy().view(prod.HIT_DTYPE).reshape(-1)
+        tris_np, _, _ = eng.scene_arrays()
+        bounce = prod.workloads.diffuse_bounce_rays(cam_np, camhits_np, tris_np, seed=2)
+        del tris_np
+        d_b = torch.from_numpy(bounce.view(np.float32).reshape(-1, 8)).cuda()
+        d_bh = torch.empty((bounce.shape[0], 4), dtype=torch.float32, device="cuda")
+        b_ms, _, _ = timed(lambda: ctx.trace_closest_device(d_b.data_ptr(), bounce.shape[0], d_bh.data_ptr(), stream.cuda_stream), args.steps, args.warmup)
+        extra["diffuse_4k"] = {"workload": "3840x2160 camera rays outside the mesh -> %d primary hits -> one cosine-weighted bounce ray each" % bounce.shape[0],
+                               "primary_mrays_s": W4 * H4 * args.steps / (prim_ms * 1e-3) / 1e6,
+                               "bounce_closest_mrays_s": bounce.shape[0] * args.steps / (b_ms * 1e-3) / 1e6,
+                               "bounce_hit_fraction": float((d_bh[:, 3].view(torch.int32) != -1).float().mean().item())}
+        del d_cam, d_camhits, d_b, d_bh
+
     # ---- end to end through the C ABI with host buffers -----------------------------------------------------------
     def e2e_step():
         ctx.trace_closest(rays_np, hits_np)      # H2D 32 B/ray, traversal, D2H 16 B/ray; synchronous
@@ -283,7 +315,6 @@ def run_b200(args, rank, world, local_rank):
     assert np.array_equal(dev_hits["tri"], hits_np["tri"]), "host-buffer and device-resident paths disagree"
 
     # ---- cornell 1920x1080, 4 bounces, 16 frames accumulated = 16 spp (configs[1]) -------------------------------------
-    extra = {}
     cornell_img = None
     if rank == 0 and not args.skip_frames:
         cornell = os.path.join(ROOT, "tests", "golden", "cornell.obj")
@@ -303,14 +334,44 @@ def run_b200(args, rank, world, local_rank):
                 cctx.execute(1920 * 1080)
             cctx.finish()
             cornell_kernel_ms = (time.perf_counter() - t0) / 16 * 1e3
+            cctx.set_option(prod.capi.OPT_RENDER_MODE, 1)
+            t0 = time.perf_counter()
+            for f in range(33, 49):
+                cctx.set_frame(f, 4)
+                cctx.execute(1920 * 1080)
+            cctx.finish()
+            cornell_mega_ms = (time.perf_counter() - t0) / 16 * 1e3
+            cctx.set_option(prod.capi.OPT_RENDER_MODE, 0)
+            ce.set_display_readback(True)                        # 8-bit RGBA quantised on the device: 8 MB instead of 33 MB per frame
+            ce.render_frame()
+            t0 = time.perf_counter()
+            for _ in range(15):
+                ce.render_frame()
+            display_ms = (time.perf_counter() - t0) / 15 * 1e3
         extra["cornell_1080p_4bounce"] = {"frame_ms": frame_ms, "kernel_only_frame_ms": cornell_kernel_ms, "spp": 16,
-                                          "api": "CLRaytracer::RenderFrame (args + KernelEntry + 33 MB read-back + finish)"}
+                                          "api": "CLRaytracer::RenderFrame (args + KernelEntry + 33 MB read-back + finish)",
+                                          "render_mode": "wavefront (generate, then trace + shade/compact per bounce)",
+                                          "megakernel_kernel_only_frame_ms": cornell_mega_ms,
+                                          "frame_ms_display_readback_rgba8": display_ms}
 
     # ---- N>1: one 4K cornell frame split into row bands over the ranks + NCCL all_gather of the framebuffer ----
     if world > 1 and not args.skip_frames:
         W, H, frames = 3840, 2160, 8
-        cornell = os.path.join(ROOT, "tests", "golden", "cornell.obj")
-        tris_c, nodes_c, mats_c = prod.host.load_scene(cornell, 4)
+        if args.tiled_faces > 0:
+            # BASELINE.json configs[3]: randomly scattered small triangles (edge 0.05-0.5, centres uniform in [-50,50]^3)
+            tiled_path = os.path.join(SCENE_DIR, "scatter_%d.obj" % args.tiled_faces)
+            if rank == 0 and not os.path.exists(tiled_path + ".done"):
+                prod.host.write_scattered_obj(tiled_path, args.tiled_faces, extent=50.0, edge_min=0.05, edge_max=0.5, seed=11)
+                prod.host.load_scene(tiled_path, 4, cache=True)          # leaves the binary cache for the other ranks
+                open(tiled_path + ".done", "w").close()
+            barrier()
+            tris_c, nodes_c, mats_c, _ = prod.host.load_scene(tiled_path, 4, cache=True)
+            tiled_name = "%d scattered triangles (%d CLTriangle) 3840x2160, 4 bounces" % (args.tiled_faces, tris_c.shape[0])
+            tiled_cam = dict(pos=(0.0, -140.0, 0.0), front=(0.0, 1.0, 0.0), up=(0.0, 0.0, 1.0))
+        else:
+            cornell = os.path.join(ROOT, "tests", "golden", "cornell.obj")
+            tris_c, nodes_c, mats_c = prod.host.load_scene(cornell, 4)
+            tiled_name, tiled_cam = "cornell.obj 3840x2160, 4 bounces", {}
         plan = prod.sharding.BandPlan(W, H, world, band_rows=8)
         with prod.Context(local_rank) as fc:
             fc.upload_scene(tris_c, nodes_c, mats_c)
@@ -319,7 +380,7 @@ def run_b200(args, rank, world, local_rank):
             frame = prod.sharding.as_tensor(ptr, nbytes, torch.device("cuda", local_rank)).view(-1, 4)
 
             def tiled_frame(frame_count):
-                fc.set_frame(frame_count, 4)
+                fc.set_frame(frame_count, 4, **tiled_cam)
                 plan.render(fc, rank)                          # b2rt_execute_bands: every world-th 8-row band, one launch sequence
                 fc.finish()
                 return prod.sharding.gather_frame(plan, frame, rank)
@@ -341,10 +402,15 @@ def run_b200(args, rank, world, local_rank):
                     one.upload_scene(tris_c, nodes_c, mats_c)
                     one.resize(W, H)
                     for k in range(1, 2 + frames):
-                        one.set_frame(k, 4)
+                        if k == 1 + frames:                        # time the last of the same frames on ONE GPU
+                            one.finish()
+                            t0 = time.perf_counter()
+                        one.set_frame(k, 4, **tiled_cam)
                         one.execute(W * H)
+                    one.finish()
+                    single_ms = (time.perf_counter() - t0) * 1e3
                     alone = one.read_pixels()
-                extra["tiled_frame_4k"] = {"scene": "cornell.obj 3840x2160, 4 bounces", "ms_per_frame": float(t.item()),
+                extra["tiled_frame_4k"] = {"scene": tiled_name, "ms_per_frame": float(t.item()), "single_gpu_ms_per_frame": single_ms,
                                            "bands": "8-row bands round-robin over %d ranks, ncclAllGather of %.1f MB shards" % (
                                                world, plan.rounds * plan.band_pixels * 16 / 1e6),
                                            "bit_identical_to_single_gpu": bool(np.array_equal(full.cpu().numpy().view(np.uint32), alone.view(np.uint32)))}
@@ -437,6 +503,7 @@ def main():
     ap.add_argument("--frequency", type=int, default=224, help="geodesic frequency: 20*f^2 OBJ faces")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--ref-rays", type=int, default=1 << 19, help="--impl reference: rays per step (bounded sample)")
+    ap.add_argument("--tiled-faces", type=int, default=0, help="N>1 tiled 4K frame: 0 = cornell.obj, else a scattered scene of this many OBJ faces (configs[3]: 10000000)")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-frames", action="store_true")
     args = ap.parse_args()

@@ -30,6 +30,9 @@ static constexpr unsigned FULL = 0xffffffffu;
 #ifndef B2_TOUCH
 #define B2_TOUCH 0
 #endif
+#ifndef B2_STREAM_HINTS
+#define B2_STREAM_HINTS 1
+#endif
 // "Touch" prefetch: an ordinary cached load whose result is never read, issued as soon as the next
 // node / leaf of a lane is known so that the line is (on its way) in L1 when the step runs.
 __device__ __forceinline__ void touch(const void* p) { unsigned d; asm volatile("ld.global.nc.b32 %0, [%1];" : "=r"(d) : "l"(p)); }
@@ -38,8 +41,14 @@ static constexpr int TRACE_BLOCK = 128;
 struct RayIn { float ox, oy, oz, tmin, dx, dy, dz, tmax; };
 
 __device__ __forceinline__ void load_ray(const RayIn* rays, uint64_t i, RayX& r, float& tmax) {
+    // rays are read once and hits written once: streaming (evict-first) accesses keep them from displacing the
+    // BVH, which every ray re-reads, from L2
     const float4* p = reinterpret_cast<const float4*>(rays + i);
+#if B2_STREAM_HINTS
+    float4 a = __ldcs(p), b = __ldcs(p + 1);
+#else
     float4 a = __ldg(p), b = __ldg(p + 1);
+#endif
     r = make_ray(a.x, a.y, a.z, b.x, b.y, b.z);
     tmax = b.w;
 }
@@ -130,8 +139,13 @@ trace_persistent(SceneView s, const RayIn* __restrict__ rays, uint64_t n, void* 
 #endif
         if (COUNT && stepped) ray_steps++;
         if (stepped && L.done()) {
+#if B2_STREAM_HINTS
+            if (ANY) __stcs(reinterpret_cast<uint32_t*>(out) + my_index, (L.h.tri != 0xFFFFFFFFu) ? 1u : 0u);
+            else __stcs(reinterpret_cast<float4*>(out) + my_index, make_float4(L.h.t, L.h.u, L.h.v, __uint_as_float(L.h.tri)));
+#else
             if (ANY) reinterpret_cast<uint32_t*>(out)[my_index] = (L.h.tri != 0xFFFFFFFFu) ? 1u : 0u;
             else reinterpret_cast<float4*>(out)[my_index] = make_float4(L.h.t, L.h.u, L.h.v, __uint_as_float(L.h.tri));
+#endif
             if (COUNT) { traced++; max_ray_steps = max_ray_steps > ray_steps ? max_ray_steps : ray_steps; ray_steps = 0; }
         }
     }

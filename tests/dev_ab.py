@@ -13,20 +13,26 @@ if len(sys.argv) > 1 and sys.argv[1] == "--child":
     import scenes
     from conftest import load_product
     prod = load_product()
-    subdiv, nrays = int(sys.argv[2]), int(sys.argv[3])
+    subdiv, nrays = sys.argv[2], int(sys.argv[3])
     opts = [a.split("=") for a in sys.argv[4:]]
     d = tempfile.mkdtemp()
-    cache = "/tmp/ab_scene_%d.npz" % subdiv
-    if os.path.exists(cache):
+    cache = "/tmp/ab_scene_%s.npz" % subdiv
+    if subdiv.startswith("f"):                      # the bench scene: geodesic frequency, e.g. f224
+        os.makedirs("/tmp/b2rt_scenes", exist_ok=True)
+        path = "/tmp/b2rt_scenes/ico_%s.obj" % subdiv
+        if not os.path.exists(path):
+            prod.host.write_icosphere_obj(path, int(subdiv[1:]), radius=10.0, amplitude=0.08, seed=7)
+        tris, nodes, mats, _ = prod.host.load_scene(path, 4, cache=True)
+    elif os.path.exists(cache):
         z = np.load(cache)
         tris, nodes, mats = z["t"], z["n"], z["m"]
     else:
-        p, n, f = scenes.displaced_sphere(subdiv)
+        p, n, f = scenes.displaced_sphere(int(subdiv))
         tris, nodes, mats = ol.ref_load_scene(scenes.write_obj(os.path.join(d, "s.obj"), p, n, f), 4)
         np.savez(cache, t=tris, n=nodes, m=mats)
     ctx = prod.Context(0)
     ctx.upload_scene(tris, nodes, mats)
-    rays = scenes.shell_rays(nrays, 10.0, seed=1)
+    rays = prod.workloads.shell_rays(nrays, 10.0, seed=1) if subdiv.startswith("f") else scenes.shell_rays(nrays, 10.0, seed=1)
     d_rays = torch.from_numpy(rays.view(np.float32).reshape(-1, 8)).cuda()
     d_hits = torch.empty((nrays, 4), dtype=torch.float32, device="cuda")
     stream = torch.cuda.Stream()

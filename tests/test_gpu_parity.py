@@ -271,3 +271,55 @@ def test_device_resident_stream(product, bumpy_ctx, bumpy_ref):
     st.synchronize()
     got = d_hits.cpu().numpy().view(product.HIT_DTYPE).reshape(-1)
     _check_hits(got, ol.oracle_closest(tris, nodes, rays))
+
+
+def test_config2_incoherent_diffuse_batch(product, bumpy_ctx, bumpy_ref):
+    """BASELINE.json configs[2] at oracle-sized scale: camera rays from outside the mesh -> primary hits -> one
+    cosine-weighted bounce ray per hit (origin pos + wi*0.01, kernel_bvh.cl:380), closest-hit on the bounce batch.
+    The whole chain runs through the product (camera rays on the device, hits through the C ABI)."""
+    import torch
+    tris, nodes, _ = bumpy_ref
+    W, H = 640, 360
+    bumpy_ctx.resize(W, H)
+    bumpy_ctx.set_frame(1, 1, pos=(0.0, -25.0, 8.5), front=(0.0, 1.0, -0.3), up=(0.0, 0.0, 1.0))
+    d = torch.empty((W * H, 8), dtype=torch.float32, device="cuda:0")
+    bumpy_ctx.camera_rays_device(0, W * H, d.data_ptr())
+    bumpy_ctx.finish()
+    cam = d.cpu().numpy().view(product.RAY_DTYPE).reshape(-1)
+    primary = bumpy_ctx.trace_closest(cam)
+    _check_hits(primary, ol.oracle_closest(tris, nodes, cam))
+    assert 0.1 < (primary["tri"] != MISS).mean() < 0.9
+    bounce = product.workloads.diffuse_bounce_rays(cam, primary, tris, seed=71)
+    assert bounce.shape[0] == int((primary["tri"] != MISS).sum())
+    want = ol.oracle_closest(tris, nodes, bounce)
+    _check_hits(bumpy_ctx.trace_closest(bounce), want)
+    assert np.array_equal(bumpy_ctx.trace_any(bounce) != 0, ol.oracle_any(tris, nodes, bounce) != 0)
+
+
+def test_config3_scattered_scene_tiled_frame(product, tmp_scene_dir):
+    """BASELINE.json configs[3] at oracle-sized scale: randomly scattered small triangles, a frame split into row
+    bands over 4 ranks (each rank's bands are ONE b2rt_execute_bands call), PSNR against the oracle and bit-equality
+    with the un-tiled frame; hit IDs on an incoherent stream through the same scene."""
+    path = os.path.join(tmp_scene_dir, "scatter_cfg3.obj")
+    assert product.host.write_scattered_obj(path, 30000, extent=20.0, edge_min=0.3, edge_max=1.5, seed=5) == 30000
+    tris, nodes, mats = product.host.load_scene(path, 4)
+    W, H, world, bounces = 384, 216, 4, 3
+    cam = dict(pos=(0.0, -60.0, 0.0), front=(0.0, 1.0, 0.0), up=(0.0, 0.0, 1.0))
+    want = np.zeros((W * H, 4), dtype=np.float32)
+    for fc in (1, 2):
+        ol.oracle_render(tris, nodes, mats, want, W, H, fc, bounces, **cam)
+    with product.Context(0) as ctx:
+        ctx.upload_scene(tris, nodes, mats)
+        whole = _render(ctx, W, H, (1, 2), bounces, **cam)
+        assert scenes.psnr(whole[:, :3], want[:, :3]) >= 50.0
+        plan = product.sharding.BandPlan(W, H, world, band_rows=8)
+        ctx.resize(W, H)
+        for fc in (1, 2):
+            ctx.set_frame(fc, bounces, **cam)
+            for r in range(world):
+                plan.render(ctx, r)
+        assert np.array_equal(ctx.read_pixels().view(np.uint32), whole.view(np.uint32))
+        rays = scenes.box_rays(200000, (-25, -25, -25), (25, 25, 25), seed=72)
+        got = ctx.trace_closest(rays)
+        _check_hits(got, ol.oracle_closest(tris, nodes, rays))
+        assert 0.2 < (got["tri"] != MISS).mean() < 0.999
