@@ -221,13 +221,15 @@ def run_b200(args, rank, world, local_rank):
     host_hits = torch.empty((n, 4), dtype=torch.float32, pin_memory=True)
     hits_np = host_hits.numpy().view(prod.HIT_DTYPE).reshape(-1)
 
-    def timed(fn, steps, warmup):
-        """W untimed steps, then K steps between barrier+synchronize, per-step CUDA events on the launch stream."""
+    def timed(fn, steps, warmup, collective=True):
+        """W untimed steps, then K steps between barrier+synchronize, per-step CUDA events on the launch stream.
+        collective=False: a measurement only this rank takes (no barrier, no max over ranks)."""
+        sync = barrier if collective else (lambda: None)
         with torch.cuda.stream(stream):
             for _ in range(warmup):
                 fn()
         torch.cuda.synchronize()
-        barrier()
+        sync()
         torch.cuda.synchronize()
         l0 = ctx.launch_count()
         evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
@@ -237,10 +239,10 @@ def run_b200(args, rank, world, local_rank):
                 fn()
                 evs[i + 1].record()
         torch.cuda.synchronize()
-        barrier()
+        sync()
         total_ms = evs[0].elapsed_time(evs[-1])
         per = [evs[i].elapsed_time(evs[i + 1]) for i in range(steps)]
-        if world > 1:
+        if world > 1 and collective:
             t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             total_ms = float(t.item())
@@ -281,7 +283,7 @@ def run_b200(args, rank, world, local_rank):
         d_cam = torch.empty((W4 * H4, 8), dtype=torch.float32, device="cuda")
         d_camhits = torch.empty((W4 * H4, 4), dtype=torch.float32, device="cuda")
         ctx.camera_rays_device(0, W4 * H4, d_cam.data_ptr(), stream.cuda_stream)
-        prim_ms, _, _ = timed(lambda: ctx.trace_closest_device(d_cam.data_ptr(), W4 * H4, d_camhits.data_ptr(), stream.cuda_stream), args.steps, args.warmup)
+        prim_ms, _, _ = timed(lambda: ctx.trace_closest_device(d_cam.data_ptr(), W4 * H4, d_camhits.data_ptr(), stream.cuda_stream), args.steps, args.warmup, collective=False)
         cam_np = d_cam.cpu().numpy().view(prod.RAY_DTYPE).reshape(-1)
         camhits_np = d_camhits.cpu().numpy().view(prod.HIT_DTYPE).reshape(-1)
         tris_np, _, _ = eng.scene_arrays()
@@ -289,7 +291,7 @@ def run_b200(args, rank, world, local_rank):
         del tris_np
         d_b = torch.from_numpy(bounce.view(np.float32).reshape(-1, 8)).cuda()
         d_bh = torch.empty((bounce.shape[0], 4), dtype=torch.float32, device="cuda")
-        b_ms, _, _ = timed(lambda: ctx.trace_closest_device(d_b.data_ptr(), bounce.shape[0], d_bh.data_ptr(), stream.cuda_stream), args.steps, args.warmup)
+        b_ms, _, _ = timed(lambda: ctx.trace_closest_device(d_b.data_ptr(), bounce.shape[0], d_bh.data_ptr(), stream.cuda_stream), args.steps, args.warmup, collective=False)
         extra["diffuse_4k"] = {"workload": "3840x2160 camera rays outside the mesh -> %d primary hits -> one cosine-weighted bounce ray each" % bounce.shape[0],
                                "primary_mrays_s": W4 * H4 * args.steps / (prim_ms * 1e-3) / 1e6,
                                "bounce_closest_mrays_s": bounce.shape[0] * args.steps / (b_ms * 1e-3) / 1e6,
@@ -379,22 +381,27 @@ def run_b200(args, rank, world, local_rank):
             ptr, nbytes = fc.output_device_pointer()
             frame = prod.sharding.as_tensor(ptr, nbytes, torch.device("cuda", local_rank)).view(-1, 4)
 
+            render_s = [0.0]
+
             def tiled_frame(frame_count):
+                t_r = time.perf_counter()
                 fc.set_frame(frame_count, 4, **tiled_cam)
                 plan.render(fc, rank)                          # b2rt_execute_bands: every world-th 8-row band, one launch sequence
                 fc.finish()
+                render_s[0] += time.perf_counter() - t_r
                 return prod.sharding.gather_frame(plan, frame, rank)
 
             tiled_frame(1)
             torch.cuda.synchronize()
             barrier()
+            render_s[0] = 0.0
             t0 = time.perf_counter()
             for f in range(frames):
                 full = tiled_frame(2 + f)
             torch.cuda.synchronize()
             barrier()
             ms = (time.perf_counter() - t0) / frames * 1e3
-            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            t = torch.tensor([ms, render_s[0] / frames * 1e3], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             if rank == 0:
                 # the gathered frame must equal what one GPU renders alone, bit for bit
@@ -410,7 +417,8 @@ def run_b200(args, rank, world, local_rank):
                     one.finish()
                     single_ms = (time.perf_counter() - t0) * 1e3
                     alone = one.read_pixels()
-                extra["tiled_frame_4k"] = {"scene": tiled_name, "ms_per_frame": float(t.item()), "single_gpu_ms_per_frame": single_ms,
+                extra["tiled_frame_4k"] = {"scene": tiled_name, "ms_per_frame": float(t[0].item()), "render_ms_per_frame_max_rank": float(t[1].item()),
+                                           "single_gpu_ms_per_frame": single_ms,
                                            "bands": "8-row bands round-robin over %d ranks, ncclAllGather of %.1f MB shards" % (
                                                world, plan.rounds * plan.band_pixels * 16 / 1e6),
                                            "bit_identical_to_single_gpu": bool(np.array_equal(full.cpu().numpy().view(np.uint32), alone.view(np.uint32)))}

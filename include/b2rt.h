@@ -106,7 +106,8 @@ enum {
     B2RT_OPT_RENDER_MODE = 3,   /* frame path: 0 = wavefront (generate, then trace + shade/compact per bounce; default),
                                    1 = megakernel (one thread per pixel, like KernelEntry); bit-identical frames */
     B2RT_OPT_REFILL_MIN = 4,    /* idle lanes of a warp that trigger a ray refill (1..32, default 8) */
-    B2RT_OPT_LEAF_BIAS = 5      /* weight of the leaf vote in sixteenths (16 = plain majority, default 28) */
+    B2RT_OPT_LEAF_BIAS = 5,     /* weight of the leaf vote in sixteenths (16 = plain majority, default 28) */
+    B2RT_OPT_WAVEFRONT_LANES = 6 /* wavefront frame path: independent wavefronts in flight per launch, 1..4 (0 = by size) */
 };
 
 /* ---- lifetime ---------------------------------------------------------------------- */

@@ -61,11 +61,13 @@ struct b2rt_context {
     void *d_wf_hits = nullptr, *d_wf_state = nullptr;
     unsigned long long* d_wf_count = nullptr;
     uint64_t wf_capacity = 0;
+    cudaStream_t wf_stream[4] = { nullptr, nullptr, nullptr, nullptr };
+    cudaEvent_t ev_wf_fork = nullptr, ev_wf_join[4] = { nullptr, nullptr, nullptr, nullptr };
     void* d_rgba8 = nullptr;            // 8-bit read-back staging
     uint64_t rgba8_capacity = 0;
     cudaEvent_t ev_in[2] = { nullptr, nullptr }, ev_comp[2] = { nullptr, nullptr }, ev_out[2] = { nullptr, nullptr };
     // options
-    int64_t opt_traversal = 0, opt_counters = 0, opt_blocks_per_sm = 0, opt_render_mode = 0, opt_refill_min = 8, opt_leaf_bias = 28;
+    int64_t opt_traversal = 0, opt_counters = 0, opt_blocks_per_sm = 0, opt_render_mode = 0, opt_refill_min = 8, opt_leaf_bias = 28, opt_wf_lanes = 0;
     int grid_closest = 0, grid_any = 0;
     uint64_t launches = 0;
     std::string error;
@@ -259,6 +261,7 @@ int trace_host(b2rt_context* ctx, const b2rt_ray* rays, uint64_t n, void* out, b
 
 int frame_args(b2rt_context* ctx, FrameArgs& a);
 
+constexpr int WF_LANES = 4;                  // concurrent wavefronts per frame launch (b2rt_context::wf_stream)
 constexpr uint32_t WF_MAX_PATHS = 1u << 24;   // paths per wavefront pass (1.9 GB of queues); larger frames take several passes
 
 void free_wavefront(b2rt_context* ctx) {
@@ -270,7 +273,7 @@ void free_wavefront(b2rt_context* ctx) {
 }
 
 int ensure_wavefront(b2rt_context* ctx, uint64_t paths) {
-    if (!ctx->d_wf_count) CK(cudaMalloc(&ctx->d_wf_count, 64));
+    if (!ctx->d_wf_count) CK(cudaMalloc(&ctx->d_wf_count, WF_LANES * 4 * sizeof(unsigned long long)));
     if (ctx->wf_capacity >= paths) return B2RT_SUCCESS;
     CK(cudaStreamSynchronize(ctx->stream));
     free_wavefront(ctx);
@@ -281,22 +284,17 @@ int ensure_wavefront(b2rt_context* ctx, uint64_t paths) {
     return B2RT_SUCCESS;
 }
 
-// KernelEntry for work items [0, n) of `map` as a wavefront: generate, then per bounce one persistent
-// traversal launch over the live ray queue and one shade/compact launch. Queue lengths stay on the device.
-int render_wavefront(b2rt_context* ctx, const FrameArgs& a, float* d_result, const GidMap& map, uint32_t n) {
-    int st = ensure_wavefront(ctx, n);
-    if (st) return st;
-    cudaStream_t s = ctx->stream;
-    unsigned long long* cnt = ctx->d_wf_count;
+// One wavefront over work items [0, n) of `map` on stream `s`, using the queue/state slices that start at path
+// `offset` and the counter block `lane`: generate, then per bounce one persistent traversal launch over the live
+// ray queue and one shade/compact launch. Queue lengths stay on the device.
+int wavefront_lane(b2rt_context* ctx, const FrameArgs& a, float* d_result, const GidMap& map, uint32_t n, int lane, uint64_t offset,
+                   cudaStream_t s) {
+    unsigned long long* cnt = ctx->d_wf_count + 4 * lane;           // three rotating queue counters + the trace kernel's ray counter
+    char* rays[2] = { static_cast<char*>(ctx->d_wf_rays[0]) + offset * sizeof(b2rt_ray), static_cast<char*>(ctx->d_wf_rays[1]) + offset * sizeof(b2rt_ray) };
+    char* hits = static_cast<char*>(ctx->d_wf_hits) + offset * sizeof(b2rt_hit);
+    char* state = static_cast<char*>(ctx->d_wf_state) + offset * 32;
     CK(cudaMemsetAsync(cnt, 0, 3 * sizeof(unsigned long long), s));
-    if (a.bounces <= 0) {
-        // Render() never enters its loop: radiance 0 for every pixel. One shade launch over an all-miss...
-        // simpler and exact: the megakernel does precisely that without tracing.
-        CK(launch_render_mega(ctx->view, a, d_result, map, n, false, ctx->stack_bound, s));
-        ctx->launches += 1;
-        return B2RT_SUCCESS;
-    }
-    CK(launch_wf_generate(a, map, n, ctx->d_wf_rays[0], ctx->d_wf_state, cnt, s));
+    CK(launch_wf_generate(a, map, n, rays[0], state, cnt, s));
     ctx->launches += 1;
     int grid = ctx->grid_closest;
     if (ctx->opt_blocks_per_sm > 0) grid = ctx->sm_count * (int)ctx->opt_blocks_per_sm;
@@ -305,12 +303,46 @@ int render_wavefront(b2rt_context* ctx, const FrameArgs& a, float* d_result, con
     for (int b = 0; b < a.bounces; ++b) {
         const int in = b & 1, out = in ^ 1;
         unsigned long long *n_in = cnt + (b % 3), *n_out = cnt + ((b + 1) % 3), *n_clear = cnt + ((b + 2) % 3);
-        CK(launch_trace_wide(ctx->view, ctx->d_wf_rays[in], n, ctx->d_wf_hits, false, ctx->opt_counters != 0, ctx->stack_bound, grid,
-                             ctx->d_next, ctx->d_counters, (uint32_t)ctx->opt_refill_min, (uint32_t)ctx->opt_leaf_bias, s, n_in));
+        CK(launch_trace_wide(ctx->view, rays[in], n, hits, false, ctx->opt_counters != 0, ctx->stack_bound, grid,
+                             cnt + 3, ctx->d_counters, (uint32_t)ctx->opt_refill_min, (uint32_t)ctx->opt_leaf_bias, s, n_in));
         CK(cudaMemsetAsync(n_clear, 0, sizeof(unsigned long long), s));   // the counter the NEXT shade stage appends to
-        CK(launch_wf_shade(ctx->view, a, map, n, ctx->d_wf_rays[in], ctx->d_wf_hits, n_in, ctx->d_wf_rays[out], n_out,
-                           ctx->d_wf_state, d_result, b == a.bounces - 1, s));
+        CK(launch_wf_shade(ctx->view, a, map, n, rays[in], hits, n_in, rays[out], n_out, state, d_result, b == a.bounces - 1, s));
         ctx->launches += 2;
+    }
+    return B2RT_SUCCESS;
+}
+
+// KernelEntry for work items [0, n) of `map` as up to WF_LANES independent wavefronts on their own streams. A
+// stage's persistent traversal kernel ends with a tail (a few rays need 10-100x the average number of steps, on
+// one lane of one warp); with several wavefronts in flight the next one's CTAs fill the SMs the tail leaves idle.
+int render_wavefront(b2rt_context* ctx, const FrameArgs& a, float* d_result, const GidMap& map, uint32_t n) {
+    int st = ensure_wavefront(ctx, n);
+    if (st) return st;
+    if (a.bounces <= 0) {
+        // Render() never enters its loop: radiance 0 for every pixel, which is what the megakernel does without tracing.
+        CK(launch_render_mega(ctx->view, a, d_result, map, n, false, ctx->stack_bound, ctx->stream));
+        ctx->launches += 1;
+        return B2RT_SUCCESS;
+    }
+    int lanes = ctx->opt_wf_lanes > 0 ? (int)ctx->opt_wf_lanes : (n >= (1u << 20) ? 2 : 1);
+    // cut at band boundaries so that every part is a GidMap again (a contiguous map can be cut anywhere)
+    const bool contiguous = map.band == map.stride;
+    const uint64_t unit = contiguous ? 32 : map.band;
+    uint64_t per = ((uint64_t)n / lanes + unit - 1) / unit * unit;
+    if (per == 0) per = unit;
+    lanes = (int)std::min<uint64_t>(lanes, ((uint64_t)n + per - 1) / per);
+    if (lanes <= 1) return wavefront_lane(ctx, a, d_result, map, n, 0, 0, ctx->stream);
+    CK(cudaEventRecord(ctx->ev_wf_fork, ctx->stream));
+    for (int l = 0; l < lanes; ++l) {
+        const uint64_t off = per * l, m = std::min<uint64_t>(per, n - off);
+        GidMap sub = map;
+        if (contiguous) { sub.begin = map.begin + off; sub.band = sub.stride = (uint32_t)m; }
+        else sub.begin = map.begin + (off / map.band) * map.stride;
+        CK(cudaStreamWaitEvent(ctx->wf_stream[l], ctx->ev_wf_fork, 0));
+        st = wavefront_lane(ctx, a, d_result, sub, (uint32_t)m, l, off, ctx->wf_stream[l]);
+        if (st) return st;
+        CK(cudaEventRecord(ctx->ev_wf_join[l], ctx->wf_stream[l]));
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_wf_join[l], 0));
     }
     return B2RT_SUCCESS;
 }
@@ -420,6 +452,11 @@ extern "C" int b2rt_create(int device_id, b2rt_context** out) {
         if ((e = cudaEventCreateWithFlags(&ctx->ev_comp[i], cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
         if ((e = cudaEventCreateWithFlags(&ctx->ev_out[i], cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
     }
+    for (int i = 0; i < 4; ++i) {
+        if ((e = cudaStreamCreateWithFlags(&ctx->wf_stream[i], cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
+        if ((e = cudaEventCreateWithFlags(&ctx->ev_wf_join[i], cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
+    }
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_wf_fork, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
     if ((e = cudaMalloc(&ctx->d_next, 64)) != cudaSuccess) return bail(e, "cudaMalloc");
     if ((e = cudaMalloc(&ctx->d_counters, 128)) != cudaSuccess) return bail(e, "cudaMalloc");
     if ((e = cudaMemset(ctx->d_counters, 0, 128)) != cudaSuccess) return bail(e, "cudaMemset");
@@ -445,6 +482,11 @@ extern "C" void b2rt_destroy(b2rt_context* ctx) {
     free_wavefront(ctx);
     if (ctx->d_wf_count) cudaFree(ctx->d_wf_count);
     if (ctx->d_rgba8) cudaFree(ctx->d_rgba8);
+    for (int i = 0; i < 4; ++i) {
+        if (ctx->wf_stream[i]) { cudaStreamSynchronize(ctx->wf_stream[i]); cudaStreamDestroy(ctx->wf_stream[i]); }
+        if (ctx->ev_wf_join[i]) cudaEventDestroy(ctx->ev_wf_join[i]);
+    }
+    if (ctx->ev_wf_fork) cudaEventDestroy(ctx->ev_wf_fork);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->stream_in) cudaStreamDestroy(ctx->stream_in);
     if (ctx->stream_out) cudaStreamDestroy(ctx->stream_out);
@@ -759,6 +801,7 @@ extern "C" int b2rt_set_option(b2rt_context* ctx, uint32_t option, int64_t value
         case B2RT_OPT_COUNTERS: ctx->opt_counters = value ? 1 : 0; break;
         case B2RT_OPT_BLOCKS_PER_SM: if (value < 0 || value > 32) return fail(ctx, B2RT_INVALID_VALUE, "blocks per SM out of range"); ctx->opt_blocks_per_sm = value; break;
         case B2RT_OPT_RENDER_MODE: if (value != 0 && value != 1) return fail(ctx, B2RT_INVALID_VALUE, "render mode must be 0 (wavefront) or 1 (megakernel)"); ctx->opt_render_mode = value; break;
+        case B2RT_OPT_WAVEFRONT_LANES: if (value < 0 || value > 4) return fail(ctx, B2RT_INVALID_VALUE, "wavefront lanes must be 0 (auto) .. 4"); ctx->opt_wf_lanes = value; break;
         case B2RT_OPT_LEAF_BIAS: if (value < 1 || value > 512) return fail(ctx, B2RT_INVALID_VALUE, "leaf bias must be 1..512 (sixteenths)"); ctx->opt_leaf_bias = value; break;
         case B2RT_OPT_REFILL_MIN: if (value < 1 || value > 32) return fail(ctx, B2RT_INVALID_VALUE, "refill threshold must be 1..32"); ctx->opt_refill_min = value; break;
         default: return fail(ctx, B2RT_INVALID_VALUE, "unknown option");

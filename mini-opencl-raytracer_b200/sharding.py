@@ -60,11 +60,18 @@ class BandPlan:
             ctx.execute_range(*tail)
 
     def pack(self, frame, rank):
-        """Own bands of a (W*H, C) frame as one contiguous (rounds*band_pixels, C) shard (zero padded)."""
+        """Own bands of a (W*H, C) frame as one contiguous (rounds*band_pixels, C) shard (zero padded). The whole
+        bands are one strided copy (every world-th band of the frame), only a clipped last band is copied apart."""
         c = frame.shape[1]
         shard = torch.zeros((self.rounds * self.band_pixels, c), dtype=frame.dtype, device=frame.device)
+        full = self.height // self.band_rows                      # bands not clipped by the bottom edge
+        mine = len(range(rank, full, self.world))
+        if mine:
+            src = frame[: full * self.band_pixels].view(full, self.band_pixels, c)[rank::self.world]
+            shard[: mine * self.band_pixels].view(mine, self.band_pixels, c).copy_(src)
         for i, (lo, hi) in enumerate(self.gid_ranges(rank)):
-            shard[i * self.band_pixels:i * self.band_pixels + (hi - lo)] = frame[lo:hi]
+            if i >= mine:
+                shard[i * self.band_pixels:i * self.band_pixels + (hi - lo)] = frame[lo:hi]
         return shard
 
     def unpack(self, gathered):

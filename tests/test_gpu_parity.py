@@ -204,6 +204,11 @@ def test_wavefront_and_megakernel_frames_are_bit_identical(product, cornell_ctx,
             imgs.append(_render(ctx, W, H, (1, 2, 3), bounces, **cam))
         ctx.set_option(product.capi.OPT_RENDER_MODE, 0)
         assert np.array_equal(imgs[0].view(np.uint32), imgs[1].view(np.uint32)), bounces
+        for lanes in (2, 3, 4):                                  # several wavefronts in flight on their own streams
+            ctx.set_option(product.capi.OPT_WAVEFRONT_LANES, lanes)
+            again = _render(ctx, W, H, (1, 2, 3), bounces, **cam)
+            assert np.array_equal(again.view(np.uint32), imgs[0].view(np.uint32)), (bounces, lanes)
+        ctx.set_option(product.capi.OPT_WAVEFRONT_LANES, 4)      # also under the strided band launches below
         # the same frames drawn as three ranks' band sets (b2rt_execute_bands) into one buffer
         plan = product.sharding.BandPlan(W, H, 3, band_rows=8)
         ctx.resize(W, H)
@@ -212,6 +217,7 @@ def test_wavefront_and_megakernel_frames_are_bit_identical(product, cornell_ctx,
             for r in range(3):
                 plan.render(ctx, r)
         assert np.array_equal(ctx.read_pixels().view(np.uint32), imgs[0].view(np.uint32)), bounces
+        ctx.set_option(product.capi.OPT_WAVEFRONT_LANES, 0)
     with pytest.raises(product.B2RTError) as e:
         cornell_ctx.execute_bands(0, W * 8, W * 24, 100)        # runs past the output buffer
     assert e.value.status == -63                                 # CL_INVALID_GLOBAL_WORK_SIZE
