@@ -24,6 +24,9 @@
 #pragma once
 #include "b2rt_types.h"
 
+#ifndef B2_LEAF_QUEUE
+#define B2_LEAF_QUEUE 2        // leaves a lane may hold back while it walks on (speculation depth)
+#endif
 #if defined(__CUDACC__)
 #define B2_HD __device__ __forceinline__
 #else
@@ -304,6 +307,9 @@ struct Lane {
     HitX h;
     uint32_t cur;          // wide node to test next, a leaf waiting for a queue slot, or REF_EMPTY
     uint32_t leaf0, leaf1; // queued leaves, leaf0 first
+#if B2_LEAF_QUEUE == 3
+    uint32_t leaf2;
+#endif
     uint32_t top;          // most recently pushed child reference, kept in a register (REF_EMPTY = stack empty)
     int sp;                // entries below `top`, in the caller's local array
     bool overflow;
@@ -313,8 +319,16 @@ struct Lane {
         r = ray;
         h.t = tmax; h.u = 0.0f; h.v = 0.0f; h.tri = 0xFFFFFFFFu;
         cur = 0; leaf0 = leaf1 = top = REF_EMPTY; sp = 0; overflow = false;
+#if B2_LEAF_QUEUE == 3
+        leaf2 = REF_EMPTY;
+#endif
     }
-    B2_HD void clear() { cur = leaf0 = leaf1 = top = REF_EMPTY; sp = 0; }
+    B2_HD void clear() {
+        cur = leaf0 = leaf1 = top = REF_EMPTY; sp = 0;
+#if B2_LEAF_QUEUE == 3
+        leaf2 = REF_EMPTY;
+#endif
+    }
     B2_HD bool done() const { return cur == REF_EMPTY && leaf0 == REF_EMPTY; }
     B2_HD bool wants_node() const { return cur != REF_EMPTY && !(cur & REF_LEAF_BIT); }
     B2_HD bool wants_leaf() const { return leaf0 != REF_EMPTY; }
@@ -332,10 +346,17 @@ struct Lane {
     }
     // Move leaves from `cur` into the queue while there is room.
     B2_HD void settle(const uint32_t* stack) {
+#if B2_LEAF_QUEUE == 3
+        while (cur != REF_EMPTY && (cur & REF_LEAF_BIT) && leaf2 == REF_EMPTY) {
+            if (leaf0 == REF_EMPTY) leaf0 = cur; else if (leaf1 == REF_EMPTY) leaf1 = cur; else leaf2 = cur;
+            cur = pop(stack);
+        }
+#else
         while (cur != REF_EMPTY && (cur & REF_LEAF_BIT) && leaf1 == REF_EMPTY) {
             if (leaf0 == REF_EMPTY) leaf0 = cur; else leaf1 = cur;
             cur = pop(stack);
         }
+#endif
     }
     // `one` must be 0x3F800000, passed as run-time data: held in one register it lets the constant
     // byte selectors of B2_PLANE_V be instruction immediates (ptxas otherwise keeps four selector registers).
@@ -358,7 +379,11 @@ struct Lane {
     // box test of the reference fails).
     B2_HD bool leaf_step(const U4* leaf, const uint32_t* stack) {
         bool got = visit_leaf<COUNT>(leaf, leaf0 & ~REF_LEAF_BIT, r, h, COUNT ? &tc : nullptr);
+#if B2_LEAF_QUEUE == 3
+        leaf0 = leaf1; leaf1 = leaf2; leaf2 = REF_EMPTY;
+#else
         leaf0 = leaf1; leaf1 = REF_EMPTY;
+#endif
         if ((ANY && got) || h.t < 0.0f) { clear(); return true; }
         settle(stack);
         return false;
