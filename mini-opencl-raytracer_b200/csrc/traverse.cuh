@@ -61,6 +61,7 @@ B2_HD uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) { uint32_t d; asm("prm
 B2_HD uint32_t top_bit(uint32_t v) { return 31u - (uint32_t)__clz((int)v); }
 B2_HD uint32_t byte_of(uint32_t w, uint32_t i) { return __byte_perm(w, 0, 0x4440u + i); }
 B2_HD uint32_t popc32(uint32_t v) { return __popc(v); }
+B2_HD uint32_t funnel_l(uint32_t lo, uint32_t hi, uint32_t n) { return __funnelshift_l(lo, hi, n); }
 B2_HD float bits2f(uint32_t v) { return __uint_as_float(v); }
 B2_HD uint32_t f2bits(float v) { return __float_as_uint(v); }
 B2_HD U4 ld128(const U4* p) {
@@ -97,6 +98,7 @@ B2_HD uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {   // PTX prmt.b32, d
 B2_HD uint32_t top_bit(uint32_t v) { return 31u - (uint32_t)__builtin_clz(v); }
 B2_HD uint32_t byte_of(uint32_t w, uint32_t i) { return (w >> (8 * i)) & 0xffu; }
 B2_HD uint32_t popc32(uint32_t v) { return (uint32_t)__builtin_popcount(v); }
+B2_HD uint32_t funnel_l(uint32_t lo, uint32_t hi, uint32_t n) { return (uint32_t)(((((uint64_t)hi) << 32) | lo) << (n & 31u) >> 32); }
 B2_HD float bits2f(uint32_t v) { float f; std::memcpy(&f, &v, 4); return f; }
 B2_HD uint32_t f2bits(float v) { uint32_t u; std::memcpy(&u, &v, 4); return u; }
 B2_HD U4 ld128(const U4* p) { return *p; }
@@ -276,20 +278,27 @@ B2_HD WideHits test_wide_node(const U4* wide, uint32_t index, const RayX& r, flo
         near_lo[a] = prmt(na, nb, sel_lo); near_hi[a] = prmt(na, nb, sel_hi);
         far_lo[a] = prmt(fa, fb, sel_lo);  far_hi[a] = prmt(fa, fb, sel_hi);
     }
-    uint32_t mask = 0;
+    // Child k overlaps [0, best] iff F >= N, F >= 0 and best >= N with N = max(near planes), F = min(far planes)
+    // (NaN planes drop out of fmaxf/fminf). All three are sign tests: the OR of the sign bits of F - N, F and
+    // best - N says "cull", and one funnel shift per child collects it -- the two subtractions run on the FMA
+    // pipe, which is idle next to the ALU pipe that PRMT/FMNMX keep busy. A NaN difference (inf - inf) has a
+    // clear sign bit: the child is visited, which is always allowed (the exact leaf gate decides).
+    uint32_t cull = 0;
 #pragma unroll
-    for (uint32_t k = 0; k < 8; ++k) {
-        const uint32_t i = k & 3u;
+    for (int kk = 7; kk >= 0; --kk) {
+        const uint32_t k = (uint32_t)kk, i = k & 3u;
         float n0 = fma_rn(B2_PLANE_V(k < 4 ? near_lo[0] : near_hi[0], i), K[0], Bn[0]);
         float n1 = fma_rn(B2_PLANE_V(k < 4 ? near_lo[1] : near_hi[1], i), K[1], Bn[1]);
         float n2 = fma_rn(B2_PLANE_V(k < 4 ? near_lo[2] : near_hi[2], i), K[2], Bn[2]);
         float f0 = fma_rn(B2_PLANE_V(k < 4 ? far_lo[0] : far_hi[0], i), K[0], Bf[0]);
         float f1 = fma_rn(B2_PLANE_V(k < 4 ? far_lo[1] : far_hi[1], i), K[1], Bf[1]);
         float f2 = fma_rn(B2_PLANE_V(k < 4 ? far_lo[2] : far_hi[2], i), K[2], Bf[2]);
-        float t0 = max_nn(max_nn(max_nn(n0, n1), n2), 0.0f);
-        float t1 = min_nn(min_nn(min_nn(f0, f1), f2), best);
-        if (t1 >= t0) mask |= 1u << k;
+        const float N = max_nn(max_nn(n0, n1), n2);
+        const float F = min_nn(min_nn(f0, f1), f2);
+        const uint32_t bad = f2bits(xsub(F, N)) | f2bits(F) | f2bits(xsub(best, N));
+        cull = funnel_l(bad, cull, 1);                      // cull = cull << 1 | sign(bad): child 0 ends up in bit 0
     }
+    const uint32_t mask = ~cull & 0xffu;
     out.mask = mask & ((1u << (w0.w >> 24)) - 1u);
     return out;
 }
