@@ -15,12 +15,17 @@
 //     g++ evaluates those arguments right to left, so the SECOND child's subtree is built -- and its
 //     triangles appended to the ordered array -- before the first child's. Node numbering is still
 //     pre-order with the first child at index+1 (CLBVHnode.cpp:161-183).
-// Here the build writes an index-linked node pool with an explicit work stack (no per-node `new`,
-// no recursion), then numbers it in pre-order.
+// Here the build writes an index-linked node pool with explicit work stacks (no per-node `new`, no recursion),
+// builds independent subtrees of large scenes on a team of threads (B2RT_BUILD_THREADS, default all cores; the
+// result does not depend on the thread count), then replays the reference's leaf emission order and numbers the
+// nodes in pre-order.
 #include <algorithm>
+#include <atomic>
 #include <cassert>
 #include <cmath>
+#include <cstdlib>
 #include <limits>
+#include <thread>
 #include "glaze3d.h"
 
 namespace Glaze3D
@@ -82,27 +87,28 @@ namespace Glaze3D
                 return b;
             }
 
-            void makeLeaf(BuildNode& n, unsigned int start, unsigned int end, const CLBounds3& bounds)
+            // A leaf remembers its range of `info`; the triangle order is emitted afterwards by emitOrder().
+            static void makeLeaf(BuildNode& n, unsigned int start, unsigned int end, const CLBounds3& bounds)
             {
-                n.firstPrim = (unsigned int)order.size();
+                n.firstPrim = start;
                 n.nPrims = end - start;
                 n.bounds = bounds;
                 n.child[0] = n.child[1] = -1;
-                for (unsigned int i = start; i < end; ++i) order.push_back(info[i].prim);
             }
 
-            // Decides what node `id` over info[start,end) is. Returns true and sets mid/dim for an interior node.
-            bool split(int id, unsigned int start, unsigned int end, unsigned int& mid, unsigned int& dim)
+            // Decides what `node` over info[start,end) is. Returns true and sets mid/dim for an interior node.
+            // Touches only `node` and info[start,end), so disjoint ranges can be split concurrently.
+            bool split(BuildNode& node, unsigned int start, unsigned int end, unsigned int& mid, unsigned int& dim)
             {
                 CLBounds3 bounds;
                 for (unsigned int i = start; i < end; ++i) bounds = Union(bounds, info[i].bounds);
                 const unsigned int n = end - start;
-                if (n == 1) { makeLeaf(pool[id], start, end, bounds); return false; }
+                if (n == 1) { makeLeaf(node, start, end, bounds); return false; }
                 CLBounds3 cb;
                 for (unsigned int i = start; i < end; ++i) cb = Union(cb, info[i].centroid);
                 dim = cb.MaximumExtent();
                 mid = (start + end) / 2;
-                if (cb.max[dim] == cb.min[dim]) { makeLeaf(pool[id], start, end, bounds); return false; }
+                if (cb.max[dim] == cb.min[dim]) { makeLeaf(node, start, end, bounds); return false; }
                 if (n <= 2)
                 {
                     const unsigned int d = dim;
@@ -131,7 +137,7 @@ namespace Glaze3D
                     unsigned int bestBucket = 0;
                     for (unsigned int i = 1; i < kBuckets - 1; ++i)
                         if (cost[i] < best) { best = cost[i]; bestBucket = i; }
-                    if (!(n > maxPrims || best < float(n))) { makeLeaf(pool[id], start, end, bounds); return false; }
+                    if (!(n > maxPrims || best < float(n))) { makeLeaf(node, start, end, bounds); return false; }
                     const CLBounds3 cbv = cb;
                     const unsigned int d = dim;
                     PrimInfo* p = std::partition(&info[start], &info[end - 1] + 1, [=](const PrimInfo& pi) {
@@ -144,33 +150,122 @@ namespace Glaze3D
                 return true;
             }
 
-            int build(unsigned int nTris)
+            struct Task { int id; unsigned int start, end; };
+
+            // Splits `t` inside `nodes`; on an interior node appends the two children and returns their tasks.
+            bool expand(std::vector<BuildNode>& nodes, const Task& t, Task& first, Task& second)
             {
-                struct Task { int id; unsigned int start, end; };
+                unsigned int mid = 0, dim = 0;
+                BuildNode node = BuildNode();
+                if (!split(node, t.start, t.end, mid, dim)) { nodes[t.id] = node; return false; }
+                int c = (int)nodes.size();
+                nodes.push_back(BuildNode());
+                nodes.push_back(BuildNode());
+                BuildNode& n = nodes[t.id];
+                n.child[0] = c; n.child[1] = c + 1; n.axis = (int)dim; n.nPrims = 0; n.firstPrim = 0;
+                first = Task{ c, t.start, mid };
+                second = Task{ c + 1, mid, t.end };
+                return true;
+            }
+
+            // Whole subtree of `root` (a task whose node already exists in `nodes`), depth-first.
+            void buildSubtree(std::vector<BuildNode>& nodes, const Task& root)
+            {
                 std::vector<Task> todo;
-                pool.reserve(2 * (size_t)nTris);
-                order.reserve(nTris);
-                pool.push_back(BuildNode());
-                todo.push_back(Task{ 0, 0u, nTris });
+                todo.push_back(root);
                 while (!todo.empty())
                 {
-                    Task t = todo.back();
+                    Task t = todo.back(), a, b;
                     todo.pop_back();
-                    unsigned int mid = 0, dim = 0;
-                    if (!split(t.id, t.start, t.end, mid, dim)) continue;
-                    int first = (int)pool.size();
-                    pool.push_back(BuildNode());
-                    pool.push_back(BuildNode());
-                    BuildNode& n = pool[t.id];
-                    n.child[0] = first; n.child[1] = first + 1; n.axis = (int)dim; n.nPrims = 0; n.firstPrim = 0;
-                    // LIFO: the second child's whole subtree is processed before the first child's (see header).
-                    todo.push_back(Task{ first, t.start, mid });
-                    todo.push_back(Task{ first + 1, mid, t.end });
+                    if (!expand(nodes, t, a, b)) continue;
+                    todo.push_back(a);
+                    todo.push_back(b);
+                }
+            }
+
+            // The topology and every leaf's triangle SET are independent of the order in which subtrees are built
+            // (a split only looks at its own range of `info`), so large scenes are built by a team of threads:
+            // the top of the tree is opened sequentially until there are enough independent subtrees, these are
+            // built into thread-private pools and spliced behind their roots. What the reference's single recursion
+            // fixes beyond the topology -- the order in which leaves hand their triangles to the ordered array -- is
+            // replayed afterwards by emitOrder().
+            int build(unsigned int nTris, unsigned int threads)
+            {
+                pool.reserve(2 * (size_t)nTris);
+                pool.push_back(BuildNode());
+                std::vector<Task> frontier;
+                frontier.push_back(Task{ 0, 0u, nTris });
+                const size_t wanted = threads > 1 && nTris >= (1u << 16) ? (size_t)threads * 8 : 1;
+                while (frontier.size() < wanted)
+                {
+                    // open the largest pending range
+                    size_t big = 0;
+                    for (size_t i = 1; i < frontier.size(); ++i)
+                        if (frontier[i].end - frontier[i].start > frontier[big].end - frontier[big].start) big = i;
+                    if (frontier[big].end - frontier[big].start < 4096) break;
+                    Task t = frontier[big], a, b;
+                    frontier.erase(frontier.begin() + big);
+                    if (expand(pool, t, a, b)) { frontier.push_back(a); frontier.push_back(b); }
+                    if (frontier.empty()) break;
+                }
+                if (wanted == 1 || frontier.size() < 2)
+                {
+                    for (const Task& t : frontier) buildSubtree(pool, t);
+                }
+                else
+                {
+                    std::sort(frontier.begin(), frontier.end(), [](const Task& x, const Task& y) { return x.end - x.start > y.end - y.start; });
+                    std::vector<std::vector<BuildNode>> local(frontier.size());
+                    std::atomic<size_t> next(0);
+                    auto work = [&]() {
+                        for (size_t i = next.fetch_add(1); i < frontier.size(); i = next.fetch_add(1))
+                        {
+                            local[i].reserve(2 * (size_t)(frontier[i].end - frontier[i].start));
+                            local[i].push_back(BuildNode());
+                            buildSubtree(local[i], Task{ 0, frontier[i].start, frontier[i].end });
+                        }
+                    };
+                    std::vector<std::thread> team;
+                    for (unsigned int k = 1; k < threads; ++k) team.emplace_back(work);
+                    work();
+                    for (std::thread& th : team) th.join();
+                    // splice: local node 0 becomes the frontier node, local node j > 0 becomes pool[base + j - 1]
+                    for (size_t i = 0; i < frontier.size(); ++i)
+                    {
+                        const int base = (int)pool.size();
+                        auto remap = [&](BuildNode n) { if (n.child[0] >= 0) { n.child[0] += base - 1; n.child[1] += base - 1; } return n; };
+                        pool[frontier[i].id] = remap(local[i][0]);
+                        for (size_t j = 1; j < local[i].size(); ++j) pool.push_back(remap(local[i][j]));
+                        std::vector<BuildNode>().swap(local[i]);
+                    }
                 }
                 // interior bounds = union of the children, bottom-up (children always have larger pool ids)
                 for (size_t i = pool.size(); i-- > 0;)
                     if (pool[i].child[0] >= 0) pool[i].bounds = Union(pool[pool[i].child[0]].bounds, pool[pool[i].child[1]].bounds);
+                emitOrder(nTris);
                 return 0;
+            }
+
+            // The reference appends a leaf's triangles to the ordered array when its recursion reaches that leaf, and
+            // it recurses into the SECOND child first (see the header): replay exactly that walk.
+            void emitOrder(unsigned int nTris)
+            {
+                order.clear();
+                order.reserve(nTris);
+                std::vector<int> todo;
+                todo.push_back(0);
+                while (!todo.empty())
+                {
+                    BuildNode& n = pool[todo.back()];
+                    todo.pop_back();
+                    if (n.child[0] < 0)
+                    {
+                        const unsigned int start = n.firstPrim;
+                        n.firstPrim = (unsigned int)order.size();
+                        for (unsigned int i = start; i < start + n.nPrims; ++i) order.push_back(info[i].prim);
+                    }
+                    else { todo.push_back(n.child[0]); todo.push_back(n.child[1]); }   // LIFO: second child first
+                }
             }
         };
     }
@@ -189,7 +284,9 @@ namespace Glaze3D
             CLBounds3 tb = m_Triangles[i].GetBounds();
             b.info[i] = PrimInfo{ i, tb, tb.min * 0.5f + tb.max * 0.5f };
         }
-        b.build((unsigned int)m_Triangles.size());
+        unsigned int threads = std::thread::hardware_concurrency();
+        if (const char* env = std::getenv("B2RT_BUILD_THREADS")) threads = (unsigned int)std::max(1, std::atoi(env));
+        b.build((unsigned int)m_Triangles.size(), std::max(1u, std::min(threads, 64u)));
         std::vector<PrimInfo>().swap(b.info);
 
         // re-order the triangles

@@ -24,16 +24,16 @@ for name, obj, W, H, cam in (("ico", path, 3840, 2160, dict(pos=(0.0, -25.0, 8.5
         ctx.upload_scene(t, n, m)
         ctx.resize(W, H)
         ctx.set_option(prod.capi.OPT_RENDER_MODE, mode)
-        for lanes in ((1, 2, 3, 4) if mode == 0 else (1,)):
+        for lanes in ((1, 2) if mode == 0 else (1,)):
             ctx.set_option(prod.capi.OPT_WAVEFRONT_LANES, lanes)
-            for frac in (1, 8):                                   # the whole frame, and one rank's share of an 8-GPU frame
-                n = W * H // frac
+            for frac in (1, 2, 8):                                # the whole frame, and one rank's share of a 2- / 8-GPU frame
+                plan = prod.sharding.BandPlan(W, H, frac, band_rows=8)
                 ctx.set_frame(1, 4, **cam)
-                ctx.execute(n)
+                plan.render(ctx, 0)
                 ctx.finish()
                 t0 = time.perf_counter()
                 for f in (2, 3, 4, 5):
                     ctx.set_frame(f, 4, **cam)
-                    ctx.execute(n)
+                    plan.render(ctx, 0)
                 ctx.finish()
                 print(name, "mode", mode, "lanes", lanes, "pixels 1/%d" % frac, "%.3f ms/frame" % ((time.perf_counter() - t0) / 4 * 1e3), flush=True)

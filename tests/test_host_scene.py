@@ -98,7 +98,6 @@ def test_loader_quirks(tmp_scene_dir):
 def test_scene_cache_round_trip_and_invalidation(tmp_scene_dir):
     """the binary cache must return byte-identical arrays (same triangle order = same hit IDs) and must
     be ignored when the source, maxPrimitivesInNode or the file itself changed."""
-    import shutil
     import time
     prod = load_product()
     p, n, f = scenes.displaced_sphere(4, amplitude=0.3)
@@ -133,4 +132,21 @@ def test_scene_cache_round_trip_and_invalidation(tmp_scene_dir):
     t3, n3, m3, hit = prod.host.load_scene(path, 4, cache=True)
     assert not hit and not np.array_equal(t3, t2)
     assert prod.host.load_scene(path, 4, cache=True)[3]
-    shutil.rmtree(tmp_scene_dir, ignore_errors=True)
+
+
+def test_parallel_build_is_identical_to_the_reference_build(tmp_scene_dir, monkeypatch):
+    """Scenes of >= 65536 triangles are built by a team of threads (host/scene_build.cpp); topology, node numbering and
+    the triangle order (= hit IDs) must not depend on the thread count and must equal the reference's recursion."""
+    prod = load_product()
+    path = os.path.join(tmp_scene_dir, "par.obj")
+    assert prod.host.write_scattered_obj(path, 50000, extent=30.0, edge_min=0.2, edge_max=1.0, seed=9) == 50000
+    want = ol.ref_load_scene(path, 4)
+    assert want[0].shape[0] == 100000
+    for threads in ("1", "3", "8"):
+        monkeypatch.setenv("B2RT_BUILD_THREADS", threads)
+        got = prod.host.load_scene(path, 4)
+        _same_scene(got, want)
+    p, n, f = scenes.displaced_sphere(6, amplitude=0.2)          # 81920 faces -> 163840 triangles, shared vertices
+    path = scenes.write_obj(os.path.join(tmp_scene_dir, "par_sphere.obj"), p, n, f)
+    monkeypatch.setenv("B2RT_BUILD_THREADS", "5")
+    _same_scene(prod.host.load_scene(path, 2), ol.ref_load_scene(path, 2))
