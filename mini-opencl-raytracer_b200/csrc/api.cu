@@ -293,8 +293,7 @@ int wavefront_lane(b2rt_context* ctx, const FrameArgs& a, float* d_result, const
     char* rays[2] = { static_cast<char*>(ctx->d_wf_rays[0]) + offset * sizeof(b2rt_ray), static_cast<char*>(ctx->d_wf_rays[1]) + offset * sizeof(b2rt_ray) };
     char* hits = static_cast<char*>(ctx->d_wf_hits) + offset * sizeof(b2rt_hit);
     char* state = static_cast<char*>(ctx->d_wf_state) + offset * 32;
-    CK(cudaMemsetAsync(cnt, 0, 3 * sizeof(unsigned long long), s));
-    CK(launch_wf_generate(a, map, n, rays[0], state, cnt, s));
+    CK(launch_wf_generate(a, map, n, rays[0], state, cnt, s));        // also resets the lane's four counters
     ctx->launches += 1;
     int grid = ctx->grid_closest;
     if (ctx->opt_blocks_per_sm > 0) grid = ctx->sm_count * (int)ctx->opt_blocks_per_sm;
@@ -305,8 +304,8 @@ int wavefront_lane(b2rt_context* ctx, const FrameArgs& a, float* d_result, const
         unsigned long long *n_in = cnt + (b % 3), *n_out = cnt + ((b + 1) % 3), *n_clear = cnt + ((b + 2) % 3);
         CK(launch_trace_wide(ctx->view, rays[in], n, hits, false, ctx->opt_counters != 0, ctx->stack_bound, grid,
                              cnt + 3, ctx->d_counters, (uint32_t)ctx->opt_refill_min, (uint32_t)ctx->opt_leaf_bias, s, n_in));
-        CK(cudaMemsetAsync(n_clear, 0, sizeof(unsigned long long), s));   // the counter the NEXT shade stage appends to
-        CK(launch_wf_shade(ctx->view, a, map, n, rays[in], hits, n_in, rays[out], n_out, state, d_result, b == a.bounces - 1, s));
+        // the shade stage also clears the counter the NEXT shade stage appends to and the traversal kernel's ray counter
+        CK(launch_wf_shade(ctx->view, a, map, n, rays[in], hits, n_in, rays[out], n_out, state, d_result, b == a.bounces - 1, n_clear, cnt + 3, s));
         ctx->launches += 2;
     }
     return B2RT_SUCCESS;

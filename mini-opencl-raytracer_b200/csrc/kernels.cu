@@ -300,7 +300,8 @@ __global__ void __launch_bounds__(256)
 wf_generate_kernel(FrameArgs a, GidMap map, uint32_t n, RayIn* __restrict__ rays, float4* __restrict__ state,
                    unsigned long long* __restrict__ queue_count) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i == 0) *queue_count = n;
+    // counter block of this wavefront: [0..2] rotating queue lengths, [3] the traversal kernel's ray counter
+    if (i == 0) { queue_count[0] = n; queue_count[1] = 0; queue_count[2] = 0; queue_count[3] = 0; }
     if (i >= n) return;
     uint32_t gid = (uint32_t)map.gid(i);
     uint32_t seed = gid + hash_u32(a.frame_count);                        // kernel_bvh.cl:445
@@ -315,9 +316,13 @@ wf_generate_kernel(FrameArgs a, GidMap map, uint32_t n, RayIn* __restrict__ rays
 __global__ void __launch_bounds__(256)
 wf_shade_kernel(SceneView s, FrameArgs a, GidMap map, const RayIn* __restrict__ rays_in, const float4* __restrict__ hits,
                 const unsigned long long* __restrict__ n_in, RayIn* __restrict__ rays_out,
-                unsigned long long* __restrict__ n_out, float4* __restrict__ state, float* __restrict__ result, int last) {
+                unsigned long long* __restrict__ n_out, float4* __restrict__ state, float* __restrict__ result, int last,
+                unsigned long long* __restrict__ clear_a, unsigned long long* __restrict__ clear_b) {
     const uint64_t n = *n_in;
     const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // reset what the NEXT stages start from: the traversal kernel's ray counter and the queue length the next
+    // shade stage appends to (neither is read or written by anything in flight now)
+    if (j == 0) { *clear_a = 0; *clear_b = 0; }
     if ((j & ~31ull) >= n) return;                      // whole warp beyond the queue
     const unsigned lane = threadIdx.x & 31u;
     bool go_on = false;
@@ -405,8 +410,10 @@ cudaError_t launch_trace_wide(const SceneView& s, const void* d_rays, uint64_t n
                               const unsigned long long* d_n) {
     int cap = pick_cap(stack_bound);
     if (!cap) return cudaErrorInvalidValue;
-    cudaError_t e = cudaMemsetAsync(d_next, 0, sizeof(unsigned long long), st);
-    if (e != cudaSuccess) return e;
+    if (!d_n) {     // wavefront stages (d_n given) get their counter reset by the preceding stage's kernel
+        cudaError_t e = cudaMemsetAsync(d_next, 0, sizeof(unsigned long long), st);
+        if (e != cudaSuccess) return e;
+    }
     if (refill_min < 1 || refill_min > 32) refill_min = 8;
     if (leaf_bias < 1 || leaf_bias > 512) leaf_bias = 16;
     if (any) return count ? launch_persistent_cap<true, true>(cap, grid_blocks, st, s, d_rays, n, d_out, d_next, d_counters, refill_min, leaf_bias, d_n)
@@ -457,11 +464,12 @@ cudaError_t launch_wf_generate(const FrameArgs& a, const GidMap& map, uint32_t n
 
 cudaError_t launch_wf_shade(const SceneView& s, const FrameArgs& a, const GidMap& map, uint32_t n_max, const void* d_rays_in,
                             const void* d_hits, const unsigned long long* d_n_in, void* d_rays_out, unsigned long long* d_n_out,
-                            void* d_state, float* d_result, bool last, cudaStream_t st) {
+                            void* d_state, float* d_result, bool last, unsigned long long* d_clear_a, unsigned long long* d_clear_b,
+                            cudaStream_t st) {
     if (n_max == 0) return cudaSuccess;
     wf_shade_kernel<<<(n_max + 255u) / 256u, 256, 0, st>>>(s, a, map, static_cast<const RayIn*>(d_rays_in), static_cast<const float4*>(d_hits),
                                                            d_n_in, static_cast<RayIn*>(d_rays_out), d_n_out, static_cast<float4*>(d_state),
-                                                           d_result, last ? 1 : 0);
+                                                           d_result, last ? 1 : 0, d_clear_a, d_clear_b);
     return cudaGetLastError();
 }
 

@@ -24,7 +24,8 @@ cudaError_t launch_wf_generate(const FrameArgs& a, const GidMap& map, uint32_t n
                                unsigned long long* d_queue_count, cudaStream_t st);
 cudaError_t launch_wf_shade(const SceneView& s, const FrameArgs& a, const GidMap& map, uint32_t n_max, const void* d_rays_in,
                             const void* d_hits, const unsigned long long* d_n_in, void* d_rays_out, unsigned long long* d_n_out,
-                            void* d_state, float* d_result, bool last, cudaStream_t st);
+                            void* d_state, float* d_result, bool last, unsigned long long* d_clear_a, unsigned long long* d_clear_b,
+                            cudaStream_t st);
 // float4 accumulation image -> clamped 8-bit RGBA (alpha 255), n pixels.
 cudaError_t launch_tonemap_rgba8(const void* d_image, void* d_out, uint64_t n, cudaStream_t st);
 int trace_block_threads();
