@@ -329,3 +329,52 @@ def test_config3_scattered_scene_tiled_frame(product, tmp_scene_dir):
         got = ctx.trace_closest(rays)
         _check_hits(got, ol.oracle_closest(tris, nodes, rays))
         assert 0.2 < (got["tri"] != MISS).mean() < 0.999
+
+
+def test_context_lifecycle_and_error_paths(product, cornell_ref, bumpy_ref):
+    """Host-API behaviour around the hot path: scene replacement, resize, two live contexts, invalid calls. Errors
+    carry the OpenCL status numbers the reference's CLException would show (CLutils.h:29-114)."""
+    cap = product.capi
+    tris, nodes, mats = cornell_ref
+    rays = ol.oracle_camera_rays(64, 64, 1)
+    with product.Context(0) as a, product.Context(0) as b:
+        with pytest.raises(product.B2RTError) as e:                  # no scene bound yet
+            a.trace_closest(rays)
+        assert e.value.status == -52                                  # CL_INVALID_KERNEL_ARGS
+        a.upload_scene(tris, nodes, mats)
+        b.upload_scene(*bumpy_ref)                                    # two contexts, two scenes, interleaved use
+        want_a = ol.oracle_closest(tris, nodes, rays)
+        shell = scenes.shell_rays(5000, 10.0, seed=81)
+        want_b = ol.oracle_closest(bumpy_ref[0], bumpy_ref[1], shell)
+        for _ in range(2):
+            _check_hits(a.trace_closest(rays), want_a)
+            _check_hits(b.trace_closest(shell), want_b)
+        a.upload_scene(*bumpy_ref)                                    # replacing the scene rebuilds the wide BVH
+        _check_hits(a.trace_closest(shell), want_b)
+        assert a.scene_info()["n_triangles"] == bumpy_ref[0].shape[0]
+        with pytest.raises(product.B2RTError) as e:                  # frame before WIDTH/HEIGHT/output exist
+            a.execute(16)
+        assert e.value.status == -52
+        a.resize(32, 16)
+        a.set_frame(1, 2)
+        with pytest.raises(product.B2RTError) as e:
+            a.execute(32 * 16 + 1)                                    # more work items than pixels
+        assert e.value.status == -63                                  # CL_INVALID_GLOBAL_WORK_SIZE
+        with pytest.raises(product.B2RTError) as e:
+            a.execute(0)
+        assert e.value.status == -63
+        a.execute(32 * 16)
+        first = a.read_pixels().copy()
+        a.resize(32, 16)                                              # a new output buffer starts from zero again
+        a.set_frame(1, 2)
+        a.execute(32 * 16)
+        assert np.array_equal(a.read_pixels().view(np.uint32), first.view(np.uint32))
+        for opt, bad in ((cap.OPT_TRAVERSAL, 7), (cap.OPT_RENDER_MODE, 9), (cap.OPT_REFILL_MIN, 0), (cap.OPT_LEAF_BIAS, 0),
+                         (cap.OPT_WAVEFRONT_LANES, 5), (99, 1)):
+            with pytest.raises(product.B2RTError) as e:
+                a.set_option(opt, bad)
+            assert e.value.status == -30                              # CL_INVALID_VALUE
+        out = np.empty((8, 4), dtype=np.uint8)
+        with pytest.raises(product.B2RTError) as e:
+            a._ck(a._L.b2rt_read_pixels_rgba8(a._h, out.ctypes.data, 32 * 16 * 4 + 4))   # more pixels than the image has
+        assert e.value.status == -30
