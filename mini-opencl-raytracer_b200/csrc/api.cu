@@ -4,6 +4,7 @@
 // missing CUDA device makes b2rt_create fail and nothing else is reachable.
 #include <cuda_runtime.h>
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 #include <memory>
@@ -233,14 +234,22 @@ int trace_host(b2rt_context* ctx, const b2rt_ray* rays, uint64_t n, void* out, b
     if (st) return st;
     if (n == 0) return B2RT_SUCCESS;
     if (!rays || !out) return fail(ctx, B2RT_INVALID_VALUE, "null ray or output pointer");
-    uint64_t chunk = std::min<uint64_t>(n, STREAM_CHUNK);
+    uint64_t chunk_rays = STREAM_CHUNK;
+    if (const char* env = getenv("B2RT_STREAM_CHUNK")) { long long v = atoll(env); if (v >= 1024) chunk_rays = (uint64_t)v; }   // tuning aid
+    uint64_t chunk = std::min<uint64_t>(n, chunk_rays);
     st = ensure_staging(ctx, chunk);
     if (st) return st;
     const size_t out_elem = any ? sizeof(uint32_t) : sizeof(b2rt_hit);
-    uint64_t k = 0;
-    for (uint64_t off = 0; off < n; off += chunk, ++k) {
+    // Chunk sizes ramp up from `ramp` to `chunk` and back down at the end: the first copy-in and the last kernel +
+    // copy-out are the only parts of the pipeline that nothing overlaps, so they are kept short.
+    const uint64_t ramp = std::min<uint64_t>(chunk, 1ull << 19);
+    uint64_t k = 0, m = 0;
+    for (uint64_t off = 0; off < n; off += m, ++k) {
         int s = (int)(k & 1);
-        uint64_t m = std::min<uint64_t>(chunk, n - off);
+        const uint64_t left = n - off;
+        m = std::min<uint64_t>(chunk, ramp << std::min<uint64_t>(k, 16));                              // ramp up
+        if (left <= ramp) m = left;
+        else m = std::min<uint64_t>(m, std::max<uint64_t>(ramp, (left / 2 + 31) & ~31ull));            // ramp down: at most half of what is left
         if (k >= 2) CK(cudaStreamWaitEvent(ctx->stream_in, ctx->ev_comp[s], 0));     // rays[s] free again
         CK(cudaMemcpyAsync(ctx->d_stage_rays[s], rays + off, m * sizeof(b2rt_ray), cudaMemcpyHostToDevice, ctx->stream_in));
         CK(cudaEventRecord(ctx->ev_in[s], ctx->stream_in));
