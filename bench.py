@@ -323,11 +323,12 @@ def run_b200(args, rank, world, local_rank):
         with prod.host.Engine(1920, 1080, device=local_rank) as ce:
             ce.load_scene(cornell, 4)
             ce.set_render(frame_count=1, bounces=4)
-            ce.render_frame()                                    # frame 1 of the accumulation doubles as warm-up
+            for _ in range(5):
+                ce.render_frame()                                # frames 1-5 of the accumulation double as warm-up (render-mode choice settles)
             t0 = time.perf_counter()
-            for _ in range(15):
+            for _ in range(11):
                 ce.render_frame()                                # RenderFrame: 8 args, kernel, full 33 MB read-back, finish
-            frame_ms = (time.perf_counter() - t0) / 15 * 1e3
+            frame_ms = (time.perf_counter() - t0) / 11 * 1e3
             cornell_img = ce.pixels().copy()
             cctx = prod.Context.borrow(ce.context_handle(), local_rank)
             t0 = time.perf_counter()
@@ -336,24 +337,30 @@ def run_b200(args, rank, world, local_rank):
                 cctx.execute(1920 * 1080)
             cctx.finish()
             cornell_kernel_ms = (time.perf_counter() - t0) / 16 * 1e3
-            cctx.set_option(prod.capi.OPT_RENDER_MODE, 1)
-            t0 = time.perf_counter()
-            for f in range(33, 49):
-                cctx.set_frame(f, 4)
+            mode_ms = {}
+            for mode, name in ((0, "wavefront"), (1, "megakernel")):
+                cctx.set_option(prod.capi.OPT_RENDER_MODE, mode)
+                cctx.set_frame(33, 4)
                 cctx.execute(1920 * 1080)
-            cctx.finish()
-            cornell_mega_ms = (time.perf_counter() - t0) / 16 * 1e3
-            cctx.set_option(prod.capi.OPT_RENDER_MODE, 0)
+                cctx.finish()
+                t0 = time.perf_counter()
+                for f in range(34, 50):
+                    cctx.set_frame(f, 4)
+                    cctx.execute(1920 * 1080)
+                cctx.finish()
+                mode_ms[name] = (time.perf_counter() - t0) / 16 * 1e3
+            cctx.set_option(prod.capi.OPT_RENDER_MODE, 2)
             ce.set_display_readback(True)                        # 8-bit RGBA quantised on the device: 8 MB instead of 33 MB per frame
-            ce.render_frame()
+            for _ in range(5):
+                ce.render_frame()
             t0 = time.perf_counter()
             for _ in range(15):
                 ce.render_frame()
             display_ms = (time.perf_counter() - t0) / 15 * 1e3
         extra["cornell_1080p_4bounce"] = {"frame_ms": frame_ms, "kernel_only_frame_ms": cornell_kernel_ms, "spp": 16,
                                           "api": "CLRaytracer::RenderFrame (args + KernelEntry + 33 MB read-back + finish)",
-                                          "render_mode": "wavefront (generate, then trace + shade/compact per bounce)",
-                                          "megakernel_kernel_only_frame_ms": cornell_mega_ms,
+                                          "render_mode": "default: the faster of wavefront / megakernel as measured per launch shape (bit-identical frames)",
+                                          "kernel_only_frame_ms_by_mode": mode_ms,
                                           "frame_ms_display_readback_rgba8": display_ms}
 
     # ---- N>1: one 4K cornell frame split into row bands over the ranks + NCCL all_gather of the framebuffer ----
@@ -391,13 +398,14 @@ def run_b200(args, rank, world, local_rank):
                 render_s[0] += time.perf_counter() - t_r
                 return prod.sharding.gather_frame(plan, frame, rank)
 
-            tiled_frame(1)
+            for f in range(5):                                 # warm-up; the render-mode choice of this launch shape settles
+                tiled_frame(1 + f)
             torch.cuda.synchronize()
             barrier()
             render_s[0] = 0.0
             t0 = time.perf_counter()
             for f in range(frames):
-                full = tiled_frame(2 + f)
+                full = tiled_frame(6 + f)
             torch.cuda.synchronize()
             barrier()
             ms = (time.perf_counter() - t0) / frames * 1e3
@@ -408,8 +416,8 @@ def run_b200(args, rank, world, local_rank):
                 with prod.Context(local_rank) as one:
                     one.upload_scene(tris_c, nodes_c, mats_c)
                     one.resize(W, H)
-                    for k in range(1, 2 + frames):
-                        if k == 1 + frames:                        # time the last of the same frames on ONE GPU
+                    for k in range(1, 6 + frames):
+                        if k == 5 + frames:                        # time the last of the same frames on ONE GPU
                             one.finish()
                             t0 = time.perf_counter()
                         one.set_frame(k, 4, **tiled_cam)

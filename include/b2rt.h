@@ -103,8 +103,9 @@ enum {
     B2RT_OPT_TRAVERSAL = 0,     /* 0 = compressed wide BVH (default), 1 = reference-layout binary walk */
     B2RT_OPT_COUNTERS = 1,      /* 1 = launches use the counting build of the kernels      */
     B2RT_OPT_BLOCKS_PER_SM = 2, /* persistent grid = value * SM count (0 = default)        */
-    B2RT_OPT_RENDER_MODE = 3,   /* frame path: 0 = wavefront (generate, then trace + shade/compact per bounce; default),
-                                   1 = megakernel (one thread per pixel, like KernelEntry); bit-identical frames */
+    B2RT_OPT_RENDER_MODE = 3,   /* frame path: 0 = wavefront (generate, then trace + shade/compact per bounce), 1 = megakernel
+                                   (one thread per pixel, like KernelEntry), 2 = whichever of the two measures faster for the
+                                   launch shape at hand (default). Frames are bit-identical in every mode. */
     B2RT_OPT_REFILL_MIN = 4,    /* idle lanes of a warp that trigger a ray refill (1..32, default 8) */
     B2RT_OPT_LEAF_BIAS = 5,     /* weight of the leaf vote in sixteenths (16 = plain majority, default 28) */
     B2RT_OPT_WAVEFRONT_LANES = 6 /* wavefront frame path: independent wavefronts in flight per launch, 1..4 (0 = by size) */

@@ -7,6 +7,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
+#include <map>
 #include <memory>
 #include <new>
 #include <string>
@@ -32,6 +33,8 @@ constexpr uint64_t STREAM_CHUNK = 1ull << 22;   // rays per pipelined chunk of t
 std::string g_create_error;
 
 }  // namespace
+
+struct ModeTrial { int calls = 0; float ms[2] = { 0.0f, 0.0f }; int choice = -1; };
 
 struct b2rt_context {
     int device = 0;
@@ -64,11 +67,15 @@ struct b2rt_context {
     uint64_t wf_capacity = 0;
     cudaStream_t wf_stream[4] = { nullptr, nullptr, nullptr, nullptr };
     cudaEvent_t ev_wf_fork = nullptr, ev_wf_join[4] = { nullptr, nullptr, nullptr, nullptr };
+    std::map<std::pair<uint64_t, int>, ModeTrial> tuner;   // render-mode auto-tuning per launch shape (work items, bounces)
+    std::pair<uint64_t, int> tune_pending_key;
+    int tune_pending_mode = -1;
+    cudaEvent_t ev_tune[2] = { nullptr, nullptr };
     void* d_rgba8 = nullptr;            // 8-bit read-back staging
     uint64_t rgba8_capacity = 0;
     cudaEvent_t ev_in[2] = { nullptr, nullptr }, ev_comp[2] = { nullptr, nullptr }, ev_out[2] = { nullptr, nullptr };
     // options
-    int64_t opt_traversal = 0, opt_counters = 0, opt_blocks_per_sm = 0, opt_render_mode = 0, opt_refill_min = 8, opt_leaf_bias = 28, opt_wf_lanes = 0;
+    int64_t opt_traversal = 0, opt_counters = 0, opt_blocks_per_sm = 0, opt_render_mode = 2, opt_refill_min = 8, opt_leaf_bias = 28, opt_wf_lanes = 0;
     int grid_closest = 0, grid_any = 0;
     uint64_t launches = 0;
     std::string error;
@@ -187,6 +194,8 @@ int ensure_scene(b2rt_context* ctx) {
     ctx->grid_closest = ctx->sm_count * std::max(occ, 1);
     CK(trace_occupancy(true, bound, &occ));
     ctx->grid_any = ctx->sm_count * std::max(occ, 1);
+    ctx->tuner.clear();
+    ctx->tune_pending_mode = -1;
     ctx->scene_dirty = false;
     return B2RT_SUCCESS;
 }
@@ -355,6 +364,48 @@ int render_wavefront(b2rt_context* ctx, const FrameArgs& a, float* d_result, con
     return B2RT_SUCCESS;
 }
 
+int render_with_mode(b2rt_context* ctx, const FrameArgs& a, float* result, const GidMap& map, uint64_t n, int mode);
+int render_tuned(b2rt_context* ctx, const FrameArgs& a, float* result, const GidMap& map, uint64_t n);
+
+// Folds a finished timing into the tuner table (waits for the timed launch if it is still running).
+int tuner_resolve(b2rt_context* ctx) {
+    if (ctx->tune_pending_mode < 0) return B2RT_SUCCESS;
+    CK(cudaEventSynchronize(ctx->ev_tune[1]));
+    float ms = 0.0f;
+    CK(cudaEventElapsedTime(&ms, ctx->ev_tune[0], ctx->ev_tune[1]));
+    ModeTrial& t = ctx->tuner[ctx->tune_pending_key];
+    t.ms[ctx->tune_pending_mode] = ms;
+    if (ctx->tune_pending_mode == 1) t.choice = t.ms[1] < t.ms[0] ? 1 : 0;
+    ctx->tune_pending_mode = -1;
+    return B2RT_SUCCESS;
+}
+
+// B2RT_OPT_RENDER_MODE = 2: the wavefront and the megakernel produce bit-identical frames, so the faster one for
+// THIS launch shape (work items, bounces) on THIS scene can simply be measured. Calls 1-2 of a shape run the
+// wavefront, calls 3-4 the megakernel, the second of each pair between two CUDA events; from call 5 on the winner
+// runs. The wavefront wins on large launches and incoherent scenes, the megakernel on a rank's small share of a
+// multi-GPU frame, where the per-bounce stage tails of the wavefront add up.
+int render_tuned(b2rt_context* ctx, const FrameArgs& a, float* result, const GidMap& map, uint64_t n) {
+    int st = tuner_resolve(ctx);
+    if (st) return st;
+    if (n >= WF_MAX_PATHS) return render_with_mode(ctx, a, result, map, n, 0);
+    const std::pair<uint64_t, int> key(n, a.bounces);
+    ModeTrial& t = ctx->tuner[key];
+    if (t.choice >= 0) return render_with_mode(ctx, a, result, map, n, t.choice);
+    const int phase = t.calls++;
+    const int mode = phase < 2 ? 0 : 1;
+    const bool timed = (phase & 1) != 0;
+    if (timed) CK(cudaEventRecord(ctx->ev_tune[0], ctx->stream));
+    st = render_with_mode(ctx, a, result, map, n, mode);
+    if (st) return st;
+    if (timed) {
+        CK(cudaEventRecord(ctx->ev_tune[1], ctx->stream));
+        ctx->tune_pending_key = key;
+        ctx->tune_pending_mode = mode;
+    }
+    return B2RT_SUCCESS;
+}
+
 // Validates and draws the work items of `map` (n of them) into the bound output buffer.
 int render_items(b2rt_context* ctx, const GidMap& map, uint64_t n) {
     int st = use_device(ctx);
@@ -374,7 +425,15 @@ int render_items(b2rt_context* ctx, const GidMap& map, uint64_t n) {
         return fail(ctx, B2RT_INVALID_GLOBAL_WORK_SIZE, "work items up to gid " + std::to_string(last) + " exceed the output buffer (" +
                     std::to_string(out->bytes / 16) + " pixels)");
     float* result = static_cast<float*>(out->d_ptr);
-    if (ctx->opt_traversal == 1 || ctx->opt_render_mode == 1) {
+    if (ctx->opt_traversal == 1) return render_with_mode(ctx, a, result, map, n, 1);
+    if (ctx->opt_render_mode != 2) return render_with_mode(ctx, a, result, map, n, (int)ctx->opt_render_mode);
+    return render_tuned(ctx, a, result, map, n);
+}
+
+// One frame launch in a given mode: 1 = megakernel, 0 = wavefront.
+int render_with_mode(b2rt_context* ctx, const FrameArgs& a, float* result, const GidMap& map, uint64_t n, int mode) {
+    int st = B2RT_SUCCESS;
+    if (mode == 1) {
         CK(launch_render_mega(ctx->view, a, result, map, (uint32_t)n, ctx->opt_traversal == 1, ctx->stack_bound, ctx->stream));
         ctx->launches += 1;
         return B2RT_SUCCESS;
@@ -465,6 +524,8 @@ extern "C" int b2rt_create(int device_id, b2rt_context** out) {
         if ((e = cudaEventCreateWithFlags(&ctx->ev_wf_join[i], cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
     }
     if ((e = cudaEventCreateWithFlags(&ctx->ev_wf_fork, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
+    for (int i = 0; i < 2; ++i)
+        if ((e = cudaEventCreate(&ctx->ev_tune[i])) != cudaSuccess) return bail(e, "cudaEventCreate");
     if ((e = cudaMalloc(&ctx->d_next, 64)) != cudaSuccess) return bail(e, "cudaMalloc");
     if ((e = cudaMalloc(&ctx->d_counters, 128)) != cudaSuccess) return bail(e, "cudaMalloc");
     if ((e = cudaMemset(ctx->d_counters, 0, 128)) != cudaSuccess) return bail(e, "cudaMemset");
@@ -495,6 +556,7 @@ extern "C" void b2rt_destroy(b2rt_context* ctx) {
         if (ctx->ev_wf_join[i]) cudaEventDestroy(ctx->ev_wf_join[i]);
     }
     if (ctx->ev_wf_fork) cudaEventDestroy(ctx->ev_wf_fork);
+    for (int i = 0; i < 2; ++i) if (ctx->ev_tune[i]) cudaEventDestroy(ctx->ev_tune[i]);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->stream_in) cudaStreamDestroy(ctx->stream_in);
     if (ctx->stream_out) cudaStreamDestroy(ctx->stream_out);
@@ -808,12 +870,14 @@ extern "C" int b2rt_set_option(b2rt_context* ctx, uint32_t option, int64_t value
         case B2RT_OPT_TRAVERSAL: if (value != 0 && value != 1) return fail(ctx, B2RT_INVALID_VALUE, "traversal must be 0 or 1"); ctx->opt_traversal = value; break;
         case B2RT_OPT_COUNTERS: ctx->opt_counters = value ? 1 : 0; break;
         case B2RT_OPT_BLOCKS_PER_SM: if (value < 0 || value > 32) return fail(ctx, B2RT_INVALID_VALUE, "blocks per SM out of range"); ctx->opt_blocks_per_sm = value; break;
-        case B2RT_OPT_RENDER_MODE: if (value != 0 && value != 1) return fail(ctx, B2RT_INVALID_VALUE, "render mode must be 0 (wavefront) or 1 (megakernel)"); ctx->opt_render_mode = value; break;
+        case B2RT_OPT_RENDER_MODE: if (value < 0 || value > 2) return fail(ctx, B2RT_INVALID_VALUE, "render mode must be 0 (wavefront), 1 (megakernel) or 2 (measured choice)"); ctx->opt_render_mode = value; break;
         case B2RT_OPT_WAVEFRONT_LANES: if (value < 0 || value > 4) return fail(ctx, B2RT_INVALID_VALUE, "wavefront lanes must be 0 (auto) .. 4"); ctx->opt_wf_lanes = value; break;
         case B2RT_OPT_LEAF_BIAS: if (value < 1 || value > 512) return fail(ctx, B2RT_INVALID_VALUE, "leaf bias must be 1..512 (sixteenths)"); ctx->opt_leaf_bias = value; break;
         case B2RT_OPT_REFILL_MIN: if (value < 1 || value > 32) return fail(ctx, B2RT_INVALID_VALUE, "refill threshold must be 1..32"); ctx->opt_refill_min = value; break;
         default: return fail(ctx, B2RT_INVALID_VALUE, "unknown option");
     }
+    ctx->tuner.clear();               // measured render-mode choices depend on the options
+    ctx->tune_pending_mode = -1;
     return B2RT_SUCCESS;
 }
 extern "C" int b2rt_get_counters(b2rt_context* ctx, b2rt_counters* out) {

@@ -193,8 +193,9 @@ def test_cornell_512_frame_and_sharded_execute(product, cornell_ctx, cornell_ref
 
 
 def test_wavefront_and_megakernel_frames_are_bit_identical(product, cornell_ctx, bumpy_ctx):
-    """B2RT_OPT_RENDER_MODE: 0 = generate / trace / shade+compact stages, 1 = one thread per pixel. Same arithmetic
-    per path, so every pixel must agree bit for bit, including bounces = 0 / 1 and a rank's strided bands."""
+    """B2RT_OPT_RENDER_MODE: 0 = generate / trace / shade+compact stages, 1 = one thread per pixel, 2 = the faster of the
+    two as measured per launch shape (default). Same arithmetic per path, so every pixel must agree bit for bit,
+    including bounces = 0 / 1 and a rank's strided bands."""
     W, H = 333, 211                                             # ragged: not a multiple of the warp or band size
     cam_b = dict(pos=(0.0, -30.0, 4.0), front=(0.0, 1.0, 0.0), up=(0.0, 0.0, 1.0))
     for ctx, cam, bounces in ((cornell_ctx, {}, 4), (cornell_ctx, {}, 1), (cornell_ctx, {}, 0), (bumpy_ctx, cam_b, 6)):
@@ -202,8 +203,15 @@ def test_wavefront_and_megakernel_frames_are_bit_identical(product, cornell_ctx,
         for mode in (0, 1):
             ctx.set_option(product.capi.OPT_RENDER_MODE, mode)
             imgs.append(_render(ctx, W, H, (1, 2, 3), bounces, **cam))
-        ctx.set_option(product.capi.OPT_RENDER_MODE, 0)
         assert np.array_equal(imgs[0].view(np.uint32), imgs[1].view(np.uint32)), bounces
+        # mode 2 (default): calls 1-2 wavefront, 3-4 megakernel, then whichever measured faster -- 7 accumulated frames
+        # cross every phase of that choice and must equal 7 frames of one fixed mode
+        seven = []
+        for mode in (2, 1):
+            ctx.set_option(product.capi.OPT_RENDER_MODE, mode)
+            seven.append(_render(ctx, W, H, range(1, 8), bounces, **cam))
+        assert np.array_equal(seven[0].view(np.uint32), seven[1].view(np.uint32)), bounces
+        ctx.set_option(product.capi.OPT_RENDER_MODE, 0)
         for lanes in (2, 3, 4):                                  # several wavefronts in flight on their own streams
             ctx.set_option(product.capi.OPT_WAVEFRONT_LANES, lanes)
             again = _render(ctx, W, H, (1, 2, 3), bounces, **cam)
@@ -218,6 +226,7 @@ def test_wavefront_and_megakernel_frames_are_bit_identical(product, cornell_ctx,
                 plan.render(ctx, r)
         assert np.array_equal(ctx.read_pixels().view(np.uint32), imgs[0].view(np.uint32)), bounces
         ctx.set_option(product.capi.OPT_WAVEFRONT_LANES, 0)
+        ctx.set_option(product.capi.OPT_RENDER_MODE, 2)
     with pytest.raises(product.B2RTError) as e:
         cornell_ctx.execute_bands(0, W * 8, W * 24, 100)        # runs past the output buffer
     assert e.value.status == -63                                 # CL_INVALID_GLOBAL_WORK_SIZE
