@@ -518,7 +518,7 @@ def main():
     ap.add_argument("--rays", type=int, default=100_000_000, help="rays per GPU per step (BASELINE.json configs[4]: 100M random rays)")
     ap.add_argument("--frequency", type=int, default=224, help="geodesic frequency: 20*f^2 OBJ faces")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
-    ap.add_argument("--ref-rays", type=int, default=1 << 19, help="--impl reference: rays per step (bounded sample)")
+    ap.add_argument("--ref-rays", type=int, default=1 << 22, help="--impl reference: rays per step (bounded sample)")
     ap.add_argument("--tiled-faces", type=int, default=0, help="N>1 tiled 4K frame: 0 = cornell.obj, else a scattered scene of this many OBJ faces (configs[3]: 10000000)")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-frames", action="store_true")

@@ -35,6 +35,7 @@ def lib():
         "g3d_scene_load": (vp, [cs, C.c_uint, cs, sz]),
         "g3d_scene_load_cached": (vp, [cs, C.c_uint, cs, C.POINTER(C.c_int), cs, sz]),
         "g3d_engine_load_scene_cached": (C.c_int, [vp, cs, C.c_uint, cs, C.POINTER(C.c_int), cs, sz]),
+        "g3d_parse_numbers": (C.c_int, [cs, vp, C.c_int]),
         "g3d_scene_from_triangles": (vp, [vp, u64, vp, u64, C.c_uint, cs, sz]),
         "g3d_scene_free": (None, [vp]),
         "g3d_scene_count": (u64, [vp, C.c_int]),
@@ -103,6 +104,13 @@ def load_scene(obj_path, max_prims=4, cache=None):
         return _arrays(L, h)
     finally:
         L.g3d_scene_free(h)
+
+
+def parse_numbers(text, max_count=1 << 20):
+    """The numbers of `text` exactly as CLOBJloader reads them (scanf("%f") semantics); test hook."""
+    out = np.empty(max_count, dtype=np.float32)
+    n = lib().g3d_parse_numbers(text.encode(), out.ctypes.data, max_count)
+    return out[:n].copy()
 
 
 def build_scene(tris, mats, max_prims=4):

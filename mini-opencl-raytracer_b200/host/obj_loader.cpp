@@ -18,6 +18,7 @@
 // Deliberate differences: malformed input that makes the reference read out of bounds (missing
 // v/vt/vn fields, indices outside the arrays, a material statement before any `newmtl`, paths longer
 // than its 80-byte buffer) raises CLException here instead.
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -43,11 +44,69 @@ namespace Glaze3D
                 out.assign(s, p);
                 return true;
             }
-            // scanf("%f"): on failure nothing is consumed beyond the leading white space
+            // scanf("%f"): on failure nothing is consumed beyond the leading white space. strtof does the work in
+            // the general case; plain decimals (what OBJ writers emit) take a fast path that returns the SAME float:
+            // up to 15 significant digits and a power of ten up to 10^22 convert exactly to a correctly rounded
+            // double (Clinger's fast path), and rounding that double to float equals the correctly rounded float
+            // unless the double sits exactly on a float rounding boundary -- the one case handed back to strtof.
             bool number(float& out)
             {
                 skipSpace();
                 if (p >= end) return false;
+                const char* q = p;
+                bool neg = false;
+                if (*q == '+' || *q == '-') { neg = *q == '-'; ++q; }
+                uint64_t mant = 0;
+                int digits = 0, exp10 = 0;
+                bool any = false, simple = true;
+                if (q + 1 < end && q[0] == '0' && (q[1] == 'x' || q[1] == 'X')) simple = false;    // hex float: strtof's business
+                while (q < end && *q >= '0' && *q <= '9')
+                {
+                    any = true;
+                    if (mant || *q != '0') { if (digits < 15) { mant = mant * 10 + (uint64_t)(*q - '0'); ++digits; } else simple = false; }
+                    ++q;
+                }
+                if (q < end && *q == '.')
+                {
+                    ++q;
+                    while (q < end && *q >= '0' && *q <= '9')
+                    {
+                        any = true;
+                        if (mant || *q != '0') { if (digits < 15) { mant = mant * 10 + (uint64_t)(*q - '0'); ++digits; --exp10; } else simple = false; }
+                        else --exp10;
+                        ++q;
+                    }
+                }
+                if (any && q < end && (*q == 'e' || *q == 'E'))
+                {
+                    const char* e = q + 1;
+                    bool eneg = false;
+                    if (e < end && (*e == '+' || *e == '-')) { eneg = *e == '-'; ++e; }
+                    if (e < end && *e >= '0' && *e <= '9')
+                    {
+                        int ev = 0;
+                        while (e < end && *e >= '0' && *e <= '9') { if (ev < 10000) ev = ev * 10 + (*e - '0'); ++e; }
+                        exp10 += eneg ? -ev : ev;
+                        q = e;
+                    }
+                }
+                if (any && simple && exp10 >= -22 && exp10 <= 22)
+                {
+                    static const double pow10[23] = { 1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11, 1e12, 1e13, 1e14, 1e15,
+                                                      1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22 };
+                    double d = (double)mant;
+                    d = exp10 < 0 ? d / pow10[-exp10] : d * pow10[exp10];
+                    uint64_t bits;
+                    std::memcpy(&bits, &d, 8);
+                    const double mag = d;
+                    if ((bits & 0x1FFFFFFFull) != 0x10000000ull && (mant == 0 || (mag > 1e-30 && mag < 1e30)))
+                    {
+                        float f = (float)d;
+                        out = neg ? -f : f;
+                        p = q;
+                        return true;
+                    }
+                }
                 char* stop = nullptr;
                 float v = std::strtof(p, &stop);
                 if (stop == p) return false;
@@ -103,6 +162,17 @@ namespace Glaze3D
                 else if (w == "Ni") c.numbers(&current().ior, 1);
             }
         }
+    }
+
+    // Test hook: the numbers of `text` as the loader reads them (scanf("%f") semantics), up to maxCount.
+    int ParseNumbersForTest(const char* text, float* out, int maxCount)
+    {
+        std::string data(text ? text : "");
+        data.push_back('\0');
+        Cursor c{ data.data(), data.data() + data.size() - 1 };
+        int n = 0;
+        while (n < maxCount && c.number(out[n])) ++n;
+        return n;
     }
 
     void CLOBJloader::LoadInto(CLBVHScene& scene, const char* filename)

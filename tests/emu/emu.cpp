@@ -54,3 +54,9 @@ extern "C" void emu_trace(const EmuRay* rays, uint64_t n, EmuHit* hits, uint32_t
     (void)total;
     st->wide_visits += sums[0]; st->leaf_blocks += sums[1]; st->leaf_pass += sums[2]; st->tri_tests += sums[3]; st->words += sums[4];
 }
+
+// Histogram of children per wide node (index 0..8) of the last emu_build.
+extern "C" void emu_child_histogram(uint64_t* hist9) {
+    for (int i = 0; i < 9; ++i) hist9[i] = 0;
+    for (const WideNode& n : g_bvh.nodes) hist9[n.n_children <= 8 ? n.n_children : 8]++;
+}

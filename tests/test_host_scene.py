@@ -150,3 +150,40 @@ def test_parallel_build_is_identical_to_the_reference_build(tmp_scene_dir, monke
     path = scenes.write_obj(os.path.join(tmp_scene_dir, "par_sphere.obj"), p, n, f)
     monkeypatch.setenv("B2RT_BUILD_THREADS", "5")
     _same_scene(prod.host.load_scene(path, 2), ol.ref_load_scene(path, 2))
+
+
+def test_number_parsing_equals_strtof():
+    """The loader's decimal fast path must return bit-for-bit what strtof (the engine behind the reference's
+    fscanf("%f"), CLOBJloader.cpp:47-62) returns, including float rounding boundaries, long digit strings, exponents,
+    signs, leading zeros, hex floats and inf/nan."""
+    import ctypes
+    prod = load_product()
+    libc = ctypes.CDLL("libc.so.6")
+    libc.strtof.restype = ctypes.c_float
+    libc.strtof.argtypes = [ctypes.c_char_p, ctypes.c_void_p]
+    rng = np.random.default_rng(123)
+    words = ["0", "-0", "+0.0", "1", "-1.5", ".5", "-.25", "5.", "1e5", "1E-5", "1.25e+3", "007.500", "0.000001", "123456.789",
+             "16777217", "16777216.5", "0.1", "0.3", "1e22", "1e23", "1e-22", "1e-45", "3.4028235e38", "3.5e38", "1e-38", "1.17549435e-38",
+             "0x10", "0x1.8p1", "inf", "-inf", "nan", "1e", "2e+", "3.e2", "123456789012345", "1234567890123456", "0.1234567890123456789",
+             "8388608.5", "8388609.5", "4194304.25", "1.00000005960464477539", "1.000000059604644775390625", "0.50000002980232238769531250"]
+    for _ in range(60000):
+        kind = rng.integers(0, 5)
+        if kind == 0:
+            words.append("%.6f" % rng.uniform(-100, 100))
+        elif kind == 1:
+            words.append(repr(float(np.float32(rng.standard_normal() * 10.0 ** int(rng.integers(-6, 7))))))
+        elif kind == 2:
+            words.append("%.*e" % (int(rng.integers(0, 17)), rng.standard_normal() * 10.0 ** int(rng.integers(-20, 21))))
+        elif kind == 3:                                          # exact float midpoints and their neighbours, printed in full
+            f = np.float32(rng.uniform(0.5, 2.0) * 2.0 ** int(rng.integers(-10, 11)))
+            mid = (float(f) + float(np.nextafter(f, np.float32(np.inf)))) / 2.0
+            words.append("%.40g" % mid)
+            words.append("%.17g" % np.nextafter(mid, np.inf))
+        else:
+            words.append("%d.%0*d" % (rng.integers(0, 1000), int(rng.integers(1, 12)), rng.integers(0, 10 ** 9)))
+    got = prod.host.parse_numbers(" ".join(w for w in words if w not in ("1e", "2e+")), len(words) + 8)
+    want = np.array([libc.strtof(w.encode(), None) for w in words if w not in ("1e", "2e+")], dtype=np.float32)
+    assert got.shape == want.shape
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    # a number with a dangling exponent marker stops where strtof stops: "1e" is 1, then the word "e" is not a number
+    assert np.array_equal(prod.host.parse_numbers("1e 7"), np.array([1.0], dtype=np.float32))
