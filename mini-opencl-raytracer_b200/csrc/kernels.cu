@@ -10,8 +10,12 @@
 //      48 B / 256 B arrays in the reference's order: the "recompiled reference
 //      kernel" baseline and an on-device cross-check of the wide path.
 //  camera_rays_kernel               CreateRay (kernel_bvh.cl:386-403) as a ray stream.
-//  render_mega_kernel               KernelEntry (kernel_bvh.cl:415-456): one thread per
-//      pixel, path loop around the same traversal primitives.
+//  wf_generate_kernel / wf_shade_kernel   KernelEntry (kernel_bvh.cl:415-456) as a wavefront:
+//      camera rays + path state, then per bounce trace_persistent over the live ray queue and
+//      one shade / accumulate / compact stage; queue lengths never leave the device.
+//  render_mega_kernel               KernelEntry as one launch: one thread per pixel, path loop
+//      around the same traversal primitives (bit-identical to the wavefront).
+//  tonemap_rgba8_kernel             accumulation image -> clamped 8-bit RGBA for display read-back.
 //
 // No tensor cores: the path is pointer chasing + fp32 slab/triangle tests, not a
 // contraction (BASELINE.json north_star). Compile with -fmad=false; all

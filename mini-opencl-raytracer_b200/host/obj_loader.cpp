@@ -17,7 +17,7 @@
 //   * the material file is the scene path with its last four characters replaced by ".mtl".
 // Deliberate differences: malformed input that makes the reference read out of bounds (missing
 // v/vt/vn fields, indices outside the arrays, a material statement before any `newmtl`, paths longer
-// than its 80-byte buffer) raises CLException here instead.
+// than its 80-byte buffer are accepted) raises CLException here instead.
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -178,7 +178,9 @@ namespace Glaze3D
     void CLOBJloader::LoadInto(CLBVHScene& scene, const char* filename)
     {
         std::string path(filename ? filename : "");
-        if (path.size() < 5 || path.size() > 75) throw CLException("Scene path must be 5..75 characters and end in a 4-character extension", B2RT_INVALID_VALUE);
+        // The reference copies the path into an 80-byte buffer and overflows it beyond ~75 characters (CLOBJloader.cpp:18-23);
+        // longer paths are simply accepted here.
+        if (path.size() < 5) throw CLException("Scene path must end in a 4-character extension", B2RT_INVALID_VALUE);
         loadMaterials(scene, path.substr(0, path.size() - 4) + ".mtl");
 
         std::string data = slurp(path, "scene");

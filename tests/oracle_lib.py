@@ -143,6 +143,18 @@ def ref_load_scene(obj_path, max_prims=4):
     L = ref()
     if L is None:
         raise RuntimeError("oracle/_ref/libref_oracle.so is not available")
+    if len(os.fsencode(obj_path)) > 70:
+        # the reference builds the .mtl name in an 80-byte buffer (CLOBJloader.cpp:18-23, 133-138): hand it a short path
+        import shutil
+        import tempfile
+        d = tempfile.mkdtemp(prefix="ref")
+        short = os.path.join(d, "s.obj")
+        shutil.copy(obj_path, short)
+        shutil.copy(obj_path[:-4] + ".mtl", short[:-4] + ".mtl")
+        try:
+            return ref_load_scene(short, max_prims)
+        finally:
+            shutil.rmtree(d, ignore_errors=True)
     s = L.ref_scene_load(os.fsencode(obj_path), max_prims)
     if not s:
         raise RuntimeError("reference loader failed on %s" % obj_path)
