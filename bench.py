@@ -315,6 +315,16 @@ def run_b200(args, rank, world, local_rank):
     e2e_value = world * n * args.steps / e2e_s / 1e6
     dev_hits = d_hits.cpu().numpy().view(prod.HIT_DTYPE).reshape(-1)
     assert np.array_equal(dev_hits["tri"], hits_np["tri"]), "host-buffer and device-resident paths disagree"
+    # full-size cross-check (not timed): the on-device walk over the REFERENCE's own 48 B / 256 B arrays in the reference's
+    # order must give the same hit for every ray of the step
+    d_ref = torch.empty_like(d_hits)
+    ctx.set_option(prod.capi.OPT_TRAVERSAL, 1)
+    ctx.trace_closest_device(d_rays.data_ptr(), n, d_ref.data_ptr(), stream.cuda_stream)
+    ctx.set_option(prod.capi.OPT_TRAVERSAL, 0)
+    torch.cuda.synchronize()
+    same_bits = bool(torch.equal(d_ref.view(torch.int32)[:, 3], d_hits.view(torch.int32)[:, 3]) and
+                     torch.equal(d_ref.view(torch.int32)[:, 0], d_hits.view(torch.int32)[:, 0]))
+    del d_ref
 
     # ---- cornell 1920x1080, 4 bounces, 16 frames accumulated = 16 spp (configs[1]) -------------------------------------
     cornell_img = None
@@ -484,6 +494,7 @@ def run_b200(args, rank, world, local_rank):
             "cpu_baseline": cpu,
             "clocks": clocks,
         }
+        out["parity_full_step_vs_reference_layout_walk"] = {"rays": n, "ids_and_t_bit_identical": same_bits}
         out.update(extra)
         emit(out)
     eng.close()

@@ -387,3 +387,41 @@ def test_context_lifecycle_and_error_paths(product, cornell_ref, bumpy_ref):
         with pytest.raises(product.B2RTError) as e:
             a._ck(a._L.b2rt_read_pixels_rgba8(a._h, out.ctypes.data, 32 * 16 * 4 + 4))   # more pixels than the image has
         assert e.value.status == -30
+
+
+def test_full_size_stream_properties(product, tmp_scene_dir):
+    """BASELINE.json configs[4] at full scene size (1 003 520 OBJ faces -> 2 007 040 CLTriangle), where the CPU oracle
+    is too slow for whole streams: size-independent properties over 2^24 incoherent rays, plus the oracle on a sample.
+      * the compressed-wide-BVH kernel and the on-device walk over the REFERENCE's own arrays in the reference's order
+        (B2RT_OPT_TRAVERSAL=1, itself checked against the oracle above) agree bit for bit on every ray;
+      * any-hit == (closest hit exists), and shortening tmax below the closest t turns every hit into a miss;
+      * results do not depend on how the stream is cut into launches or on the order of the rays."""
+    import torch
+    path = os.path.join(tmp_scene_dir, "ico224.obj")
+    assert product.host.write_icosphere_obj(path, 224, radius=10.0, amplitude=0.08, seed=7) == 1003520
+    tris, nodes, mats = product.host.load_scene(path, 4)
+    n = 1 << 24
+    rays = product.workloads.shell_rays(n, 10.0, seed=1000)
+    with product.Context(0) as ctx:
+        ctx.upload_scene(tris, nodes, mats)
+        wide = ctx.trace_closest(rays)
+        ctx.set_option(product.capi.OPT_TRAVERSAL, 1)
+        ref_layout = ctx.trace_closest(rays)
+        ctx.set_option(product.capi.OPT_TRAVERSAL, 0)
+        assert np.array_equal(wide["tri"], ref_layout["tri"])
+        assert np.array_equal(wide["t"].view(np.uint32), ref_layout["t"].view(np.uint32))
+        hit = wide["tri"] != MISS
+        assert hit.mean() > 0.95
+        assert np.array_equal(wide["u"][hit].view(np.uint32), ref_layout["u"][hit].view(np.uint32))
+        assert np.array_equal(ctx.trace_any(rays) != 0, hit)
+        short = rays[: 1 << 22].copy()
+        short["tmax"] = np.where(hit[: 1 << 22], wide["t"][: 1 << 22] * np.float32(0.999), np.float32(1.0))
+        assert not (ctx.trace_any(short) != 0).any()              # nothing lies in front of the closest hit
+        # cut the stream differently / permute it
+        cut = np.concatenate([ctx.trace_closest(rays[:5000001]), ctx.trace_closest(rays[5000001:])])
+        assert np.array_equal(cut.view(np.uint32), wide.view(np.uint32))
+        perm = np.random.default_rng(3).permutation(1 << 22)
+        again = ctx.trace_closest(rays[perm])
+        assert np.array_equal(again.view(np.uint32), wide[perm].view(np.uint32))
+        sample = slice(0, 60000)
+        _check_hits(wide[sample], ol.oracle_closest(tris, nodes, rays[sample]))
