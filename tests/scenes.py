@@ -183,3 +183,72 @@ def psnr(a, b):
     b = np.clip(np.nan_to_num(b.astype(np.float64), nan=0.0, posinf=1.0, neginf=0.0), 0, 1)
     mse = np.mean((a - b) ** 2)
     return float("inf") if mse == 0 else 10.0 * np.log10(1.0 / mse)
+
+
+def tie_grid(n=48, layers=3):
+    """A scene made to produce exact `t` ties between DIFFERENT triangles in DIFFERENT leaves: `layers` coincident copies
+    of an n x n lattice of unit squares in the plane z = 0 (each square two triangles, normals +z), plus a second set of
+    copies at z = -1. Rays aimed at lattice points, edge midpoints and cell centres hit vertices / edges exactly, so up
+    to 6 x layers x 2 candidates share one bit-identical t; the reference keeps the first one ITS walk reaches
+    (strict `<`, kernel_bvh.cl:140), which only an order-faithful traversal reproduces. Also includes degenerate
+    (zero-area) triangles, which every walk must reject (det < 1e-8, kernel_bvh.cl:116)."""
+    xs = np.arange(n + 1, dtype=np.float32)
+    gx, gy = np.meshgrid(xs, xs, indexing="ij")
+    pos, faces = [], []
+    for z in (0.0, -1.0):
+        for _ in range(layers):
+            base = len(pos) * (n + 1) * (n + 1)
+            pos.append(np.stack([gx.ravel(), gy.ravel(), np.full(gx.size, z, dtype=np.float32)], 1))
+            idx = (np.arange(n)[:, None] * (n + 1) + np.arange(n)[None, :]).ravel() + base
+            # counter-clockwise seen from +z: front faces for rays coming down the z axis
+            faces.append(np.stack([idx, idx + (n + 1), idx + (n + 2)], 1))
+            faces.append(np.stack([idx, idx + (n + 2), idx + 1], 1))
+    pos = np.concatenate(pos).astype(np.float32)
+    faces = np.concatenate(faces)
+    degenerate = np.stack([np.arange(0, 200), np.arange(0, 200), np.arange(1, 201)], 1)      # two equal vertices
+    faces = np.concatenate([faces, degenerate])
+    normals = np.tile(np.array([[0.0, 0.0, 1.0]], dtype=np.float32), (pos.shape[0], 1))
+    return pos, normals, faces
+
+
+def tie_rays(n=48, seed=8):
+    """Straight-down and slanted rays through lattice points, edge midpoints and cell centres of tie_grid(n)."""
+    rng = np.random.default_rng(seed)
+    half = np.arange(0, 2 * n + 1, dtype=np.float64) * 0.5
+    tx, ty = np.meshgrid(half, half, indexing="ij")
+    tgt = np.stack([tx.ravel(), ty.ravel(), np.zeros(tx.size)], 1)
+    down = pack_rays(tgt + np.array([0.0, 0.0, 8.0]), np.tile(np.array([[0.0, 0.0, -1.0]]), (tgt.shape[0], 1)))
+    # slanted: origins with coordinates that are exact in binary, so that many of these still hit vertices exactly
+    o = np.stack([rng.integers(0, n + 1, tgt.shape[0]), rng.integers(0, n + 1, tgt.shape[0]), np.full(tgt.shape[0], 16)], 1).astype(np.float64)
+    slant = pack_rays(o, tgt - o)
+    return np.concatenate([down, slant])
+
+
+def moller_trumbore_all(tris_u8, rays):
+    """RayTriangle (kernel_bvh.cl:98-153) for every (ray, triangle) pair in numpy float32, one rounding per operation
+    in the reference's order: returns (accept, t) of shape (rays, tris) with accept = every test except `t < best`."""
+    f = tris_u8.view(np.float32).reshape(-1, 64)
+    v1, v2, v3 = f[None, :, 0:3], f[None, :, 20:23], f[None, :, 40:43]
+    o = np.stack([rays["ox"], rays["oy"], rays["oz"]], 1).astype(np.float32)[:, None, :]
+    d = np.stack([rays["dx"], rays["dy"], rays["dz"]], 1).astype(np.float32)
+    ln = np.sqrt((d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2], dtype=np.float32)
+    d = (d / ln[:, None]).astype(np.float32)[:, None, :]
+
+    def dot(a, b):
+        return ((a[..., 0] * b[..., 0] + a[..., 1] * b[..., 1]) + a[..., 2] * b[..., 2]).astype(np.float32)
+
+    def cross(a, b):
+        return np.stack([a[..., 1] * b[..., 2] - a[..., 2] * b[..., 1], a[..., 2] * b[..., 0] - a[..., 0] * b[..., 2],
+                         a[..., 0] * b[..., 1] - a[..., 1] * b[..., 0]], -1).astype(np.float32)
+    with np.errstate(all="ignore"):
+        e1, e2 = v2 - v1, v3 - v1
+        pvec = cross(np.broadcast_to(d, (d.shape[0], f.shape[0], 3)), np.broadcast_to(e2, (d.shape[0], f.shape[0], 3)))
+        det = dot(np.broadcast_to(e1, pvec.shape), pvec)
+        inv = (np.float32(1.0) / det).astype(np.float32)
+        tvec = (o - v1).astype(np.float32)
+        u = (dot(tvec, pvec) * inv).astype(np.float32)
+        qvec = cross(tvec, np.broadcast_to(e1, tvec.shape))
+        v = (dot(np.broadcast_to(d, qvec.shape), qvec) * inv).astype(np.float32)
+        t = (dot(np.broadcast_to(e2, qvec.shape), qvec) * inv).astype(np.float32)
+        ok = (det >= np.float32(1e-8)) & (u >= 0) & (u <= 1) & (v >= 0) & ((u + v).astype(np.float32) <= 1)
+    return ok, t

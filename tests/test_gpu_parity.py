@@ -425,3 +425,26 @@ def test_full_size_stream_properties(product, tmp_scene_dir):
         assert np.array_equal(again.view(np.uint32), wide[perm].view(np.uint32))
         sample = slice(0, 60000)
         _check_hits(wide[sample], ol.oracle_closest(tris, nodes, rays[sample]))
+
+
+def test_exact_ties_across_leaves_follow_the_reference_order(product, tmp_scene_dir):
+    """Coincident lattices (scenes.tie_grid): most hits are bit-exact t ties between triangles of DIFFERENT leaves, so the
+    winner is decided by the reference's visiting order alone (tests/test_emu_traversal.py shows that on the CPU). The
+    speculative, warp-voted kernel must still report the reference's winner for every ray."""
+    p, n, f = scenes.tie_grid(48, layers=3)
+    path = scenes.write_obj(os.path.join(tmp_scene_dir, "ties_gpu.obj"), p, n, f)
+    tris, nodes, mats = product.host.load_scene(path, 4)
+    rays = np.concatenate([scenes.tie_rays(48), scenes.tie_rays(48, seed=9)])
+    want = ol.oracle_closest(tris, nodes, rays)
+    assert (want["tri"] != MISS).mean() > 0.9
+    with product.Context(0) as ctx:
+        ctx.upload_scene(tris, nodes, mats)
+        for _ in range(3):                                      # scheduling differs from launch to launch; the result must not
+            _check_hits(ctx.trace_closest(rays), want)
+        assert np.array_equal(ctx.trace_any(rays) != 0, want["tri"] != MISS)
+        W, H = 96, 96
+        cam = dict(pos=(24.0, 24.0, 60.0), front=(0.0, 0.0, -1.0), up=(0.0, 1.0, 0.0))
+        ref_img = np.zeros((W * H, 4), dtype=np.float32)
+        for fc in (1, 2):
+            ol.oracle_render(tris, nodes, mats, ref_img, W, H, fc, 3, **cam)
+        assert scenes.psnr(_render(ctx, W, H, (1, 2), 3, **cam)[:, :3], ref_img[:, :3]) >= 50.0
