@@ -107,7 +107,7 @@ enum {
                                    (one thread per pixel, like KernelEntry), 2 = whichever of the two measures faster for the
                                    launch shape at hand (default). Frames are bit-identical in every mode. */
     B2RT_OPT_REFILL_MIN = 4,    /* idle lanes of a warp that trigger a ray refill (1..32, default 8) */
-    B2RT_OPT_LEAF_BIAS = 5,     /* weight of the leaf vote in sixteenths (16 = plain majority, default 28) */
+    B2RT_OPT_LEAF_BIAS = 5,     /* weight of the leaf vote in sixteenths (16 = plain majority, default 32) */
     B2RT_OPT_WAVEFRONT_LANES = 6 /* wavefront frame path: independent wavefronts in flight per launch, 1..4 (0 = by size) */
 };
 
