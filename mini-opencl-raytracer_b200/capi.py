@@ -187,13 +187,13 @@ class Context:
     def set_frame(self, frame_count, bounces, light_type=0, sky=1.0, pos=(0.0, -25.0, 8.5), front=(0.0, 1.0, 0.0),
                   up=(0.0, 0.0, 1.0), seed=0):
         """The eight per-frame SetUniform calls of CLRaytracer::RenderFrame (CLRaytracer.cpp:36-47)."""
-        self.set_arg(ARG_FRAME_COUNT, np.uint32(frame_count))
-        self.set_arg(ARG_FRAME_SEED, np.uint32(seed))
-        self.set_arg(ARG_LIGHT_BOUNCES, np.int32(bounces))
-        self.set_arg(ARG_LIGHT_TYPE, np.int32(light_type))
-        self.set_arg(ARG_SKYBOX_INTENSITY, np.float32(sky))
+        L, h = self._L, self._h
+        for slot, v in ((ARG_FRAME_COUNT, C.c_uint32(frame_count)), (ARG_FRAME_SEED, C.c_uint32(seed)), (ARG_LIGHT_BOUNCES, C.c_int32(bounces)),
+                        (ARG_LIGHT_TYPE, C.c_int32(light_type)), (ARG_SKYBOX_INTENSITY, C.c_float(sky))):
+            self._ck(L.b2rt_set_arg(h, slot, C.byref(v), 4))
         for slot, v in ((ARG_CAMERA_POS, pos), (ARG_CAMERA_FRONT, front), (ARG_CAMERA_UP, up)):
-            self.set_arg(slot, np.array([v[0], v[1], v[2], 0.0], dtype=np.float32))
+            f3 = (C.c_float * 4)(v[0], v[1], v[2], 0.0)
+            self._ck(L.b2rt_set_arg(h, slot, f3, 16))
 
     def set_option(self, option, value):
         self._ck(self._L.b2rt_set_option(self._h, int(option), int(value)))

@@ -59,11 +59,19 @@ class BandPlan:
         if tail:
             ctx.execute_range(*tail)
 
+    def _buffer(self, name, shape, like):
+        """Scratch tensors are allocated once per plan (a frame gather runs every frame)."""
+        key = (name, tuple(shape), like.dtype, like.device)
+        cache = self.__dict__.setdefault("_scratch", {})
+        if key not in cache:
+            cache[key] = torch.zeros(shape, dtype=like.dtype, device=like.device)
+        return cache[key]
+
     def pack(self, frame, rank):
         """Own bands of a (W*H, C) frame as one contiguous (rounds*band_pixels, C) shard (zero padded). The whole
         bands are one strided copy (every world-th band of the frame), only a clipped last band is copied apart."""
         c = frame.shape[1]
-        shard = torch.zeros((self.rounds * self.band_pixels, c), dtype=frame.dtype, device=frame.device)
+        shard = self._buffer("shard%d" % rank, (self.rounds * self.band_pixels, c), frame)      # padding rows stay zero
         full = self.height // self.band_rows                      # bands not clipped by the bottom edge
         mine = len(range(rank, full, self.world))
         if mine:
@@ -75,19 +83,22 @@ class BandPlan:
         return shard
 
     def unpack(self, gathered):
-        """(world*rounds*band_pixels, C) all-gather result -> (W*H, C) frame."""
+        """(world*rounds*band_pixels, C) all-gather result -> (W*H, C) frame (one de-interleave copy into a reused buffer)."""
         c = gathered.shape[1]
         g = gathered.view(self.world, self.rounds, self.band_pixels, c).permute(1, 0, 2, 3)   # band index = round*world + rank
-        return g.reshape(-1, c)[: self.width * self.height]
+        out = self._buffer("frame", (self.rounds, self.world, self.band_pixels, c), gathered)
+        out.copy_(g)
+        return out.view(-1, c)[: self.width * self.height]
 
 
 def gather_frame(plan, frame, rank, group=None):
     """All ranks end up with the complete frame. `frame` is this rank's (W*H, C) buffer in which only its own
-    bands are valid. One collective: all_gather of equal contiguous shards."""
+    bands are valid. One collective: all_gather of equal contiguous shards. The returned tensor is a buffer owned by
+    `plan` and is overwritten by the next gather."""
     shard = plan.pack(frame, rank)
     if plan.world == 1:
         return plan.unpack(shard)
-    out = torch.empty((plan.world * shard.shape[0], shard.shape[1]), dtype=shard.dtype, device=shard.device)
+    out = plan._buffer("gathered", (plan.world * shard.shape[0], shard.shape[1]), shard)
     dist.all_gather_into_tensor(out, shard, group=group)
     return plan.unpack(out)
 
