@@ -162,6 +162,17 @@ int b2rt_read_pixels(b2rt_context* ctx, void* dst, size_t bytes);   /* read_buff
  * The accumulation image itself is not modified. */
 int b2rt_read_pixels_rgba8(b2rt_context* ctx, void* dst, size_t bytes);
 
+/* ---- BVH build on the device (new) ------------------------------------------------------ */
+/* Stands in for CLBVHScene::RecursiveBuild + FlattenBVHTree (CLBVHnode.cpp:7-183): builds a binary BVH over
+ * `triangles` (CLTriangle[n] in LOADER order, host memory) on the GPU -- Morton order, Karras hierarchy, bottom-up
+ * boxes -- and returns it in the reference's own format: nodes_out receives CLLinearBVHNode[*n_nodes_out] (pre-order,
+ * first child at index+1, at most 2n-1 nodes), order_out[k] the input index of the triangle that must become triangle
+ * k of the scene array (the caller re-orders its triangles like CreateBVHTrees does, CLBVHnode.cpp:197). The tree is
+ * NOT the reference's SAH tree: hit IDs refer to this order, and where the reference's result depends on visiting
+ * order (equal-t ties, negative t) the winner can differ from a scene built by the host builder. */
+int b2rt_build_bvh(b2rt_context* ctx, const void* triangles, uint64_t n_triangles, void* nodes_out, uint64_t nodes_capacity,
+                   uint64_t* n_nodes_out, uint32_t* order_out);
+
 /* ---- ray-stream path (new) ----------------------------------------------------------- */
 /* Host buffers: H2D copy, trace, D2H copy, synchronous on return.
  * closest: hits[i] = {t,u,v,tri} of Intersect() (kernel_bvh.cl:171-219), tri = B2RT_MISS and

@@ -23,7 +23,7 @@ SYMBOLS = [
     "b2rt_create", "b2rt_destroy", "b2rt_last_error", "b2rt_status_string", "b2rt_buffer_create",
     "b2rt_buffer_release", "b2rt_set_arg", "b2rt_execute", "b2rt_execute_range", "b2rt_execute_bands", "b2rt_read_buffer",
     "b2rt_finish", "b2rt_host_register", "b2rt_host_unregister", "b2rt_upload_scene", "b2rt_resize", "b2rt_read_pixels", "b2rt_read_pixels_rgba8", "b2rt_trace_closest",
-    "b2rt_trace_any", "b2rt_trace_closest_device", "b2rt_trace_any_device", "b2rt_camera_rays_device",
+    "b2rt_trace_any", "b2rt_build_bvh", "b2rt_trace_closest_device", "b2rt_trace_any_device", "b2rt_camera_rays_device",
     "b2rt_device_pointer", "b2rt_bound_buffer", "b2rt_scene_info_get", "b2rt_set_option",
     "b2rt_get_counters", "b2rt_reset_counters", "b2rt_launch_count", "b2rt_device_count",
 ]
@@ -82,6 +82,7 @@ def lib():
         "b2rt_host_register": (C.c_int, [vp, vp, sz]),
         "b2rt_host_unregister": (C.c_int, [vp, vp]),
         "b2rt_upload_scene": (C.c_int, [vp, vp, u64, vp, u64, vp, u64]),
+        "b2rt_build_bvh": (C.c_int, [vp, vp, u64, vp, u64, C.POINTER(u64), vp]),
         "b2rt_resize": (C.c_int, [vp, u32, u32]),
         "b2rt_read_pixels": (C.c_int, [vp, vp, sz]),
         "b2rt_read_pixels_rgba8": (C.c_int, [vp, vp, sz]),
@@ -175,6 +176,16 @@ class Context:
         n, nn = _raw(nodes, NODE_BYTES, "nodes")
         m, nm = _raw(mats, MAT_BYTES, "materials")
         self._ck(self._L.b2rt_upload_scene(self._h, _ptr(t), nt, _ptr(n), nn, _ptr(m), nm))
+
+    def build_bvh(self, tris):
+        """b2rt_build_bvh: binary BVH over loader-order triangles on the GPU, in the reference's format.
+        Returns (re-ordered triangles, nodes, order) with order[k] = input index of output triangle k."""
+        t, nt = _raw(tris, TRI_BYTES, "triangles")
+        nodes = np.zeros((2 * nt - 1, NODE_BYTES), dtype=np.uint8)
+        order = np.empty(nt, dtype=np.uint32)
+        n_nodes = C.c_uint64(0)
+        self._ck(self._L.b2rt_build_bvh(self._h, _ptr(t), nt, _ptr(nodes), nodes.shape[0], C.byref(n_nodes), _ptr(order)))
+        return np.ascontiguousarray(t.reshape(nt, TRI_BYTES)[order]), nodes[: n_nodes.value].copy(), order
 
     def resize(self, width, height):
         self._ck(self._L.b2rt_resize(self._h, int(width), int(height)))

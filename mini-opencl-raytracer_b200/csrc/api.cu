@@ -15,6 +15,7 @@
 #include <vector>
 #include "b2rt.h"
 #include "kernels.h"
+#include "lbvh.h"
 #include "wide_bvh.h"
 
 using namespace b2rt;
@@ -791,6 +792,112 @@ extern "C" int b2rt_read_pixels_rgba8(b2rt_context* ctx, void* dst, size_t bytes
     CK(launch_tonemap_rgba8(b->d_ptr, ctx->d_rgba8, n, ctx->stream));
     ctx->launches += 1;
     CK(cudaMemcpyAsync(dst, ctx->d_rgba8, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return B2RT_SUCCESS;
+}
+
+// ---- device BVH build ----------------------------------------------------------
+extern "C" int b2rt_build_bvh(b2rt_context* ctx, const void* triangles, uint64_t n_triangles, void* nodes_out, uint64_t nodes_capacity,
+                              uint64_t* n_nodes_out, uint32_t* order_out) {
+    if (!ctx) return B2RT_INVALID_CONTEXT;
+    if (!triangles || !n_triangles || !nodes_out || !n_nodes_out || !order_out) return fail(ctx, B2RT_INVALID_VALUE, "null or empty argument");
+    if (n_triangles >= 0x7fffffffull) return fail(ctx, B2RT_INVALID_VALUE, "scene too large for 32-bit indices");
+    int st = use_device(ctx);
+    if (st) return st;
+    const RefTriangle* tris = static_cast<const RefTriangle*>(triangles);
+    // 1. groups: runs of consecutive triangles with bit-identical centroids (the loader's copies of one face)
+    std::vector<uint32_t> first;
+    std::vector<float> gb;
+    float clo[3] = { INFINITY, INFINITY, INFINITY }, chi[3] = { -INFINITY, -INFINITY, -INFINITY };
+    try {
+        first.reserve(n_triangles / 2 + 2);
+        gb.reserve(3 * n_triangles + 6);
+        float prev[3] = { 0, 0, 0 };
+        for (uint64_t i = 0; i < n_triangles; ++i) {
+            const RefVec &a = tris[i].v1.position, &b = tris[i].v2.position, &c = tris[i].v3.position;
+            float lo[3] = { std::min(a.x, std::min(b.x, c.x)), std::min(a.y, std::min(b.y, c.y)), std::min(a.z, std::min(b.z, c.z)) };
+            float hi[3] = { std::max(a.x, std::max(b.x, c.x)), std::max(a.y, std::max(b.y, c.y)), std::max(a.z, std::max(b.z, c.z)) };
+            float cen[3] = { lo[0] * 0.5f + hi[0] * 0.5f, lo[1] * 0.5f + hi[1] * 0.5f, lo[2] * 0.5f + hi[2] * 0.5f };   // CLBVHnode.cpp:190-193
+            const bool fresh = first.empty() || memcmp(cen, prev, 12) != 0 || i - first.back() >= 255;
+            if (fresh) {
+                first.push_back((uint32_t)i);
+                gb.insert(gb.end(), { lo[0], lo[1], lo[2], hi[0], hi[1], hi[2] });
+                memcpy(prev, cen, 12);
+                for (int k = 0; k < 3; ++k) { clo[k] = std::min(clo[k], cen[k]); chi[k] = std::max(chi[k], cen[k]); }
+            } else {
+                float* g = &gb[gb.size() - 6];
+                for (int k = 0; k < 3; ++k) { g[k] = std::min(g[k], lo[k]); g[3 + k] = std::max(g[3 + k], hi[k]); }
+            }
+        }
+        first.push_back((uint32_t)n_triangles);
+    } catch (const std::bad_alloc&) {
+        return fail(ctx, B2RT_OUT_OF_HOST_MEMORY, "BVH build ran out of host memory");
+    }
+    const uint32_t m = (uint32_t)first.size() - 1;
+    if (nodes_capacity < 2ull * m - 1) return fail(ctx, B2RT_INVALID_VALUE, "node buffer too small: " + std::to_string(2ull * m - 1) + " nodes needed");
+    RefNode* out = static_cast<RefNode*>(nodes_out);
+    auto leaf_node = [&](RefNode& nd, uint32_t group, uint32_t first_tri) {
+        memset(&nd, 0, sizeof(nd));
+        const float* g = &gb[6 * (size_t)group];
+        nd.bmin.x = g[0]; nd.bmin.y = g[1]; nd.bmin.z = g[2]; nd.bmax.x = g[3]; nd.bmax.y = g[4]; nd.bmax.z = g[5];
+        nd.offset = first_tri;
+        nd.nPrimitives = (uint16_t)(first[group + 1] - first[group]);
+    };
+    if (m == 1) {
+        leaf_node(out[0], 0, 0);
+        for (uint64_t i = 0; i < n_triangles; ++i) order_out[i] = (uint32_t)i;
+        *n_nodes_out = 1;
+        return B2RT_SUCCESS;
+    }
+    // 2. Morton order, hierarchy and boxes on the device
+    void *d_gb = nullptr, *d_scratch = nullptr, *d_children = nullptr, *d_bounds = nullptr, *d_axis = nullptr, *d_sorted = nullptr;
+    auto release = [&]() { for (void* p : { d_gb, d_scratch, d_children, d_bounds, d_axis, d_sorted }) if (p) cudaFree(p); };
+    std::vector<int2> children;
+    std::vector<float> nb;
+    std::vector<uint8_t> axis;
+    std::vector<uint32_t> sorted;
+    cudaError_t e = cudaSuccess;
+    try { children.resize(m - 1); nb.resize(6 * (size_t)(m - 1)); axis.resize(m - 1); sorted.resize(m); }
+    catch (const std::bad_alloc&) { return fail(ctx, B2RT_OUT_OF_HOST_MEMORY, "BVH build ran out of host memory"); }
+    if ((e = cudaMalloc(&d_gb, (size_t)m * 24)) == cudaSuccess && (e = cudaMalloc(&d_scratch, lbvh_scratch_bytes(m))) == cudaSuccess &&
+        (e = cudaMalloc(&d_children, (size_t)(m - 1) * sizeof(int2))) == cudaSuccess && (e = cudaMalloc(&d_bounds, (size_t)(m - 1) * 24)) == cudaSuccess &&
+        (e = cudaMalloc(&d_axis, m)) == cudaSuccess && (e = cudaMalloc(&d_sorted, (size_t)m * 4)) == cudaSuccess &&
+        (e = cudaMemcpyAsync(d_gb, gb.data(), (size_t)m * 24, cudaMemcpyHostToDevice, ctx->stream)) == cudaSuccess &&
+        (e = lbvh_build(static_cast<const float*>(d_gb), m, clo, chi, d_scratch, static_cast<int2*>(d_children), static_cast<float*>(d_bounds),
+                        static_cast<uint8_t*>(d_axis), static_cast<uint32_t*>(d_sorted), &ctx->launches, ctx->stream)) == cudaSuccess &&
+        (e = cudaMemcpyAsync(children.data(), d_children, (size_t)(m - 1) * sizeof(int2), cudaMemcpyDeviceToHost, ctx->stream)) == cudaSuccess &&
+        (e = cudaMemcpyAsync(nb.data(), d_bounds, (size_t)(m - 1) * 24, cudaMemcpyDeviceToHost, ctx->stream)) == cudaSuccess &&
+        (e = cudaMemcpyAsync(axis.data(), d_axis, m - 1, cudaMemcpyDeviceToHost, ctx->stream)) == cudaSuccess &&
+        (e = cudaMemcpyAsync(sorted.data(), d_sorted, (size_t)m * 4, cudaMemcpyDeviceToHost, ctx->stream)) == cudaSuccess)
+        e = cudaStreamSynchronize(ctx->stream);
+    release();
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "device BVH build");
+    // 3. the reference's format: pre-order numbering, first child at index + 1, `offset` = second child (interior) or
+    //    first triangle (leaf); triangles re-ordered leaf by leaf (FlattenBVHTree, CLBVHnode.cpp:161-183)
+    struct Visit { int ref; int64_t parent; };
+    std::vector<Visit> todo;
+    todo.push_back(Visit{ 0, -1 });
+    uint64_t next = 0, tri_out = 0;
+    while (!todo.empty()) {
+        const Visit v = todo.back();
+        todo.pop_back();
+        const uint64_t me = next++;
+        if (v.parent >= 0) out[v.parent].offset = (uint32_t)me;
+        if (v.ref < 0) {
+            const uint32_t g = sorted[~v.ref];
+            leaf_node(out[me], g, (uint32_t)tri_out);
+            for (uint32_t t = first[g]; t < first[g + 1]; ++t) order_out[tri_out++] = t;
+        } else {
+            RefNode& nd = out[me];
+            memset(&nd, 0, sizeof(nd));
+            const float* b = &nb[6 * (size_t)v.ref];
+            nd.bmin.x = b[0]; nd.bmin.y = b[1]; nd.bmin.z = b[2]; nd.bmax.x = b[3]; nd.bmax.y = b[4]; nd.bmax.z = b[5];
+            nd.axis = axis[v.ref];
+            todo.push_back(Visit{ children[v.ref].y, (int64_t)me });    // numbered after the whole first subtree
+            todo.push_back(Visit{ children[v.ref].x, -1 });             // numbered next: index me + 1
+        }
+    }
+    if (next != 2ull * m - 1 || tri_out != n_triangles) return fail(ctx, B2RT_OUT_OF_RESOURCES, "device BVH build produced an inconsistent tree");
+    *n_nodes_out = next;
     return B2RT_SUCCESS;
 }
 

@@ -36,6 +36,8 @@ def lib():
         "g3d_scene_load_cached": (vp, [cs, C.c_uint, cs, C.POINTER(C.c_int), cs, sz]),
         "g3d_engine_load_scene_cached": (C.c_int, [vp, cs, C.c_uint, cs, C.POINTER(C.c_int), cs, sz]),
         "g3d_parse_numbers": (C.c_int, [cs, vp, C.c_int]),
+        "g3d_scene_load_triangles": (vp, [cs, cs, sz]),
+        "g3d_engine_load_scene_device_bvh": (C.c_int, [vp, cs, cs, sz]),
         "g3d_scene_from_triangles": (vp, [vp, u64, vp, u64, C.c_uint, cs, sz]),
         "g3d_scene_free": (None, [vp]),
         "g3d_scene_count": (u64, [vp, C.c_int]),
@@ -102,6 +104,20 @@ def load_scene(obj_path, max_prims=4, cache=None):
         raise HostError(e.value.decode())
     try:
         return _arrays(L, h)
+    finally:
+        L.g3d_scene_free(h)
+
+
+def load_triangles(obj_path):
+    """CLOBJloader only: (tris, mats) in LOADER order, no BVH -- the input of Context.build_bvh / b2rt_build_bvh."""
+    L = lib()
+    e = _err()
+    h = L.g3d_scene_load_triangles(os.fsencode(obj_path), e, len(e))
+    if not h:
+        raise HostError(e.value.decode())
+    try:
+        t, _, m = _arrays(L, h)
+        return t, m
     finally:
         L.g3d_scene_free(h)
 
@@ -181,6 +197,11 @@ class Engine:
             return bool(hit.value)
         self._ck(self._L.g3d_engine_load_scene(self._h, os.fsencode(obj_path), max_prims, e, len(e)), e)
         return False
+
+    def load_scene_device_bvh(self, obj_path):
+        """CLOBJloader::Load, then CLBVHScene::CreateBVHTreesDevice: the binary BVH is built on the GPU."""
+        e = _err()
+        self._ck(self._L.g3d_engine_load_scene_device_bvh(self._h, os.fsencode(obj_path), e, len(e)), e)
 
     def scene_arrays(self):
         h = self._L.g3d_engine_scene(self._h)

@@ -196,6 +196,10 @@ namespace Glaze3D
         // renderer exists (`eng->render`), uploads the three arrays like the reference does.
         void CreateBVHTrees(unsigned int maxPrimitivesInNode);
         void BuildOnly(unsigned int maxPrimitivesInNode);                 // build + flatten, no upload
+        // Same result TYPE as CreateBVHTrees (re-ordered m_Triangles + flattened node array, uploaded), but the tree is
+        // built on the GPU by b2rt_build_bvh (Morton order + Karras hierarchy) instead of the SAH recursion: a few
+        // milliseconds of device time instead of seconds. It is a different tree: hit IDs index THIS order.
+        void CreateBVHTreesDevice();
         const std::vector<CLLinearBVHNode>& Nodes() const { return m_Nodes; }
         void SetupBuffers();                                              // CLBVHnode.cpp:209-236
 

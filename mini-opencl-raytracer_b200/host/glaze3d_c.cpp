@@ -46,6 +46,15 @@ extern "C" void* g3d_scene_load_cached(const char* objPath, unsigned maxPrims, c
     return new SceneBox{ s };
     G3D_CATCH(nullptr)
 }
+// CLOBJloader only: the triangles in LOADER order, no BVH (input of b2rt_build_bvh).
+extern "C" void* g3d_scene_load_triangles(const char* objPath, char* err, size_t errLen)
+{
+    G3D_TRY
+    auto s = std::make_shared<CLBVHScene>();
+    CLOBJloader::LoadInto(*s, objPath);
+    return new SceneBox{ s };
+    G3D_CATCH(nullptr)
+}
 extern "C" void* g3d_scene_from_triangles(const void* tris, uint64_t nTris, const void* mats, uint64_t nMats, unsigned maxPrims, char* err, size_t errLen)
 {
     G3D_TRY
@@ -114,6 +123,19 @@ extern "C" int g3d_engine_load_scene_cached(void* engine, const char* objPath, u
     bool h = CLOBJloader::LoadCached(*e->render->m_Scene, objPath, maxPrims, cachePath);
     if (hit) *hit = h ? 1 : 0;
     e->render->m_Scene->SetupBuffers();
+    return 0;
+    G3D_CATCH(-1)
+}
+// CLOBJloader::Load, then the BVH built on the GPU (CLBVHScene::CreateBVHTreesDevice) instead of the SAH recursion.
+extern "C" int g3d_engine_load_scene_device_bvh(void* engine, const char* objPath, char* err, size_t errLen)
+{
+    G3D_TRY
+    auto& e = static_cast<EngineBox*>(engine)->engine;
+    eng = e;
+    e->render->m_Scene = std::make_shared<CLBVHScene>();
+    CLOBJloader loader;
+    loader.Load(objPath, 4);
+    e->render->m_Scene->CreateBVHTreesDevice();
     return 0;
     G3D_CATCH(-1)
 }

@@ -334,6 +334,26 @@ namespace Glaze3D
         if (eng && eng->render && eng->render->m_CLContext) SetupBuffers();
     }
 
+    void CLBVHScene::CreateBVHTreesDevice()
+    {
+        if (!eng || !eng->render || !eng->render->m_CLContext)
+            throw CLException("CLBVHScene::CreateBVHTreesDevice needs eng->render->m_CLContext", B2RT_INVALID_CONTEXT);
+        if (m_Triangles.empty()) throw CLException("Cannot build a BVH over an empty scene", B2RT_INVALID_VALUE);
+        b2rt_context* ctx = eng->render->m_CLContext->GetContext();
+        std::vector<CLLinearBVHNode> nodes(2 * m_Triangles.size() - 1);
+        std::vector<uint32_t> order(m_Triangles.size());
+        uint64_t n_nodes = 0;
+        int st = b2rt_build_bvh(ctx, m_Triangles.data(), m_Triangles.size(), nodes.data(), nodes.size(), &n_nodes, order.data());
+        if (st) throw CLException(std::string("Failed to build the BVH on the device: ") + b2rt_last_error(ctx), st);
+        nodes.resize(n_nodes);
+        std::vector<CLTriangle> ordered;
+        ordered.reserve(order.size());
+        for (uint32_t src : order) ordered.push_back(m_Triangles[src]);
+        m_Triangles.swap(ordered);
+        m_Nodes.swap(nodes);
+        SetupBuffers();
+    }
+
     void CLBVHScene::SetupBuffers()
     {
         if (!eng || !eng->render || !eng->render->m_CLContext)
