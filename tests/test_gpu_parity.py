@@ -526,3 +526,46 @@ def test_device_bvh_build(product, tmp_scene_dir, bumpy_ref):
         ref_img = np.zeros((160 * 120, 4), dtype=np.float32)
         ol.oracle_render(t2, n2, m2, ref_img, 160, 120, 1, 3, pos=(0.0, -30.0, 4.0), front=(0.0, 1.0, 0.0), up=(0.0, 0.0, 1.0))
         assert scenes.psnr(eng.pixels()[:, :3], ref_img[:, :3]) >= 50.0
+
+
+def test_device_bvh_build_edge_cases(product, tmp_scene_dir):
+    """Device-built trees on awkward inputs: coincident lattices (identical Morton codes, exact t ties across leaves), a
+    single face (one group: the root is a leaf), quads (3-triangle groups) and a scene whose centroids all lie on one line."""
+    with product.Context(0) as ctx:
+        # coincident lattices
+        p, n, f = scenes.tie_grid(24, layers=3)
+        path = scenes.write_obj(os.path.join(tmp_scene_dir, "lbvh_ties.obj"), p, n, f)
+        lt, mats = product.host.load_triangles(path)
+        tris, nodes, order = ctx.build_bvh(lt)
+        _tree_is_valid(tris, nodes)
+        ctx.upload_scene(tris, nodes, mats)
+        rays = scenes.tie_rays(24)
+        _check_hits(ctx.trace_closest(rays), ol.oracle_closest(tris, nodes, rays))
+        # one face and one quad
+        p = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [1, 1, 0]], dtype=np.float32)
+        n = np.tile(np.array([[0, 0, 1]], dtype=np.float32), (4, 1))
+        for name, faces, quads, n_nodes in (("lbvh_one.obj", [[0, 1, 2]], None, 1), ("lbvh_quad.obj", [[0, 1, 2]], [[0, 1, 3, 2]], None)):
+            path = scenes.write_obj(os.path.join(tmp_scene_dir, name), p, n, np.array(faces), quads)
+            lt, mats = product.host.load_triangles(path)
+            tris, nodes, order = ctx.build_bvh(lt)
+            _tree_is_valid(tris, nodes)
+            if n_nodes:
+                assert nodes.shape[0] == n_nodes
+            ctx.upload_scene(tris, nodes, mats)
+            rays = scenes.box_rays(3000, (-1, -1, 0.5), (2, 2, 3), seed=45)
+            _check_hits(ctx.trace_closest(rays), ol.oracle_closest(tris, nodes, rays))
+        # all centroids on one line (two of the three Morton axes carry no information)
+        k = 5000
+        x = np.arange(k, dtype=np.float32)
+        p = np.stack([np.stack([x, np.zeros(k), np.zeros(k)], 1), np.stack([x + 0.9, np.zeros(k), np.zeros(k)], 1),
+                      np.stack([x + 0.45, np.ones(k), np.zeros(k)], 1)], 1).reshape(-1, 3).astype(np.float32)
+        n = np.tile(np.array([[0, 0, 1]], dtype=np.float32), (3 * k, 1))
+        path = scenes.write_obj(os.path.join(tmp_scene_dir, "lbvh_line.obj"), p, n, np.arange(3 * k).reshape(k, 3))
+        lt, mats = product.host.load_triangles(path)
+        tris, nodes, order = ctx.build_bvh(lt)
+        _tree_is_valid(tris, nodes)
+        ctx.upload_scene(tris, nodes, mats)
+        rays = scenes.box_rays(20000, (0, -1, 0.5), (k, 2, 3), seed=46)
+        got = ctx.trace_closest(rays)
+        _check_hits(got, ol.oracle_closest(tris, nodes, rays))
+        assert (got["tri"] != MISS).mean() > 0.01
