@@ -298,6 +298,36 @@ def run_b200(args, rank, world, local_rank):
                                "bounce_hit_fraction": float((d_bh[:, 3].view(torch.int32) != -1).float().mean().item())}
         del d_cam, d_camhits, d_b, d_bh
 
+    # ---- device BVH build: b2rt_build_bvh on the loader-order triangles of the same OBJ, and the same
+    # ray stream through the tree it returns. Rank 0 only, outside every timed region of the headline.
+    if rank == 0 and not args.skip_frames:
+        loader_tris, loader_mats = prod.host.load_triangles(path)
+        with prod.Context(local_rank) as bctx:
+            bctx.build_bvh(loader_tris[:4096])                       # warm-up (allocator, first launches)
+            t0 = time.perf_counter()
+            b_tris, b_nodes, _ = bctx.build_bvh(loader_tris)
+            build_s = time.perf_counter() - t0
+            del loader_tris
+            bctx.upload_scene(b_tris, b_nodes, loader_mats)
+            nb = min(n, 1 << 24)
+            d_bh = torch.empty((nb, 4), dtype=torch.float32, device="cuda")
+            for _ in range(2):
+                bctx.trace_closest_device(d_rays.data_ptr(), nb, d_bh.data_ptr(), stream.cuda_stream)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(stream):
+                e0.record()
+                for _ in range(3):
+                    bctx.trace_closest_device(d_rays.data_ptr(), nb, d_bh.data_ptr(), stream.cuda_stream)
+                e1.record()
+            torch.cuda.synchronize()
+            same_miss = bool(torch.equal(d_bh.view(torch.int32)[:, 3] == -1, d_hits.view(torch.int32)[:nb, 3] == -1))
+            extra["device_bvh_build"] = {"api": "b2rt_build_bvh (Morton order + Karras hierarchy on the GPU, reference-format tree out)",
+                                         "triangles": int(b_tris.shape[0]), "nodes": int(b_nodes.shape[0]),
+                                         "b2rt_build_bvh_s": bctx.last_build_seconds, "with_numpy_triangle_reorder_s": build_s,
+                                         "closest_mrays_s_on_device_built_tree": nb * 3 / (e0.elapsed_time(e1) * 1e-3) / 1e6,
+                                         "rays_per_launch": nb, "same_hit_or_miss_as_sah_tree": same_miss}
+            del d_bh, b_tris, b_nodes
+
     # ---- end to end through the C ABI with host buffers -----------------------------------------------------------
     def e2e_step():
         ctx.trace_closest(rays_np, hits_np)      # H2D 32 B/ray, traversal, D2H 16 B/ray; synchronous

@@ -2,6 +2,7 @@
 no fallback: a missing library or CUDA device raises."""
 import ctypes as C
 import os
+import time
 
 import numpy as np
 
@@ -184,7 +185,9 @@ class Context:
         nodes = np.zeros((2 * nt - 1, NODE_BYTES), dtype=np.uint8)
         order = np.empty(nt, dtype=np.uint32)
         n_nodes = C.c_uint64(0)
+        t0 = time.perf_counter()
         self._ck(self._L.b2rt_build_bvh(self._h, _ptr(t), nt, _ptr(nodes), nodes.shape[0], C.byref(n_nodes), _ptr(order)))
+        self.last_build_seconds = time.perf_counter() - t0          # the C call alone (grouping, device build, flattening)
         return np.ascontiguousarray(t.reshape(nt, TRI_BYTES)[order]), nodes[: n_nodes.value].copy(), order
 
     def resize(self, width, height):
