@@ -516,7 +516,7 @@ def run_b200(args, rank, world, local_rank):
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
                          "traffic": measured_traffic(args.frequency, n), "traffic_unit": "GB per launch (ncu dram bytes, profiles/r1_traffic.json)",
-                         "algorithmic_gb_per_launch": n * bytes_per_ray / 1e9, "peak_source": which + " copy bandwidth (MEASURED_PEAKS.json)" if which == "measured" else "fallback",
+                         "algorithmic_gb_per_launch": n * bytes_per_ray / 1e9, "peak_source": "measured copy bandwidth (MEASURED_PEAKS.json)" if which == "measured" else "of fallback (6.65 TB/s, B200_PROFILING.md; MEASURED_PEAKS.json absent)",
                          "kernel": "trace_persistent<closest>", "kernel_ms": kernel_ms,
                          "bytes_per_ray": bytes_per_ray, "traversal_bytes_per_ray": trav_bytes,
                          "per_ray": {k: v / max(cnt["rays"], 1) for k, v in cnt.items() if k not in ("rays", "max_steps_per_ray")},
