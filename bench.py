@@ -66,16 +66,17 @@ def measured_peaks():
 
 def measured_traffic(frequency, rays):
     """dram__bytes_{read,write}.sum of one launch of the dominant kernel from the committed ncu --set full
-    capture, when that capture was taken on this exact workload; else None."""
+    capture, when that capture was taken on this exact workload; else None. Second value: the capture's other
+    headline metrics (L2 / DRAM throughput, pipes, stalls) for the same launch."""
     p = os.path.join(ROOT, "profiles", "r1_traffic.json")
     if not os.path.exists(p):
-        return None
+        return None, None
     with open(p) as f:
         t = json.load(f)
     w = t.get("workload", {})
     if w.get("frequency") == frequency and w.get("rays_per_launch") == rays:
-        return t["dram_bytes_per_launch"] / 1e9
-    return None
+        return t["dram_bytes_per_launch"] / 1e9, t.get("ncu")
+    return None, None
 
 
 def ensure_scene(prod, frequency, rank, world, barrier):
@@ -501,6 +502,8 @@ def run_b200(args, rank, world, local_rank):
     if rank == 0:
         peaks, which = measured_peaks()
         achieved = n * bytes_per_ray / (kernel_ms * 1e-3) / 1e9
+        traffic_gb, ncu_metrics = measured_traffic(args.frequency, n)
+        compulsory = (info["wide_node_bytes"] + info["leaf_bytes"] + 48.0 * n) / (kernel_ms * 1e-3) / 1e9
         out = {
             "metric": "closest_hit_ray_throughput", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -515,7 +518,8 @@ def run_b200(args, rank, world, local_rank):
                     "api": "b2rt_trace_closest (pinned host buffers, chunked H2D/kernel/D2H pipeline)"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-                         "traffic": measured_traffic(args.frequency, n), "traffic_unit": "GB per launch (ncu dram bytes, profiles/r1_traffic.json)",
+                         "traffic": traffic_gb, "traffic_unit": "GB per launch (ncu dram bytes, profiles/r1_traffic.json)",
+                         "compulsory_floor_gbs": compulsory, "ncu_same_launch": ncu_metrics,
                          "algorithmic_gb_per_launch": n * bytes_per_ray / 1e9, "peak_source": "measured copy bandwidth (MEASURED_PEAKS.json)" if which == "measured" else "of fallback (6.65 TB/s, B200_PROFILING.md; MEASURED_PEAKS.json absent)",
                          "kernel": "trace_persistent<closest>", "kernel_ms": kernel_ms,
                          "bytes_per_ray": bytes_per_ray, "traversal_bytes_per_ray": trav_bytes,
