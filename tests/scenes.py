@@ -252,3 +252,29 @@ def moller_trumbore_all(tris_u8, rays):
         t = (dot(np.broadcast_to(e2, qvec.shape), qvec) * inv).astype(np.float32)
         ok = (det >= np.float32(1e-8)) & (u >= 0) & (u <= 1) & (v >= 0) & ((u + v).astype(np.float32) <= 1)
     return ok, t
+
+
+def fuzz_scene(case, rng):
+    """Small random scenes of awkward shapes, by `case % 6`: uniform soup, slivers, two distant clusters, a few huge
+    triangles over many tiny ones, an axis-aligned sheet on an exact lattice, many exact duplicates. Every 17th face has
+    zero area. Returns (positions, faces)."""
+    k = int(rng.integers(20, 400))
+    kind = case % 6
+    if kind == 0:                                             # uniform soup
+        c = rng.uniform(-5, 5, (k, 1, 3)); e = rng.normal(0, 1.0, (k, 3, 3))
+    elif kind == 1:                                           # slivers: one long edge, tiny height
+        c = rng.uniform(-5, 5, (k, 1, 3)); e = rng.normal(0, 1.0, (k, 3, 3)) * np.array([3.0, 0.01, 0.01])
+    elif kind == 2:                                           # two tight clusters far apart
+        c = np.where(rng.random((k, 1, 1)) < 0.5, -40.0, 40.0) + rng.normal(0, 0.2, (k, 1, 3)); e = rng.normal(0, 0.1, (k, 3, 3))
+    elif kind == 3:                                           # a few huge triangles over many tiny ones
+        c = rng.uniform(-5, 5, (k, 1, 3)); e = rng.normal(0, 0.05, (k, 3, 3)); e[:5] *= 400.0
+    elif kind == 4:                                           # axis-aligned sheet at z = 0 on an exact lattice
+        c = np.concatenate([rng.integers(-8, 8, (k, 1, 2)).astype(np.float64), np.zeros((k, 1, 1))], 2)
+        e = np.concatenate([rng.integers(-2, 3, (k, 3, 2)).astype(np.float64), np.zeros((k, 3, 1))], 2)
+    else:                                                     # many exact duplicates of a handful of triangles
+        base_c = rng.uniform(-3, 3, (6, 1, 3)); base_e = rng.normal(0, 1.0, (6, 3, 3))
+        pick = rng.integers(0, 6, k); c, e = base_c[pick], base_e[pick]
+    pos = (c + e).reshape(-1, 3).astype(np.float32)
+    faces = np.arange(3 * k).reshape(k, 3)
+    faces[:: 17, 1] = faces[:: 17, 0]                          # a few zero-area faces (two equal vertices)
+    return pos, faces

@@ -113,3 +113,33 @@ def test_exact_ties_across_leaves_follow_the_reference_order(tmp_scene_dir):
     for schedule in (0, 1, 12345):
         _same(ol.emu_trace(rays, schedule=schedule), want)
     assert np.array_equal(ol.emu_trace(rays, any_hit=True) != 0, ol.oracle_any(tris, nodes, rays) != 0)
+
+
+def test_random_scenes_fuzz(tmp_scene_dir):
+    """Small random scenes of awkward shapes (slivers, clusters, huge + tiny triangles, axis-aligned sheets, duplicated
+    vertices, zero-area faces) with several maxPrimitivesInNode values: the product's wide-BVH builder + traversal state
+    machine, under random step interleavings, must reproduce the oracle's walk over the reference-format arrays bit for
+    bit -- closest hits, any-hit, and rays that start inside / on the geometry."""
+    import os
+    prod_host = __import__("conftest").load_product().host
+    rng = np.random.default_rng(2024)
+    for case in range(12):
+        pos, faces = scenes.fuzz_scene(case, rng)
+        nrm = np.tile(np.array([[0.0, 0.0, 1.0]], dtype=np.float32), (pos.shape[0], 1))
+        path = scenes.write_obj(os.path.join(tmp_scene_dir, "fuzz%d.obj" % case), pos, nrm, faces)
+        max_prims = int(rng.choice([1, 2, 4, 8, 64]))
+        tris, nodes, _ = prod_host.load_scene(path, max_prims)
+        if ol.ref() is not None:                                   # same arrays as the reference's own loader + builder
+            rt, rn, _ = ol.ref_load_scene(path, max_prims)
+            assert np.array_equal(rn.view(np.uint32).reshape(-1, 12)[:, 8], nodes.view(np.uint32).reshape(-1, 12)[:, 8])
+        ol.emu_build(tris, nodes)
+        lo, hi = pos.min(0) - 1.0, pos.max(0) + 1.0
+        rays = np.concatenate([scenes.box_rays(1500, lo, hi, seed=case), scenes.axis_rays(lo, hi, 20, seed=case),
+                               scenes.pack_rays(pos[rng.integers(0, pos.shape[0], 300)], rng.normal(size=(300, 3)))])   # origins ON vertices
+        rays["tmax"][::5] = rng.uniform(0.1, 20.0, size=rays["tmax"][::5].shape).astype(np.float32)
+        want = ol.oracle_closest(tris, nodes, rays)
+        for schedule in (0, 7 + case):
+            st = ol.EmuStats()
+            _same(ol.emu_trace(rays, stats=st, schedule=schedule), want)
+            assert st.overflow == 0
+        assert np.array_equal(ol.emu_trace(rays, any_hit=True, schedule=99) != 0, ol.oracle_any(tris, nodes, rays) != 0)

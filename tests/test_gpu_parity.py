@@ -569,3 +569,31 @@ def test_device_bvh_build_edge_cases(product, tmp_scene_dir):
         got = ctx.trace_closest(rays)
         _check_hits(got, ol.oracle_closest(tris, nodes, rays))
         assert (got["tri"] != MISS).mean() > 0.01
+
+
+def test_random_scenes_fuzz(product, tmp_scene_dir):
+    """The random awkward scenes of tests/test_emu_traversal.py through the GPU kernels: host-built and device-built trees,
+    wide kernel and reference-layout walk, closest and any-hit -- all bit-identical to the oracle on the same arrays."""
+    rng = np.random.default_rng(2024)
+    with product.Context(0) as ctx:
+        for case in range(12):
+            pos, faces = scenes.fuzz_scene(case, rng)
+            nrm = np.tile(np.array([[0.0, 0.0, 1.0]], dtype=np.float32), (pos.shape[0], 1))
+            path = scenes.write_obj(os.path.join(tmp_scene_dir, "gfuzz%d.obj" % case), pos, nrm, faces)
+            max_prims = int(rng.choice([1, 2, 4, 8, 64]))
+            lo, hi = pos.min(0) - 1.0, pos.max(0) + 1.0
+            rays = np.concatenate([scenes.box_rays(3000, lo, hi, seed=case), scenes.axis_rays(lo, hi, 20, seed=case),
+                                   scenes.pack_rays(pos[rng.integers(0, pos.shape[0], 300)], rng.normal(size=(300, 3)))])
+            rays["tmax"][::5] = rng.uniform(0.1, 20.0, size=rays["tmax"][::5].shape).astype(np.float32)
+            host_scene = product.host.load_scene(path, max_prims)
+            lt, mats = product.host.load_triangles(path)
+            dt, dn, _ = ctx.build_bvh(lt)
+            _tree_is_valid(dt, dn)
+            for tris, nodes in ((host_scene[0], host_scene[1]), (dt, dn)):
+                ctx.upload_scene(tris, nodes, mats)
+                want = ol.oracle_closest(tris, nodes, rays)
+                _check_hits(ctx.trace_closest(rays), want)
+                assert np.array_equal(ctx.trace_any(rays) != 0, ol.oracle_any(tris, nodes, rays) != 0)
+                ctx.set_option(product.capi.OPT_TRAVERSAL, 1)
+                _check_hits(ctx.trace_closest(rays), want)
+                ctx.set_option(product.capi.OPT_TRAVERSAL, 0)
