@@ -4,9 +4,11 @@
 // missing CUDA device makes b2rt_create fail and nothing else is reachable.
 #include <cuda_runtime.h>
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
+#include <chrono>
 #include <map>
 #include <memory>
 #include <new>
@@ -527,6 +529,14 @@ extern "C" int b2rt_create(int device_id, b2rt_context** out) {
     if ((e = cudaEventCreateWithFlags(&ctx->ev_wf_fork, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
     for (int i = 0; i < 2; ++i)
         if ((e = cudaEventCreate(&ctx->ev_tune[i])) != cudaSuccess) return bail(e, "cudaEventCreate");
+    {   // stream-ordered allocations (b2rt_build_bvh) stay mapped between calls up to 256 MB
+        cudaMemPool_t pool = nullptr;
+        if (cudaDeviceGetDefaultMemPool(&pool, device_id) == cudaSuccess) {
+            unsigned long long keep = 256ull << 20;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+    }
     if ((e = cudaMalloc(&ctx->d_next, 64)) != cudaSuccess) return bail(e, "cudaMalloc");
     if ((e = cudaMalloc(&ctx->d_counters, 128)) != cudaSuccess) return bail(e, "cudaMalloc");
     if ((e = cudaMemset(ctx->d_counters, 0, 128)) != cudaSuccess) return bail(e, "cudaMemset");
@@ -804,6 +814,9 @@ extern "C" int b2rt_build_bvh(b2rt_context* ctx, const void* triangles, uint64_t
     int st = use_device(ctx);
     if (st) return st;
     const RefTriangle* tris = static_cast<const RefTriangle*>(triangles);
+    const bool trace = getenv("B2RT_TRACE_BUILD") != nullptr;        // developer aid: phase times on stderr
+    auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_start = now();
     // 1. groups: runs of consecutive triangles with bit-identical centroids (the loader's copies of one face)
     std::vector<uint32_t> first;
     std::vector<float> gb;
@@ -848,29 +861,34 @@ extern "C" int b2rt_build_bvh(b2rt_context* ctx, const void* triangles, uint64_t
         *n_nodes_out = 1;
         return B2RT_SUCCESS;
     }
+    const double t_grouped = now();
     // 2. Morton order, hierarchy and boxes on the device
-    void *d_gb = nullptr, *d_scratch = nullptr, *d_children = nullptr, *d_bounds = nullptr, *d_axis = nullptr, *d_sorted = nullptr;
-    auto release = [&]() { for (void* p : { d_gb, d_scratch, d_children, d_bounds, d_axis, d_sorted }) if (p) cudaFree(p); };
+    // one stream-ordered allocation for everything (the pool keeps it mapped between builds)
+    auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    const size_t o_gb = 0, o_children = o_gb + up((size_t)m * 24), o_bounds = o_children + up((size_t)(m - 1) * sizeof(int2)),
+                 o_axis = o_bounds + up((size_t)(m - 1) * 24), o_sorted = o_axis + up(m), o_scratch = o_sorted + up((size_t)m * 4),
+                 total = o_scratch + up(lbvh_scratch_bytes(m));
     std::vector<int2> children;
     std::vector<float> nb;
     std::vector<uint8_t> axis;
     std::vector<uint32_t> sorted;
-    cudaError_t e = cudaSuccess;
     try { children.resize(m - 1); nb.resize(6 * (size_t)(m - 1)); axis.resize(m - 1); sorted.resize(m); }
     catch (const std::bad_alloc&) { return fail(ctx, B2RT_OUT_OF_HOST_MEMORY, "BVH build ran out of host memory"); }
-    if ((e = cudaMalloc(&d_gb, (size_t)m * 24)) == cudaSuccess && (e = cudaMalloc(&d_scratch, lbvh_scratch_bytes(m))) == cudaSuccess &&
-        (e = cudaMalloc(&d_children, (size_t)(m - 1) * sizeof(int2))) == cudaSuccess && (e = cudaMalloc(&d_bounds, (size_t)(m - 1) * 24)) == cudaSuccess &&
-        (e = cudaMalloc(&d_axis, m)) == cudaSuccess && (e = cudaMalloc(&d_sorted, (size_t)m * 4)) == cudaSuccess &&
-        (e = cudaMemcpyAsync(d_gb, gb.data(), (size_t)m * 24, cudaMemcpyHostToDevice, ctx->stream)) == cudaSuccess &&
-        (e = lbvh_build(static_cast<const float*>(d_gb), m, clo, chi, d_scratch, static_cast<int2*>(d_children), static_cast<float*>(d_bounds),
-                        static_cast<uint8_t*>(d_axis), static_cast<uint32_t*>(d_sorted), &ctx->launches, ctx->stream)) == cudaSuccess &&
-        (e = cudaMemcpyAsync(children.data(), d_children, (size_t)(m - 1) * sizeof(int2), cudaMemcpyDeviceToHost, ctx->stream)) == cudaSuccess &&
-        (e = cudaMemcpyAsync(nb.data(), d_bounds, (size_t)(m - 1) * 24, cudaMemcpyDeviceToHost, ctx->stream)) == cudaSuccess &&
-        (e = cudaMemcpyAsync(axis.data(), d_axis, m - 1, cudaMemcpyDeviceToHost, ctx->stream)) == cudaSuccess &&
-        (e = cudaMemcpyAsync(sorted.data(), d_sorted, (size_t)m * 4, cudaMemcpyDeviceToHost, ctx->stream)) == cudaSuccess)
+    char* d_all = nullptr;
+    cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&d_all), total, ctx->stream);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "device BVH build allocation");
+    if ((e = cudaMemcpyAsync(d_all + o_gb, gb.data(), (size_t)m * 24, cudaMemcpyHostToDevice, ctx->stream)) == cudaSuccess &&
+        (e = lbvh_build(reinterpret_cast<const float*>(d_all + o_gb), m, clo, chi, d_all + o_scratch, reinterpret_cast<int2*>(d_all + o_children),
+                        reinterpret_cast<float*>(d_all + o_bounds), reinterpret_cast<uint8_t*>(d_all + o_axis),
+                        reinterpret_cast<uint32_t*>(d_all + o_sorted), &ctx->launches, ctx->stream)) == cudaSuccess &&
+        (e = cudaMemcpyAsync(children.data(), d_all + o_children, (size_t)(m - 1) * sizeof(int2), cudaMemcpyDeviceToHost, ctx->stream)) == cudaSuccess &&
+        (e = cudaMemcpyAsync(nb.data(), d_all + o_bounds, (size_t)(m - 1) * 24, cudaMemcpyDeviceToHost, ctx->stream)) == cudaSuccess &&
+        (e = cudaMemcpyAsync(axis.data(), d_all + o_axis, m - 1, cudaMemcpyDeviceToHost, ctx->stream)) == cudaSuccess &&
+        (e = cudaMemcpyAsync(sorted.data(), d_all + o_sorted, (size_t)m * 4, cudaMemcpyDeviceToHost, ctx->stream)) == cudaSuccess)
         e = cudaStreamSynchronize(ctx->stream);
-    release();
+    cudaFreeAsync(d_all, ctx->stream);
     if (e != cudaSuccess) return cuda_fail(ctx, e, "device BVH build");
+    const double t_device = now();
     // 3. the reference's format: pre-order numbering, first child at index + 1, `offset` = second child (interior) or
     //    first triangle (leaf); triangles re-ordered leaf by leaf (FlattenBVHTree, CLBVHnode.cpp:161-183)
     struct Visit { int ref; int64_t parent; };
@@ -897,6 +915,8 @@ extern "C" int b2rt_build_bvh(b2rt_context* ctx, const void* triangles, uint64_t
         }
     }
     if (next != 2ull * m - 1 || tri_out != n_triangles) return fail(ctx, B2RT_OUT_OF_RESOURCES, "device BVH build produced an inconsistent tree");
+    if (trace) fprintf(stderr, "[b2rt_build_bvh] %llu triangles, %u groups: grouping %.1f ms, device (alloc + copies + 93 launches) %.1f ms, flatten %.1f ms\n",
+                       (unsigned long long)n_triangles, m, (t_grouped - t_start) * 1e3, (t_device - t_grouped) * 1e3, (now() - t_device) * 1e3);
     *n_nodes_out = next;
     return B2RT_SUCCESS;
 }
