@@ -57,6 +57,17 @@ __device__ __forceinline__ void load_ray(const RayIn* rays, uint64_t i, RayX& r,
     tmax = b.w;
 }
 
+template <bool ANY>
+__device__ __forceinline__ void write_result(void* __restrict__ out, uint64_t i, const HitX& h) {
+#if B2_STREAM_HINTS
+    if (ANY) __stcs(reinterpret_cast<uint32_t*>(out) + i, (h.tri != 0xFFFFFFFFu) ? 1u : 0u);
+    else __stcs(reinterpret_cast<float4*>(out) + i, make_float4(h.t, h.u, h.v, __uint_as_float(h.tri)));
+#else
+    if (ANY) reinterpret_cast<uint32_t*>(out)[i] = (h.tri != 0xFFFFFFFFu) ? 1u : 0u;
+    else reinterpret_cast<float4*>(out)[i] = make_float4(h.t, h.u, h.v, __uint_as_float(h.tri));
+#endif
+}
+
 // ---------------------------------------------------------------------------------------
 // Persistent speculative while-while traversal.
 //
@@ -86,7 +97,9 @@ trace_persistent(SceneView s, const RayIn* __restrict__ rays, uint64_t n, void* 
     L.overflow = false;
     L.tc.wide_nodes = L.tc.leaf_blocks = L.tc.leaf_pass = L.tc.tri_tests = L.tc.words = 0;
     uint64_t my_index = 0;
-    uint64_t pool_next = 0, pool_end = 0;    // warp-uniform
+    bool has_out = false;                    // this lane's finished ray still has to be written (done together with the next refill)
+    uint64_t pool_next = 0;                  // warp-uniform: next ray of the warp's pool ...
+    uint32_t pool_left = 0;                  // ... and how many it still holds
     bool exhausted = false;                  // warp-uniform: the global counter ran past n
     uint32_t traced = 0;
     uint32_t ray_steps = 0, max_ray_steps = 0;   // COUNT only: node + leaf steps of the current ray / the worst ray of this lane
@@ -97,17 +110,19 @@ trace_persistent(SceneView s, const RayIn* __restrict__ rays, uint64_t n, void* 
         const unsigned vn = __ballot_sync(FULL, L.wants_node());
         const unsigned vl = __ballot_sync(FULL, L.wants_leaf());
         const unsigned idle = ~(vn | vl);
-        const bool pool_dry = exhausted && pool_next == pool_end;
+        const bool pool_dry = exhausted && pool_left == 0u;
         if (idle && !pool_dry && ((unsigned)__popc(idle) >= refill_min || (vn | vl) == 0u)) {
             // ---- refill idle lanes from the warp pool -------------------------------------------
-            if (pool_next == pool_end) {
+            // Finished rays are written here, several lanes at a time, instead of one lane at a time when they finish.
+            if (has_out) { write_result<ANY>(out, my_index, L.h); has_out = false; }
+            if (pool_left == 0u) {
                 unsigned long long base = 0;
                 if (lane == 0) base = atomicAdd(next, (unsigned long long)chunk);
                 base = __shfl_sync(FULL, base, 0);
                 if (base >= n) exhausted = true;
-                else { pool_next = base; pool_end = (base + chunk < n) ? base + chunk : n; }
+                else { pool_next = base; pool_left = (base + chunk < n) ? chunk : (uint32_t)(n - base); }
             }
-            const uint64_t avail = pool_end - pool_next;
+            const uint32_t avail = pool_left;
             if (avail) {
                 const unsigned rank = __popc(idle & ((1u << lane) - 1u));
                 if (((idle >> lane) & 1u) && rank < avail) {
@@ -116,9 +131,10 @@ trace_persistent(SceneView s, const RayIn* __restrict__ rays, uint64_t n, void* 
                     load_ray(rays, my_index, r, tmax);
                     L.start(r, tmax);
                 }
-                const unsigned taken = __popc(idle);
-                if (COUNT) { ph_refill++; ph_refill_lanes += (taken < avail) ? taken : (unsigned)avail; }
-                pool_next += (taken < avail) ? taken : avail;
+                const unsigned taken = __popc(idle), used = (taken < avail) ? taken : avail;
+                if (COUNT) { ph_refill++; ph_refill_lanes += used; }
+                pool_next += used;
+                pool_left -= used;
             }
             continue;
         }
@@ -143,16 +159,11 @@ trace_persistent(SceneView s, const RayIn* __restrict__ rays, uint64_t n, void* 
 #endif
         if (COUNT && stepped) ray_steps++;
         if (stepped && L.done()) {
-#if B2_STREAM_HINTS
-            if (ANY) __stcs(reinterpret_cast<uint32_t*>(out) + my_index, (L.h.tri != 0xFFFFFFFFu) ? 1u : 0u);
-            else __stcs(reinterpret_cast<float4*>(out) + my_index, make_float4(L.h.t, L.h.u, L.h.v, __uint_as_float(L.h.tri)));
-#else
-            if (ANY) reinterpret_cast<uint32_t*>(out)[my_index] = (L.h.tri != 0xFFFFFFFFu) ? 1u : 0u;
-            else reinterpret_cast<float4*>(out)[my_index] = make_float4(L.h.t, L.h.u, L.h.v, __uint_as_float(L.h.tri));
-#endif
+            has_out = true;
             if (COUNT) { traced++; max_ray_steps = max_ray_steps > ray_steps ? max_ray_steps : ray_steps; ray_steps = 0; }
         }
     }
+    if (has_out) write_result<ANY>(out, my_index, L.h);       // rays that finished after the last refill
 
     if (COUNT) {
         // one atomic per counter per warp
