@@ -25,7 +25,15 @@ __device__ __forceinline__ V3 vcross(V3 a, V3 b) {
 __device__ __forceinline__ V3 vnormalize(V3 a) { return vdiv(a, xsqrt(vdot(a, a))); }
 __device__ __forceinline__ V3 ldv(const RefVec& p) { return v3(p.x, p.y, p.z); }
 
-__device__ __forceinline__ float pow_cr(float a, float b) { return (float)pow((double)a, (double)b); }
+// powf as glibc evaluates it for the CPU oracle (correctly rounded except very near rounding boundaries): a double result
+// good to ~1e-14 relative, rounded once to float. exp2(b * log2(a)) in fp64 delivers that at half the cost of CUDA's
+// full double-precision pow(); the square (pow(x, 2.0), used twice by SampleBrdf) is exact in fp64 and also correct for
+// negative x, where the logarithm route would give NaN. Special values follow powf for the exponents the kernel uses
+// (2.0, 2.2, 0.4545.., 1/(alpha+1)): pow(0, b>0) = 0, pow(x<0, non-integer) = NaN, pow(inf, b>0) = inf, NaN propagates.
+__device__ __forceinline__ float pow_cr(float a, float b) {
+    if (b == 2.0f) return (float)((double)a * (double)a);
+    return (float)exp2((double)b * log2((double)a));
+}
 __device__ __forceinline__ float sin_cr(float a) { return (float)sin((double)a); }
 __device__ __forceinline__ float cos_cr(float a) { return (float)cos((double)a); }
 
