@@ -322,10 +322,21 @@ def run_b200(args, rank, world, local_rank):
                 e1.record()
             torch.cuda.synchronize()
             same_miss = bool(torch.equal(d_bh.view(torch.int32)[:, 3] == -1, d_hits.view(torch.int32)[:nb, 3] == -1))
+            # the SAH-built scene at the same launch size, measured the same way
+            for _ in range(2):
+                ctx.trace_closest_device(d_rays.data_ptr(), nb, d_bh.data_ptr(), stream.cuda_stream)
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(stream):
+                s0.record()
+                for _ in range(3):
+                    ctx.trace_closest_device(d_rays.data_ptr(), nb, d_bh.data_ptr(), stream.cuda_stream)
+                s1.record()
+            torch.cuda.synchronize()
             extra["device_bvh_build"] = {"api": "b2rt_build_bvh (Morton order + Karras hierarchy on the GPU, reference-format tree out)",
                                          "triangles": int(b_tris.shape[0]), "nodes": int(b_nodes.shape[0]),
                                          "b2rt_build_bvh_s": bctx.last_build_seconds, "with_numpy_triangle_reorder_s": build_s,
                                          "closest_mrays_s_on_device_built_tree": nb * 3 / (e0.elapsed_time(e1) * 1e-3) / 1e6,
+                                         "closest_mrays_s_on_sah_tree_same_launch_size": nb * 3 / (s0.elapsed_time(s1) * 1e-3) / 1e6,
                                          "rays_per_launch": nb, "same_hit_or_miss_as_sah_tree": same_miss}
             del d_bh, b_tris, b_nodes
 
