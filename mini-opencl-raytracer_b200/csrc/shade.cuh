@@ -61,7 +61,9 @@ __device__ __forceinline__ V3 frame_sample(V3 n, float phi, float sin_theta, flo
     V3 axis = fabsf(n.x) > 0.001f ? v3(0.0f, 1.0f, 0.0f) : v3(1.0f, 0.0f, 0.0f);
     V3 t = vnormalize(vcross(axis, n));
     V3 s = vcross(n, t);
-    return vnormalize(vadd(vadd(vscale(vscale(s, cos_cr(phi)), sin_theta), vscale(vscale(t, sin_cr(phi)), sin_theta)),
+    double sp, cp;
+    sincos((double)phi, &sp, &cp);                       // sinf / cosf of the oracle: fp64 result rounded once (one range reduction for both)
+    return vnormalize(vadd(vadd(vscale(vscale(s, (float)cp), sin_theta), vscale(vscale(t, (float)sp), sin_theta)),
                            vscale(n, cos_term)));
 }
 
