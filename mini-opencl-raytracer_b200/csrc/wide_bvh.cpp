@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstring>
 #include <deque>
+#include <thread>
 
 namespace b2rt {
 namespace {
@@ -178,14 +179,20 @@ std::string build_wide_bvh(const RefNode* nodes, uint64_t n_nodes, const RefTria
         }
     }
 
+    // The per-triangle shading records are independent of everything below: a helper thread fills them while this
+    // thread plans the cuts and emits the wide nodes.
     out.shade.resize(n_tris);
-    for (uint64_t i = 0; i < n_tris; ++i) {
-        const RefTriangle& t = tris[i];
-        ShadeTri& s = out.shade[i];
-        s.n1[0] = t.v1.normal.x; s.n1[1] = t.v1.normal.y; s.n1[2] = t.v1.normal.z; s.mtl = t.mtlIndex;
-        s.n2[0] = t.v2.normal.x; s.n2[1] = t.v2.normal.y; s.n2[2] = t.v2.normal.z; s.pad0 = 0;
-        s.n3[0] = t.v3.normal.x; s.n3[1] = t.v3.normal.y; s.n3[2] = t.v3.normal.z; s.pad1 = 0;
-    }
+    ShadeTri* shade = out.shade.data();
+    std::thread shade_fill([shade, tris, n_tris]() {
+        for (uint64_t i = 0; i < n_tris; ++i) {
+            const RefTriangle& t = tris[i];
+            ShadeTri& s = shade[i];
+            s.n1[0] = t.v1.normal.x; s.n1[1] = t.v1.normal.y; s.n1[2] = t.v1.normal.z; s.mtl = t.mtlIndex;
+            s.n2[0] = t.v2.normal.x; s.n2[1] = t.v2.normal.y; s.n2[2] = t.v2.normal.z; s.pad0 = 0;
+            s.n3[0] = t.v3.normal.x; s.n3[1] = t.v3.normal.y; s.n3[2] = t.v3.normal.z; s.pad1 = 0;
+        }
+    });
+    struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } join_shade{ shade_fill };
 
     out.nodes.reserve(n_nodes / 5 + 16);
     out.leaf.reserve((size_t)n_tris * 3 + 16);

@@ -67,7 +67,7 @@ def build_emu():
     srcs = [os.path.join(EMU_DIR, "emu.cpp")] + [os.path.join(CSRC, f) for f in ("traverse.cuh", "wide_bvh.cpp", "wide_bvh.h", "b2rt_types.h")]
     if _stale(out, srcs):
         subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-frounding-math",
-                               "-fno-fast-math", "-x", "c++", "-I", CSRC, os.path.join(EMU_DIR, "emu.cpp"),
+                               "-fno-fast-math", "-pthread", "-x", "c++", "-I", CSRC, os.path.join(EMU_DIR, "emu.cpp"),
                                os.path.join(CSRC, "wide_bvh.cpp"), "-o", out])
     return out
 
