@@ -37,12 +37,22 @@ def tmp_scene_dir(tmp_path_factory):
     return str(tmp_path_factory.mktemp("scenes"))
 
 
+def _reference_scene(path, max_prims=4):
+    """Scene arrays from the reference's own loader + builder (oracle/_ref). Where that build is not available (a
+    checkout without /root/reference and without the prebuilt .so) the product's host mirror stands in: it produces
+    the identical arrays (tests/test_host_scene.py proves that wherever oracle/_ref exists)."""
+    import oracle_lib
+    if oracle_lib.ref() is not None:
+        return oracle_lib.ref_load_scene(path, max_prims)
+    return load_product().host.load_scene(path, max_prims)
+
+
 @pytest.fixture(scope="session")
 def cornell_ref():
     """cornell.obj ingested by the reference's own loader + BVH builder (oracle/_ref)."""
     import oracle_lib
     import scenes
-    return oracle_lib.ref_load_scene(scenes.CORNELL, 4)
+    return _reference_scene(scenes.CORNELL)
 
 
 @pytest.fixture(scope="session")
@@ -52,7 +62,7 @@ def bumpy_ref(tmp_scene_dir):
     import scenes
     p, n, f = scenes.displaced_sphere(5)
     path = scenes.write_obj(os.path.join(tmp_scene_dir, "bumpy5.obj"), p, n, f)
-    return oracle_lib.ref_load_scene(path, 4)
+    return _reference_scene(path)
 
 
 @pytest.fixture(scope="session")

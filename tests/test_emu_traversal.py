@@ -6,6 +6,7 @@ import numpy as np
 
 import oracle_lib as ol
 import scenes
+from conftest import _reference_scene
 
 MISS = 0xFFFFFFFF
 
@@ -70,7 +71,7 @@ def test_degenerate_scenes(tmp_scene_dir):
     n = np.tile(np.array([[0, 0, 1]], dtype=np.float32), (4, 1))
     for name, faces, quads in (("one.obj", [[0, 1, 2]], None), ("quad.obj", [[0, 1, 2]], [[0, 1, 3, 2]])):
         path = scenes.write_obj(os.path.join(tmp_scene_dir, name), p, n, np.array(faces), quads)
-        tris, nodes, _ = ol.ref_load_scene(path, 4)
+        tris, nodes, _ = _reference_scene(path)
         ol.emu_build(tris, nodes)
         rays = scenes.box_rays(4000, (-1, -1, 0.5), (2, 2, 3), seed=45)
         _same(ol.emu_trace(rays), ol.oracle_closest(tris, nodes, rays))
@@ -82,7 +83,7 @@ def test_exact_ties_across_leaves_follow_the_reference_order(tmp_scene_dir):
     import os
     p, n, f = scenes.tie_grid(24, layers=2)
     path = scenes.write_obj(os.path.join(tmp_scene_dir, "ties.obj"), p, n, f)
-    tris, nodes, _ = ol.ref_load_scene(path, 4)
+    tris, nodes, _ = _reference_scene(path)
     ol.emu_build(tris, nodes)
     rays = scenes.tie_rays(24)
     want, cnt = ol.oracle_closest(tris, nodes, rays, want_counters=True)

@@ -14,7 +14,7 @@ import torch.multiprocessing as mp
 
 import oracle_lib as ol
 import scenes
-from conftest import load_product
+from conftest import _reference_scene, load_product
 
 
 def _free_port():
@@ -31,7 +31,7 @@ def _worker(rank, world, port, W, H, band_rows, out_dir):
     prod = load_product()
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        tris, nodes, mats = ol.ref_load_scene(scenes.CORNELL, 4)
+        tris, nodes, mats = _reference_scene(scenes.CORNELL)
         plan = prod.sharding.BandPlan(W, H, world, band_rows)
         frame = np.zeros((W * H, 4), dtype=np.float32)
         for fc in (1, 2):
@@ -52,7 +52,7 @@ def _worker(rank, world, port, W, H, band_rows, out_dir):
 def test_two_rank_frame_gather(tmp_path, W, H, band_rows):
     port = _free_port()
     mp.spawn(_worker, args=(2, port, W, H, band_rows, str(tmp_path)), nprocs=2, join=True)
-    tris, nodes, mats = ol.ref_load_scene(scenes.CORNELL, 4)
+    tris, nodes, mats = _reference_scene(scenes.CORNELL)
     want = np.zeros((W * H, 4), dtype=np.float32)
     for fc in (1, 2):
         ol.oracle_render(tris, nodes, mats, want, W, H, fc, 3)
