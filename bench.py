@@ -40,6 +40,8 @@ def product():
     mod = importlib.util.module_from_spec(spec)
     sys.modules["mor_b200"] = mod
     spec.loader.exec_module(mod)
+    if not (os.path.exists(mod.lib_path()) and os.path.exists(mod.host.lib_path())):
+        mod.build_all(verbose=False)          # built artefacts missing: compile in-tree (nvcc needs no GPU)
     return mod
 
 

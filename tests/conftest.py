@@ -20,6 +20,8 @@ def load_product():
     mod = importlib.util.module_from_spec(spec)
     sys.modules["mor_b200"] = mod
     spec.loader.exec_module(mod)
+    if not (os.path.exists(mod.lib_path()) and os.path.exists(mod.host.lib_path())):
+        mod.build_all(verbose=False)          # a checkout without built artefacts: compile in-tree (nvcc needs no GPU)
     return mod
 
 
