@@ -496,6 +496,44 @@ def run_b200(args, rank, world, local_rank):
         same = float((want["tri"] == hits_np["tri"][:100000]).mean())
         extra["parity_ids_identical_frac_100k"] = same
         extra["parity_t_bit_identical_frac_100k"] = float((want["t"] == hits_np["t"][:100000]).mean())
+        # configs[0]: cornell.obj 512x512, primary rays + one shadow ray per hit towards the kernel's light (kernel_bvh.cl:307):
+        # the reference's Intersect() on the host cores (stand-in for the PoCL CPU device), and the same rays on the B200
+        ct0, cn0, cm0 = prod.host.load_scene(os.path.join(ROOT, "tests", "golden", "cornell.obj"), 4)
+        cam = ol.oracle_camera_rays(512, 512, 1)
+        threads = os.cpu_count() or 1
+        closest_fn = (lambda r: ol.ref_closest(ct0, cn0, r, threads)) if ol.ref() is not None else (lambda r: ol.oracle_closest(ct0, cn0, r, threads))
+        closest_fn(cam)
+        t0 = time.perf_counter()
+        for _ in range(5):
+            closest_fn(cam)
+        cpu_primary_ms = (time.perf_counter() - t0) / 5 * 1e3
+        ph = ol.oracle_closest(ct0, cn0, cam, threads)
+        hitm = ph["tri"] != 0xFFFFFFFF
+        o = np.stack([cam["ox"], cam["oy"], cam["oz"]], 1)[hitm] + np.stack([cam["dx"], cam["dy"], cam["dz"]], 1)[hitm] * ph["t"][hitm, None]
+        dl = np.array([0.0, -10.0, 16.0], dtype=np.float32) - o
+        shadow = prod.workloads.pack((o + 0.01 * dl / np.linalg.norm(dl, axis=1, keepdims=True)).astype(np.float32), dl.astype(np.float32))
+        ol.oracle_any(ct0, cn0, shadow, threads)
+        t0 = time.perf_counter()
+        for _ in range(5):
+            occ_cpu = ol.oracle_any(ct0, cn0, shadow, threads)
+        cpu_shadow_ms = (time.perf_counter() - t0) / 5 * 1e3
+        with prod.Context(local_rank) as c0:
+            c0.upload_scene(ct0, cn0, cm0)
+            c0.trace_closest(cam); c0.trace_any(shadow)
+            t0 = time.perf_counter()
+            for _ in range(20):
+                gh = c0.trace_closest(cam)
+            gpu_primary_ms = (time.perf_counter() - t0) / 20 * 1e3
+            t0 = time.perf_counter()
+            for _ in range(20):
+                occ_gpu = c0.trace_any(shadow)
+            gpu_shadow_ms = (time.perf_counter() - t0) / 20 * 1e3
+        extra["cornell_512_primary_plus_shadow"] = {
+            "rays": {"primary": int(cam.shape[0]), "shadow": int(shadow.shape[0])},
+            "cpu_reference_ms": {"primary": cpu_primary_ms, "shadow": cpu_shadow_ms, "threads": threads,
+                                 "what": "reference Intersect() compiled as C++ on the host cores (PoCL unavailable); shadow rays: the oracle's early-exit variant"},
+            "b200_host_buffers_ms": {"primary": gpu_primary_ms, "shadow": gpu_shadow_ms, "api": "b2rt_trace_closest / b2rt_trace_any, synchronous, copies included"},
+            "identical": bool(np.array_equal(gh["tri"], ph["tri"]) and np.array_equal(occ_gpu != 0, occ_cpu != 0))}
         if cornell_img is not None:
             # the same 16 accumulated frames by the reference's KernelEntry on the host cores
             ct, cn, cm = prod.host.load_scene(os.path.join(ROOT, "tests", "golden", "cornell.obj"), 4)
