@@ -95,7 +95,7 @@ trace_persistent(SceneView s, const RayIn* __restrict__ rays, uint64_t n, void* 
     uint32_t stack[CAP];
     L.clear();
     L.overflow = false;
-    L.tc.wide_nodes = L.tc.leaf_blocks = L.tc.leaf_pass = L.tc.tri_tests = L.tc.words = 0;
+    L.tc.wide_nodes = L.tc.leaf_blocks = L.tc.leaf_pass = L.tc.tri_tests = L.tc.words = L.tc.max_stack = 0;
     uint64_t my_index = 0;
     bool has_out = false;                    // this lane's finished ray still has to be written (done together with the next refill)
     uint64_t pool_next = 0;                  // warp-uniform: next ray of the warp's pool ...

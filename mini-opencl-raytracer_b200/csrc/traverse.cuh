@@ -134,7 +134,7 @@ struct HitX {
     uint32_t tri;          // B2RT_MISS (0xFFFFFFFF) until a triangle is accepted
 };
 
-struct TravCounters { uint32_t wide_nodes, leaf_blocks, leaf_pass, tri_tests, words; };
+struct TravCounters { uint32_t wide_nodes, leaf_blocks, leaf_pass, tri_tests, words, max_stack; };   // max_stack: most deferred references at once (incl. the register-held top)
 
 // RayBounds, kernel_bvh.cl:156-169, on an exact fp32 box.
 B2_HD bool box_gate_exact(const RayX& r, float lox, float loy, float loz, float hix, float hiy, float hiz, float best) {
@@ -347,6 +347,7 @@ struct Lane {
     B2_HD void push(uint32_t* stack, uint32_t ref) {
         if (top != REF_EMPTY) { if (sp < CAP) stack[sp++] = top; else overflow = true; }
         top = ref;
+        if (COUNT && (uint32_t)sp + 1u > tc.max_stack) tc.max_stack = (uint32_t)sp + 1u;
     }
     B2_HD uint32_t pop(const uint32_t* stack) {
         uint32_t ref = top;
@@ -407,7 +408,7 @@ B2_HD HitX trace_wide(const U4* wide, const U4* leaf, const RayX& r, float tmax,
                       uint32_t one, uint32_t schedule = 0) {
     Lane<ANY, COUNT, CAP> L;
     uint32_t stack[CAP];
-    L.tc.wide_nodes = L.tc.leaf_blocks = L.tc.leaf_pass = L.tc.tri_tests = L.tc.words = 0;
+    L.tc.wide_nodes = L.tc.leaf_blocks = L.tc.leaf_pass = L.tc.tri_tests = L.tc.words = L.tc.max_stack = 0;
     L.start(r, tmax);
     while (!L.done()) {
         const bool node = L.wants_node(), lf = L.wants_leaf();

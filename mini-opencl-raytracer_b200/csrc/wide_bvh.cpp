@@ -323,6 +323,18 @@ std::string build_wide_bvh(const RefNode* nodes, uint64_t n_nodes, const RefTria
         }
         out.nodes[w.wide] = wn;
     }
+    // exact stack bound: children always follow their parent in `nodes`, so one reverse sweep is bottom-up
+    {
+        std::vector<uint32_t> need(out.nodes.size(), 0);
+        for (size_t i = out.nodes.size(); i-- > 0;) {
+            const WideNode& n = out.nodes[i];
+            uint32_t below = 0;
+            for (int c = 0; c < n.n_children; ++c)
+                if (n.meta[c] & META_INTERIOR) below = std::max(below, need[n.child_base + (n.meta[c] & 0x7f)]);
+            need[i] = (n.n_children ? n.n_children - 1u : 0u) + below;
+        }
+        out.stack_entries = need.empty() ? 0 : need[0];
+    }
     return std::string();
 }
 

@@ -19,6 +19,7 @@ struct WideBVH {
     uint32_t max_depth_wide = 0;      // deepest wide node (root = 0)
     uint32_t max_leaf_records = 0;
     uint64_t n_children = 0;          // occupied child slots, for fill statistics
+    uint32_t stack_entries = 0;       // most child references any walk can have deferred at once (exact, see build_wide_bvh)
 };
 
 // Returns an empty string on success, else a description of why the input
@@ -26,7 +27,8 @@ struct WideBVH {
 std::string build_wide_bvh(const RefNode* nodes, uint64_t n_nodes, const RefTriangle* tris, uint64_t n_tris,
                            WideBVH& out);
 
-// Worst-case traversal stack entries for this tree (see trace_wide).
-inline uint32_t wide_stack_bound(const WideBVH& b) { return 7u * (b.max_depth_wide + 1u) + 1u; }
+// Worst-case traversal stack entries for this tree (see trace_wide): along one root-to-leaf path a walk defers at most
+// n_children - 1 references per wide node, so the exact bound is the maximum of that sum over all paths (+1 spare).
+inline uint32_t wide_stack_bound(const WideBVH& b) { return b.stack_entries + 1u; }
 
 }  // namespace b2rt

@@ -14,7 +14,7 @@ struct EmuRay { float ox, oy, oz, tmin, dx, dy, dz, tmax; };
 struct EmuHit { float t, u, v; uint32_t tri; };
 struct EmuStats {
     uint64_t n_wide, n_leaf_blocks, leaf_words, n_children, max_depth_binary, max_depth_wide, stack_bound;
-    uint64_t wide_visits, leaf_blocks, leaf_pass, tri_tests, words, overflow;
+    uint64_t wide_visits, leaf_blocks, leaf_pass, tri_tests, words, overflow, max_stack;
 };
 
 static WideBVH g_bvh;
@@ -37,11 +37,11 @@ extern "C" const char* emu_build(const void* nodes, uint64_t n_nodes, const void
 extern "C" void emu_trace(const EmuRay* rays, uint64_t n, EmuHit* hits, uint32_t* occluded, int any, EmuStats* st, uint32_t schedule) {
     const U4* wide = reinterpret_cast<const U4*>(g_bvh.nodes.data());
     const U4* leaf = g_bvh.leaf.data();
-    TravCounters total = { 0, 0, 0, 0, 0 };
+    TravCounters total = { 0, 0, 0, 0, 0, 0 };
     uint64_t sums[5] = { 0, 0, 0, 0, 0 };
     for (uint64_t i = 0; i < n; ++i) {
         RayX r = make_ray(rays[i].ox, rays[i].oy, rays[i].oz, rays[i].dx, rays[i].dy, rays[i].dz);
-        TravCounters c = { 0, 0, 0, 0, 0 };
+        TravCounters c = { 0, 0, 0, 0, 0, 0 };
         bool overflow = false;
         uint32_t sched = schedule ? schedule + (uint32_t)i * 2654435761u : 0u;   // 0 = leaves first; else a per-ray pseudo-random interleaving
         HitX h = any ? trace_wide<true, true, 256>(wide, leaf, r, rays[i].tmax, &c, &overflow, 0x3F800000u, sched)
@@ -49,6 +49,7 @@ extern "C" void emu_trace(const EmuRay* rays, uint64_t n, EmuHit* hits, uint32_t
         if (overflow) st->overflow++;
         if (any) occluded[i] = h.tri != 0xFFFFFFFFu;
         else { hits[i].t = h.t; hits[i].u = h.u; hits[i].v = h.v; hits[i].tri = h.tri; }
+        if (c.max_stack > st->max_stack) st->max_stack = c.max_stack;
         sums[0] += c.wide_nodes; sums[1] += c.leaf_blocks; sums[2] += c.leaf_pass; sums[3] += c.tri_tests; sums[4] += c.words;
     }
     (void)total;

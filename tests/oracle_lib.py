@@ -34,7 +34,7 @@ class OrCounters(C.Structure):
 class EmuStats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("n_wide", "n_leaf_blocks", "leaf_words", "n_children", "max_depth_binary",
                                           "max_depth_wide", "stack_bound", "wide_visits", "leaf_blocks", "leaf_pass",
-                                          "tri_tests", "words", "overflow")]
+                                          "tri_tests", "words", "overflow", "max_stack")]
 
 
 def _stale(target, sources):

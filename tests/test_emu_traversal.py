@@ -133,7 +133,7 @@ def test_random_scenes_fuzz(tmp_scene_dir):
         if ol.ref() is not None:                                   # same arrays as the reference's own loader + builder
             rt, rn, _ = ol.ref_load_scene(path, max_prims)
             assert np.array_equal(rn.view(np.uint32).reshape(-1, 12)[:, 8], nodes.view(np.uint32).reshape(-1, 12)[:, 8])
-        ol.emu_build(tris, nodes)
+        bound = ol.emu_build(tris, nodes).stack_bound
         lo, hi = pos.min(0) - 1.0, pos.max(0) + 1.0
         rays = np.concatenate([scenes.box_rays(1500, lo, hi, seed=case), scenes.axis_rays(lo, hi, 20, seed=case),
                                scenes.pack_rays(pos[rng.integers(0, pos.shape[0], 300)], rng.normal(size=(300, 3)))])   # origins ON vertices
@@ -142,5 +142,5 @@ def test_random_scenes_fuzz(tmp_scene_dir):
         for schedule in (0, 7 + case):
             st = ol.EmuStats()
             _same(ol.emu_trace(rays, stats=st, schedule=schedule), want)
-            assert st.overflow == 0
+            assert st.overflow == 0 and st.max_stack <= bound          # the exact stack bound of the wide tree holds
         assert np.array_equal(ol.emu_trace(rays, any_hit=True, schedule=99) != 0, ol.oracle_any(tris, nodes, rays) != 0)
