@@ -164,6 +164,37 @@ namespace Glaze3D
         }
     }
 
+    namespace
+    {
+        // sscanf(token, "%d/%d/%d", &a, &b, &n) (CLOBJloader.cpp:96) without the library call: each %d skips white space, takes
+        // an optional sign and at least one digit; a conversion or a '/' that does not match ends the scan and leaves the
+        // remaining outputs untouched (0). Values wrap like the reference's int -> unsigned int assignment.
+        bool scanInt(const char*& p, const char* end, unsigned int& out)
+        {
+            const char* q = p;
+            while (q < end && (*q == ' ' || (*q >= '\t' && *q <= '\r'))) ++q;
+            bool neg = false;
+            if (q < end && (*q == '+' || *q == '-')) { neg = *q == '-'; ++q; }
+            if (q >= end || *q < '0' || *q > '9') return false;
+            unsigned long long v = 0;
+            while (q < end && *q >= '0' && *q <= '9') { if (v < (1ull << 40)) v = v * 10 + (unsigned)(*q - '0'); ++q; }
+            if (v > 0x7fffffffull) v = neg ? 0x80000000ull : 0x7fffffffull;       // strtol-style clamp of out-of-range input
+            out = neg ? (unsigned int)(0u - (unsigned int)v) : (unsigned int)v;
+            p = q;
+            return true;
+        }
+        void scanTriplet(const char* p, const char* end, unsigned int& a, unsigned int& b, unsigned int& n)
+        {
+            if (!scanInt(p, end, a)) return;
+            if (p >= end || *p != '/') return;
+            ++p;
+            if (!scanInt(p, end, b)) return;
+            if (p >= end || *p != '/') return;
+            ++p;
+            scanInt(p, end, n);
+        }
+    }
+
     // Test hook: the numbers of `text` as the loader reads them (scanf("%f") semantics), up to maxCount.
     int ParseNumbersForTest(const char* text, float* out, int maxCount)
     {
@@ -187,6 +218,19 @@ namespace Glaze3D
         Cursor c{ data.data(), data.data() + data.size() - 1 };
         std::vector<float3> positions, normals;
         std::vector<float2> texcoords;
+        {   // size the arrays once: count the lines by their first two characters (a hint only, the parse below decides)
+            size_t nf = 0, nv = 0, nn = 0, nt = 0;
+            const char* e = data.data() + data.size() - 1;
+            for (const char* q = data.data(); q && q + 2 < e; q = static_cast<const char*>(std::memchr(q, '\n', (size_t)(e - q))), q = q ? q + 1 : nullptr)
+            {
+                if (q[0] == 'f' && q[1] == ' ') ++nf;
+                else if (q[0] == 'v' && q[1] == ' ') ++nv;
+                else if (q[0] == 'v' && q[1] == 'n') ++nn;
+                else if (q[0] == 'v' && q[1] == 't') ++nt;
+            }
+            positions.reserve(nv); normals.reserve(nn); texcoords.reserve(nt);
+            scene.m_Triangles.reserve(scene.m_Triangles.size() + 2 * nf);
+        }
         unsigned int materialIndex = 0xFFFFFFFFu;
         std::string w;
         std::vector<unsigned int> iv, it, in;
@@ -223,7 +267,7 @@ namespace Glaze3D
                     if (stop - pos > 1)
                     {
                         unsigned int a = 0, b = 0, n = 0;
-                        std::sscanf(line.substr(pos, stop - pos).c_str(), "%d/%d/%d", (int*)&a, (int*)&b, (int*)&n);
+                        scanTriplet(line.data() + pos, line.data() + stop, a, b, n);
                         iv.push_back(a); it.push_back(b); in.push_back(n);
                     }
                     pos = stop + 1;
