@@ -23,6 +23,8 @@ namespace
       catch (...) { setError(err, errLen, "unknown exception"); return failValue; }
 
 namespace Glaze3D { int ParseNumbersForTest(const char* text, float* out, int maxCount); }
+namespace Glaze3D { void ScanTripletForTest(const char* token, unsigned int out[3]); }
+extern "C" void g3d_scan_triplet(const char* token, unsigned int* out) { ScanTripletForTest(token, out); }
 extern "C" int g3d_parse_numbers(const char* text, float* out, int maxCount) { return ParseNumbersForTest(text, out, maxCount); }
 
 // ---- scenes without a device: CLOBJloader + CLBVHScene::BuildOnly ---------------------------------

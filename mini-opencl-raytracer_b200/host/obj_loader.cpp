@@ -168,7 +168,8 @@ namespace Glaze3D
     {
         // sscanf(token, "%d/%d/%d", &a, &b, &n) (CLOBJloader.cpp:96) without the library call: each %d skips white space, takes
         // an optional sign and at least one digit; a conversion or a '/' that does not match ends the scan and leaves the
-        // remaining outputs untouched (0). Values wrap like the reference's int -> unsigned int assignment.
+        // remaining outputs untouched (0). Values wrap like the reference's int -> unsigned int assignment, out-of-range
+        // digit strings like glibc's.
         bool scanInt(const char*& p, const char* end, unsigned int& out)
         {
             const char* q = p;
@@ -176,10 +177,19 @@ namespace Glaze3D
             bool neg = false;
             if (q < end && (*q == '+' || *q == '-')) { neg = *q == '-'; ++q; }
             if (q >= end || *q < '0' || *q > '9') return false;
+            // glibc reads %d through a 64-bit strtol (saturating at LONG_MAX / LONG_MIN) and stores the low 32 bits
+            const unsigned long long limit = neg ? (1ull << 63) : (1ull << 63) - 1;
             unsigned long long v = 0;
-            while (q < end && *q >= '0' && *q <= '9') { if (v < (1ull << 40)) v = v * 10 + (unsigned)(*q - '0'); ++q; }
-            if (v > 0x7fffffffull) v = neg ? 0x80000000ull : 0x7fffffffull;       // strtol-style clamp of out-of-range input
-            out = neg ? (unsigned int)(0u - (unsigned int)v) : (unsigned int)v;
+            bool sat = false;
+            while (q < end && *q >= '0' && *q <= '9')
+            {
+                const unsigned d = (unsigned)(*q - '0');
+                if (!sat && (v > (limit - d) / 10)) sat = true;
+                if (!sat) v = v * 10 + d;
+                ++q;
+            }
+            if (sat) v = limit;
+            out = neg ? (unsigned int)(0ull - v) : (unsigned int)v;
             p = q;
             return true;
         }
@@ -193,6 +203,13 @@ namespace Glaze3D
             ++p;
             scanInt(p, end, n);
         }
+    }
+
+    // Test hook: one face-vertex token through the triplet scanner.
+    void ScanTripletForTest(const char* token, unsigned int out[3])
+    {
+        out[0] = out[1] = out[2] = 0;
+        scanTriplet(token, token + std::strlen(token), out[0], out[1], out[2]);
     }
 
     // Test hook: the numbers of `text` as the loader reads them (scanf("%f") semantics), up to maxCount.

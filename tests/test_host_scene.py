@@ -187,3 +187,22 @@ def test_number_parsing_equals_strtof():
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
     # a number with a dangling exponent marker stops where strtof stops: "1e" is 1, then the word "e" is not a number
     assert np.array_equal(prod.host.parse_numbers("1e 7"), np.array([1.0], dtype=np.float32))
+
+
+def test_face_token_scanner_equals_sscanf():
+    """`f` vertices are read with sscanf("%d/%d/%d") by the reference (CLOBJloader.cpp:96); the loader's own scanner must
+    give the same three values for well-formed and malformed tokens alike."""
+    import ctypes
+    prod = load_product()
+    libc = ctypes.CDLL("libc.so.6")
+    rng = np.random.default_rng(5)
+    tokens = ["1/2/3", "12/34/56", "1//3", "1/2", "7", "/2/3", "-1/2/3", "+5/6/7", "1/-2/3", "12abc/3/4", "1/2/3/4", "1/2/3x", "0/0/0",
+              "2147483647/1/1", "99999999999/1/1", "1/ 2/3", " 1/2/3", "1 /2/3", "a/b/c", "", "-", "1/", "1/2/", "//", "1/+2/-3", "007/08/09"]
+    for _ in range(3000):
+        parts = [str(int(rng.integers(-50, 5_000_000))) if rng.random() < 0.9 else "" for _ in range(int(rng.integers(1, 5)))]
+        tokens.append("/".join(parts))
+    for tok in tokens:
+        a, b, c = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_int(0)
+        libc.sscanf(tok.encode(), b"%d/%d/%d", ctypes.byref(a), ctypes.byref(b), ctypes.byref(c))
+        want = tuple(v.value & 0xFFFFFFFF for v in (a, b, c))
+        assert prod.host.scan_triplet(tok) == want, tok
