@@ -81,18 +81,39 @@ def measured_traffic(frequency, rays):
     return None, None
 
 
-def ensure_scene(prod, frequency, rank, world, barrier):
+def scenegen(*argv):
+    """Synthetic scenes are written by a stand-alone executable (host/scene_gen.cpp with its own main, built by
+    build.py), so that the reference arm can synthesise the identical workload without loading a product library."""
+    exe = os.path.join(PKG, "scenegen")
+    src = os.path.join(PKG, "host", "scene_gen.cpp")
+    if not os.path.exists(exe) or os.path.getmtime(exe) < os.path.getmtime(src):
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-DB2RT_SCENEGEN_MAIN", src, "-o", exe])
+    return int(subprocess.check_output([exe] + [str(a) for a in argv]).split()[-1])
+
+
+def ensure_scene(frequency, rank, world, barrier):
     os.makedirs(SCENE_DIR, exist_ok=True)
     path = os.path.join(SCENE_DIR, "ico_f%d.obj" % frequency)
     done = path + ".done"
     if rank == 0 and not os.path.exists(done):
         t0 = time.time()
-        faces = prod.host.write_icosphere_obj(path, frequency, radius=RADIUS, amplitude=0.08, seed=7)
+        faces = scenegen("icosphere", path, frequency, RADIUS, 0.08, 7)
         with open(done, "w") as f:
             f.write(str(faces))
         log("[bench] wrote %s: %d faces (%.1f s)" % (path, faces, time.time() - t0))
     barrier()
     return path
+
+
+def workloads_only():
+    """workloads.py + layouts.py (numpy only) without the package __init__, i.e. without any product library."""
+    import types
+    name = "mor_b200_numpy_only"
+    if name not in sys.modules:
+        pkg = types.ModuleType(name)
+        pkg.__path__ = [PKG]
+        sys.modules[name] = pkg
+    return importlib.import_module(name + ".workloads")
 
 
 class ClockSampler:
@@ -150,18 +171,24 @@ def cpu_baseline(ol, kind_pref, tris, nodes, rays, seconds, threads):
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference's own CPU implementation of the path on the host cores."""
+    """--impl reference: the reference's own CPU implementation of the path on the host cores. Nothing of the product is
+    loaded: the scene file comes from the stand-alone generator, CLOBJloader::Load + CLBVHScene::CreateBVHTrees are the
+    reference's own (oracle/_ref, CLBVHnode.cpp:185-207), the rays come from workloads.py (numpy)."""
     if rank != 0:
         return
-    prod = product()
     ol = checkers()
-    path = ensure_scene(prod, args.frequency, 0, 1, lambda: None)
-    tris, nodes, mats = prod.host.load_scene(path, 4)
+    wl = workloads_only()
+    path = ensure_scene(args.frequency, 0, 1, lambda: None)
     threads = os.cpu_count() or 1
-    n = args.ref_rays
-    rays = prod.workloads.shell_rays(n * (args.steps + args.warmup), RADIUS, seed=1000)
     kind = "reference" if ol.ref() is not None else "port"
-    fn = (lambda r: ol.ref_closest(tris, nodes, r, threads)) if kind == "reference" else (lambda r: ol.oracle_closest(tris, nodes, r, threads))
+    if kind != "reference":
+        raise RuntimeError("oracle/_ref/libref_oracle.so is missing: build it where /root/reference exists (python oracle/build_ref.py)")
+    t0 = time.time()
+    tris, nodes, mats = ol.ref_load_scene(path, 4)
+    log("[bench reference] reference loader + builder: %d CLTriangle, %d nodes in %.1f s" % (tris.shape[0], nodes.shape[0], time.time() - t0))
+    n = args.ref_rays
+    rays = wl.shell_rays(n * (args.steps + args.warmup), RADIUS, seed=1000)
+    fn = lambda r: ol.ref_closest(tris, nodes, r, threads)
     for w in range(args.warmup):
         fn(rays[w * n:(w + 1) * n])
     t0 = time.perf_counter()
@@ -199,7 +226,7 @@ def run_b200(args, rank, world, local_rank):
         if world > 1:
             dist.barrier()
 
-    path = ensure_scene(prod, args.frequency, rank, world, barrier)
+    path = ensure_scene(args.frequency, rank, world, barrier)
     t0 = time.time()
     eng = prod.host.Engine(1920, 1080, device=local_rank)        # CLEngineBase + CLRaytracer::Init on this GPU
     # CLOBJloader::Load + CreateBVHTrees (+ upload). Rank 0 parses + builds and leaves the binary scene cache behind;

@@ -21,6 +21,7 @@ HOST = os.path.join(HERE, "host")
 INCLUDE = os.path.join(ROOT, "include")
 LIB_B2RT = os.path.join(HERE, "libb2rt.so")
 LIB_HOST = os.path.join(HERE, "libglaze3d.so")
+SCENEGEN = os.path.join(HERE, "scenegen")        # stand-alone synthetic-scene writer (host/scene_gen.cpp with its main)
 
 NVCC = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -70,8 +71,17 @@ def build_host(force=False, verbose=True):
     return LIB_HOST
 
 
+def build_scenegen(force=False, verbose=True):
+    src = os.path.join(HOST, "scene_gen.cpp")
+    if force or _stale(SCENEGEN, [src, __file__]):
+        _run(["g++", "-std=c++17", "-O2", "-DB2RT_SCENEGEN_MAIN", src, "-o", SCENEGEN], verbose)
+    return SCENEGEN
+
+
 def build_all(force=False, verbose=True):
-    return build_b2rt(force, verbose), build_host(force, verbose)
+    out = build_b2rt(force, verbose), build_host(force, verbose)
+    build_scenegen(force, verbose)
+    return out
 
 
 if __name__ == "__main__":

@@ -32,6 +32,7 @@ struct Buffer {
 };
 
 constexpr uint64_t STREAM_CHUNK = 1ull << 22;   // rays per pipelined chunk of the host-buffer entry points
+constexpr uint64_t NEXT_RING = 256;             // per-launch ray counters of the persistent kernels (b2rt_context::d_next)
 
 std::string g_create_error;
 
@@ -58,7 +59,8 @@ struct b2rt_context {
     uint32_t stack_bound = 8;
     SceneView view;
     // scratch
-    unsigned long long* d_next = nullptr;
+    unsigned long long* d_next = nullptr;      // NEXT_RING counters, one per in-flight ray-stream launch
+    uint64_t next_seq = 0;
     unsigned long long* d_counters = nullptr;
     void* d_stage_rays[2] = { nullptr, nullptr };
     void* d_stage_out[2] = { nullptr, nullptr };
@@ -215,7 +217,10 @@ int trace_device(b2rt_context* ctx, const void* d_rays, uint64_t n, void* d_out,
     if (ctx->opt_blocks_per_sm > 0) grid = ctx->sm_count * (int)ctx->opt_blocks_per_sm;
     uint64_t warps_needed = (n + 31) / 32, blocks_needed = (warps_needed * 32 + trace_block_threads() - 1) / trace_block_threads();
     if ((uint64_t)grid > blocks_needed) grid = (int)blocks_needed;
-    CK(launch_trace_wide(ctx->view, d_rays, n, d_out, any, ctx->opt_counters != 0, ctx->stack_bound, grid, ctx->d_next,
+    // every launch pulls rays from its OWN counter (a ring of NEXT_RING slots): launches on different caller streams may
+    // overlap, and a shared counter would be reset under a running kernel
+    unsigned long long* next = ctx->d_next + (ctx->next_seq++ % NEXT_RING);
+    CK(launch_trace_wide(ctx->view, d_rays, n, d_out, any, ctx->opt_counters != 0, ctx->stack_bound, grid, next,
                          ctx->d_counters, (uint32_t)ctx->opt_refill_min, (uint32_t)ctx->opt_leaf_bias, st));
     ctx->launches += 1;
     return B2RT_SUCCESS;
@@ -348,7 +353,8 @@ int render_wavefront(b2rt_context* ctx, const FrameArgs& a, float* d_result, con
     // cut at band boundaries so that every part is a GidMap again (a contiguous map can be cut anywhere)
     const bool contiguous = map.band == map.stride;
     const uint64_t unit = contiguous ? 32 : map.band;
-    uint64_t per = ((uint64_t)n / lanes + unit - 1) / unit * unit;
+    // ceil(n / lanes) rounded up to whole units: per * lanes >= n, so no work item is left over
+    uint64_t per = (((uint64_t)n + lanes - 1) / lanes + unit - 1) / unit * unit;
     if (per == 0) per = unit;
     lanes = (int)std::min<uint64_t>(lanes, ((uint64_t)n + per - 1) / per);
     if (lanes <= 1) return wavefront_lane(ctx, a, d_result, map, n, 0, 0, ctx->stream);
@@ -537,7 +543,7 @@ extern "C" int b2rt_create(int device_id, b2rt_context** out) {
         }
         cudaGetLastError();
     }
-    if ((e = cudaMalloc(&ctx->d_next, 64)) != cudaSuccess) return bail(e, "cudaMalloc");
+    if ((e = cudaMalloc(&ctx->d_next, NEXT_RING * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMalloc");
     if ((e = cudaMalloc(&ctx->d_counters, 128)) != cudaSuccess) return bail(e, "cudaMalloc");
     if ((e = cudaMemset(ctx->d_counters, 0, 128)) != cudaSuccess) return bail(e, "cudaMemset");
     *out = ctx;

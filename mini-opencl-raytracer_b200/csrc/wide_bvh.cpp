@@ -168,15 +168,33 @@ std::string build_wide_bvh(const RefNode* nodes, uint64_t n_nodes, const RefTria
     if (!tris && n_tris) return "null triangle array";
 
     // ---- validate the flattened tree (guards the kernels against wild offsets) -----------
-    for (uint64_t i = 0; i < n_nodes; ++i) {
-        const RefNode& n = nodes[i];
-        if (n.nPrimitives > 0) {
-            if ((uint64_t)n.offset + n.nPrimitives > n_tris) return "leaf " + std::to_string(i) + " references triangles out of range";
-        } else {
-            if (i + 1 >= n_nodes || n.offset <= i + 1 || n.offset >= n_nodes)
-                return "interior node " + std::to_string(i) + " has an invalid child offset";
-            if (n.axis > 2) return "interior node " + std::to_string(i) + " has an invalid split axis";
+    // It must be a proper pre-order tree: the first child's subtree ends exactly where the second child starts and the
+    // root's subtree is the whole array (every node reached exactly once). Children follow their parent, so one reverse
+    // sweep computes every subtree's end. Child boxes must lie inside their parent's box: the argument that the leaf
+    // gate alone reproduces the reference's culling (traverse.cuh) rests on it.
+    {
+        std::vector<uint32_t> end(n_nodes);
+        auto inside = [](const RefNode& c, const RefNode& p) {
+            return c.bmin.x >= p.bmin.x && c.bmin.y >= p.bmin.y && c.bmin.z >= p.bmin.z &&
+                   c.bmax.x <= p.bmax.x && c.bmax.y <= p.bmax.y && c.bmax.z <= p.bmax.z;
+        };
+        for (uint64_t i = n_nodes; i-- > 0;) {
+            const RefNode& n = nodes[i];
+            if (n.nPrimitives > 0) {
+                if ((uint64_t)n.offset + n.nPrimitives > n_tris) return "leaf " + std::to_string(i) + " references triangles out of range";
+                end[i] = (uint32_t)(i + 1);
+            } else {
+                if (i + 1 >= n_nodes || n.offset <= i + 1 || n.offset >= n_nodes)
+                    return "interior node " + std::to_string(i) + " has an invalid child offset";
+                if (n.axis > 2) return "interior node " + std::to_string(i) + " has an invalid split axis";
+                if (end[i + 1] != n.offset)
+                    return "interior node " + std::to_string(i) + ": the first child's subtree does not end at the second child (not a pre-order tree)";
+                if (!inside(nodes[i + 1], n) || !inside(nodes[n.offset], n))
+                    return "interior node " + std::to_string(i) + " does not contain its children's bounds";
+                end[i] = end[n.offset];
+            }
         }
+        if (end[0] != n_nodes) return "node array holds " + std::to_string(n_nodes - end[0]) + " nodes outside the root's subtree";
     }
 
     // The per-triangle shading records are independent of everything below: a helper thread fills them while this
