@@ -1,0 +1,224 @@
+// coop.cuh -- warp-cooperative traversal of ONE ray: the tail mode of trace_persistent (kernels.cu).
+//
+// A persistent traversal launch ends with a latency-bound tail: when the ray pool is dry, the few rays
+// still alive advance one dependent step (a whole 8-child node test or a leaf, plus a memory round trip)
+// at a time on one lane each while the other lanes idle. A multi-GPU frame share or a wavefront stage is
+// short enough for that tail to dominate. Here all 32 lanes work on ONE ray at a time instead:
+//
+//  * the ray's pending work -- its queued leaves, current node and short stack -- is laid out as one
+//    FRONTIER in shared memory, in the reference's depth-first order (kernel_bvh.cl:182-216), front at the
+//    highest index;
+//  * leaves at the front are resolved in parallel: one lane per (leaf record, loader copy) evaluates the
+//    reference's exact Moller-Trumbore sequence; results are committed leaf by leaf in frontier order,
+//    every leaf gated by its exact fp32 box against the `best` of that moment -- the reference's own
+//    sequence of decisions, so ties and negative t resolve as in the solo walk (traverse.cuh);
+//  * the first B2_COOP_NODES interior entries of the frontier are expanded in one round, 8 lanes per
+//    node, one lane per child in the reference's visiting order (same conservative quantised slab test
+//    as test_wide_node); passing children replace their parent in place, keeping the order. Interior
+//    nodes behind unresolved leaves are thereby tested with a stale (larger) `best`, which can only let
+//    more children through -- allowed for the same reason as the solo walk's speculation.
+//
+// The same text runs on the CPU in tests/emu (32 coroutine lanes in lock step) against the oracle.
+#pragma once
+#include "traverse.cuh"
+
+#ifndef B2_COOP_NODES
+#define B2_COOP_NODES 4
+#endif
+
+namespace b2rt {
+
+// Monotone float -> uint32 key for a warp min-reduction; -0 is folded onto +0 (they compare equal, and the
+// reference keeps the FIRST of equal candidates: ties are then broken by the lowest lane).
+B2_HD uint32_t order_key(float t) {
+    const uint32_t b = f2bits(xadd(t, 0.0f));
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+B2_HD uint32_t lanes_below(uint32_t l) { return l >= 32u ? 0xffffffffu : (1u << l) - 1u; }
+B2_HD uint32_t lanes_upto(uint32_t l) { return 0xffffffffu >> (31u - (l & 31u)); }
+
+// Child slot `slot` of a wide node against [0, best]: the arithmetic of test_wide_node for one child.
+B2_HD bool coop_child_test(const U4& w0, const U4& w2, const U4& w3, const U4& w4, uint32_t slot, const RayX& r, float best) {
+    const float o[3] = { r.ox, r.oy, r.oz };
+    const float inv[3] = { r.ix, r.iy, r.iz };
+    const float base[3] = { bits2f(w0.x), bits2f(w0.y), bits2f(w0.z) };
+    const uint32_t qlo_a[3] = { w2.x, w2.z, w3.x }, qlo_b[3] = { w2.y, w2.w, w3.y };
+    const uint32_t qhi_a[3] = { w3.z, w4.x, w4.z }, qhi_b[3] = { w3.w, w4.y, w4.w };
+    float nn[3], ff[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const uint32_t e = (w0.w >> (8 * a)) & 0xffu;
+        const float K = xmul(bits2f((e + 15u) << 23), inv[a]);
+        const float A = xmul(xsub(base[a], o[a]), inv[a]);
+        const float B = xsub(A, K);
+        const float slack = fma_rn(xadd(fabsf(A), fabsf(K)), 9.5367431640625e-7f, 1.0e-35f);
+        const bool neg = (r.sign >> a) & 1u;
+        const uint32_t qn = prmt(neg ? qhi_a[a] : qlo_a[a], neg ? qhi_b[a] : qlo_b[a], slot) & 0xffu;
+        const uint32_t qf = prmt(neg ? qlo_a[a] : qhi_a[a], neg ? qlo_b[a] : qhi_b[a], slot) & 0xffu;
+        nn[a] = fma_rn(bits2f(0x3F800000u | (qn << 8)), K, xsub(B, slack));
+        ff[a] = fma_rn(bits2f(0x3F800000u | (qf << 8)), K, xadd(B, slack));
+    }
+    const float N = max_nn(max_nn(nn[0], nn[1]), nn[2]);
+    const float Fr = min_nn(min_nn(ff[0], ff[1]), ff[2]);
+    const uint32_t bad = f2bits(xsub(Fr, N)) | f2bits(Fr) | f2bits(xsub(best, N));
+    return !(bad >> 31);
+}
+
+// Lays out a solo lane's pending work as a frontier, back to front: the short stack (oldest first), its register-held
+// top, the current node (or leaf waiting for a queue slot), then the queued leaves -- the reverse of the order in which
+// the solo walk would get to them. Returns the number of entries.
+template <class LaneT>
+B2_HD uint32_t coop_dump(const LaneT& L, const uint32_t* stack, uint32_t* F) {
+    uint32_t k = 0;
+    for (int i = 0; i < L.sp; ++i) F[k++] = stack[i];
+    if (L.top != REF_EMPTY) F[k++] = L.top;
+    if (L.cur != REF_EMPTY) F[k++] = L.cur;
+#if B2_LEAF_QUEUE == 3
+    if (L.leaf2 != REF_EMPTY) F[k++] = L.leaf2;
+#endif
+    if (L.leaf1 != REF_EMPTY) F[k++] = L.leaf1;
+    if (L.leaf0 != REF_EMPTY) F[k++] = L.leaf0;
+    return k;
+}
+
+// Finishes the ray whose frontier F[0..n) (front = F[n-1]) and state (r, h) every lane holds identically.
+// `fcap` = capacity of F; while n <= wide_limit up to B2_COOP_NODES nodes are expanded per round, beyond it one
+// (depth-first: the frontier then grows by at most the solo walk's stack bound). On return h is the final hit on
+// every lane; `overflow` is set if F would have overflowed (the ray is then abandoned: the caller reports it).
+template <bool ANY, bool COUNT>
+B2_HD void coop_trace(const U4* wide, const U4* leaf, uint32_t* F, uint32_t n, uint32_t fcap, uint32_t wide_limit,
+                      const RayX& r, HitX& h, TravCounters& tc, bool& overflow) {
+    const uint32_t lane = w_lane();
+    while (n) {
+        const uint32_t win = n < 32u ? n : 32u;
+        const uint32_t e = lane < win ? F[n - 1u - lane] : REF_EMPTY;
+        const bool is_node = lane < win && !(e & REF_LEAF_BIT);
+        const uint32_t mnode = w_ballot(is_node);
+        const uint32_t lead = mnode ? ctz32(mnode) : win;
+        if (lead) {
+            // ---- leaves at the front of the frontier: two lanes per record (the loader's two copies) ------------
+            uint32_t need = 0;
+            if (lane < lead) need = 2u * ld128(leaf + (e & ~REF_LEAF_BIT) + 1).w;
+            uint32_t incl = need;
+            for (uint32_t d = 1; d < 32u; d <<= 1) {
+                const uint32_t up = w_shfl(incl, lane >= d ? lane - d : 0u);
+                if (lane >= d) incl += up;
+            }
+            const uint32_t need0 = w_shfl(need, 0);
+            if (need0 > 32u || need0 == 0u) {
+                // more than 16 records: every lane walks the block like the solo path (same result on every lane)
+                const bool got = visit_leaf<COUNT>(leaf, w_shfl(e, 0) & ~REF_LEAF_BIT, r, h, &tc);
+                n -= 1u;
+                if ((ANY && got) || h.t < 0.0f) { n = 0; break; }
+                continue;
+            }
+            const uint32_t m = popc32(w_ballot(lane < lead && incl <= 32u));      // leaves taken this round (>= 1)
+            const uint32_t excl = incl - need;
+            const uint32_t heads = w_redor(lane < m ? (1u << excl) : 0u);           // bit = first lane of a leaf
+            const uint32_t used = w_shfl(incl, m - 1u);
+            const bool active = lane < used;
+            const uint32_t my_leaf = popc32(heads & lanes_upto(lane)) - 1u;
+            const uint32_t my_start = w_shfl(excl, my_leaf);
+            const uint32_t my_ref = w_shfl(e, my_leaf);
+            const uint32_t slot = active ? lane - my_start : 0u;
+            const uint32_t rec = slot >> 1, copy = slot & 1u;
+            U4 g0 = { 0, 0, 0, 0 }, g1 = g0, va = g0, vb = g0, vc = g0;
+            if (active) {
+                const U4* p = leaf + (my_ref & ~REF_LEAF_BIT);
+                g0 = ld128(p); g1 = ld128(p + 1);
+                const U4* q = p + LEAF_HEADER_WORDS + LEAF_RECORD_WORDS * rec;
+                va = ld128(q); vb = ld128(q + 1); vc = ld128(q + 2);
+            }
+            const uint32_t flags = va.w;
+            const uint32_t dup = w_ballot(active && copy == 0u && flags != 0u);
+            // triangle id: first id of the block + one per earlier record + one more per earlier doubled record
+            const uint32_t earlier = active ? (lanes_below(my_start + 2u * rec) & ~lanes_below(my_start)) : 0u;
+            const uint32_t id = g0.w + rec + popc32(dup & earlier) + copy;
+            const bool valid = active && (copy == 0u || flags != 0u);
+            float t = 0.0f, u = 0.0f, v = 0.0f;
+            bool ok = false;
+            if (valid) {
+                // copy 1 is the loader's rotated duplicate: (v2,v3,v1) or (v3,v1,v2)
+                const bool left = flags == REC_ROT_LEFT;
+                const U4 p1 = copy ? (left ? vb : vc) : va, p2 = copy ? (left ? vc : va) : vb, p3 = copy ? (left ? va : vb) : vc;
+                ok = tri_eval_exact(r, bits2f(p1.x), bits2f(p1.y), bits2f(p1.z), bits2f(p2.x), bits2f(p2.y), bits2f(p2.z),
+                                    bits2f(p3.x), bits2f(p3.y), bits2f(p3.z), t, u, v);
+            }
+            if (COUNT) {
+                const bool g = active && box_gate_exact(r, bits2f(g0.x), bits2f(g0.y), bits2f(g0.z), bits2f(g1.x), bits2f(g1.y), bits2f(g1.z), h.t);
+                tc.leaf_blocks += m;
+                tc.leaf_pass += popc32(w_ballot(g) & heads);
+                tc.tri_tests += popc32(w_ballot(valid && g));
+                tc.words += LEAF_HEADER_WORDS * m + LEAF_RECORD_WORDS * (used >> 1);
+            }
+            // Commit in frontier order. Only a leaf holding a candidate under the current `best` can change it, and
+            // `best` only shrinks: jump from one such leaf to the next, re-evaluating gates and candidates in between.
+            uint32_t lo = 0;
+            bool finished = false;
+            for (;;) {
+                const bool gate = active && box_gate_exact(r, bits2f(g0.x), bits2f(g0.y), bits2f(g0.z), bits2f(g1.x), bits2f(g1.y), bits2f(g1.z), h.t);
+                const bool cand = valid && ok && t < h.t && gate && my_leaf >= lo;
+                const uint32_t cm = w_ballot(cand);
+                if (!cm) break;
+                const uint32_t first = w_shfl(my_leaf, ctz32(cm));
+                const bool mine = cand && my_leaf == first;
+                const uint32_t key = mine ? order_key(t) : 0xffffffffu;
+                const uint32_t kmin = w_redmin(key);
+                const uint32_t wl = ctz32(w_ballot(mine && key == kmin));            // lowest lane = lowest triangle id of the minimum
+                h.t = bits2f(w_shfl(f2bits(t), wl)); h.u = bits2f(w_shfl(f2bits(u), wl)); h.v = bits2f(w_shfl(f2bits(v), wl));
+                h.tri = w_shfl(id, wl);
+                lo = first + 1u;
+                if (ANY || h.t < 0.0f) { finished = true; break; }
+            }
+            if (finished || h.t < 0.0f) { n = 0; break; }
+            n -= m;
+            continue;
+        }
+        // ---- the front is an interior node: expand the first Q interior entries of the window -----------------
+        uint32_t Q = n <= wide_limit ? (uint32_t)B2_COOP_NODES : 1u;
+        const uint32_t have = popc32(mnode);
+        if (Q > have) Q = have;
+        uint32_t pos0 = 32, pos1 = 32, pos2 = 32, pos3 = 32;
+        {
+            uint32_t mm = mnode;
+            pos0 = ctz32(mm); mm &= mm - 1u;
+            if (Q > 1u) { pos1 = ctz32(mm); mm &= mm - 1u; }
+            if (Q > 2u) { pos2 = ctz32(mm); mm &= mm - 1u; }
+            if (Q > 3u) { pos3 = ctz32(mm); }
+        }
+        const uint32_t K = (Q > 3u ? pos3 : (Q > 2u ? pos2 : (Q > 1u ? pos1 : pos0))) + 1u;   // window entries rewritten
+        const uint32_t grp = lane >> 3, j = lane & 7u;
+        const bool gact = grp < Q;
+        const uint32_t gpos = grp == 0u ? pos0 : (grp == 1u ? pos1 : (grp == 2u ? pos2 : pos3));
+        const uint32_t node = w_shfl(e, gact ? gpos : 0u);
+        bool pass = false;
+        uint32_t ref = REF_EMPTY;
+        if (gact) {
+            const U4* p = wide + (uint32_t)WIDE_NODE_WORDS * node;
+            const U4 w0 = ld128(p), w1 = ld128(p + 1), w2 = ld128(p + 2), w3 = ld128(p + 3), w4 = ld128(p + 4);
+            const uint32_t order = ld32(reinterpret_cast<const uint32_t*>(p + 5) + r.sign);
+            const uint32_t slot = (order >> (4u * j)) & 7u;                           // child visited j-th (reference order)
+            if (j < (w0.w >> 24) && coop_child_test(w0, w2, w3, w4, slot, r, h.t)) {
+                pass = true;
+                const uint32_t mb = prmt(w1.z, w1.w, slot) & 0xffu;
+                ref = mb + ((mb & META_INTERIOR) ? w1.x - (uint32_t)META_INTERIOR : (REF_LEAF_BIT | w1.y));
+            }
+        }
+        const uint32_t hm = w_ballot(pass);
+        const int c0 = (int)popc32(hm & 0xffu) - 1, c1 = Q > 1u ? (int)popc32((hm >> 8) & 0xffu) - 1 : 0,
+                  c2 = Q > 2u ? (int)popc32((hm >> 16) & 0xffu) - 1 : 0, c3 = Q > 3u ? (int)popc32(hm >> 24) - 1 : 0;
+        // position (front first) of window entry p after the rewrite: every expanded node before it adds (children - 1)
+        #define B2_COOP_FP(p) ((int)(p) + (pos0 < (p) ? c0 : 0) + (pos1 < (p) ? c1 : 0) + (pos2 < (p) ? c2 : 0) + (pos3 < (p) ? c3 : 0))
+        const uint32_t newn = (uint32_t)((int)(n - K) + (int)K + c0 + c1 + c2 + c3);
+        if (COUNT) { tc.wide_nodes += Q; tc.words += WIDE_NODE_WORDS * Q; if (newn > tc.max_stack) tc.max_stack = newn; }
+        if (newn > fcap) { overflow = true; n = 0; break; }
+        w_sync();                                                    // every lane holds its window entry
+        if (lane < K && !is_node) F[newn - 1u - (uint32_t)B2_COOP_FP(lane)] = e;
+        if (pass) F[newn - 1u - (uint32_t)(B2_COOP_FP(gpos) + (int)popc32((hm >> (8u * grp)) & 0xffu & lanes_below(j)))] = ref;
+        #undef B2_COOP_FP
+        w_sync();
+        n = newn;
+    }
+}
+
+}  // namespace b2rt

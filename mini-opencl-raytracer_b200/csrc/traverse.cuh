@@ -69,6 +69,14 @@ B2_HD U4 ld128(const U4* p) {
     U4 r; r.x = v.x; r.y = v.y; r.z = v.z; r.w = v.w; return r;
 }
 B2_HD uint32_t ld32(const uint32_t* p) { return __ldg(p); }
+// warp collectives of the cooperative tail mode (coop.cuh); every lane of the warp calls them together
+B2_HD uint32_t w_lane() { return threadIdx.x & 31u; }
+B2_HD uint32_t w_ballot(bool p) { return __ballot_sync(0xffffffffu, p); }
+B2_HD uint32_t w_shfl(uint32_t v, uint32_t src) { return __shfl_sync(0xffffffffu, v, (int)src); }
+B2_HD uint32_t w_redmin(uint32_t v) { return __reduce_min_sync(0xffffffffu, v); }
+B2_HD uint32_t w_redor(uint32_t v) { return __reduce_or_sync(0xffffffffu, v); }
+B2_HD void w_sync() { __syncwarp(); }
+B2_HD uint32_t ctz32(uint32_t v) { return (uint32_t)__ffs((int)v) - 1u; }     // v != 0
 #else
 // Host emulation (tests only). Built with -ffp-contract=off -frounding-math.
 B2_HD float xadd(float a, float b) { volatile float r = a + b; return r; }
@@ -103,6 +111,17 @@ B2_HD float bits2f(uint32_t v) { float f; std::memcpy(&f, &v, 4); return f; }
 B2_HD uint32_t f2bits(float v) { uint32_t u; std::memcpy(&u, &v, 4); return u; }
 B2_HD U4 ld128(const U4* p) { return *p; }
 B2_HD uint32_t ld32(const uint32_t* p) { return *p; }
+}  // namespace b2rt
+// Warp collectives on the host: tests/emu/warp_emu.cpp runs the 32 lanes of a warp as coroutines in lock step.
+namespace b2rt_emu { uint32_t lane(); uint32_t exchange(uint32_t v, int op, uint32_t arg); }
+namespace b2rt {
+B2_HD uint32_t w_lane() { return b2rt_emu::lane(); }
+B2_HD uint32_t w_ballot(bool p) { return b2rt_emu::exchange(p ? 1u : 0u, 0, 0); }
+B2_HD uint32_t w_shfl(uint32_t v, uint32_t src) { return b2rt_emu::exchange(v, 1, src); }
+B2_HD uint32_t w_redmin(uint32_t v) { return b2rt_emu::exchange(v, 2, 0); }
+B2_HD uint32_t w_redor(uint32_t v) { return b2rt_emu::exchange(v, 3, 0); }
+B2_HD void w_sync() { (void)b2rt_emu::exchange(0, 4, 0); }
+B2_HD uint32_t ctz32(uint32_t v) { return (uint32_t)__builtin_ctz(v); }
 #endif
 
 // OpenCL max()/min() as worded by the spec ("y if x < y, otherwise x"), the
@@ -155,8 +174,8 @@ B2_HD bool box_gate_exact(const RayX& r, float lox, float loy, float loz, float 
 // Branch-free: the reference's early returns only skip work, so evaluating every comparison
 // of the sequence and AND-ing them gives the same decision (NaN/inf operands included -- each
 // comparison is the negation the reference tests, in its order) without divergent exits.
-B2_HD void tri_test_exact(const RayX& r, float ax, float ay, float az, float bx, float by, float bz,
-                          float cx, float cy, float cz, uint32_t tri, HitX& h) {
+B2_HD bool tri_eval_exact(const RayX& r, float ax, float ay, float az, float bx, float by, float bz,
+                          float cx, float cy, float cz, float& t, float& u, float& v) {
     float e1x = xsub(bx, ax), e1y = xsub(by, ay), e1z = xsub(bz, az);
     float e2x = xsub(cx, ax), e2y = xsub(cy, ay), e2z = xsub(cz, az);
     float px = xsub(xmul(r.dy, e2z), xmul(r.dz, e2y));
@@ -166,14 +185,20 @@ B2_HD void tri_test_exact(const RayX& r, float ax, float ay, float az, float bx,
     bool ok = !(det < 1.0e-8f) && !(-det > 1.0e-8f);                                   // :116
     float inv = xdiv(1.0f, det);
     float tx = xsub(r.ox, ax), ty = xsub(r.oy, ay), tz = xsub(r.oz, az);
-    float u = xmul(xadd(xadd(xmul(tx, px), xmul(ty, py)), xmul(tz, pz)), inv);
+    u = xmul(xadd(xadd(xmul(tx, px), xmul(ty, py)), xmul(tz, pz)), inv);
     ok = ok && !(u < 0.0f) && !(u > 1.0f);                                             // :125
     float qx = xsub(xmul(ty, e1z), xmul(tz, e1y));
     float qy = xsub(xmul(tz, e1x), xmul(tx, e1z));
     float qz = xsub(xmul(tx, e1y), xmul(ty, e1x));
-    float v = xmul(xadd(xadd(xmul(r.dx, qx), xmul(r.dy, qy)), xmul(r.dz, qz)), inv);
+    v = xmul(xadd(xadd(xmul(r.dx, qx), xmul(r.dy, qy)), xmul(r.dz, qz)), inv);
     ok = ok && !(v < 0.0f) && !(xadd(u, v) > 1.0f);                                    // :132
-    float t = xmul(xadd(xadd(xmul(e2x, qx), xmul(e2y, qy)), xmul(e2z, qz)), inv);
+    t = xmul(xadd(xadd(xmul(e2x, qx), xmul(e2y, qy)), xmul(e2z, qz)), inv);
+    return ok;
+}
+B2_HD void tri_test_exact(const RayX& r, float ax, float ay, float az, float bx, float by, float bz,
+                          float cx, float cy, float cz, uint32_t tri, HitX& h) {
+    float t, u, v;
+    const bool ok = tri_eval_exact(r, ax, ay, az, bx, by, bz, cx, cy, cz, t, u, v);
     if (ok && t < h.t) { h.t = t; h.u = u; h.v = v; h.tri = tri; }                      // :140
 }
 

@@ -5,7 +5,11 @@
 #include <cstdint>
 #include <cstring>
 #include <string>
+#include <functional>
+#include <thread>
+#include <vector>
 #include "traverse.cuh"
+#include "coop.cuh"
 #include "wide_bvh.h"
 
 using namespace b2rt;
@@ -60,4 +64,73 @@ extern "C" void emu_trace(const EmuRay* rays, uint64_t n, EmuHit* hits, uint32_t
 extern "C" void emu_child_histogram(uint64_t* hist9) {
     for (int i = 0; i < 9; ++i) hist9[i] = 0;
     for (const WideNode& n : g_bvh.nodes) hist9[n.n_children <= 8 ? n.n_children : 8]++;
+}
+
+// ---- warp-cooperative tail mode (csrc/coop.cuh) on 32 emulated lanes -------------------------------------------
+namespace b2rt_emu { void run_warp(const std::function<void(uint32_t)>& body); }
+
+template <bool ANY>
+static void coop_one(const U4* wide, const U4* leaf, const EmuRay& in, uint32_t handoff, uint32_t wide_limit, uint32_t fcap,
+                     uint32_t seed, HitX& out, EmuStats* st) {
+    const RayX r = make_ray(in.ox, in.oy, in.oz, in.dx, in.dy, in.dz);
+    Lane<ANY, true, 256> L;
+    uint32_t stack[256];
+    L.tc = TravCounters{ 0, 0, 0, 0, 0, 0 };
+    L.start(r, in.tmax);
+    // solo steps first (a random number of them under a random interleaving), then the hand-over
+    uint32_t steps = handoff ? seed % handoff : 0u;
+    uint32_t sched = seed | 1u;
+    while (steps-- && !L.done()) {
+        const bool node = L.wants_node(), lf = L.wants_leaf();
+        bool do_leaf = lf;
+        if (node && lf) { sched = sched * 1664525u + 1013904223u; do_leaf = (sched >> 16) & 1u; }
+        if (do_leaf) { if (L.leaf_step(leaf, stack)) break; }
+        else L.node_step(wide, stack, 0x3F800000u);
+    }
+    if (L.done()) { out = L.h; return; }
+    std::vector<uint32_t> F(fcap + 64);
+    const uint32_t n = coop_dump(L, stack, F.data());
+    HitX res[32];
+    bool ovf[32];
+    b2rt_emu::run_warp([&](uint32_t lane) {
+        HitX h = L.h;
+        TravCounters tc = { 0, 0, 0, 0, 0, 0 };
+        bool o = false;
+        coop_trace<ANY, true>(wide, leaf, F.data(), n, fcap, wide_limit, r, h, tc, o);
+        res[lane] = h;
+        ovf[lane] = o;
+        if (lane == 0) { st->wide_visits += tc.wide_nodes; st->leaf_blocks += tc.leaf_blocks; st->tri_tests += tc.tri_tests; if (tc.max_stack > st->max_stack) st->max_stack = tc.max_stack; }
+    });
+    for (int l = 1; l < 32; ++l)
+        if (std::memcmp(&res[l], &res[0], sizeof(HitX)) != 0 || ovf[l] != ovf[0]) st->overflow += 1000000;   // lanes must agree
+    if (ovf[0]) st->overflow++;
+    out = res[0];
+}
+
+extern "C" void emu_trace_coop(const EmuRay* rays, uint64_t n, EmuHit* hits, uint32_t* occluded, int any, EmuStats* st,
+                               uint32_t handoff, uint32_t wide_limit, uint32_t fcap) {
+    const U4* wide = reinterpret_cast<const U4*>(g_bvh.nodes.data());
+    const U4* leaf = g_bvh.leaf.data();
+    unsigned nt = std::thread::hardware_concurrency();
+    if (nt < 1) nt = 1;
+    if (nt > 16) nt = 16;
+    std::vector<EmuStats> part(nt);
+    std::vector<std::thread> pool;
+    for (unsigned w = 0; w < nt; ++w)
+        pool.emplace_back([&, w]() {
+            std::memset(&part[w], 0, sizeof(EmuStats));
+            for (uint64_t i = n * w / nt; i < n * (w + 1) / nt; ++i) {
+                HitX h;
+                const uint32_t seed = (uint32_t)i * 2654435761u + 12345u;
+                if (any) coop_one<true>(wide, leaf, rays[i], handoff, wide_limit, fcap, seed, h, &part[w]);
+                else coop_one<false>(wide, leaf, rays[i], handoff, wide_limit, fcap, seed, h, &part[w]);
+                if (any) occluded[i] = h.tri != 0xFFFFFFFFu;
+                else { hits[i].t = h.t; hits[i].u = h.u; hits[i].v = h.v; hits[i].tri = h.tri; }
+            }
+        });
+    for (auto& t : pool) t.join();
+    for (const EmuStats& p : part) {
+        st->wide_visits += p.wide_visits; st->leaf_blocks += p.leaf_blocks; st->tri_tests += p.tri_tests; st->overflow += p.overflow;
+        if (p.max_stack > st->max_stack) st->max_stack = p.max_stack;
+    }
 }

@@ -64,11 +64,12 @@ def build_ref():
 
 def build_emu():
     out = os.path.join(EMU_DIR, "libemu.so")
-    srcs = [os.path.join(EMU_DIR, "emu.cpp")] + [os.path.join(CSRC, f) for f in ("traverse.cuh", "wide_bvh.cpp", "wide_bvh.h", "b2rt_types.h")]
+    srcs = [os.path.join(EMU_DIR, "emu.cpp"), os.path.join(EMU_DIR, "warp_emu.cpp")] + \
+           [os.path.join(CSRC, f) for f in ("traverse.cuh", "coop.cuh", "wide_bvh.cpp", "wide_bvh.h", "b2rt_types.h")]
     if _stale(out, srcs):
         subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-frounding-math",
                                "-fno-fast-math", "-pthread", "-x", "c++", "-I", CSRC, os.path.join(EMU_DIR, "emu.cpp"),
-                               os.path.join(CSRC, "wide_bvh.cpp"), "-o", out])
+                               os.path.join(EMU_DIR, "warp_emu.cpp"), os.path.join(CSRC, "wide_bvh.cpp"), "-o", out])
     return out
 
 
@@ -236,6 +237,24 @@ def emu_build(tris, nodes):
     if err:
         raise RuntimeError(err.decode())
     return st
+
+
+def emu_trace_coop(rays, any_hit=False, stats=None, handoff=0, wide_limit=192, fcap=256):
+    """The warp-cooperative tail mode (csrc/coop.cuh) on 32 emulated lanes (tests/emu/warp_emu.cpp). handoff = 0: the
+    whole ray runs cooperatively from the root; > 0: a pseudo-random number (< handoff) of solo steps first, then the
+    solo lane's state is handed over like trace_persistent does when its ray pool runs dry."""
+    rays = np.ascontiguousarray(rays)
+    st = stats if stats is not None else EmuStats()
+    L = emu()
+    L.emu_trace_coop.restype = None
+    L.emu_trace_coop.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]
+    if any_hit:
+        occ = np.empty(rays.shape[0], dtype=np.uint32)
+        L.emu_trace_coop(_p(rays), rays.shape[0], None, _p(occ), 1, C.addressof(st), handoff, wide_limit, fcap)
+        return occ
+    hits = np.empty(rays.shape[0], dtype=HIT)
+    L.emu_trace_coop(_p(rays), rays.shape[0], _p(hits), None, 0, C.addressof(st), handoff, wide_limit, fcap)
+    return hits
 
 
 def emu_trace(rays, any_hit=False, stats=None, schedule=0):

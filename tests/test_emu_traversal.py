@@ -144,3 +144,83 @@ def test_random_scenes_fuzz(tmp_scene_dir):
             _same(ol.emu_trace(rays, stats=st, schedule=schedule), want)
             assert st.overflow == 0 and st.max_stack <= bound          # the exact stack bound of the wide tree holds
         assert np.array_equal(ol.emu_trace(rays, any_hit=True, schedule=99) != 0, ol.oracle_any(tris, nodes, rays) != 0)
+
+
+# ---- warp-cooperative tail mode (csrc/coop.cuh) on 32 emulated lanes (tests/emu/warp_emu.cpp) ----------------------
+def _coop_same(rays, want, occluded=None):
+    """Whole rays cooperatively from the root, hand-overs after a few / many solo steps, one node per round (the
+    depth-first fallback) and four: all must give the oracle's hit, bit for bit."""
+    for handoff, wide_limit in ((0, 192), (6, 192), (60, 192), (0, 0), (9, 0)):
+        st = ol.EmuStats()
+        _same(ol.emu_trace_coop(rays, stats=st, handoff=handoff, wide_limit=wide_limit), want)
+        assert st.overflow == 0
+    if occluded is not None:
+        for handoff in (0, 7):
+            assert np.array_equal(ol.emu_trace_coop(rays, any_hit=True, handoff=handoff) != 0, occluded != 0)
+
+
+def test_coop_cornell(cornell_ref):
+    tris, nodes, _ = cornell_ref
+    ol.emu_build(tris, nodes)
+    rays = np.concatenate([ol.oracle_camera_rays(80, 60, 1), scenes.shell_rays(2000, 12.0, seed=5, centre=(0.0, 7.0, 8.0)),
+                           scenes.box_rays(2000, (-9, -2, -1), (9, 16, 17), seed=6), scenes.axis_rays((-9, -2, -1), (9, 16, 17), 40, seed=7)])
+    _coop_same(rays, ol.oracle_closest(tris, nodes, rays), ol.oracle_any(tris, nodes, rays))
+
+
+def test_coop_bumpy_negative_t_and_short_rays(bumpy_ref):
+    tris, nodes, _ = bumpy_ref
+    ol.emu_build(tris, nodes)
+    rays = scenes.shell_rays(2500, 10.0, seed=41)
+    h = ol.oracle_closest(tris, nodes, rays)
+    _coop_same(rays, h)
+    b = scenes.bounce_rays(rays, h, scenes.tri_normals(tris, h), seed=42)
+    hb = ol.oracle_closest(tris, nodes, b)
+    assert (hb["t"] < 0).mean() > 0.01
+    _coop_same(b, hb, ol.oracle_any(tris, nodes, b))            # negative t ends the search at the reference's leaf
+    short = b.copy()
+    short["tmax"] = 3.0
+    _coop_same(short, ol.oracle_closest(tris, nodes, short), ol.oracle_any(tris, nodes, short))
+    inside = scenes.box_rays(1500, (-5, -5, -5), (5, 5, 5), seed=43)
+    _coop_same(inside, ol.oracle_closest(tris, nodes, inside))
+
+
+def test_coop_exact_ties_follow_the_reference_order(tmp_scene_dir):
+    import os
+    p, n, f = scenes.tie_grid(24, layers=2)
+    path = scenes.write_obj(os.path.join(tmp_scene_dir, "ties.obj"), p, n, f)
+    tris, nodes, _ = _reference_scene(path)
+    ol.emu_build(tris, nodes)
+    rays = scenes.tie_rays(24)[::5]
+    _coop_same(rays, ol.oracle_closest(tris, nodes, rays), ol.oracle_any(tris, nodes, rays))
+
+
+def test_coop_random_scenes_fuzz(tmp_scene_dir):
+    """The fuzz scenes of test_random_scenes_fuzz (slivers, clusters, duplicated vertices, zero-area faces; leaves of
+    1..64 primitives incl. blocks of more than 16 records, which take the every-lane path) in cooperative mode."""
+    import os
+    prod_host = __import__("conftest").load_product().host
+    rng = np.random.default_rng(2025)
+    for case in range(12):
+        pos, faces = scenes.fuzz_scene(case, rng)
+        nrm = np.tile(np.array([[0.0, 0.0, 1.0]], dtype=np.float32), (pos.shape[0], 1))
+        path = scenes.write_obj(os.path.join(tmp_scene_dir, "cfuzz%d.obj" % case), pos, nrm, faces)
+        max_prims = int(rng.choice([1, 2, 4, 8, 64]))
+        tris, nodes, _ = prod_host.load_scene(path, max_prims)
+        ol.emu_build(tris, nodes)
+        lo, hi = pos.min(0) - 1.0, pos.max(0) + 1.0
+        rays = np.concatenate([scenes.box_rays(600, lo, hi, seed=case), scenes.axis_rays(lo, hi, 10, seed=case),
+                               scenes.pack_rays(pos[rng.integers(0, pos.shape[0], 150)], rng.normal(size=(150, 3)))])
+        rays["tmax"][::5] = rng.uniform(0.1, 20.0, size=rays["tmax"][::5].shape).astype(np.float32)
+        _coop_same(rays, ol.oracle_closest(tris, nodes, rays), ol.oracle_any(tris, nodes, rays))
+
+
+def test_coop_degenerate_scenes(tmp_scene_dir):
+    import os
+    p = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [1, 1, 0]], dtype=np.float32)
+    n = np.tile(np.array([[0, 0, 1]], dtype=np.float32), (4, 1))
+    for name, faces, quads in (("cone.obj", [[0, 1, 2]], None), ("cquad.obj", [[0, 1, 2]], [[0, 1, 3, 2]])):
+        path = scenes.write_obj(os.path.join(tmp_scene_dir, name), p, n, np.array(faces), quads)
+        tris, nodes, _ = _reference_scene(path)
+        ol.emu_build(tris, nodes)
+        rays = scenes.box_rays(2000, (-1, -1, 0.5), (2, 2, 3), seed=45)
+        _coop_same(rays, ol.oracle_closest(tris, nodes, rays))
