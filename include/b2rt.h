@@ -96,7 +96,11 @@ typedef struct {
     uint64_t bytes_fetched;     /* algorithmic bytes: 112 B per wide node + leaf block bytes */
     /* warp scheduling of the persistent kernels: phases run and lanes that took part in them */
     uint64_t node_phases, node_phase_lanes, leaf_phases, leaf_phase_lanes, refills, refill_lanes;
-    uint64_t max_steps_per_ray; /* node + leaf steps of the most expensive ray (tail detector) */
+    uint64_t max_steps_per_ray; /* node + leaf steps of the most expensive ray (tail detector; solo steps only) */
+    uint64_t stack_overflows;   /* lanes whose traversal stack or cooperative frontier overflowed: always 0 for trees that
+                                   passed upload validation (counted by every build, not only the counting one)          */
+    uint64_t coop_rays;         /* rays finished by the warp-cooperative tail mode ...                                   */
+    uint64_t coop_steps;        /* ... and the node + leaf visits done for them                                          */
 } b2rt_counters;
 
 enum {
@@ -108,7 +112,10 @@ enum {
                                    launch shape at hand (default). Frames are bit-identical in every mode. */
     B2RT_OPT_REFILL_MIN = 4,    /* idle lanes of a warp that trigger a ray refill (1..32, default 8) */
     B2RT_OPT_LEAF_BIAS = 5,     /* weight of the leaf vote in sixteenths (16 = plain majority, default 32) */
-    B2RT_OPT_WAVEFRONT_LANES = 6 /* wavefront frame path: independent wavefronts in flight per launch, 1..4 (0 = by size) */
+    B2RT_OPT_WAVEFRONT_LANES = 6, /* wavefront frame path: independent wavefronts in flight per launch, 1..4 (0 = by size) */
+    B2RT_OPT_COOP_MAX = 7       /* tail mode of the persistent kernels: a warp whose ray pool is dry and that has at most this many
+                                   rays alive hands them to the cooperative tail kernel, 32 lanes per ray (0 = off .. 16, default 8). Results do not
+                                   depend on it. */
 };
 
 /* ---- lifetime ---------------------------------------------------------------------- */

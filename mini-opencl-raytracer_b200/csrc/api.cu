@@ -32,6 +32,8 @@ struct Buffer {
 };
 
 constexpr uint64_t STREAM_CHUNK = 1ull << 22;   // rays per pipelined chunk of the host-buffer entry points
+constexpr int TAIL_RING = 4;                     // tail queues shared round robin by ray-stream launches (see trace_device)
+constexpr int64_t COOP_MAX_LIMIT = 16;           // upper bound of B2RT_OPT_COOP_MAX: the tail queues hold this many records per warp
 constexpr uint64_t NEXT_RING = 256;             // per-launch ray counters of the persistent kernels (b2rt_context::d_next)
 
 std::string g_create_error;
@@ -59,8 +61,13 @@ struct b2rt_context {
     uint32_t stack_bound = 8;
     SceneView view;
     // scratch
-    unsigned long long* d_next = nullptr;      // NEXT_RING counters, one per in-flight ray-stream launch
-    uint64_t next_seq = 0;
+    unsigned long long* d_next = nullptr;      // NEXT_RING counter blocks (4 x u64: ray counter, tail-queue length, tail-queue read
+    uint64_t next_seq = 0;                     // position, pad), one per in-flight ray-stream launch
+    // cooperative tail mode: queues of unfinished rays, one per launch that may be in flight at the same time
+    void* d_tail[TAIL_RING + 4] = { nullptr };  // [0, TAIL_RING): ray-stream launches (round robin); then one per wavefront lane
+    uint64_t tail_capacity_records = 0;
+    uint32_t tail_rec_words = 0;
+    int grid_tail = 0;
     unsigned long long* d_counters = nullptr;
     void* d_stage_rays[2] = { nullptr, nullptr };
     void* d_stage_out[2] = { nullptr, nullptr };
@@ -80,7 +87,7 @@ struct b2rt_context {
     uint64_t rgba8_capacity = 0;
     cudaEvent_t ev_in[2] = { nullptr, nullptr }, ev_comp[2] = { nullptr, nullptr }, ev_out[2] = { nullptr, nullptr };
     // options
-    int64_t opt_traversal = 0, opt_counters = 0, opt_blocks_per_sm = 0, opt_render_mode = 2, opt_refill_min = 8, opt_leaf_bias = 32, opt_wf_lanes = 0;
+    int64_t opt_traversal = 0, opt_counters = 0, opt_blocks_per_sm = 0, opt_render_mode = 2, opt_refill_min = 8, opt_leaf_bias = 32, opt_wf_lanes = 0, opt_coop_max = 8;
     int grid_closest = 0, grid_any = 0;
     uint64_t launches = 0;
     std::string error;
@@ -111,6 +118,10 @@ int use_device(b2rt_context* ctx) {
 Buffer* find(b2rt_context* ctx, b2rt_buffer id) {
     auto it = ctx->buffers.find(id);
     return it == ctx->buffers.end() ? nullptr : &it->second;
+}
+
+void free_tail(b2rt_context* ctx) {
+    for (void*& p : ctx->d_tail) { if (p) cudaFree(p); p = nullptr; }
 }
 
 void free_scene(b2rt_context* ctx) {
@@ -199,9 +210,27 @@ int ensure_scene(b2rt_context* ctx) {
     ctx->grid_closest = ctx->sm_count * std::max(occ, 1);
     CK(trace_occupancy(true, bound, &occ));
     ctx->grid_any = ctx->sm_count * std::max(occ, 1);
+    // cooperative tail mode: queue geometry for this tree (buffers are allocated on first use)
+    free_tail(ctx);
+    ctx->tail_rec_words = tail_record_words(bound);
+    const int max_grid = ctx->sm_count * 32;                       // B2RT_OPT_BLOCKS_PER_SM is at most 32
+    ctx->tail_capacity_records = (uint64_t)max_grid * (trace_block_threads() / 32) * COOP_MAX_LIMIT;
+    CK(tail_occupancy(bound, &occ));
+    ctx->grid_tail = ctx->sm_count * std::max(occ, 1);
     ctx->tuner.clear();
     ctx->tune_pending_mode = -1;
     ctx->scene_dirty = false;
+    return B2RT_SUCCESS;
+}
+
+// The tail queue in slot `which` (allocated on first use), wired to the given device counters. coop_max = 0 when the
+// tail mode is off or the launch runs the reference-layout walk.
+int tail_queue(b2rt_context* ctx, int which, unsigned long long* count, unsigned long long* next, TailQueue& q) {
+    q = TailQueue{ count, next, nullptr, ctx->tail_rec_words, 0u };
+    if (ctx->opt_coop_max <= 0 || ctx->opt_traversal == 1 || ctx->tail_capacity_records == 0) return B2RT_SUCCESS;
+    if (!ctx->d_tail[which]) CK(cudaMalloc(&ctx->d_tail[which], ctx->tail_capacity_records * ctx->tail_rec_words * sizeof(uint32_t)));
+    q.records = static_cast<uint32_t*>(ctx->d_tail[which]);
+    q.coop_max = (uint32_t)ctx->opt_coop_max;
     return B2RT_SUCCESS;
 }
 
@@ -219,10 +248,16 @@ int trace_device(b2rt_context* ctx, const void* d_rays, uint64_t n, void* d_out,
     if ((uint64_t)grid > blocks_needed) grid = (int)blocks_needed;
     // every launch pulls rays from its OWN counter (a ring of NEXT_RING slots): launches on different caller streams may
     // overlap, and a shared counter would be reset under a running kernel
-    unsigned long long* next = ctx->d_next + (ctx->next_seq++ % NEXT_RING);
+    const uint64_t seq = ctx->next_seq++;
+    unsigned long long* next = ctx->d_next + 4 * (seq % NEXT_RING);
+    // Tail queues are shared round robin: launches on the context's own stream are ordered anyway, and up to TAIL_RING
+    // launches on different caller streams may overlap (documented in b2rt.h).
+    TailQueue tail;
+    int st_tail = tail_queue(ctx, (int)(seq % TAIL_RING), next + 1, next + 2, tail);
+    if (st_tail) return st_tail;
     CK(launch_trace_wide(ctx->view, d_rays, n, d_out, any, ctx->opt_counters != 0, ctx->stack_bound, grid, next,
-                         ctx->d_counters, (uint32_t)ctx->opt_refill_min, (uint32_t)ctx->opt_leaf_bias, st));
-    ctx->launches += 1;
+                         ctx->d_counters, (uint32_t)ctx->opt_refill_min, (uint32_t)ctx->opt_leaf_bias, st, nullptr, &tail, ctx->grid_tail));
+    ctx->launches += tail.coop_max ? 2 : 1;
     return B2RT_SUCCESS;
 }
 
@@ -299,7 +334,7 @@ void free_wavefront(b2rt_context* ctx) {
 }
 
 int ensure_wavefront(b2rt_context* ctx, uint64_t paths) {
-    if (!ctx->d_wf_count) CK(cudaMalloc(&ctx->d_wf_count, WF_LANES * 4 * sizeof(unsigned long long)));
+    if (!ctx->d_wf_count) CK(cudaMalloc(&ctx->d_wf_count, WF_LANES * 8 * sizeof(unsigned long long)));
     if (ctx->wf_capacity >= paths) return B2RT_SUCCESS;
     CK(cudaStreamSynchronize(ctx->stream));
     free_wavefront(ctx);
@@ -315,7 +350,7 @@ int ensure_wavefront(b2rt_context* ctx, uint64_t paths) {
 // ray queue and one shade/compact launch. Queue lengths stay on the device.
 int wavefront_lane(b2rt_context* ctx, const FrameArgs& a, float* d_result, const GidMap& map, uint32_t n, int lane, uint64_t offset,
                    cudaStream_t s) {
-    unsigned long long* cnt = ctx->d_wf_count + 4 * lane;           // three rotating queue counters + the trace kernel's ray counter
+    unsigned long long* cnt = ctx->d_wf_count + 8 * lane;           // three rotating queue counters, the trace kernel's ray counter, its tail queue's two
     char* rays[2] = { static_cast<char*>(ctx->d_wf_rays[0]) + offset * sizeof(b2rt_ray), static_cast<char*>(ctx->d_wf_rays[1]) + offset * sizeof(b2rt_ray) };
     char* hits = static_cast<char*>(ctx->d_wf_hits) + offset * sizeof(b2rt_hit);
     char* state = static_cast<char*>(ctx->d_wf_state) + offset * 32;
@@ -325,14 +360,17 @@ int wavefront_lane(b2rt_context* ctx, const FrameArgs& a, float* d_result, const
     if (ctx->opt_blocks_per_sm > 0) grid = ctx->sm_count * (int)ctx->opt_blocks_per_sm;
     uint64_t blocks_needed = ((uint64_t)n + trace_block_threads() - 1) / trace_block_threads();
     if ((uint64_t)grid > blocks_needed) grid = (int)blocks_needed;
+    TailQueue tail;
+    int tq = tail_queue(ctx, TAIL_RING + lane, cnt + 4, cnt + 5, tail);
+    if (tq) return tq;
     for (int b = 0; b < a.bounces; ++b) {
         const int in = b & 1, out = in ^ 1;
         unsigned long long *n_in = cnt + (b % 3), *n_out = cnt + ((b + 1) % 3), *n_clear = cnt + ((b + 2) % 3);
         CK(launch_trace_wide(ctx->view, rays[in], n, hits, false, ctx->opt_counters != 0, ctx->stack_bound, grid,
-                             cnt + 3, ctx->d_counters, (uint32_t)ctx->opt_refill_min, (uint32_t)ctx->opt_leaf_bias, s, n_in));
-        // the shade stage also clears the counter the NEXT shade stage appends to and the traversal kernel's ray counter
+                             cnt + 3, ctx->d_counters, (uint32_t)ctx->opt_refill_min, (uint32_t)ctx->opt_leaf_bias, s, n_in, &tail, ctx->grid_tail));
+        // the shade stage also clears the counter the NEXT shade stage appends to and the traversal kernels' three counters
         CK(launch_wf_shade(ctx->view, a, map, n, rays[in], hits, n_in, rays[out], n_out, state, d_result, b == a.bounces - 1, n_clear, cnt + 3, s));
-        ctx->launches += 2;
+        ctx->launches += tail.coop_max ? 3 : 2;
     }
     return B2RT_SUCCESS;
 }
@@ -543,7 +581,7 @@ extern "C" int b2rt_create(int device_id, b2rt_context** out) {
         }
         cudaGetLastError();
     }
-    if ((e = cudaMalloc(&ctx->d_next, NEXT_RING * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMalloc");
+    if ((e = cudaMalloc(&ctx->d_next, NEXT_RING * 4 * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMalloc");
     if ((e = cudaMalloc(&ctx->d_counters, 128)) != cudaSuccess) return bail(e, "cudaMalloc");
     if ((e = cudaMemset(ctx->d_counters, 0, 128)) != cudaSuccess) return bail(e, "cudaMemset");
     *out = ctx;
@@ -566,6 +604,7 @@ extern "C" void b2rt_destroy(b2rt_context* ctx) {
     if (ctx->d_next) cudaFree(ctx->d_next);
     if (ctx->d_counters) cudaFree(ctx->d_counters);
     free_wavefront(ctx);
+    free_tail(ctx);
     if (ctx->d_wf_count) cudaFree(ctx->d_wf_count);
     if (ctx->d_rgba8) cudaFree(ctx->d_rgba8);
     for (int i = 0; i < 4; ++i) {
@@ -1006,6 +1045,7 @@ extern "C" int b2rt_set_option(b2rt_context* ctx, uint32_t option, int64_t value
         case B2RT_OPT_RENDER_MODE: if (value < 0 || value > 2) return fail(ctx, B2RT_INVALID_VALUE, "render mode must be 0 (wavefront), 1 (megakernel) or 2 (measured choice)"); ctx->opt_render_mode = value; break;
         case B2RT_OPT_WAVEFRONT_LANES: if (value < 0 || value > 4) return fail(ctx, B2RT_INVALID_VALUE, "wavefront lanes must be 0 (auto) .. 4"); ctx->opt_wf_lanes = value; break;
         case B2RT_OPT_LEAF_BIAS: if (value < 1 || value > 512) return fail(ctx, B2RT_INVALID_VALUE, "leaf bias must be 1..512 (sixteenths)"); ctx->opt_leaf_bias = value; break;
+        case B2RT_OPT_COOP_MAX: if (value < 0 || value > COOP_MAX_LIMIT) return fail(ctx, B2RT_INVALID_VALUE, "cooperative tail threshold must be 0 (off) .. 16"); ctx->opt_coop_max = value; break;
         case B2RT_OPT_REFILL_MIN: if (value < 1 || value > 32) return fail(ctx, B2RT_INVALID_VALUE, "refill threshold must be 1..32"); ctx->opt_refill_min = value; break;
         default: return fail(ctx, B2RT_INVALID_VALUE, "unknown option");
     }
@@ -1018,13 +1058,14 @@ extern "C" int b2rt_get_counters(b2rt_context* ctx, b2rt_counters* out) {
     if (!out) return fail(ctx, B2RT_INVALID_VALUE, "null output");
     int st = use_device(ctx);
     if (st) return st;
-    unsigned long long v[13];
+    unsigned long long v[16];
     CK(cudaDeviceSynchronize());     // counted launches may sit on caller-provided streams
     CK(cudaMemcpy(v, ctx->d_counters, sizeof(v), cudaMemcpyDeviceToHost));
     out->rays = v[0]; out->wide_nodes = v[1]; out->leaf_blocks = v[2]; out->leaf_gate_pass = v[3]; out->tri_tests = v[4];
     out->bytes_fetched = v[5] * 16ull;
     out->node_phases = v[6]; out->node_phase_lanes = v[7]; out->leaf_phases = v[8]; out->leaf_phase_lanes = v[9];
     out->refills = v[10]; out->refill_lanes = v[11]; out->max_steps_per_ray = v[12];
+    out->stack_overflows = v[13]; out->coop_rays = v[14]; out->coop_steps = v[15];
     return B2RT_SUCCESS;
 }
 extern "C" int b2rt_reset_counters(b2rt_context* ctx) {

@@ -24,6 +24,7 @@
 #include <stdint.h>
 #include "kernels.h"
 #include "shade.cuh"
+#include "coop.cuh"
 
 namespace b2rt {
 
@@ -69,6 +70,60 @@ __device__ __forceinline__ void write_result(void* __restrict__ out, uint64_t i,
 }
 
 // ---------------------------------------------------------------------------------------
+// Cooperative tail (coop.cuh). trace_persistent hands the rays that are still alive when its pool is dry and a warp is
+// down to a few of them to trace_tail_kernel, launched right behind it on the same stream: persistent warps pull the
+// records off the queue (balanced over the whole GPU) and finish each ray with all 32 lanes.
+//   record = { index lo, index hi, t, u, v, tri, n, 0, frontier[n] }   (frontier back to front, see coop_dump)
+// ---------------------------------------------------------------------------------------
+enum { TAIL_HEADER_WORDS = 8 };
+static constexpr int TAIL_BLOCK = 128;
+
+template <bool ANY, bool COUNT>
+__global__ void __launch_bounds__(TAIL_BLOCK)
+trace_tail_kernel(SceneView s, const RayIn* __restrict__ rays, void* __restrict__ out, TailQueue tail,
+                  unsigned long long* __restrict__ counters, uint32_t fcap, uint32_t wide_limit) {
+    extern __shared__ uint32_t tail_frontiers[];                        // fcap words per warp
+    uint32_t* F = tail_frontiers + (threadIdx.x >> 5) * fcap;
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned long long total = *tail.count;
+    TravCounters tc = { 0, 0, 0, 0, 0, 0 };
+    unsigned long long done = 0;
+    bool overflow = false;
+    for (;;) {
+        unsigned long long slot = 0;
+        if (lane == 0) slot = atomicAdd(tail.next, 1ull);
+        slot = __shfl_sync(FULL, slot, 0);
+        if (slot >= total) break;
+        const uint32_t* rec = tail.records + slot * tail.rec_words;
+        const uint32_t head = lane < TAIL_HEADER_WORDS ? rec[lane] : 0u;
+        const uint64_t index = (uint64_t)__shfl_sync(FULL, head, 0) | ((uint64_t)__shfl_sync(FULL, head, 1) << 32);
+        HitX h;
+        h.t = __uint_as_float(__shfl_sync(FULL, head, 2)); h.u = __uint_as_float(__shfl_sync(FULL, head, 3));
+        h.v = __uint_as_float(__shfl_sync(FULL, head, 4)); h.tri = __shfl_sync(FULL, head, 5);
+        const uint32_t n = __shfl_sync(FULL, head, 6);
+        for (uint32_t i = lane; i < n; i += 32u) F[i] = rec[TAIL_HEADER_WORDS + i];
+        RayX r; float tmax;
+        load_ray(rays, index, r, tmax);                                 // every lane: the same 32 bytes, the same arithmetic
+        __syncwarp();
+        coop_trace<ANY, COUNT>(s.wide, s.leaf, F, n, fcap, wide_limit, r, h, tc, overflow);
+        if (lane == 0) write_result<ANY>(out, index, h);
+        ++done;
+        __syncwarp();
+    }
+    if (lane == 0) {
+        if (overflow) atomicAdd(&counters[13], 1ull);
+        if (COUNT && done) {
+            atomicAdd(&counters[0], done);
+            atomicAdd(&counters[1], (unsigned long long)tc.wide_nodes); atomicAdd(&counters[2], (unsigned long long)tc.leaf_blocks);
+            atomicAdd(&counters[3], (unsigned long long)tc.leaf_pass); atomicAdd(&counters[4], (unsigned long long)tc.tri_tests);
+            atomicAdd(&counters[5], (unsigned long long)tc.words);
+            atomicAdd(&counters[14], done);                                              // rays finished cooperatively ...
+            atomicAdd(&counters[15], (unsigned long long)tc.wide_nodes + tc.leaf_blocks);   // ... and their node + leaf visits
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // Persistent speculative while-while traversal.
 //
 // Every lane owns one ray (Lane<> in traverse.cuh). Per iteration the warp votes: lanes whose
@@ -82,7 +137,7 @@ template <bool ANY, bool COUNT, int CAP>
 __global__ void __launch_bounds__(TRACE_BLOCK, B2_MIN_BLOCKS)
 trace_persistent(SceneView s, const RayIn* __restrict__ rays, uint64_t n, void* __restrict__ out,
                  unsigned long long* __restrict__ next, unsigned long long* __restrict__ counters, uint32_t chunk,
-                 uint32_t refill_min, uint32_t leaf_bias, const unsigned long long* __restrict__ n_dev) {
+                 uint32_t refill_min, uint32_t leaf_bias, const unsigned long long* __restrict__ n_dev, TailQueue tail) {
     const unsigned lane = threadIdx.x & 31u;
     if (n_dev) {
         // wavefront stages: the ray count is the previous stage's queue counter, never seen by the host
@@ -111,6 +166,8 @@ trace_persistent(SceneView s, const RayIn* __restrict__ rays, uint64_t n, void* 
         const unsigned vl = __ballot_sync(FULL, L.wants_leaf());
         const unsigned idle = ~(vn | vl);
         const bool pool_dry = exhausted && pool_left == 0u;
+        // tail: nothing left to fetch and only a few rays alive in this warp -> hand them to the cooperative tail kernel
+        if (pool_dry && tail.coop_max && (vn | vl) != 0u && (unsigned)__popc(vn | vl) <= tail.coop_max) break;
         if (idle && !pool_dry && ((unsigned)__popc(idle) >= refill_min || (vn | vl) == 0u)) {
             // ---- refill idle lanes from the warp pool -------------------------------------------
             // Finished rays are written here, several lanes at a time, instead of one lane at a time when they finish.
@@ -164,6 +221,18 @@ trace_persistent(SceneView s, const RayIn* __restrict__ rays, uint64_t n, void* 
         }
     }
     if (has_out) write_result<ANY>(out, my_index, L.h);       // rays that finished after the last refill
+    if (tail.coop_max && !L.done()) {
+        // Unfinished ray: its index, best hit so far and pending work (in the reference's depth-first order) go to the tail
+        // queue; trace_tail_kernel finishes it with a whole warp. At most coop_max lanes per warp get here, and the queue
+        // holds coop_max records per warp of the grid.
+        const unsigned long long slot = atomicAdd(tail.count, 1ull);
+        uint32_t* rec = tail.records + slot * tail.rec_words;
+        rec[0] = (uint32_t)my_index; rec[1] = (uint32_t)(my_index >> 32);
+        rec[2] = __float_as_uint(L.h.t); rec[3] = __float_as_uint(L.h.u); rec[4] = __float_as_uint(L.h.v); rec[5] = L.h.tri;
+        rec[6] = coop_dump(L, stack, rec + TAIL_HEADER_WORDS);
+        rec[7] = 0u;
+    }
+    if (L.overflow) atomicAdd(&counters[13], 1ull);            // never expected: the stack capacity is the tree's exact bound
 
     if (COUNT) {
         // one atomic per counter per warp
@@ -315,8 +384,8 @@ __global__ void __launch_bounds__(256)
 wf_generate_kernel(FrameArgs a, GidMap map, uint32_t n, RayIn* __restrict__ rays, float4* __restrict__ state,
                    unsigned long long* __restrict__ queue_count) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    // counter block of this wavefront: [0..2] rotating queue lengths, [3] the traversal kernel's ray counter
-    if (i == 0) { queue_count[0] = n; queue_count[1] = 0; queue_count[2] = 0; queue_count[3] = 0; }
+    // counter block of this wavefront: [0..2] rotating queue lengths, [3] the traversal kernel's ray counter, [4] [5] its tail queue's length and read position
+    if (i == 0) { queue_count[0] = n; queue_count[1] = 0; queue_count[2] = 0; queue_count[3] = 0; queue_count[4] = 0; queue_count[5] = 0; }
     if (i >= n) return;
     uint32_t gid = (uint32_t)map.gid(i);
     uint32_t seed = gid + hash_u32(a.frame_count);                        // kernel_bvh.cl:445
@@ -337,7 +406,7 @@ wf_shade_kernel(SceneView s, FrameArgs a, GidMap map, const RayIn* __restrict__ 
     const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     // reset what the NEXT stages start from: the traversal kernel's ray counter and the queue length the next
     // shade stage appends to (neither is read or written by anything in flight now)
-    if (j == 0) { *clear_a = 0; *clear_b = 0; }
+    if (j == 0) { *clear_a = 0; clear_b[0] = 0; clear_b[1] = 0; clear_b[2] = 0; }
     if ((j & ~31ull) >= n) return;                      // whole warp beyond the queue
     const unsigned lane = threadIdx.x & 31u;
     bool go_on = false;
@@ -403,17 +472,17 @@ static int pick_cap(uint32_t bound) { return bound <= 32 ? 32 : (bound <= 64 ? 6
 template <bool ANY, bool COUNT>
 static cudaError_t launch_persistent_cap(int cap, int grid, cudaStream_t st, const SceneView& s, const void* rays,
                                          uint64_t n, void* out, unsigned long long* next, unsigned long long* counters,
-                                         uint32_t refill_min, uint32_t leaf_bias, const unsigned long long* n_dev) {
+                                         uint32_t refill_min, uint32_t leaf_bias, const unsigned long long* n_dev, const TailQueue& tail) {
     const RayIn* r = static_cast<const RayIn*>(rays);
     // rays per pool top-up: about 1/8 of a warp's fair share, a multiple of 32 in [32, 512]
     uint64_t warps = (uint64_t)grid * (TRACE_BLOCK / 32);
     uint64_t c = n / (warps * 8u + 1u);
     uint32_t chunk = (uint32_t)(c < 32 ? 32 : (c > 512 ? 512 : (c & ~31ull)));
     switch (cap) {
-        case 32: trace_persistent<ANY, COUNT, 32><<<grid, TRACE_BLOCK, 0, st>>>(s, r, n, out, next, counters, chunk, refill_min, leaf_bias, n_dev); break;
-        case 64: trace_persistent<ANY, COUNT, 64><<<grid, TRACE_BLOCK, 0, st>>>(s, r, n, out, next, counters, chunk, refill_min, leaf_bias, n_dev); break;
-        case 128: trace_persistent<ANY, COUNT, 128><<<grid, TRACE_BLOCK, 0, st>>>(s, r, n, out, next, counters, chunk, refill_min, leaf_bias, n_dev); break;
-        case 256: trace_persistent<ANY, COUNT, 256><<<grid, TRACE_BLOCK, 0, st>>>(s, r, n, out, next, counters, chunk, refill_min, leaf_bias, n_dev); break;
+        case 32: trace_persistent<ANY, COUNT, 32><<<grid, TRACE_BLOCK, 0, st>>>(s, r, n, out, next, counters, chunk, refill_min, leaf_bias, n_dev, tail); break;
+        case 64: trace_persistent<ANY, COUNT, 64><<<grid, TRACE_BLOCK, 0, st>>>(s, r, n, out, next, counters, chunk, refill_min, leaf_bias, n_dev, tail); break;
+        case 128: trace_persistent<ANY, COUNT, 128><<<grid, TRACE_BLOCK, 0, st>>>(s, r, n, out, next, counters, chunk, refill_min, leaf_bias, n_dev, tail); break;
+        case 256: trace_persistent<ANY, COUNT, 256><<<grid, TRACE_BLOCK, 0, st>>>(s, r, n, out, next, counters, chunk, refill_min, leaf_bias, n_dev, tail); break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
@@ -422,20 +491,37 @@ static cudaError_t launch_persistent_cap(int cap, int grid, cudaStream_t st, con
 cudaError_t launch_trace_wide(const SceneView& s, const void* d_rays, uint64_t n, void* d_out, bool any, bool count,
                               uint32_t stack_bound, int grid_blocks, unsigned long long* d_next,
                               unsigned long long* d_counters, uint32_t refill_min, uint32_t leaf_bias, cudaStream_t st,
-                              const unsigned long long* d_n) {
+                              const unsigned long long* d_n, const TailQueue* tail_in, int tail_grid) {
     int cap = pick_cap(stack_bound);
     if (!cap) return cudaErrorInvalidValue;
-    if (!d_n) {     // wavefront stages (d_n given) get their counter reset by the preceding stage's kernel
-        cudaError_t e = cudaMemsetAsync(d_next, 0, sizeof(unsigned long long), st);
+    TailQueue tail = { nullptr, nullptr, nullptr, 0, 0 };
+    if (tail_in && tail_in->coop_max && tail_in->records) tail = *tail_in;
+    if (!d_n) {     // wavefront stages (d_n given) get their counters reset by the preceding stage's kernel
+        // [0] the ray counter, [1] tail-queue length, [2] tail-queue read position
+        cudaError_t e = cudaMemsetAsync(d_next, 0, 3 * sizeof(unsigned long long), st);
         if (e != cudaSuccess) return e;
     }
     if (refill_min < 1 || refill_min > 32) refill_min = 8;
     if (leaf_bias < 1 || leaf_bias > 512) leaf_bias = 16;
-    if (any) return count ? launch_persistent_cap<true, true>(cap, grid_blocks, st, s, d_rays, n, d_out, d_next, d_counters, refill_min, leaf_bias, d_n)
-                          : launch_persistent_cap<true, false>(cap, grid_blocks, st, s, d_rays, n, d_out, d_next, d_counters, refill_min, leaf_bias, d_n);
-    return count ? launch_persistent_cap<false, true>(cap, grid_blocks, st, s, d_rays, n, d_out, d_next, d_counters, refill_min, leaf_bias, d_n)
-                 : launch_persistent_cap<false, false>(cap, grid_blocks, st, s, d_rays, n, d_out, d_next, d_counters, refill_min, leaf_bias, d_n);
+    cudaError_t e;
+    if (any) e = count ? launch_persistent_cap<true, true>(cap, grid_blocks, st, s, d_rays, n, d_out, d_next, d_counters, refill_min, leaf_bias, d_n, tail)
+                       : launch_persistent_cap<true, false>(cap, grid_blocks, st, s, d_rays, n, d_out, d_next, d_counters, refill_min, leaf_bias, d_n, tail);
+    else e = count ? launch_persistent_cap<false, true>(cap, grid_blocks, st, s, d_rays, n, d_out, d_next, d_counters, refill_min, leaf_bias, d_n, tail)
+                   : launch_persistent_cap<false, false>(cap, grid_blocks, st, s, d_rays, n, d_out, d_next, d_counters, refill_min, leaf_bias, d_n, tail);
+    if (e != cudaSuccess || !tail.coop_max) return e;
+    // the tail kernel: frontier capacity per warp and the size up to which four nodes are expanded per round
+    const uint32_t fcap = tail_frontier_words(stack_bound), wide_limit = fcap - (stack_bound + 8u) - 32u;
+    const size_t smem = (size_t)(TAIL_BLOCK / 32) * fcap * sizeof(uint32_t);
+    const RayIn* r = static_cast<const RayIn*>(d_rays);
+    if (any) { if (count) trace_tail_kernel<true, true><<<tail_grid, TAIL_BLOCK, smem, st>>>(s, r, d_out, tail, d_counters, fcap, wide_limit);
+               else trace_tail_kernel<true, false><<<tail_grid, TAIL_BLOCK, smem, st>>>(s, r, d_out, tail, d_counters, fcap, wide_limit); }
+    else { if (count) trace_tail_kernel<false, true><<<tail_grid, TAIL_BLOCK, smem, st>>>(s, r, d_out, tail, d_counters, fcap, wide_limit);
+           else trace_tail_kernel<false, false><<<tail_grid, TAIL_BLOCK, smem, st>>>(s, r, d_out, tail, d_counters, fcap, wide_limit); }
+    return cudaGetLastError();
 }
+
+uint32_t tail_frontier_words(uint32_t stack_bound) { uint32_t w = 4u * (stack_bound + 8u); return w < 256u ? 256u : w; }
+uint32_t tail_record_words(uint32_t stack_bound) { return TAIL_HEADER_WORDS + ((stack_bound + 8u + 3u) & ~3u); }
 
 cudaError_t launch_trace_binary(const SceneView& s, const void* d_rays, uint64_t n, void* d_out, bool any, cudaStream_t st) {
     if (n == 0) return cudaSuccess;
@@ -497,6 +583,11 @@ cudaError_t launch_tonemap_rgba8(const void* d_image, void* d_out, uint64_t n, c
 }
 
 int trace_block_threads() { return TRACE_BLOCK; }
+
+cudaError_t tail_occupancy(uint32_t stack_bound, int* blocks_per_sm) {
+    const size_t smem = (size_t)(TAIL_BLOCK / 32) * tail_frontier_words(stack_bound) * sizeof(uint32_t);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, trace_tail_kernel<false, false>, TAIL_BLOCK, smem);
+}
 
 cudaError_t trace_occupancy(bool any, uint32_t stack_bound, int* blocks_per_sm) {
     int cap = pick_cap(stack_bound);

@@ -6,13 +6,27 @@
 
 namespace b2rt {
 
+// Tail queue of a persistent traversal launch (see trace_tail_kernel in kernels.cu). coop_max = 0 switches the tail mode off.
+struct TailQueue {
+    unsigned long long* count;     // records written by the launch (device counter, zeroed before it)
+    unsigned long long* next;      // read position of the tail kernel (zeroed likewise)
+    uint32_t* records;             // capacity: coop_max records per warp of the persistent grid
+    uint32_t rec_words;            // tail_record_words(stack_bound)
+    uint32_t coop_max;             // a dry warp with at most this many live rays hands them over
+};
+uint32_t tail_frontier_words(uint32_t stack_bound);   // shared-memory words per warp of the tail kernel
+uint32_t tail_record_words(uint32_t stack_bound);
+
 // Persistent while-while traversal of the compressed wide BVH over a device-resident ray
-// stream. d_out is b2rt_hit[n] (closest) or uint32_t[n] (any). d_next is an 8-byte scratch
-// counter (reset by the wrapper), d_counters six 64-bit accumulators (used when count).
+// stream. d_out is b2rt_hit[n] (closest) or uint32_t[n] (any). d_next points at three 64-bit scratch
+// counters (ray counter, tail-queue length, tail-queue read position; reset by the wrapper unless d_n is given),
+// d_counters sixteen 64-bit accumulators (used when count; [13] = stack/frontier overflows, always). With a tail
+// queue the cooperative tail kernel is launched right behind the persistent one (tail_grid blocks).
 cudaError_t launch_trace_wide(const SceneView& s, const void* d_rays, uint64_t n, void* d_out, bool any, bool count,
                               uint32_t stack_bound, int grid_blocks, unsigned long long* d_next,
                               unsigned long long* d_counters, uint32_t refill_min, uint32_t leaf_bias, cudaStream_t st,
-                              const unsigned long long* d_n = nullptr);   // d_n != null: ray count read on the device (n = upper bound)
+                              const unsigned long long* d_n = nullptr,    // d_n != null: ray count read on the device (n = upper bound)
+                              const TailQueue* tail = nullptr, int tail_grid = 0);
 // One thread per ray over the reference-layout arrays (baseline / cross-check).
 cudaError_t launch_trace_binary(const SceneView& s, const void* d_rays, uint64_t n, void* d_out, bool any, cudaStream_t st);
 cudaError_t launch_camera_rays(const FrameArgs& a, uint64_t gid0, uint64_t gid1, void* d_rays, cudaStream_t st);
@@ -29,6 +43,7 @@ cudaError_t launch_wf_shade(const SceneView& s, const FrameArgs& a, const GidMap
 // float4 accumulation image -> clamped 8-bit RGBA (alpha 255), n pixels.
 cudaError_t launch_tonemap_rgba8(const void* d_image, void* d_out, uint64_t n, cudaStream_t st);
 int trace_block_threads();
+cudaError_t tail_occupancy(uint32_t stack_bound, int* blocks_per_sm);
 cudaError_t trace_occupancy(bool any, uint32_t stack_bound, int* blocks_per_sm);
 
 }  // namespace b2rt

@@ -1,0 +1,182 @@
+"""-m gpu, round 2: the cooperative tail mode, direct comparisons with the VERBATIM reference build (oracle/_ref),
+the advisor's regression cases, and a >= 1 M-face scattered scene checked against oracle-rendered pixels."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+import scenes
+from test_gpu_parity import _check_hits, _render
+
+pytestmark = pytest.mark.gpu
+MISS = 0xFFFFFFFF
+
+
+def _counted(product, ctx, fn):
+    ctx.set_option(product.capi.OPT_COUNTERS, 1)
+    ctx.reset_counters()
+    try:
+        out = fn()
+        return out, ctx.counters()
+    finally:
+        ctx.set_option(product.capi.OPT_COUNTERS, 0)
+
+
+def test_cooperative_tail_is_result_neutral(product, bumpy_ref, tmp_scene_dir):
+    """B2RT_OPT_COOP_MAX: a dry warp hands its last rays to trace_tail_kernel (32 lanes per ray, csrc/coop.cuh). Hits must
+    not depend on the threshold -- primary rays, negative-t bounce rays, exact cross-leaf ties, any-hit -- and the
+    counting build must show that the tail kernel really ran."""
+    cap = product.capi
+    tris, nodes, mats = bumpy_ref
+    rays = scenes.shell_rays(150000, 10.0, seed=151)
+    want = ol.oracle_closest(tris, nodes, rays)
+    b = scenes.bounce_rays(rays, want, scenes.tri_normals(tris, want), seed=152)
+    wb = ol.oracle_closest(tris, nodes, b)
+    assert (wb["t"] < 0).mean() > 0.01
+    occ_want = ol.oracle_any(tris, nodes, b)
+    with product.Context(0) as ctx:
+        ctx.upload_scene(tris, nodes, mats)
+        for coop in (0, 1, 8, 16):
+            ctx.set_option(cap.OPT_COOP_MAX, coop)
+            got, c = _counted(product, ctx, lambda: ctx.trace_closest(rays))
+            _check_hits(got, want)
+            assert c["rays"] == rays.shape[0] and c["stack_overflows"] == 0
+            assert (c["coop_rays"] > 0) == (coop > 0)
+            _check_hits(ctx.trace_closest(b), wb)
+            assert np.array_equal(ctx.trace_any(b) != 0, occ_want != 0)
+            for n in (1, 31, 33, 1000):                           # launches so small that (almost) every ray ends in the tail kernel
+                _check_hits(ctx.trace_closest(b[:n]), wb[:n])
+        # every ray through the tail kernel: 16 rays per launch leave each warp with <= 16 live rays and a dry pool at once
+        ctx.set_option(cap.OPT_COOP_MAX, 16)
+        got, c = _counted(product, ctx, lambda: np.concatenate([ctx.trace_closest(b[i:i + 16]) for i in range(0, 4000, 16)]))
+        _check_hits(got, wb[:4000])
+        assert c["coop_rays"] > 2000
+        with pytest.raises(product.B2RTError):
+            ctx.set_option(cap.OPT_COOP_MAX, 17)
+    p, n, f = scenes.tie_grid(24, layers=2)
+    path = scenes.write_obj(os.path.join(tmp_scene_dir, "ties_coop.obj"), p, n, f)
+    t2, n2, m2 = product.host.load_scene(path, 4)
+    tr = scenes.tie_rays(24)
+    tw = ol.oracle_closest(t2, n2, tr)
+    with product.Context(0) as ctx:
+        ctx.upload_scene(t2, n2, m2)
+        for coop in (0, 16):
+            ctx.set_option(cap.OPT_COOP_MAX, coop)
+            _check_hits(ctx.trace_closest(tr), tw)
+            _check_hits(np.concatenate([ctx.trace_closest(tr[i:i + 16]) for i in range(0, 1600, 16)]), tw[:1600])
+
+
+def test_cuda_path_against_the_verbatim_reference_build(product, bumpy_ref):
+    """no port in between -- CUDA hits and a CUDA frame compared directly with the reference's own
+    Intersect() / KernelEntry compiled from /root/reference (oracle/_ref)."""
+    if ol.ref() is None:
+        pytest.skip("oracle/_ref/libref_oracle.so not available on this machine")
+    tris, nodes, mats = bumpy_ref
+    rays = scenes.shell_rays(200000, 10.0, seed=161)
+    ref = ol.ref_closest(tris, nodes, rays)
+    hit = ref["hit"] != 0
+    b = scenes.bounce_rays(rays, ol.oracle_closest(tris, nodes, rays), scenes.tri_normals(tris, ol.oracle_closest(tris, nodes, rays)), seed=162)
+    refb = ol.ref_closest(tris, nodes, b)
+    hitb = refb["hit"] != 0
+    W, H = 256, 192
+    cam = dict(pos=(0.0, -30.0, 4.0), front=(0.0, 1.0, 0.0), up=(0.0, 0.0, 1.0))
+    want = np.zeros((W * H, 4), dtype=np.float32)
+    for fc in (1, 2, 3):
+        ol.ref_render(tris, nodes, mats, want, W, H, fc, 4, **cam)
+    with product.Context(0) as ctx:
+        ctx.upload_scene(tris, nodes, mats)
+        for r, want_hits, m in ((rays, ref, hit), (b, refb, hitb)):
+            got = ctx.trace_closest(r)
+            assert np.array_equal(got["tri"] != MISS, m)
+            assert np.array_equal(got["tri"][m], want_hits["tri"][m].astype(np.uint32))
+            assert np.array_equal(got["t"][m].view(np.uint32), want_hits["t"][m].view(np.uint32))
+        assert (refb["t"][hitb] < 0).mean() > 0.01                 # the negative-t trap is in the sample
+        img = _render(ctx, W, H, (1, 2, 3), 4, **cam)
+    assert scenes.psnr(img[:, :3], want[:, :3]) >= 50.0
+    assert (img[:, :3] == want[:, :3]).all(axis=1).mean() > 0.95
+
+
+def test_oracle_and_host_suites_on_this_machine():
+    """the pins port <-> verbatim reference <-> golden files and host arrays <-> reference builder are CPU
+    tests; run them on the GPU box too, so that the chain GPU = port = reference is closed on one machine."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "not gpu", os.path.join(root, "tests", "test_oracle.py"),
+                        os.path.join(root, "tests", "test_host_scene.py")], cwd=root, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_wavefront_lane_split_keeps_every_work_item(product, cornell_ref):
+    """n = 1 (mod 64) work items split over 2 or 3 wavefront lanes used to lose the last item."""
+    cap = product.capi
+    tris, nodes, mats = cornell_ref
+    with product.Context(0) as ctx:
+        ctx.upload_scene(tris, nodes, mats)
+        for W, H, lanes in ((65, 1, 2), (97, 1, 3), (1025, 1025, 0), (1025, 1025, 3)):
+            frames = {}
+            for mode in (1, 0):
+                ctx.set_option(cap.OPT_RENDER_MODE, mode)
+                ctx.set_option(cap.OPT_WAVEFRONT_LANES, lanes)
+                ctx.resize(W, H)
+                ctx.set_frame(1, 3)
+                ctx.execute(W * H)
+                frames[mode] = ctx.read_pixels().copy()
+            assert np.array_equal(frames[0].view(np.uint32), frames[1].view(np.uint32)), (W, H, lanes)
+            assert frames[0][-1, :3].max() > 0.0
+
+
+def test_launches_on_different_streams_may_overlap(product, bumpy_ref):
+    """every launch has its own ray counter, so traces enqueued on different caller streams (and on the
+    context's stream) at the same time do not disturb each other."""
+    import torch
+    tris, nodes, mats = bumpy_ref
+    sets = [scenes.shell_rays(400000, 10.0, seed=171 + i) for i in range(3)]
+    wants = [ol.oracle_closest(tris, nodes, r) for r in sets]
+    with product.Context(0) as ctx:
+        ctx.upload_scene(tris, nodes, mats)
+        d_rays = [torch.from_numpy(r.view(np.float32).reshape(-1, 8)).to("cuda:0") for r in sets]
+        d_hits = [torch.empty((r.shape[0], 4), dtype=torch.float32, device="cuda:0") for r in sets]
+        streams = [torch.cuda.Stream(device="cuda:0") for _ in range(2)]
+        torch.cuda.synchronize()
+        for rep in range(4):
+            for h in d_hits:
+                h.zero_()
+            torch.cuda.synchronize()
+            ctx.trace_closest_device(d_rays[0].data_ptr(), sets[0].shape[0], d_hits[0].data_ptr(), streams[0].cuda_stream)
+            ctx.trace_closest_device(d_rays[1].data_ptr(), sets[1].shape[0], d_hits[1].data_ptr(), streams[1].cuda_stream)
+            ctx.trace_closest_device(d_rays[2].data_ptr(), sets[2].shape[0], d_hits[2].data_ptr(), 0)   # the context's own stream
+            torch.cuda.synchronize()
+            ctx.finish()
+            for h, w in zip(d_hits, wants):
+                _check_hits(h.cpu().numpy().view(product.HIT_DTYPE).reshape(-1), w)
+
+
+def test_million_face_scattered_scene_against_oracle_pixels(product, tmp_scene_dir):
+    """BASELINE.json configs[3] at >= 1 M OBJ faces (2 M CLTriangle): pixels of the 4-bounce frame, rendered
+    through the wavefront path with the tail kernel, against the SAME pixels rendered by the oracle (oracle_render over gid
+    ranges), and incoherent rays against the oracle's hits."""
+    path = os.path.join(tmp_scene_dir, "scatter_1m.obj")
+    assert product.host.write_scattered_obj(path, 1000000, extent=50.0, edge_min=0.25, edge_max=1.0, seed=11) == 1000000
+    tris, nodes, mats = product.host.load_scene(path, 4)
+    assert tris.shape[0] == 2000000
+    W, H, bounces = 1280, 720, 4
+    cam = dict(pos=(0.0, -140.0, 0.0), front=(0.0, 1.0, 0.0), up=(0.0, 0.0, 1.0))
+    rows = (5, 200, 359, 360, 511, 700)                          # image rows rendered by the oracle
+    want = np.zeros((W * H, 4), dtype=np.float32)
+    for fc in (1, 2):
+        for y in rows:
+            ol.oracle_render(tris, nodes, mats, want, W, H, fc, bounces, gid0=y * W, gid1=(y + 1) * W, **cam)
+    with product.Context(0) as ctx:
+        ctx.upload_scene(tris, nodes, mats)
+        img = _render(ctx, W, H, (1, 2), bounces, **cam)
+        sel = np.concatenate([np.arange(y * W, (y + 1) * W) for y in rows])
+        assert scenes.psnr(img[sel, :3], want[sel, :3]) >= 50.0
+        assert (img[sel, :3] == want[sel, :3]).all(axis=1).mean() > 0.95
+        assert 0.2 < (img[sel, :3].max(axis=1) > 0).mean()
+        rays = scenes.box_rays(300000, (-60, -60, -60), (60, 60, 60), seed=181)
+        got = ctx.trace_closest(rays)
+        _check_hits(got, ol.oracle_closest(tris, nodes, rays))
+        assert 0.2 < (got["tri"] != MISS).mean() < 0.999
+        assert np.array_equal(ctx.trace_any(rays) != 0, got["tri"] != MISS)
