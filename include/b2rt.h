@@ -187,12 +187,50 @@ int b2rt_build_bvh(b2rt_context* ctx, const void* triangles, uint64_t n_triangle
 int b2rt_trace_closest(b2rt_context* ctx, const b2rt_ray* rays, uint64_t n, b2rt_hit* hits);
 int b2rt_trace_any(b2rt_context* ctx, const b2rt_ray* rays, uint64_t n, uint32_t* occluded);
 /* Device-resident buffers (plain device pointers, e.g. torch tensor data_ptr()); enqueued on
- * `cuda_stream` (a cudaStream_t passed as void*; NULL = the context's own stream). Asynchronous. */
+ * `cuda_stream` (a cudaStream_t passed as void*; NULL = the context's own stream). Asynchronous.
+ * Every launch has its own work counter, so launches on different streams may overlap; at most 4
+ * of them at a time while the cooperative tail mode is on (B2RT_OPT_COOP_MAX > 0: they share 4 tail queues). */
 int b2rt_trace_closest_device(b2rt_context* ctx, const b2rt_ray* d_rays, uint64_t n, b2rt_hit* d_hits, void* cuda_stream);
 int b2rt_trace_any_device(b2rt_context* ctx, const b2rt_ray* d_rays, uint64_t n, uint32_t* d_occluded, void* cuda_stream);
 /* CreateRay (kernel_bvh.cl:386-403) for gid in [gid_begin, gid_end) with the currently bound
  * WIDTH/HEIGHT/FRAME_COUNT/CAMERA_* arguments, written to device memory as b2rt_ray. */
 int b2rt_camera_rays_device(b2rt_context* ctx, size_t gid_begin, size_t gid_end, b2rt_ray* d_rays, void* cuda_stream);
+
+/* ---- multi-GPU (new) ----------------------------------------------------------- */
+/* ONE handle that drives n devices of this process. The reference creates its context over all devices of platform 0
+ * (CLutils.cpp:20-26) but binds the queue to device 0 (CLutils.cpp:29); here every entry point really fans out:
+ *  - buffers created with host data are uploaded to device_ids[0] (the root) and broadcast to the others over NVLink
+ *    (ncclBroadcast); the compressed wide BVH is built once and broadcast likewise;
+ *  - b2rt_execute / b2rt_execute_range deal 8-row bands of gid = y*W + x (kernel_bvh.cl:394-395) round robin to the
+ *    devices; each device keeps the running average of ITS pixels and stores every finished pixel through to the root's
+ *    image over a peer mapping, so b2rt_read_buffer / b2rt_read_pixels after it return the complete frame (the root's
+ *    stream waits for all devices);
+ *  - b2rt_trace_closest / b2rt_trace_any cut the host ray stream into contiguous ranges, one per device;
+ *  - the *_device entry points, b2rt_build_bvh and b2rt_execute_bands address one device: the root.
+ * n_devices == 1 gives an ordinary handle. CLRaytracer code written against the single-device calls runs unchanged. */
+int b2rt_create_multi(const int* device_ids, int n_devices, b2rt_context** out);
+/* Devices behind a handle (b2rt_create_multi), or ranks of its job (b2rt_comm_init); 1 otherwise. */
+int b2rt_group_size(const b2rt_context* ctx);
+/* peer_store: finished pixels reach the root's image by direct stores over NVLink (else by copies / send-recv);
+ * nccl_loaded: NCCL was found at run time (dlopen "libnccl.so.2"). Either pointer may be NULL. */
+int b2rt_group_info(const b2rt_context* ctx, int* peer_store, int* nccl_loaded);
+
+/* One process per GPU (e.g. torchrun): the same partition, every rank with its own single-device handle and scene.
+ * b2rt_comm_unique_id: on one rank; distribute the bytes (>= 128) to all ranks by any means. b2rt_comm_init: collective,
+ * creates the NCCL communicator. b2rt_comm_share_output: collective, after every rank has bound an output image of the
+ * same size (b2rt_resize): rank 0's image is mapped into the other ranks (CUDA IPC handle broadcast over NCCL) as their
+ * store-through target. b2rt_execute_shard: KernelEntry for this rank's bands of the WIDTH x HEIGHT frame, then the
+ * gather on rank 0 -- a 4-byte ncclAllReduce as completion barrier when the image is mapped (pixels were stored through
+ * by the kernels), else grouped ncclSend/ncclRecv of the bands straight into place. Asynchronous: rank 0 reads the
+ * complete frame with b2rt_read_pixels + b2rt_finish. */
+int b2rt_comm_unique_id(void* id_out, size_t bytes);
+int b2rt_comm_init(b2rt_context* ctx, const void* id, size_t bytes, int rank, int world);
+int b2rt_comm_share_output(b2rt_context* ctx);
+int b2rt_execute_shard(b2rt_context* ctx);
+/* The partition itself (no device needed): rank's n_full_bands whole bands of band_pixels gids start at gid_begin and
+ * are stride_pixels apart; [tail_begin, tail_end) is the frame's clipped last band if this rank owns it (else empty). */
+int b2rt_shard_bands(uint32_t width, uint32_t height, int rank, int world, uint64_t* gid_begin, uint32_t* band_pixels,
+                     uint32_t* stride_pixels, uint32_t* n_full_bands, uint64_t* tail_begin, uint64_t* tail_end);
 
 /* ---- introspection -------------------------------------------------------------------- */
 int b2rt_device_pointer(b2rt_context* ctx, b2rt_buffer buf, void** d_ptr, size_t* bytes);

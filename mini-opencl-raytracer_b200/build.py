@@ -44,7 +44,7 @@ def _run(cmd, verbose):
 
 
 def build_b2rt(force=False, verbose=True):
-    srcs = [os.path.join(CSRC, f) for f in ("kernels.cu", "lbvh.cu", "api.cu", "wide_bvh.cpp")]
+    srcs = [os.path.join(CSRC, f) for f in ("kernels.cu", "lbvh.cu", "api.cu", "multi.cu", "wide_bvh.cpp")]
     deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(INCLUDE, "b2rt.h"), __file__]
     if not force and not _stale(LIB_B2RT, deps):
         return LIB_B2RT
@@ -55,7 +55,7 @@ def build_b2rt(force=False, verbose=True):
         o = os.path.join(objdir, os.path.basename(s) + ".o")
         _run([NVCC] + NVCC_FLAGS + ["-x", "cu", "-c", s, "-o", o], verbose)
         objs.append(o)
-    _run([NVCC, "-shared", "-o", LIB_B2RT] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"], verbose)
+    _run([NVCC, "-shared", "-o", LIB_B2RT] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-ldl"], verbose)
     return LIB_B2RT
 
 

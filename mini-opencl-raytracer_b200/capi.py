@@ -27,6 +27,8 @@ SYMBOLS = [
     "b2rt_trace_any", "b2rt_build_bvh", "b2rt_trace_closest_device", "b2rt_trace_any_device", "b2rt_camera_rays_device",
     "b2rt_device_pointer", "b2rt_bound_buffer", "b2rt_scene_info_get", "b2rt_set_option",
     "b2rt_get_counters", "b2rt_reset_counters", "b2rt_launch_count", "b2rt_device_count",
+    "b2rt_create_multi", "b2rt_group_size", "b2rt_group_info", "b2rt_comm_unique_id", "b2rt_comm_init", "b2rt_comm_share_output",
+    "b2rt_execute_shard", "b2rt_shard_bands",
 ]
 
 
@@ -101,6 +103,15 @@ def lib():
         "b2rt_reset_counters": (C.c_int, [vp]),
         "b2rt_launch_count": (u64, [vp]),
         "b2rt_device_count": (C.c_int, []),
+        "b2rt_create_multi": (C.c_int, [C.POINTER(C.c_int), C.c_int, C.POINTER(vp)]),
+        "b2rt_group_size": (C.c_int, [vp]),
+        "b2rt_group_info": (C.c_int, [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+        "b2rt_comm_unique_id": (C.c_int, [vp, sz]),
+        "b2rt_comm_init": (C.c_int, [vp, vp, sz, C.c_int, C.c_int]),
+        "b2rt_comm_share_output": (C.c_int, [vp]),
+        "b2rt_execute_shard": (C.c_int, [vp]),
+        "b2rt_shard_bands": (C.c_int, [u32, u32, C.c_int, C.c_int, C.POINTER(u64), C.POINTER(u32), C.POINTER(u32), C.POINTER(u32),
+                                       C.POINTER(u64), C.POINTER(u64)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -118,6 +129,25 @@ def _status_name(status):
 
 def device_count():
     return int(lib().b2rt_device_count())
+
+
+def comm_unique_id():
+    """128 bytes identifying a new NCCL communicator (b2rt_comm_unique_id); hand them to every rank's Context.comm_init."""
+    buf = C.create_string_buffer(128)
+    st = lib().b2rt_comm_unique_id(buf, 128)
+    if st:
+        raise B2RTError(st, lib().b2rt_last_error(None).decode())
+    return buf.raw
+
+
+def shard_bands(width, height, rank, world):
+    """b2rt_shard_bands: (gid_begin, band_pixels, stride_pixels, n_full_bands, tail_begin, tail_end) of `rank`."""
+    g, t0, t1 = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+    b, s, n = C.c_uint32(0), C.c_uint32(0), C.c_uint32(0)
+    st = lib().b2rt_shard_bands(int(width), int(height), int(rank), int(world), C.byref(g), C.byref(b), C.byref(s), C.byref(n), C.byref(t0), C.byref(t1))
+    if st:
+        raise B2RTError(st, "bad shard arguments")
+    return g.value, b.value, s.value, n.value, t0.value, t1.value
 
 
 def _ptr(a):
@@ -145,14 +175,40 @@ class Context:
         return self
 
     def __init__(self, device=0):
+        """device: one CUDA device id, or a sequence of ids for ONE handle driving all of them (b2rt_create_multi)."""
         self._L = lib()
         self._borrowed = False
         h = C.c_void_p()
-        st = self._L.b2rt_create(int(device), C.byref(h))
+        if isinstance(device, (list, tuple)):
+            ids = (C.c_int * len(device))(*[int(d) for d in device])
+            st = self._L.b2rt_create_multi(ids, len(device), C.byref(h))
+            device = device[0] if device else 0
+        else:
+            st = self._L.b2rt_create(int(device), C.byref(h))
         if st:
             raise B2RTError(st, self._L.b2rt_last_error(None).decode())
         self._h = h
         self.device = int(device)
+
+    # ---- multi-GPU ------------------------------------------------------------------------------
+    def group_size(self):
+        return int(self._L.b2rt_group_size(self._h))
+
+    def group_info(self):
+        a, b = C.c_int(0), C.c_int(0)
+        self._ck(self._L.b2rt_group_info(self._h, C.byref(a), C.byref(b)))
+        return {"peer_store": bool(a.value), "nccl_loaded": bool(b.value)}
+
+    def comm_init(self, unique_id, rank, world):
+        """unique_id: the bytes of comm_unique_id() made on one rank and distributed to all."""
+        buf = C.create_string_buffer(bytes(unique_id), len(unique_id))
+        self._ck(self._L.b2rt_comm_init(self._h, buf, len(unique_id), int(rank), int(world)))
+
+    def comm_share_output(self):
+        self._ck(self._L.b2rt_comm_share_output(self._h))
+
+    def execute_shard(self):
+        self._ck(self._L.b2rt_execute_shard(self._h))
 
     def close(self):
         if getattr(self, "_h", None):

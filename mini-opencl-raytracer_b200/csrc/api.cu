@@ -22,78 +22,21 @@
 
 using namespace b2rt;
 
-namespace {
+#include <mutex>
+#include <set>
+#include "context.h"
 
-struct Buffer {
-    void* d_ptr = nullptr;
-    size_t bytes = 0;
-    uint32_t flags = 0;
-    std::vector<uint8_t> shadow;   // host copy of COPY_HOST_PTR data, dropped once the wide BVH is built
-};
+using namespace b2rt_detail;
 
-constexpr uint64_t STREAM_CHUNK = 1ull << 22;   // rays per pipelined chunk of the host-buffer entry points
-constexpr int TAIL_RING = 4;                     // tail queues shared round robin by ray-stream launches (see trace_device)
-constexpr int64_t COOP_MAX_LIMIT = 16;           // upper bound of B2RT_OPT_COOP_MAX: the tail queues hold this many records per warp
-constexpr uint64_t NEXT_RING = 256;             // per-launch ray counters of the persistent kernels (b2rt_context::d_next)
+namespace b2rt_detail {
 
 std::string g_create_error;
 
-}  // namespace
-
-struct ModeTrial { int calls = 0; float ms[2] = { 0.0f, 0.0f }; int choice = -1; };
-
-struct b2rt_context {
-    int device = 0;
-    int sm_count = 0;
-    cudaStream_t stream = nullptr, stream_in = nullptr, stream_out = nullptr;
-    std::unordered_map<uint64_t, Buffer> buffers;
-    uint64_t next_id = 1;
-    b2rt_buffer bound[4] = { 0, 0, 0, 0 };
-    bool arg_set[B2RT_ARG_COUNT] = { false };
-    uint32_t width = 0, height = 0, frame_count = 0, frame_seed = 0;
-    int32_t bounces = 0, light_type = 0;
-    float sky = 0.0f;
-    float cam_pos[4] = { 0, 0, 0, 0 }, cam_front[4] = { 0, 0, 0, 0 }, cam_up[4] = { 0, 0, 0, 0 };
-    // derived scene
-    bool scene_dirty = true;
-    void *d_wide = nullptr, *d_leaf = nullptr, *d_shade = nullptr;
-    b2rt_scene_info info;
-    uint32_t stack_bound = 8;
-    SceneView view;
-    // scratch
-    unsigned long long* d_next = nullptr;      // NEXT_RING counter blocks (4 x u64: ray counter, tail-queue length, tail-queue read
-    uint64_t next_seq = 0;                     // position, pad), one per in-flight ray-stream launch
-    // cooperative tail mode: queues of unfinished rays, one per launch that may be in flight at the same time
-    void* d_tail[TAIL_RING + 4] = { nullptr };  // [0, TAIL_RING): ray-stream launches (round robin); then one per wavefront lane
-    uint64_t tail_capacity_records = 0;
-    uint32_t tail_rec_words = 0;
-    int grid_tail = 0;
-    unsigned long long* d_counters = nullptr;
-    void* d_stage_rays[2] = { nullptr, nullptr };
-    void* d_stage_out[2] = { nullptr, nullptr };
-    uint64_t stage_capacity = 0;
-    // wavefront frame path: two ray queues, hits, per-path state, three rotating queue counters
-    void* d_wf_rays[2] = { nullptr, nullptr };
-    void *d_wf_hits = nullptr, *d_wf_state = nullptr;
-    unsigned long long* d_wf_count = nullptr;
-    uint64_t wf_capacity = 0;
-    cudaStream_t wf_stream[4] = { nullptr, nullptr, nullptr, nullptr };
-    cudaEvent_t ev_wf_fork = nullptr, ev_wf_join[4] = { nullptr, nullptr, nullptr, nullptr };
-    std::map<std::pair<uint64_t, int>, ModeTrial> tuner;   // render-mode auto-tuning per launch shape (work items, bounces)
-    std::pair<uint64_t, int> tune_pending_key;
-    int tune_pending_mode = -1;
-    cudaEvent_t ev_tune[2] = { nullptr, nullptr };
-    void* d_rgba8 = nullptr;            // 8-bit read-back staging
-    uint64_t rgba8_capacity = 0;
-    cudaEvent_t ev_in[2] = { nullptr, nullptr }, ev_comp[2] = { nullptr, nullptr }, ev_out[2] = { nullptr, nullptr };
-    // options
-    int64_t opt_traversal = 0, opt_counters = 0, opt_blocks_per_sm = 0, opt_render_mode = 2, opt_refill_min = 8, opt_leaf_bias = 32, opt_wf_lanes = 0, opt_coop_max = 8;
-    int grid_closest = 0, grid_any = 0;
-    uint64_t launches = 0;
-    std::string error;
-};
-
-namespace {
+// Live handles: a buffer wrapper that outlives its context (host/runtime.cpp CLBuffer::State) must get an error from
+// b2rt_buffer_release, not a use-after-free.
+static std::mutex g_live_mutex;
+static std::set<const b2rt_context*> g_live;
+bool context_alive(const b2rt_context* ctx) { std::lock_guard<std::mutex> lk(g_live_mutex); return g_live.count(ctx) != 0; }
 
 int fail(b2rt_context* c, int status, const std::string& msg) {
     if (c) c->error = msg; else g_create_error = msg;
@@ -103,12 +46,6 @@ int cuda_fail(b2rt_context* c, cudaError_t e, const char* what) {
     int status = (e == cudaErrorMemoryAllocation) ? B2RT_MEM_OBJECT_ALLOCATION_FAILURE : B2RT_OUT_OF_RESOURCES;
     return fail(c, status, std::string(what) + ": " + cudaGetErrorString(e));
 }
-#define CK(call)                                                         \
-    do {                                                                 \
-        cudaError_t e__ = (call);                                        \
-        if (e__ != cudaSuccess) return cuda_fail(ctx, e__, #call);       \
-    } while (0)
-
 int use_device(b2rt_context* ctx) {
     cudaError_t e = cudaSetDevice(ctx->device);
     if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaSetDevice");
@@ -220,6 +157,7 @@ int ensure_scene(b2rt_context* ctx) {
     ctx->tuner.clear();
     ctx->tune_pending_mode = -1;
     ctx->scene_dirty = false;
+    if (ctx->group) return group_adopt_scene(ctx);       // the other devices of the handle take copies over NVLink
     return B2RT_SUCCESS;
 }
 
@@ -280,6 +218,7 @@ int ensure_staging(b2rt_context* ctx, uint64_t chunk) {
 // Host-buffer ray stream: chunks are copied in, traced and copied out on three streams so
 // that PCIe transfers overlap the traversal kernels.
 int trace_host(b2rt_context* ctx, const b2rt_ray* rays, uint64_t n, void* out, bool any) {
+    if (ctx->group) return group_trace_host(ctx, rays, n, out, any);
     int st = use_device(ctx);
     if (st) return st;
     st = ensure_scene(ctx);
@@ -521,11 +460,12 @@ int frame_args(b2rt_context* ctx, FrameArgs& a) {
     a.bounces = ctx->bounces; a.light_type = ctx->light_type; a.sky = ctx->sky;
     for (int k = 0; k < 3; ++k) { a.pos[k] = ctx->cam_pos[k]; a.front[k] = ctx->cam_front[k]; a.up[k] = ctx->cam_up[k]; }
     a.angle = tanf(0.5f * (45.0f * 3.1415f / 180.0f));   // kernel_bvh.cl:392, evaluated by the host libm like the oracle
+    a.mirror = ctx->mirror;
     if (a.width == 0 || a.height == 0) return fail(ctx, B2RT_INVALID_KERNEL_ARGS, "WIDTH/HEIGHT must be non-zero");
     return B2RT_SUCCESS;
 }
 
-}  // namespace
+}  // namespace b2rt_detail
 
 // ---- lifetime ---------------------------------------------------------------------------
 extern "C" int b2rt_device_count(void) {
@@ -584,12 +524,19 @@ extern "C" int b2rt_create(int device_id, b2rt_context** out) {
     if ((e = cudaMalloc(&ctx->d_next, NEXT_RING * 4 * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMalloc");
     if ((e = cudaMalloc(&ctx->d_counters, 128)) != cudaSuccess) return bail(e, "cudaMalloc");
     if ((e = cudaMemset(ctx->d_counters, 0, 128)) != cudaSuccess) return bail(e, "cudaMemset");
+    { std::lock_guard<std::mutex> lk(g_live_mutex); g_live.insert(ctx); }
     *out = ctx;
     return B2RT_SUCCESS;
 }
 
 extern "C" void b2rt_destroy(b2rt_context* ctx) {
     if (!ctx) return;
+    {
+        std::lock_guard<std::mutex> lk(g_live_mutex);
+        if (!g_live.erase(ctx) && !ctx->stream) return;      // never registered and nothing created: a failed b2rt_create cleaning up twice
+    }
+    if (ctx->group) group_destroy(ctx);
+    if (ctx->comm) comm_destroy(ctx);
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     free_scene(ctx);
@@ -643,6 +590,11 @@ extern "C" const char* b2rt_status_string(int status) {
 // ---- buffers and arguments --------------------------------------------------------------
 extern "C" int b2rt_buffer_create(b2rt_context* ctx, uint32_t flags, size_t bytes, const void* host_ptr, b2rt_buffer* out) {
     if (!ctx) return B2RT_INVALID_CONTEXT;
+    if (ctx->group) return group_buffer_create(ctx, flags, bytes, host_ptr, out);
+    return buffer_create_single(ctx, flags, bytes, host_ptr, out, true);
+}
+
+int b2rt_detail::buffer_create_single(b2rt_context* ctx, uint32_t flags, size_t bytes, const void* host_ptr, b2rt_buffer* out, bool zero_fill) {
     if (!out) return fail(ctx, B2RT_INVALID_VALUE, "null output buffer handle");
     *out = 0;
     if (bytes == 0) return fail(ctx, -61 /* CL_INVALID_BUFFER_SIZE */, "zero-sized buffer");
@@ -663,7 +615,7 @@ extern "C" int b2rt_buffer_create(b2rt_context* ctx, uint32_t flags, size_t byte
             catch (const std::bad_alloc&) { b.shadow.clear(); }   // fall back to a read-back at build time
         }
     } else {
-        e = cudaMemsetAsync(b.d_ptr, 0, bytes, ctx->stream);
+        e = zero_fill ? cudaMemsetAsync(b.d_ptr, 0, bytes, ctx->stream) : cudaSuccess;
     }
     if (e != cudaSuccess) { cudaFree(b.d_ptr); return cuda_fail(ctx, e, "buffer initialisation"); }
     uint64_t id = ctx->next_id++;
@@ -672,8 +624,16 @@ extern "C" int b2rt_buffer_create(b2rt_context* ctx, uint32_t flags, size_t byte
     return B2RT_SUCCESS;
 }
 
+static int buffer_release_one(b2rt_context* ctx, void* arg);
+
 extern "C" int b2rt_buffer_release(b2rt_context* ctx, b2rt_buffer buf) {
-    if (!ctx) return B2RT_INVALID_CONTEXT;
+    if (!ctx || !context_alive(ctx)) return B2RT_INVALID_CONTEXT;
+    if (ctx->group) { int st = group_each(ctx, buffer_release_one, &buf, false); group_bind_output(ctx); return st; }
+    return buffer_release_one(ctx, &buf);
+}
+
+static int buffer_release_one(b2rt_context* ctx, void* arg) {
+    const b2rt_buffer buf = *static_cast<b2rt_buffer*>(arg);
     Buffer* b = find(ctx, buf);
     if (!b) return fail(ctx, B2RT_INVALID_MEM_OBJECT, "unknown buffer");
     int st = use_device(ctx);
@@ -686,8 +646,22 @@ extern "C" int b2rt_buffer_release(b2rt_context* ctx, b2rt_buffer buf) {
     return B2RT_SUCCESS;
 }
 
+struct SetArg { uint32_t slot; const void* data; size_t size; };
+static int set_arg_one(b2rt_context* ctx, uint32_t slot, const void* data, size_t size);
+static int set_arg_each(b2rt_context* ctx, void* arg) { const SetArg* a = static_cast<const SetArg*>(arg); return set_arg_one(ctx, a->slot, a->data, a->size); }
+
 extern "C" int b2rt_set_arg(b2rt_context* ctx, uint32_t slot, const void* data, size_t size) {
     if (!ctx) return B2RT_INVALID_CONTEXT;
+    if (ctx->group) {
+        SetArg a{ slot, data, size };
+        int st = group_each(ctx, set_arg_each, &a, false);
+        if (!st && slot == B2RT_ARG_BUFFER_OUT) group_bind_output(ctx);
+        return st;
+    }
+    return set_arg_one(ctx, slot, data, size);
+}
+
+static int set_arg_one(b2rt_context* ctx, uint32_t slot, const void* data, size_t size) {
     if (slot >= B2RT_ARG_COUNT) return fail(ctx, B2RT_INVALID_ARG_INDEX, "argument index " + std::to_string(slot) + " out of range");
     if (!data) return fail(ctx, B2RT_INVALID_ARG_VALUE, "null argument value");
     static const size_t want[B2RT_ARG_COUNT] = { 8, 8, 8, 8, 4, 4, 4, 4, 4, 4, 4, 16, 16, 16 };
@@ -722,6 +696,7 @@ extern "C" int b2rt_execute_range(b2rt_context* ctx, size_t gid_begin, size_t gi
     if (!ctx) return B2RT_INVALID_CONTEXT;
     if (gid_end < gid_begin || gid_end > 0xffffffffull)
         return fail(ctx, B2RT_INVALID_GLOBAL_WORK_SIZE, "bad work range [" + std::to_string(gid_begin) + "," + std::to_string(gid_end) + ")");
+    if (ctx->group) return group_execute(ctx, gid_begin, gid_end);
     const uint64_t n = gid_end - gid_begin;
     GidMap map;
     map.begin = gid_begin;
@@ -732,6 +707,7 @@ extern "C" int b2rt_execute_range(b2rt_context* ctx, size_t gid_begin, size_t gi
 extern "C" int b2rt_execute_bands(b2rt_context* ctx, size_t gid_begin, uint32_t band_pixels, uint32_t stride_pixels, uint32_t n_bands) {
     if (!ctx) return B2RT_INVALID_CONTEXT;
     if (band_pixels == 0 || stride_pixels < band_pixels) return fail(ctx, B2RT_INVALID_GLOBAL_WORK_SIZE, "band must be non-empty and stride >= band");
+    if (ctx->group) return fail(ctx, B2RT_INVALID_VALUE, "b2rt_execute_bands addresses one device; a device-group handle partitions b2rt_execute itself");
     GidMap map;
     map.begin = gid_begin;
     map.band = band_pixels;
@@ -758,6 +734,7 @@ extern "C" int b2rt_read_buffer(b2rt_context* ctx, b2rt_buffer buf, void* dst, s
 
 extern "C" int b2rt_finish(b2rt_context* ctx) {
     if (!ctx) return B2RT_INVALID_CONTEXT;
+    if (ctx->group) return group_finish(ctx);
     int st = use_device(ctx);
     if (st) return st;
     CK(cudaStreamSynchronize(ctx->stream));
@@ -769,7 +746,7 @@ extern "C" int b2rt_host_register(b2rt_context* ctx, void* ptr, size_t bytes) {
     if (!ptr || !bytes) return fail(ctx, B2RT_INVALID_VALUE, "null or empty host range");
     int st = use_device(ctx);
     if (st) return st;
-    cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterDefault);
+    cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterPortable);
     if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return B2RT_SUCCESS; }
     if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaHostRegister");
     return B2RT_SUCCESS;
@@ -1036,8 +1013,17 @@ extern "C" int b2rt_scene_info_get(b2rt_context* ctx, b2rt_scene_info* out) {
     *out = ctx->info;
     return B2RT_SUCCESS;
 }
+struct SetOpt { uint32_t option; int64_t value; };
+static int set_option_one(b2rt_context* ctx, uint32_t option, int64_t value);
+static int set_option_each(b2rt_context* ctx, void* arg) { const SetOpt* o = static_cast<const SetOpt*>(arg); return set_option_one(ctx, o->option, o->value); }
+
 extern "C" int b2rt_set_option(b2rt_context* ctx, uint32_t option, int64_t value) {
     if (!ctx) return B2RT_INVALID_CONTEXT;
+    if (ctx->group) { SetOpt o{ option, value }; return group_each(ctx, set_option_each, &o, false); }
+    return set_option_one(ctx, option, value);
+}
+
+static int set_option_one(b2rt_context* ctx, uint32_t option, int64_t value) {
     switch (option) {
         case B2RT_OPT_TRAVERSAL: if (value != 0 && value != 1) return fail(ctx, B2RT_INVALID_VALUE, "traversal must be 0 or 1"); ctx->opt_traversal = value; break;
         case B2RT_OPT_COUNTERS: ctx->opt_counters = value ? 1 : 0; break;
@@ -1056,6 +1042,24 @@ extern "C" int b2rt_set_option(b2rt_context* ctx, uint32_t option, int64_t value
 extern "C" int b2rt_get_counters(b2rt_context* ctx, b2rt_counters* out) {
     if (!ctx) return B2RT_INVALID_CONTEXT;
     if (!out) return fail(ctx, B2RT_INVALID_VALUE, "null output");
+    if (ctx->group) {                                     // sums over the devices (maxima for the per-ray maximum)
+        b2rt_counters sum;
+        memset(&sum, 0, sizeof(sum));
+        for (b2rt_context* m : group_members(ctx)) {
+            b2rt_counters c;
+            Group* g = m->group;
+            m->group = nullptr;
+            int st = b2rt_get_counters(m, &c);
+            m->group = g;
+            if (st) return st;
+            const uint64_t* a = reinterpret_cast<const uint64_t*>(&c);
+            uint64_t* b = reinterpret_cast<uint64_t*>(&sum);
+            for (size_t i = 0; i < sizeof(c) / 8; ++i) b[i] += a[i];
+            sum.max_steps_per_ray = std::max(sum.max_steps_per_ray - c.max_steps_per_ray, c.max_steps_per_ray);
+        }
+        *out = sum;
+        return B2RT_SUCCESS;
+    }
     int st = use_device(ctx);
     if (st) return st;
     unsigned long long v[16];
@@ -1068,11 +1072,24 @@ extern "C" int b2rt_get_counters(b2rt_context* ctx, b2rt_counters* out) {
     out->stack_overflows = v[13]; out->coop_rays = v[14]; out->coop_steps = v[15];
     return B2RT_SUCCESS;
 }
-extern "C" int b2rt_reset_counters(b2rt_context* ctx) {
-    if (!ctx) return B2RT_INVALID_CONTEXT;
+static int reset_counters_each(b2rt_context* ctx, void*) {
     int st = use_device(ctx);
     if (st) return st;
     CK(cudaMemsetAsync(ctx->d_counters, 0, 128, ctx->stream));
     return B2RT_SUCCESS;
 }
-extern "C" uint64_t b2rt_launch_count(const b2rt_context* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" int b2rt_reset_counters(b2rt_context* ctx) {
+    if (!ctx) return B2RT_INVALID_CONTEXT;
+    if (ctx->group) return group_each(ctx, reset_counters_each, nullptr, false);
+    int st = use_device(ctx);
+    if (st) return st;
+    CK(cudaMemsetAsync(ctx->d_counters, 0, 128, ctx->stream));
+    return B2RT_SUCCESS;
+}
+extern "C" uint64_t b2rt_launch_count(const b2rt_context* ctx) {
+    if (!ctx) return 0;
+    if (!ctx->group) return ctx->launches;
+    uint64_t n = 0;
+    for (const b2rt_context* m : group_members(ctx)) n += m->launches;
+    return n;
+}

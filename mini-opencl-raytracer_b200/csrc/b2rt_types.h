@@ -113,6 +113,7 @@ struct FrameArgs {
     float sky;
     float pos[3], front[3], up[3];
     float angle;            // tanf(0.5f * (45.0f * 3.1415f / 180.0f)) evaluated by the host libm (kernel_bvh.cl:392)
+    float* mirror;          // multi-GPU: finished pixels are ALSO stored into this image (the root GPU's, peer-mapped over NVLink); null = none
 };
 
 }  // namespace b2rt

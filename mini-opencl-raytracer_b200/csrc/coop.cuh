@@ -148,7 +148,7 @@ B2_HD void coop_trace(const U4* wide, const U4* leaf, uint32_t* F, uint32_t n, u
                 const bool g = active && box_gate_exact(r, bits2f(g0.x), bits2f(g0.y), bits2f(g0.z), bits2f(g1.x), bits2f(g1.y), bits2f(g1.z), h.t);
                 tc.leaf_blocks += m;
                 tc.leaf_pass += popc32(w_ballot(g) & heads);
-                tc.tri_tests += popc32(w_ballot(valid && g));
+                tc.tri_tests += popc32(w_ballot(valid));                 // evaluations actually made (some behind a gate that fails later)
                 tc.words += LEAF_HEADER_WORDS * m + LEAF_RECORD_WORDS * (used >> 1);
             }
             // Commit in frontier order. Only a leaf holding a candidate under the current `best` can change it, and

@@ -369,7 +369,7 @@ render_mega_kernel(SceneView s, FrameArgs a, float* __restrict__ result, GidMap 
         r = make_ray(no.x, no.y, no.z, nd.x, nd.y, nd.z);
     }
     radiance = v3(max_cl(radiance.x, 0.0f), max_cl(radiance.y, 0.0f), max_cl(radiance.z, 0.0f));
-    accumulate(result + 4 * g, radiance, a.frame_count);
+    accumulate(result + 4 * g, a.mirror ? a.mirror + 4 * g : nullptr, radiance, a.frame_count);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -427,7 +427,8 @@ wf_shade_kernel(SceneView s, FrameArgs a, GidMap map, const RayIn* __restrict__ 
         go_on = path_step(s, a, r, h, radiance, beta, seed, no, nd) && !last;
         if (!go_on) {
             radiance = v3(max_cl(radiance.x, 0.0f), max_cl(radiance.y, 0.0f), max_cl(radiance.z, 0.0f));
-            accumulate(result + 4 * map.gid(i), radiance, a.frame_count);
+            const uint64_t g = map.gid(i);
+            accumulate(result + 4 * g, a.mirror ? a.mirror + 4 * g : nullptr, radiance, a.frame_count);
         }
     }
     // append the surviving rays to the next queue: one atomic per warp

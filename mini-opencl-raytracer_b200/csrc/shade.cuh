@@ -124,10 +124,16 @@ __device__ __forceinline__ V3 hit_normal(const ShadeTri* shade, const HitX& h) {
 }
 
 // Accumulation, kernel_bvh.cl:449-455.
-__device__ __forceinline__ void accumulate(float* px, V3 rad, uint32_t frame_count) {
+// `mirror` (may be null): the same pixel of the root GPU's image in a multi-GPU frame. The running average is kept in the
+// rank's own image (`px`, read and written locally); the finished value is stored through to the root as well, so the
+// frame is complete there when the ranks' kernels end -- the gather is fused into the compute kernel's epilogue instead
+// of a pack / all-gather / unpack sequence afterwards.
+__device__ __forceinline__ void accumulate(float* px, float* mirror, V3 rad, uint32_t frame_count) {
     float4* out = reinterpret_cast<float4*>(px);
     if (frame_count == 0) {
-        *out = make_float4(pow_cr(rad.x, 0.45454545f), pow_cr(rad.y, 0.45454545f), pow_cr(rad.z, 0.45454545f), 0.0f);
+        const float4 v0 = make_float4(pow_cr(rad.x, 0.45454545f), pow_cr(rad.y, 0.45454545f), pow_cr(rad.z, 0.45454545f), 0.0f);
+        *out = v0;
+        if (mirror) __stcs(reinterpret_cast<float4*>(mirror), v0);
         return;
     }
     float4 old = *out;
@@ -136,6 +142,7 @@ __device__ __forceinline__ void accumulate(float* px, V3 rad, uint32_t frame_cou
     float g = pow_cr(xdiv(xadd(xmul(pow_cr(old.y, 2.2f), fm1), rad.y), fc), 0.454545f);
     float b = pow_cr(xdiv(xadd(xmul(pow_cr(old.z, 2.2f), fm1), rad.z), fc), 0.454545f);
     *out = make_float4(r, g, b, 0.0f);
+    if (mirror) __stcs(reinterpret_cast<float4*>(mirror), make_float4(r, g, b, 0.0f));
 }
 
 }  // namespace b2rt

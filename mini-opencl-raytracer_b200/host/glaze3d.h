@@ -155,6 +155,9 @@ namespace Glaze3D
     {
     public:
         explicit CLContext(int device = 0);            // the reference takes a cl::Platform and uses its device 0
+        // All of these devices behind one context (b2rt_create_multi): what the reference's context over
+        // platform.getDevices(CL_DEVICE_TYPE_ALL) (CLutils.cpp:20-26) promises and its single queue never delivers.
+        explicit CLContext(const std::vector<int>& devices);
         ~CLContext();
         CLContext(const CLContext&) = delete;
         CLContext& operator=(const CLContext&) = delete;
@@ -256,6 +259,8 @@ namespace Glaze3D
         std::vector<uint32_t> pixels8;
         CLBuffer m_OutputBuffer;
         int device = 0;                 // which GPU Init() opens
+        std::vector<int> devices;       // non-empty: Init() opens ALL of these behind one context; RenderFrame then splits every
+                                        // frame into screen bands over them and reads the gathered image from devices[0]
         size_t shardBegin = 0, shardEnd = 0;   // [begin,end) of gids this renderer draws; 0,0 = whole frame
     };
 

@@ -26,6 +26,11 @@ namespace Glaze3D
         int st = b2rt_create(device, &m_Context);
         if (st) throw CLException(std::string("Failed to create context: ") + b2rt_last_error(nullptr), st);
     }
+    CLContext::CLContext(const std::vector<int>& devices) : m_Device(devices.empty() ? 0 : devices[0])
+    {
+        int st = b2rt_create_multi(devices.data(), (int)devices.size(), &m_Context);
+        if (st) throw CLException(std::string("Failed to create context: ") + b2rt_last_error(nullptr), st);
+    }
     CLContext::~CLContext() { b2rt_destroy(m_Context); }
 
     void CLContext::ReadBuffer(const CLBuffer& buffer, void* ptr, size_t size) const
@@ -82,7 +87,7 @@ namespace Glaze3D
 
     void CLRaytracer::Init()
     {
-        m_CLContext = std::make_shared<CLContext>(device);
+        m_CLContext = devices.empty() ? std::make_shared<CLContext>(device) : std::make_shared<CLContext>(devices);
         m_RenderKernel = std::make_shared<CLKernel>("kernel_bvh.cl", *m_CLContext);
         SetupBuffers();
     }
