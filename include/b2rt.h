@@ -93,7 +93,8 @@ typedef struct {
     uint64_t leaf_blocks;       /* leaf blocks fetched                                     */
     uint64_t leaf_gate_pass;    /* ... of which passed the exact fp32 leaf box             */
     uint64_t tri_tests;         /* Moller-Trumbore evaluations                             */
-    uint64_t bytes_fetched;     /* algorithmic bytes: 112 B per wide node + leaf block bytes */
+    uint64_t bytes_fetched;     /* algorithmic (requested) bytes: 84 B per wide-node visit (5 x 16 B + one 4-byte order word of
+                                   the 112-byte record) + 32 B header + 48 B per record of every leaf block fetched */
     /* warp scheduling of the persistent kernels: phases run and lanes that took part in them */
     uint64_t node_phases, node_phase_lanes, leaf_phases, leaf_phase_lanes, refills, refill_lanes;
     uint64_t max_steps_per_ray; /* node + leaf steps of the most expensive ray (tail detector; solo steps only) */
@@ -114,7 +115,8 @@ enum {
     B2RT_OPT_LEAF_BIAS = 5,     /* weight of the leaf vote in sixteenths (16 = plain majority, default 32) */
     B2RT_OPT_WAVEFRONT_LANES = 6, /* wavefront frame path: independent wavefronts in flight per launch, 1..4 (0 = by size) */
     B2RT_OPT_COOP_MAX = 7       /* tail mode of the persistent kernels: a warp whose ray pool is dry and that has at most this many
-                                   rays alive hands them to the cooperative tail kernel, 32 lanes per ray (0 = off .. 16, default 8). Results do not
+                                   rays alive hands them to the cooperative tail kernel, 32 lanes per ray (0 = off .. 16; default -1 = 8, but off for scenes
+                                   of fewer than ~1000 nodes, whose rays are too short to gain). Results do not
                                    depend on it. */
 };
 

@@ -165,10 +165,12 @@ int ensure_scene(b2rt_context* ctx) {
 // tail mode is off or the launch runs the reference-layout walk.
 int tail_queue(b2rt_context* ctx, int which, unsigned long long* count, unsigned long long* next, TailQueue& q) {
     q = TailQueue{ count, next, nullptr, ctx->tail_rec_words, 0u };
-    if (ctx->opt_coop_max <= 0 || ctx->opt_traversal == 1 || ctx->tail_capacity_records == 0) return B2RT_SUCCESS;
+    // auto (-1): on; but a tree this small has no long rays -- a hand-over would cost more than the few steps it saves
+    const int64_t coop = ctx->opt_coop_max >= 0 ? ctx->opt_coop_max : (ctx->info.n_wide_nodes + ctx->info.n_leaf_blocks > 1000 ? 8 : 0);
+    if (coop <= 0 || ctx->opt_traversal == 1 || ctx->tail_capacity_records == 0) return B2RT_SUCCESS;
     if (!ctx->d_tail[which]) CK(cudaMalloc(&ctx->d_tail[which], ctx->tail_capacity_records * ctx->tail_rec_words * sizeof(uint32_t)));
     q.records = static_cast<uint32_t*>(ctx->d_tail[which]);
-    q.coop_max = (uint32_t)ctx->opt_coop_max;
+    q.coop_max = (uint32_t)coop;
     return B2RT_SUCCESS;
 }
 
@@ -218,7 +220,6 @@ int ensure_staging(b2rt_context* ctx, uint64_t chunk) {
 // Host-buffer ray stream: chunks are copied in, traced and copied out on three streams so
 // that PCIe transfers overlap the traversal kernels.
 int trace_host(b2rt_context* ctx, const b2rt_ray* rays, uint64_t n, void* out, bool any) {
-    if (ctx->group) return group_trace_host(ctx, rays, n, out, any);
     int st = use_device(ctx);
     if (st) return st;
     st = ensure_scene(ctx);
@@ -946,10 +947,12 @@ extern "C" int b2rt_build_bvh(b2rt_context* ctx, const void* triangles, uint64_t
 // ---- ray streams -----------------------------------------------------------------------------
 extern "C" int b2rt_trace_closest(b2rt_context* ctx, const b2rt_ray* rays, uint64_t n, b2rt_hit* hits) {
     if (!ctx) return B2RT_INVALID_CONTEXT;
+    if (ctx->group) return group_trace_host(ctx, rays, n, hits, false);      // contiguous ranges, one per device
     return trace_host(ctx, rays, n, hits, false);
 }
 extern "C" int b2rt_trace_any(b2rt_context* ctx, const b2rt_ray* rays, uint64_t n, uint32_t* occluded) {
     if (!ctx) return B2RT_INVALID_CONTEXT;
+    if (ctx->group) return group_trace_host(ctx, rays, n, occluded, true);
     return trace_host(ctx, rays, n, occluded, true);
 }
 extern "C" int b2rt_trace_closest_device(b2rt_context* ctx, const b2rt_ray* d_rays, uint64_t n, b2rt_hit* d_hits, void* cuda_stream) {
@@ -1031,7 +1034,7 @@ static int set_option_one(b2rt_context* ctx, uint32_t option, int64_t value) {
         case B2RT_OPT_RENDER_MODE: if (value < 0 || value > 2) return fail(ctx, B2RT_INVALID_VALUE, "render mode must be 0 (wavefront), 1 (megakernel) or 2 (measured choice)"); ctx->opt_render_mode = value; break;
         case B2RT_OPT_WAVEFRONT_LANES: if (value < 0 || value > 4) return fail(ctx, B2RT_INVALID_VALUE, "wavefront lanes must be 0 (auto) .. 4"); ctx->opt_wf_lanes = value; break;
         case B2RT_OPT_LEAF_BIAS: if (value < 1 || value > 512) return fail(ctx, B2RT_INVALID_VALUE, "leaf bias must be 1..512 (sixteenths)"); ctx->opt_leaf_bias = value; break;
-        case B2RT_OPT_COOP_MAX: if (value < 0 || value > COOP_MAX_LIMIT) return fail(ctx, B2RT_INVALID_VALUE, "cooperative tail threshold must be 0 (off) .. 16"); ctx->opt_coop_max = value; break;
+        case B2RT_OPT_COOP_MAX: if (value < -1 || value > COOP_MAX_LIMIT) return fail(ctx, B2RT_INVALID_VALUE, "cooperative tail threshold must be -1 (auto), 0 (off) .. 16"); ctx->opt_coop_max = value; break;
         case B2RT_OPT_REFILL_MIN: if (value < 1 || value > 32) return fail(ctx, B2RT_INVALID_VALUE, "refill threshold must be 1..32"); ctx->opt_refill_min = value; break;
         default: return fail(ctx, B2RT_INVALID_VALUE, "unknown option");
     }
@@ -1066,7 +1069,7 @@ extern "C" int b2rt_get_counters(b2rt_context* ctx, b2rt_counters* out) {
     CK(cudaDeviceSynchronize());     // counted launches may sit on caller-provided streams
     CK(cudaMemcpy(v, ctx->d_counters, sizeof(v), cudaMemcpyDeviceToHost));
     out->rays = v[0]; out->wide_nodes = v[1]; out->leaf_blocks = v[2]; out->leaf_gate_pass = v[3]; out->tri_tests = v[4];
-    out->bytes_fetched = v[5] * 16ull;
+    out->bytes_fetched = v[5] * 16ull - v[1] * 28ull;     // a node visit REQUESTS 84 of the record's 112 bytes: five 16-byte words + one of the eight order words
     out->node_phases = v[6]; out->node_phase_lanes = v[7]; out->leaf_phases = v[8]; out->leaf_phase_lanes = v[9];
     out->refills = v[10]; out->refill_lanes = v[11]; out->max_steps_per_ray = v[12];
     out->stack_overflows = v[13]; out->coop_rays = v[14]; out->coop_steps = v[15];

@@ -85,6 +85,11 @@ B2_HD uint32_t coop_dump(const LaneT& L, const uint32_t* stack, uint32_t* F) {
 // `fcap` = capacity of F; while n <= wide_limit up to B2_COOP_NODES nodes are expanded per round, beyond it one
 // (depth-first: the frontier then grows by at most the solo walk's stack bound). On return h is the final hit on
 // every lane; `overflow` is set if F would have overflowed (the ray is then abandoned: the caller reports it).
+//
+// One round = one memory round trip: the (up to 8) leaves at the front of the frontier and the first Q interior
+// entries of the 32-entry window are fetched together; the leaves are resolved and committed in order, then the nodes
+// are tested against the `best` just updated, and the window is rewritten in place (leaves consumed, nodes replaced by
+// their passing children). Children just found are prefetched towards L2 for the next round.
 template <bool ANY, bool COUNT>
 B2_HD void coop_trace(const U4* wide, const U4* leaf, uint32_t* F, uint32_t n, uint32_t fcap, uint32_t wide_limit,
                       const RayX& r, HitX& h, TravCounters& tc, bool& overflow) {
@@ -95,45 +100,63 @@ B2_HD void coop_trace(const U4* wide, const U4* leaf, uint32_t* F, uint32_t n, u
         const bool is_node = lane < win && !(e & REF_LEAF_BIT);
         const uint32_t mnode = w_ballot(is_node);
         const uint32_t lead = mnode ? ctz32(mnode) : win;
-        if (lead) {
-            // ---- leaves at the front of the frontier: two lanes per record (the loader's two copies) ------------
-            uint32_t need = 0;
-            if (lane < lead) need = 2u * ld128(leaf + (e & ~REF_LEAF_BIT) + 1).w;
-            uint32_t incl = need;
-            for (uint32_t d = 1; d < 32u; d <<= 1) {
-                const uint32_t up = w_shfl(incl, lane >= d ? lane - d : 0u);
-                if (lane >= d) incl += up;
-            }
-            const uint32_t need0 = w_shfl(need, 0);
-            if (need0 > 32u || need0 == 0u) {
-                // more than 16 records: every lane walks the block like the solo path (same result on every lane)
+
+        // ---- fetch: leaves at the front, four lanes each = (record 0 | record 1) x (the loader's two copies) -----------
+        const uint32_t lg = lane >> 2, rec = (lane >> 1) & 1u, copy = lane & 1u;
+        uint32_t nl = lead < 8u ? lead : 8u;
+        const uint32_t lref = w_shfl(e, lg);
+        U4 g0 = { 0, 0, 0, 0 }, g1 = g0, va = g0, vb = g0, vc = g0;
+        if (lg < nl) {
+            const U4* p = leaf + (lref & ~REF_LEAF_BIT);
+            g0 = ld128(p); g1 = ld128(p + 1);
+            // record 1 is fetched before the record count is known: a one-record block is followed by another block or
+            // by the buffer's 64 bytes of padding, and the lanes are switched off below when the record does not exist
+            const U4* q = p + LEAF_HEADER_WORDS + LEAF_RECORD_WORDS * rec;
+            va = ld128(q); vb = ld128(q + 1); vc = ld128(q + 2);
+        }
+        // ---- fetch: the first Q interior entries of the window, eight lanes each = one lane per child ---------------------
+        uint32_t Q = n <= wide_limit ? (uint32_t)B2_COOP_NODES : 1u;
+        const uint32_t have = popc32(mnode);
+        if (Q > have) Q = have;
+        uint32_t pos0 = 32, pos1 = 32, pos2 = 32, pos3 = 32;
+        {
+            uint32_t mm = mnode;
+            if (Q > 0u) { pos0 = ctz32(mm); mm &= mm - 1u; }
+            if (Q > 1u) { pos1 = ctz32(mm); mm &= mm - 1u; }
+            if (Q > 2u) { pos2 = ctz32(mm); mm &= mm - 1u; }
+            if (Q > 3u) { pos3 = ctz32(mm); }
+        }
+        const uint32_t grp = lane >> 3, j = lane & 7u;
+        const bool gact = grp < Q;
+        const uint32_t gpos = grp == 0u ? pos0 : (grp == 1u ? pos1 : (grp == 2u ? pos2 : pos3));
+        const uint32_t node = w_shfl(e, gact ? gpos : 0u);
+        U4 w0 = { 0, 0, 0, 0 }, w1 = w0, w2 = w0, w3 = w0, w4 = w0;
+        uint32_t order = 0;
+        if (gact) {
+            const U4* p = wide + (uint32_t)WIDE_NODE_WORDS * node;
+            w0 = ld128(p); w1 = ld128(p + 1); w2 = ld128(p + 2); w3 = ld128(p + 3); w4 = ld128(p + 4);
+            order = ld32(reinterpret_cast<const uint32_t*>(p + 5) + r.sign);
+        }
+
+        // ---- leaves: blocks of more than two records leave the fast path -------------------------------------------------
+        if (nl) {
+            const uint32_t big = w_ballot(lg < nl && g1.w > 2u);           // all four lanes of a group agree
+            if (big & 1u) {
+                // the first leaf is a big block: every lane walks it like the solo path (same result on every lane)
                 const bool got = visit_leaf<COUNT>(leaf, w_shfl(e, 0) & ~REF_LEAF_BIT, r, h, &tc);
                 n -= 1u;
                 if ((ANY && got) || h.t < 0.0f) { n = 0; break; }
                 continue;
             }
-            const uint32_t m = popc32(w_ballot(lane < lead && incl <= 32u));      // leaves taken this round (>= 1)
-            const uint32_t excl = incl - need;
-            const uint32_t heads = w_redor(lane < m ? (1u << excl) : 0u);           // bit = first lane of a leaf
-            const uint32_t used = w_shfl(incl, m - 1u);
-            const bool active = lane < used;
-            const uint32_t my_leaf = popc32(heads & lanes_upto(lane)) - 1u;
-            const uint32_t my_start = w_shfl(excl, my_leaf);
-            const uint32_t my_ref = w_shfl(e, my_leaf);
-            const uint32_t slot = active ? lane - my_start : 0u;
-            const uint32_t rec = slot >> 1, copy = slot & 1u;
-            U4 g0 = { 0, 0, 0, 0 }, g1 = g0, va = g0, vb = g0, vc = g0;
-            if (active) {
-                const U4* p = leaf + (my_ref & ~REF_LEAF_BIT);
-                g0 = ld128(p); g1 = ld128(p + 1);
-                const U4* q = p + LEAF_HEADER_WORDS + LEAF_RECORD_WORDS * rec;
-                va = ld128(q); vb = ld128(q + 1); vc = ld128(q + 2);
-            }
+            if (big) nl = ctz32(big) >> 2;                                   // stop before the first big block
+        }
+        bool finished = false;
+        if (nl) {
+            const bool active = lg < nl && rec < g1.w;
             const uint32_t flags = va.w;
-            const uint32_t dup = w_ballot(active && copy == 0u && flags != 0u);
+            const uint32_t dup0 = w_ballot(active && rec == 0u && copy == 0u && flags != 0u);    // bit 4*lg: record 0 of leaf lg is doubled
             // triangle id: first id of the block + one per earlier record + one more per earlier doubled record
-            const uint32_t earlier = active ? (lanes_below(my_start + 2u * rec) & ~lanes_below(my_start)) : 0u;
-            const uint32_t id = g0.w + rec + popc32(dup & earlier) + copy;
+            const uint32_t id = g0.w + rec + (rec ? ((dup0 >> (4u * lg)) & 1u) : 0u) + copy;
             const bool valid = active && (copy == 0u || flags != 0u);
             float t = 0.0f, u = 0.0f, v = 0.0f;
             bool ok = false;
@@ -145,75 +168,61 @@ B2_HD void coop_trace(const U4* wide, const U4* leaf, uint32_t* F, uint32_t n, u
                                     bits2f(p3.x), bits2f(p3.y), bits2f(p3.z), t, u, v);
             }
             if (COUNT) {
-                const bool g = active && box_gate_exact(r, bits2f(g0.x), bits2f(g0.y), bits2f(g0.z), bits2f(g1.x), bits2f(g1.y), bits2f(g1.z), h.t);
-                tc.leaf_blocks += m;
-                tc.leaf_pass += popc32(w_ballot(g) & heads);
-                tc.tri_tests += popc32(w_ballot(valid));                 // evaluations actually made (some behind a gate that fails later)
-                tc.words += LEAF_HEADER_WORDS * m + LEAF_RECORD_WORDS * (used >> 1);
+                const bool g = lg < nl && box_gate_exact(r, bits2f(g0.x), bits2f(g0.y), bits2f(g0.z), bits2f(g1.x), bits2f(g1.y), bits2f(g1.z), h.t);
+                tc.leaf_blocks += nl;
+                tc.leaf_pass += popc32(w_ballot(g) & 0x11111111u);
+                tc.tri_tests += popc32(w_ballot(valid));                     // evaluations actually made (some behind a gate that fails later)
+                tc.words += LEAF_HEADER_WORDS * nl + LEAF_RECORD_WORDS * popc32(w_ballot(active && copy == 0u));
             }
             // Commit in frontier order. Only a leaf holding a candidate under the current `best` can change it, and
             // `best` only shrinks: jump from one such leaf to the next, re-evaluating gates and candidates in between.
             uint32_t lo = 0;
-            bool finished = false;
             for (;;) {
-                const bool gate = active && box_gate_exact(r, bits2f(g0.x), bits2f(g0.y), bits2f(g0.z), bits2f(g1.x), bits2f(g1.y), bits2f(g1.z), h.t);
-                const bool cand = valid && ok && t < h.t && gate && my_leaf >= lo;
+                const bool gate = lg < nl && box_gate_exact(r, bits2f(g0.x), bits2f(g0.y), bits2f(g0.z), bits2f(g1.x), bits2f(g1.y), bits2f(g1.z), h.t);
+                const bool cand = valid && ok && t < h.t && gate && lg >= lo;
                 const uint32_t cm = w_ballot(cand);
                 if (!cm) break;
-                const uint32_t first = w_shfl(my_leaf, ctz32(cm));
-                const bool mine = cand && my_leaf == first;
+                const uint32_t first = ctz32(cm) >> 2;                        // the first leaf (frontier order) with a candidate
+                const bool mine = cand && lg == first;
                 const uint32_t key = mine ? order_key(t) : 0xffffffffu;
                 const uint32_t kmin = w_redmin(key);
-                const uint32_t wl = ctz32(w_ballot(mine && key == kmin));            // lowest lane = lowest triangle id of the minimum
+                const uint32_t wl = ctz32(w_ballot(mine && key == kmin));    // lowest lane = lowest triangle id of the minimum
                 h.t = bits2f(w_shfl(f2bits(t), wl)); h.u = bits2f(w_shfl(f2bits(u), wl)); h.v = bits2f(w_shfl(f2bits(v), wl));
                 h.tri = w_shfl(id, wl);
                 lo = first + 1u;
                 if (ANY || h.t < 0.0f) { finished = true; break; }
             }
             if (finished || h.t < 0.0f) { n = 0; break; }
-            n -= m;
-            continue;
         }
-        // ---- the front is an interior node: expand the first Q interior entries of the window -----------------
-        uint32_t Q = n <= wide_limit ? (uint32_t)B2_COOP_NODES : 1u;
-        const uint32_t have = popc32(mnode);
-        if (Q > have) Q = have;
-        uint32_t pos0 = 32, pos1 = 32, pos2 = 32, pos3 = 32;
-        {
-            uint32_t mm = mnode;
-            pos0 = ctz32(mm); mm &= mm - 1u;
-            if (Q > 1u) { pos1 = ctz32(mm); mm &= mm - 1u; }
-            if (Q > 2u) { pos2 = ctz32(mm); mm &= mm - 1u; }
-            if (Q > 3u) { pos3 = ctz32(mm); }
-        }
-        const uint32_t K = (Q > 3u ? pos3 : (Q > 2u ? pos2 : (Q > 1u ? pos1 : pos0))) + 1u;   // window entries rewritten
-        const uint32_t grp = lane >> 3, j = lane & 7u;
-        const bool gact = grp < Q;
-        const uint32_t gpos = grp == 0u ? pos0 : (grp == 1u ? pos1 : (grp == 2u ? pos2 : pos3));
-        const uint32_t node = w_shfl(e, gact ? gpos : 0u);
+
+        // ---- nodes, against the `best` the leaves of this round left ---------------------------------------------------------
         bool pass = false;
         uint32_t ref = REF_EMPTY;
         if (gact) {
-            const U4* p = wide + (uint32_t)WIDE_NODE_WORDS * node;
-            const U4 w0 = ld128(p), w1 = ld128(p + 1), w2 = ld128(p + 2), w3 = ld128(p + 3), w4 = ld128(p + 4);
-            const uint32_t order = ld32(reinterpret_cast<const uint32_t*>(p + 5) + r.sign);
-            const uint32_t slot = (order >> (4u * j)) & 7u;                           // child visited j-th (reference order)
+            const uint32_t slot = (order >> (4u * j)) & 7u;                   // child visited j-th (reference order)
             if (j < (w0.w >> 24) && coop_child_test(w0, w2, w3, w4, slot, r, h.t)) {
                 pass = true;
                 const uint32_t mb = prmt(w1.z, w1.w, slot) & 0xffu;
                 ref = mb + ((mb & META_INTERIOR) ? w1.x - (uint32_t)META_INTERIOR : (REF_LEAF_BIT | w1.y));
+                // towards L2 for the next round: the child's node record or leaf block (either may straddle two lines)
+                const U4* c = (ref & REF_LEAF_BIT) ? leaf + (ref & ~REF_LEAF_BIT) : wide + (uint32_t)WIDE_NODE_WORDS * ref;
+                prefetch_l2(c); prefetch_l2(c + 6);
             }
         }
         const uint32_t hm = w_ballot(pass);
-        const int c0 = (int)popc32(hm & 0xffu) - 1, c1 = Q > 1u ? (int)popc32((hm >> 8) & 0xffu) - 1 : 0,
+        const int c0 = Q > 0u ? (int)popc32(hm & 0xffu) - 1 : 0, c1 = Q > 1u ? (int)popc32((hm >> 8) & 0xffu) - 1 : 0,
                   c2 = Q > 2u ? (int)popc32((hm >> 16) & 0xffu) - 1 : 0, c3 = Q > 3u ? (int)popc32(hm >> 24) - 1 : 0;
-        // position (front first) of window entry p after the rewrite: every expanded node before it adds (children - 1)
-        #define B2_COOP_FP(p) ((int)(p) + (pos0 < (p) ? c0 : 0) + (pos1 < (p) ? c1 : 0) + (pos2 < (p) ? c2 : 0) + (pos3 < (p) ? c3 : 0))
-        const uint32_t newn = (uint32_t)((int)(n - K) + (int)K + c0 + c1 + c2 + c3);
+        // window entries [0, K) are rewritten: the nl leaves at the front are consumed, every expanded node is replaced by
+        // its passing children, leaves in between keep their place
+        const uint32_t lastpos = Q > 3u ? pos3 : (Q > 2u ? pos2 : (Q > 1u ? pos1 : (Q > 0u ? pos0 : 0u)));
+        const uint32_t K = Q ? lastpos + 1u : nl;
+        // position (front first) of window entry p >= nl after the rewrite
+        #define B2_COOP_FP(p) ((int)(p) - (int)nl + (pos0 < (p) ? c0 : 0) + (pos1 < (p) ? c1 : 0) + (pos2 < (p) ? c2 : 0) + (pos3 < (p) ? c3 : 0))
+        const uint32_t newn = (uint32_t)((int)(n - nl) + c0 + c1 + c2 + c3);
         if (COUNT) { tc.wide_nodes += Q; tc.words += WIDE_NODE_WORDS * Q; if (newn > tc.max_stack) tc.max_stack = newn; }
         if (newn > fcap) { overflow = true; n = 0; break; }
         w_sync();                                                    // every lane holds its window entry
-        if (lane < K && !is_node) F[newn - 1u - (uint32_t)B2_COOP_FP(lane)] = e;
+        if (lane >= nl && lane < K && !is_node) F[newn - 1u - (uint32_t)B2_COOP_FP(lane)] = e;
         if (pass) F[newn - 1u - (uint32_t)(B2_COOP_FP(gpos) + (int)popc32((hm >> (8u * grp)) & 0xffu & lanes_below(j)))] = ref;
         #undef B2_COOP_FP
         w_sync();

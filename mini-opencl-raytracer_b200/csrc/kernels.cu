@@ -77,9 +77,12 @@ __device__ __forceinline__ void write_result(void* __restrict__ out, uint64_t i,
 // ---------------------------------------------------------------------------------------
 enum { TAIL_HEADER_WORDS = 8 };
 static constexpr int TAIL_BLOCK = 128;
+#ifndef B2_TAIL_MIN_BLOCKS
+#define B2_TAIL_MIN_BLOCKS 8      // 64 registers: as many rays in flight as possible (the tail is latency-bound)
+#endif
 
 template <bool ANY, bool COUNT>
-__global__ void __launch_bounds__(TAIL_BLOCK)
+__global__ void __launch_bounds__(TAIL_BLOCK, B2_TAIL_MIN_BLOCKS)
 trace_tail_kernel(SceneView s, const RayIn* __restrict__ rays, void* __restrict__ out, TailQueue tail,
                   unsigned long long* __restrict__ counters, uint32_t fcap, uint32_t wide_limit) {
     extern __shared__ uint32_t tail_frontiers[];                        // fcap words per warp
@@ -167,7 +170,9 @@ trace_persistent(SceneView s, const RayIn* __restrict__ rays, uint64_t n, void* 
         const unsigned idle = ~(vn | vl);
         const bool pool_dry = exhausted && pool_left == 0u;
         // tail: nothing left to fetch and only a few rays alive in this warp -> hand them to the cooperative tail kernel
-        if (pool_dry && tail.coop_max && (vn | vl) != 0u && (unsigned)__popc(vn | vl) <= tail.coop_max) break;
+        // (lanes whose stack is empty are about to finish on their own: wait for them)
+        if (pool_dry && tail.coop_max && (vn | vl) != 0u && (unsigned)__popc(vn | vl) <= tail.coop_max &&
+            __ballot_sync(FULL, !L.done() && L.top == REF_EMPTY) == 0u) break;
         if (idle && !pool_dry && ((unsigned)__popc(idle) >= refill_min || (vn | vl) == 0u)) {
             // ---- refill idle lanes from the warp pool -------------------------------------------
             // Finished rays are written here, several lanes at a time, instead of one lane at a time when they finish.

@@ -77,6 +77,7 @@ B2_HD uint32_t w_redmin(uint32_t v) { return __reduce_min_sync(0xffffffffu, v); 
 B2_HD uint32_t w_redor(uint32_t v) { return __reduce_or_sync(0xffffffffu, v); }
 B2_HD void w_sync() { __syncwarp(); }
 B2_HD uint32_t ctz32(uint32_t v) { return (uint32_t)__ffs((int)v) - 1u; }     // v != 0
+B2_HD void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
 #else
 // Host emulation (tests only). Built with -ffp-contract=off -frounding-math.
 B2_HD float xadd(float a, float b) { volatile float r = a + b; return r; }
@@ -122,6 +123,7 @@ B2_HD uint32_t w_redmin(uint32_t v) { return b2rt_emu::exchange(v, 2, 0); }
 B2_HD uint32_t w_redor(uint32_t v) { return b2rt_emu::exchange(v, 3, 0); }
 B2_HD void w_sync() { (void)b2rt_emu::exchange(0, 4, 0); }
 B2_HD uint32_t ctz32(uint32_t v) { return (uint32_t)__builtin_ctz(v); }
+B2_HD void prefetch_l2(const void*) {}
 #endif
 
 // OpenCL max()/min() as worded by the spec ("y if x < y, otherwise x"), the

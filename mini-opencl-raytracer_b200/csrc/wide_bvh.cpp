@@ -341,6 +341,9 @@ std::string build_wide_bvh(const RefNode* nodes, uint64_t n_nodes, const RefTria
         }
         out.nodes[w.wide] = wn;
     }
+    // The cooperative tail kernel fetches a block's SECOND record before it knows the record count (coop.cuh): keep 64 readable
+    // bytes behind the last block.
+    for (int i = 0; i < 4; ++i) out.leaf.push_back(U4{ 0u, 0u, 0u, 0u });
     // exact stack bound: children always follow their parent in `nodes`, so one reverse sweep is bottom-up
     {
         std::vector<uint32_t> need(out.nodes.size(), 0);

@@ -113,7 +113,7 @@ def test_counters_report_the_same_triangle_tests_as_the_reference(product, bumpy
         c = bumpy_ctx.counters()
     finally:
         bumpy_ctx.set_option(product.capi.OPT_COUNTERS, 0)
-        bumpy_ctx.set_option(product.capi.OPT_COOP_MAX, 8)
+        bumpy_ctx.set_option(product.capi.OPT_COOP_MAX, -1)
     assert c["rays"] == rays.shape[0]
     assert c["tri_tests"] == cnt["tris_tested"]
     assert c["leaf_gate_pass"] == cnt["leaves_entered"]
