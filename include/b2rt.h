@@ -114,6 +114,9 @@ enum {
     B2RT_OPT_REFILL_MIN = 4,    /* idle lanes of a warp that trigger a ray refill (1..32, default 8) */
     B2RT_OPT_LEAF_BIAS = 5,     /* weight of the leaf vote in sixteenths (16 = plain majority, default 32) */
     B2RT_OPT_WAVEFRONT_LANES = 6, /* wavefront frame path: independent wavefronts in flight per launch, 1..4 (0 = by size) */
+    B2RT_OPT_L2_PERSIST = 8,    /* 1 (default): the wide-node array is kept resident in L2 by an access-policy window (persisting
+                                   carve-out sized to it) on every stream that runs traversal kernels; 0 = plain caching.
+                                   Results do not depend on it. */
     B2RT_OPT_COOP_MAX = 7       /* tail mode of the persistent kernels: a warp whose ray pool is dry and that has at most this many
                                    rays alive hands them to the cooperative tail kernel, 32 lanes per ray (0 = off .. 16; default -1 = 8, but off for scenes
                                    of fewer than ~1000 nodes, whose rays are too short to gain). Results do not

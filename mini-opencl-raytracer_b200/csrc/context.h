@@ -37,6 +37,8 @@ struct ModeTrial { int calls = 0; float ms[2] = { 0.0f, 0.0f }; int choice = -1;
 struct b2rt_context {
     int device = 0;
     int sm_count = 0;
+    size_t l2_persist_max = 0, l2_window_max = 0;   // cudaDeviceProp persistingL2CacheMaxSize / accessPolicyMaxWindowSize
+    std::vector<cudaStream_t> policy_streams;       // streams that carry the wide-node access-policy window of the current scene
     cudaStream_t stream = nullptr, stream_in = nullptr, stream_out = nullptr;
     std::unordered_map<uint64_t, Buffer> buffers;
     uint64_t next_id = 1;
@@ -79,7 +81,7 @@ struct b2rt_context {
     uint64_t rgba8_capacity = 0;
     cudaEvent_t ev_in[2] = { nullptr, nullptr }, ev_comp[2] = { nullptr, nullptr }, ev_out[2] = { nullptr, nullptr };
     // options
-    int64_t opt_traversal = 0, opt_counters = 0, opt_blocks_per_sm = 0, opt_render_mode = 2, opt_refill_min = 8, opt_leaf_bias = 32, opt_wf_lanes = 0, opt_coop_max = -1;
+    int64_t opt_traversal = 0, opt_counters = 0, opt_blocks_per_sm = 0, opt_render_mode = 2, opt_refill_min = 8, opt_leaf_bias = 32, opt_wf_lanes = 0, opt_coop_max = -1, opt_l2_persist = 1;
     int grid_closest = 0, grid_any = 0;
     uint64_t launches = 0;
     // ---- multi-GPU (multi.cu) ----
@@ -101,6 +103,7 @@ Buffer* find(b2rt_context* ctx, b2rt_buffer id);
 int ensure_scene(b2rt_context* ctx);
 void free_scene(b2rt_context* ctx);
 void free_tail(b2rt_context* ctx);
+void scene_l2_setup(b2rt_context* ctx);
 int buffer_create_single(b2rt_context* ctx, uint32_t flags, size_t bytes, const void* host_ptr, b2rt_buffer* out, bool zero_fill);
 bool context_alive(const b2rt_context* ctx);
 int render_items(b2rt_context* ctx, const b2rt::GidMap& map, uint64_t n);

@@ -272,7 +272,10 @@ int group_adopt_scene(b2rt_context* root) {
         m->tuner.clear();
         m->tune_pending_mode = -1;
         m->scene_dirty = false;
+        cudaSetDevice(m->device);
+        scene_l2_setup(m);
     }
+    cudaSetDevice(root->device);
     return B2RT_SUCCESS;
 }
 
