@@ -185,6 +185,15 @@ int b2rt_read_pixels_rgba8(b2rt_context* ctx, void* dst, size_t bytes);
 int b2rt_build_bvh(b2rt_context* ctx, const void* triangles, uint64_t n_triangles, void* nodes_out, uint64_t nodes_capacity,
                    uint64_t* n_nodes_out, uint32_t* order_out);
 
+/* Refit (new): `triangles` = CLTriangle[n_triangles] with NEW vertex data for the bound scene, same count and order
+ * (animated / deformed geometry). The bound triangle buffer is replaced, the bound CLLinearBVHNode buffer gets the boxes
+ * refitted bottom-up (read it back with b2rt_read_buffer to see the tree in the reference's format), and the compressed
+ * wide BVH -- quantised child boxes, leaf blocks, shading records -- is refreshed in place by device kernels; topology,
+ * triangle order and therefore hit IDs stay. Stands in for re-running CLBVHScene::RecursiveBuild (CLBVHnode.cpp:7-159) +
+ * SetupBuffers for every frame of an animation. Results equal the reference's walk over (new triangles, refitted nodes).
+ * Fails (rebuild instead) when two triangles that were the loader's copies of one face no longer are. Synchronous. */
+int b2rt_refit_scene(b2rt_context* ctx, const void* triangles, uint64_t n_triangles);
+
 /* ---- ray-stream path (new) ----------------------------------------------------------- */
 /* Host buffers: H2D copy, trace, D2H copy, synchronous on return.
  * closest: hits[i] = {t,u,v,tri} of Intersect() (kernel_bvh.cl:171-219), tri = B2RT_MISS and

@@ -28,7 +28,7 @@ SYMBOLS = [
     "b2rt_device_pointer", "b2rt_bound_buffer", "b2rt_scene_info_get", "b2rt_set_option",
     "b2rt_get_counters", "b2rt_reset_counters", "b2rt_launch_count", "b2rt_device_count",
     "b2rt_create_multi", "b2rt_group_size", "b2rt_group_info", "b2rt_comm_unique_id", "b2rt_comm_init", "b2rt_comm_share_output",
-    "b2rt_execute_shard", "b2rt_shard_bands",
+    "b2rt_execute_shard", "b2rt_shard_bands", "b2rt_refit_scene",
 ]
 
 
@@ -103,6 +103,7 @@ def lib():
         "b2rt_reset_counters": (C.c_int, [vp]),
         "b2rt_launch_count": (u64, [vp]),
         "b2rt_device_count": (C.c_int, []),
+        "b2rt_refit_scene": (C.c_int, [vp, vp, u64]),
         "b2rt_create_multi": (C.c_int, [C.POINTER(C.c_int), C.c_int, C.POINTER(vp)]),
         "b2rt_group_size": (C.c_int, [vp]),
         "b2rt_group_info": (C.c_int, [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
@@ -234,6 +235,21 @@ class Context:
         n, nn = _raw(nodes, NODE_BYTES, "nodes")
         m, nm = _raw(mats, MAT_BYTES, "materials")
         self._ck(self._L.b2rt_upload_scene(self._h, _ptr(t), nt, _ptr(n), nn, _ptr(m), nm))
+
+    def refit_scene(self, tris):
+        """b2rt_refit_scene: new vertex data (same triangle count and order) for the bound scene."""
+        tris, n = _raw(tris, 256, "CLTriangle")
+        self._ck(self._L.b2rt_refit_scene(self._h, _ptr(tris), n))
+
+    def read_nodes(self):
+        """The bound CLLinearBVHNode buffer (slot 2) read back: (n, 48) uint8."""
+        buf = C.c_uint64(0)
+        self._ck(self._L.b2rt_bound_buffer(self._h, 2, C.byref(buf)))
+        n = self.scene_info()["n_nodes"]
+        out = np.empty((n, 48), dtype=np.uint8)
+        self._ck(self._L.b2rt_read_buffer(self._h, buf, _ptr(out), out.nbytes))
+        self.finish()
+        return out
 
     def build_bvh(self, tris):
         """b2rt_build_bvh: binary BVH over loader-order triangles on the GPU, in the reference's format.

@@ -65,7 +65,10 @@ void free_scene(b2rt_context* ctx) {
     if (ctx->d_wide) cudaFree(ctx->d_wide);
     if (ctx->d_leaf) cudaFree(ctx->d_leaf);
     if (ctx->d_shade) cudaFree(ctx->d_shade);
+    if (ctx->d_child_bin) cudaFree(ctx->d_child_bin);
+    if (ctx->d_leaf_dir) cudaFree(ctx->d_leaf_dir);
     ctx->d_wide = ctx->d_leaf = ctx->d_shade = nullptr;
+    ctx->d_child_bin = ctx->d_leaf_dir = nullptr;
 }
 
 // Host view of a buffer's contents: the creation-time shadow if still held, else a read-back.
@@ -114,6 +117,10 @@ int ensure_scene(b2rt_context* ctx) {
     CK(cudaMemcpyAsync(ctx->d_wide, w.nodes.data(), wb, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_leaf, w.leaf.data(), lb, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_shade, w.shade.data(), sb, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMalloc(reinterpret_cast<void**>(&ctx->d_child_bin), std::max<size_t>(w.child_bin.size() * 4, 32)));
+    CK(cudaMalloc(reinterpret_cast<void**>(&ctx->d_leaf_dir), std::max<size_t>(w.leaf_dir.size() * 4, 8)));
+    CK(cudaMemcpyAsync(ctx->d_child_bin, w.child_bin.data(), w.child_bin.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_leaf_dir, w.leaf_dir.data(), w.leaf_dir.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     memset(&ctx->info, 0, sizeof(ctx->info));
     ctx->info.n_triangles = n_tris;

@@ -51,6 +51,7 @@ struct b2rt_context {
     // derived scene
     bool scene_dirty = true;
     void *d_wide = nullptr, *d_leaf = nullptr, *d_shade = nullptr;
+    uint32_t *d_child_bin = nullptr, *d_leaf_dir = nullptr;   // refit support: binary node behind every wide child slot / leaf block
     b2rt_scene_info info;
     uint32_t stack_bound = 8;
     b2rt::SceneView view;

@@ -234,7 +234,8 @@ int group_adopt_scene(b2rt_context* root) {
     Group* g = root->group;
     const size_t wb = std::max<size_t>(root->info.wide_node_bytes, sizeof(WideNode)), lb = std::max<size_t>(root->info.leaf_bytes, 16) + 64,
                  sb = std::max<size_t>(root->info.shading_bytes, 48);
-    std::vector<void*> pw{ root->d_wide }, pl{ root->d_leaf }, ps{ root->d_shade };
+    const size_t cb = std::max<size_t>(root->info.n_wide_nodes * 32, 32), db = std::max<size_t>(root->info.n_leaf_blocks * 8, 8);
+    std::vector<void*> pw{ root->d_wide }, pl{ root->d_leaf }, ps{ root->d_shade }, pc{ root->d_child_bin }, pd{ root->d_leaf_dir };
     for (size_t k = 1; k < g->members.size(); ++k) {
         b2rt_context* ctx = g->members[k];
         CK(cudaSetDevice(ctx->device));
@@ -243,13 +244,17 @@ int group_adopt_scene(b2rt_context* root) {
         CK(cudaMalloc(&ctx->d_wide, wb));
         CK(cudaMalloc(&ctx->d_leaf, lb));
         CK(cudaMalloc(&ctx->d_shade, sb));
-        pw.push_back(ctx->d_wide); pl.push_back(ctx->d_leaf); ps.push_back(ctx->d_shade);
+        CK(cudaMalloc(reinterpret_cast<void**>(&ctx->d_child_bin), cb));
+        CK(cudaMalloc(reinterpret_cast<void**>(&ctx->d_leaf_dir), db));
+        pw.push_back(ctx->d_wide); pl.push_back(ctx->d_leaf); ps.push_back(ctx->d_shade); pc.push_back(ctx->d_child_bin); pd.push_back(ctx->d_leaf_dir);
     }
     b2rt_context* ctx = root;
     CK(cudaSetDevice(root->device));
     int st = broadcast(root, pw.data(), wb);
     if (!st) st = broadcast(root, pl.data(), lb);
     if (!st) st = broadcast(root, ps.data(), sb);
+    if (!st) st = broadcast(root, pc.data(), cb);
+    if (!st) st = broadcast(root, pd.data(), db);
     if (st) return st;
     for (size_t k = 1; k < g->members.size(); ++k) {
         b2rt_context* m = g->members[k];

@@ -28,8 +28,10 @@ inline bool same_pos(const RefVec& a, const RefVec& b) {
 inline uint32_t fbits(float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; }
 
 // Append the leaf block of binary leaf `n`; returns the number of 16-byte words written.
-uint32_t emit_leaf(const RefNode& n, const RefTriangle* tris, WideBVH& out) {
+uint32_t emit_leaf(const RefNode& n, uint32_t bin, const RefTriangle* tris, WideBVH& out) {
     size_t head = out.leaf.size();
+    out.leaf_dir.push_back(bin);
+    out.leaf_dir.push_back((uint32_t)head);
     out.leaf.push_back(U4{ fbits(n.bmin.x), fbits(n.bmin.y), fbits(n.bmin.z), n.offset });
     out.leaf.push_back(U4{ fbits(n.bmax.x), fbits(n.bmax.y), fbits(n.bmax.z), 0u });
     uint32_t nrec = 0;
@@ -327,7 +329,7 @@ std::string build_wide_bvh(const RefNode* nodes, uint64_t n_nodes, const RefTria
             if (rel > META_MAX_LEAF_OFFSET && n_children > 1) { wrap[c] = true; continue; }
             if (rel > META_MAX_LEAF_OFFSET) return "internal error: lone leaf not at offset 0";
             wn.meta[c] = (uint8_t)rel;
-            emit_leaf(nodes[slots[c].bin], tris, out);
+            emit_leaf(nodes[slots[c].bin], slots[c].bin, tris, out);
         }
         wn.child_base = (uint32_t)out.nodes.size();
         uint32_t n_interior = 0;
@@ -340,7 +342,10 @@ std::string build_wide_bvh(const RefNode* nodes, uint64_t n_nodes, const RefTria
             }
         }
         out.nodes[w.wide] = wn;
+        if (out.child_bin.size() < out.nodes.size() * 8) out.child_bin.resize(out.nodes.size() * 8, 0xFFFFFFFFu);
+        for (int c = 0; c < n_children; ++c) out.child_bin[(size_t)w.wide * 8 + c] = slots[c].bin;
     }
+    out.child_bin.resize(out.nodes.size() * 8, 0xFFFFFFFFu);
     // The cooperative tail kernel fetches a block's SECOND record before it knows the record count (coop.cuh): keep 64 readable
     // bytes behind the last block.
     for (int i = 0; i < 4; ++i) out.leaf.push_back(U4{ 0u, 0u, 0u, 0u });

@@ -20,6 +20,9 @@ struct WideBVH {
     uint32_t max_leaf_records = 0;
     uint64_t n_children = 0;          // occupied child slots, for fill statistics
     uint32_t stack_entries = 0;       // most child references any walk can have deferred at once (exact, see build_wide_bvh)
+    // refit support (refit.cu): where every child box and leaf block came from in the binary tree
+    std::vector<uint32_t> child_bin;  // [8 * wide node + slot] = binary node of that child, 0xFFFFFFFF = empty slot
+    std::vector<uint32_t> leaf_dir;   // [2 * block] = binary leaf node, [2 * block + 1] = offset of the block in `leaf` (16-byte words)
 };
 
 // Returns an empty string on success, else a description of why the input

@@ -203,6 +203,10 @@ namespace Glaze3D
         // built on the GPU by b2rt_build_bvh (Morton order + Karras hierarchy) instead of the SAH recursion: a few
         // milliseconds of device time instead of seconds. It is a different tree: hit IDs index THIS order.
         void CreateBVHTreesDevice();
+        // New: the vertices of m_Triangles were changed in place (same count and order): refit the device scene -- node boxes,
+        // compressed wide BVH, shading records -- by b2rt_refit_scene instead of building and uploading again, and read the
+        // refitted node boxes back into Nodes().
+        void Refit();
         const std::vector<CLLinearBVHNode>& Nodes() const { return m_Nodes; }
         void SetupBuffers();                                              // CLBVHnode.cpp:209-236
 

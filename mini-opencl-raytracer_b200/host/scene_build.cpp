@@ -370,4 +370,17 @@ namespace Glaze3D
         if (err) throw CLException("Failed to create material buffer", err);
         eng->render->SetUniform<CLBuffer>((int)RenderKernelArgument_t::BUFFER_MATERIAL, m_MaterialBuffer);
     }
+
+    void CLBVHScene::Refit()
+    {
+        if (!eng || !eng->render || !eng->render->m_CLContext)
+            throw CLException("CLBVHScene::Refit needs eng->render->m_CLContext", B2RT_INVALID_CONTEXT);
+        if (!m_TriangleBuffer.id() || !m_NodeBuffer.id()) throw CLException("CLBVHScene::Refit needs an uploaded scene", B2RT_INVALID_MEM_OBJECT);
+        b2rt_context* c = eng->render->m_CLContext->GetContext();
+        int st = b2rt_refit_scene(c, m_Triangles.data(), m_Triangles.size());
+        if (st) throw CLException(std::string("Failed to refit scene: ") + b2rt_last_error(c), st);
+        st = b2rt_read_buffer(c, m_NodeBuffer.id(), m_Nodes.data(), m_Nodes.size() * sizeof(CLLinearBVHNode));
+        if (!st) st = b2rt_finish(c);
+        if (st) throw CLException(std::string("Failed to read refitted nodes: ") + b2rt_last_error(c), st);
+    }
 }

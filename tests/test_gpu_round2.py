@@ -245,3 +245,66 @@ def test_cpp_program_drives_a_device_group(product, tmp_scene_dir, cornell_ref):
     for fc in range(1, frames + 1):
         ol.oracle_render(tris, nodes, mats, want, W, H, fc, bounces)
     assert scenes.psnr(outs[1][:, :3], want[:, :3]) >= 50.0
+
+
+# ---- refit (csrc/refit.cu) ------------------------------------------------------------------------------------------------
+def _deform(tris, scale, wobble):
+    """New vertex positions as a function of the OLD position only: the loader's duplicate copies of a face stay
+    bit-identical rotations of each other. Normals are recomputed per face (flat) to change the shading records too."""
+    t = tris.copy()
+    f = t.view(np.float32).reshape(-1, 64)
+    for v in (0, 20, 40):                                       # v1 / v2 / v3: position at float 0, normal at float 8 of each 80-byte vertex
+        p = f[:, v:v + 3]
+        q = p * np.float32(scale)
+        q[:, 2] += np.float32(wobble) * np.sin(p[:, 0] * np.float32(0.7)).astype(np.float32)
+        f[:, v:v + 3] = q
+    e1, e2 = f[:, 20:23] - f[:, 0:3], f[:, 40:43] - f[:, 0:3]
+    nrm = np.cross(e1, e2)
+    nrm /= np.maximum(np.linalg.norm(nrm, axis=1, keepdims=True), 1e-30)
+    for v in (0, 20, 40):
+        f[:, v + 8:v + 11] = nrm.astype(np.float32)
+    return t
+
+
+def test_refit_scene_matches_the_oracle_on_the_refitted_tree(product, bumpy_ref):
+    """b2rt_refit_scene: deformed vertices, same topology. (1) refitting with UNCHANGED data reproduces the host builder's
+    boxes bit for bit; (2) after a deformation the CUDA hits and frames equal the oracle's walk over (new triangles,
+    refitted nodes read back from the device); (3) data that breaks a duplicate pair is refused."""
+    tris, nodes, mats = bumpy_ref
+    rays = scenes.shell_rays(200000, 12.0, seed=201)
+    with product.Context(0) as ctx:
+        ctx.upload_scene(tris, nodes, mats)
+        before = ctx.trace_closest(rays)
+        ctx.refit_scene(tris)
+        assert np.array_equal(ctx.read_nodes(), nodes)                      # boxes, offsets, counts, axes: all as the host built them
+        assert np.array_equal(ctx.trace_closest(rays).view(np.uint32), before.view(np.uint32))
+        for scale, wobble in ((1.2, 0.8), (0.6, 0.0), (1.0, 2.5)):
+            new = _deform(tris, scale, wobble)
+            ctx.refit_scene(new)
+            rn = ctx.read_nodes()
+            assert np.array_equal(rn[:, 32:39], nodes[:, 32:39])             # topology untouched
+            want = ol.oracle_closest(new, rn, rays)
+            got = ctx.trace_closest(rays)
+            _check_hits(got, want)
+            assert 0.05 < (got["tri"] != MISS).mean()
+            b = scenes.bounce_rays(rays, want, scenes.tri_normals(new, want), seed=202)
+            _check_hits(ctx.trace_closest(b), ol.oracle_closest(new, rn, b))
+            assert np.array_equal(ctx.trace_any(b) != 0, ol.oracle_any(new, rn, b) != 0)
+            W, H = 160, 120
+            cam = dict(pos=(0.0, -36.0, 4.0), front=(0.0, 1.0, 0.0), up=(0.0, 0.0, 1.0))
+            ref_img = np.zeros((W * H, 4), dtype=np.float32)
+            for fc in (1, 2):
+                ol.oracle_render(new, rn, mats, ref_img, W, H, fc, 3, **cam)
+            assert scenes.psnr(_render(ctx, W, H, (1, 2), 3, **cam)[:, :3], ref_img[:, :3]) >= 50.0      # the shading records follow too
+            ctx.set_option(product.capi.OPT_TRAVERSAL, 1)                # the reference-layout walk sees the same refitted arrays
+            _check_hits(ctx.trace_closest(rays), want)
+            ctx.set_option(product.capi.OPT_TRAVERSAL, 0)
+        broken = tris.copy()
+        broken.view(np.float32).reshape(-1, 64)[0, 0] += np.float32(0.25)      # one copy of a duplicated face moves alone
+        with pytest.raises(product.B2RTError) as e:
+            ctx.refit_scene(broken)
+        assert e.value.status == -50                                          # CL_INVALID_ARG_VALUE
+        with pytest.raises(product.B2RTError):
+            ctx.refit_scene(tris[:-2])
+        ctx.refit_scene(tris)                                                 # and back
+        assert np.array_equal(ctx.trace_closest(rays).view(np.uint32), before.view(np.uint32))
