@@ -117,6 +117,8 @@ enum {
     B2RT_OPT_L2_PERSIST = 8,    /* 1 (default): the wide-node array is kept resident in L2 by an access-policy window (persisting
                                    carve-out sized to it) on every stream that runs traversal kernels; 0 = plain caching.
                                    Results do not depend on it. */
+    B2RT_OPT_STAGE_TIMES = 9,   /* 1: the wavefront frame path records a CUDA event after every stage of the launch's first wavefront;
+                                   read the durations with b2rt_stage_times (profiling aid, default 0) */
     B2RT_OPT_COOP_MAX = 7       /* tail mode of the persistent kernels: a warp whose ray pool is dry and that has at most this many
                                    rays alive hands them to the cooperative tail kernel, 32 lanes per ray (0 = off .. 16; default -1 = 8, but off for scenes
                                    of fewer than ~1000 nodes, whose rays are too short to gain). Results do not
@@ -253,6 +255,10 @@ int b2rt_scene_info_get(b2rt_context* ctx, b2rt_scene_info* out);
 int b2rt_set_option(b2rt_context* ctx, uint32_t option, int64_t value);
 int b2rt_get_counters(b2rt_context* ctx, b2rt_counters* out);   /* accumulated since reset */
 int b2rt_reset_counters(b2rt_context* ctx);
+/* Stage durations of the LAST wavefront frame launch made with B2RT_OPT_STAGE_TIMES = 1 (waits for it): kinds[i] is a
+ * B2RT_STAGE_* code, ms[i] the time between the end of the previous stage and the end of this one on the device. */
+enum { B2RT_STAGE_BEGIN = 0, B2RT_STAGE_GENERATE = 1, B2RT_STAGE_TRACE = 2, B2RT_STAGE_TAIL = 3, B2RT_STAGE_SHADE = 4 };
+int b2rt_stage_times(b2rt_context* ctx, uint32_t* kinds, float* ms, uint32_t capacity, uint32_t* n_out);
 /* Kernels launched by this context since creation (for bench.py's gpu_launches). */
 uint64_t b2rt_launch_count(const b2rt_context* ctx);
 int b2rt_device_count(void);

@@ -16,7 +16,7 @@ ARG_BUFFER_OUT, ARG_BUFFER_SCENE, ARG_BUFFER_NODE, ARG_BUFFER_MATERIAL = 0, 1, 2
 ARG_WIDTH, ARG_HEIGHT, ARG_FRAME_COUNT, ARG_FRAME_SEED = 4, 5, 6, 7
 ARG_LIGHT_BOUNCES, ARG_LIGHT_TYPE, ARG_SKYBOX_INTENSITY = 8, 9, 10
 ARG_CAMERA_POS, ARG_CAMERA_FRONT, ARG_CAMERA_UP = 11, 12, 13
-OPT_TRAVERSAL, OPT_COUNTERS, OPT_BLOCKS_PER_SM, OPT_RENDER_MODE, OPT_REFILL_MIN, OPT_LEAF_BIAS, OPT_WAVEFRONT_LANES, OPT_COOP_MAX, OPT_L2_PERSIST = 0, 1, 2, 3, 4, 5, 6, 7, 8
+OPT_TRAVERSAL, OPT_COUNTERS, OPT_BLOCKS_PER_SM, OPT_RENDER_MODE, OPT_REFILL_MIN, OPT_LEAF_BIAS, OPT_WAVEFRONT_LANES, OPT_COOP_MAX, OPT_L2_PERSIST, OPT_STAGE_TIMES = 0, 1, 2, 3, 4, 5, 6, 7, 8, 9
 MEM_WRITE_ONLY, MEM_READ_ONLY, MEM_COPY_HOST_PTR = 1 << 1, 1 << 2, 1 << 5
 
 # every symbol include/b2rt.h declares (tests/test_abi.py checks the header against this list)
@@ -28,7 +28,7 @@ SYMBOLS = [
     "b2rt_device_pointer", "b2rt_bound_buffer", "b2rt_scene_info_get", "b2rt_set_option",
     "b2rt_get_counters", "b2rt_reset_counters", "b2rt_launch_count", "b2rt_device_count",
     "b2rt_create_multi", "b2rt_group_size", "b2rt_group_info", "b2rt_comm_unique_id", "b2rt_comm_init", "b2rt_comm_share_output",
-    "b2rt_execute_shard", "b2rt_shard_bands", "b2rt_refit_scene",
+    "b2rt_execute_shard", "b2rt_shard_bands", "b2rt_refit_scene", "b2rt_stage_times",
 ]
 
 
@@ -104,6 +104,7 @@ def lib():
         "b2rt_launch_count": (u64, [vp]),
         "b2rt_device_count": (C.c_int, []),
         "b2rt_refit_scene": (C.c_int, [vp, vp, u64]),
+        "b2rt_stage_times": (C.c_int, [vp, C.POINTER(u32), C.POINTER(C.c_float), u32, C.POINTER(u32)]),
         "b2rt_create_multi": (C.c_int, [C.POINTER(C.c_int), C.c_int, C.POINTER(vp)]),
         "b2rt_group_size": (C.c_int, [vp]),
         "b2rt_group_info": (C.c_int, [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
@@ -361,6 +362,13 @@ class Context:
         s = SceneInfo()
         self._ck(self._L.b2rt_scene_info_get(self._h, C.byref(s)))
         return {n: int(getattr(s, n)) for n, _ in SceneInfo._fields_}
+
+    def stage_times(self):
+        """[(stage name, ms)] of the last wavefront frame launch made with OPT_STAGE_TIMES = 1."""
+        kinds, ms, n = (C.c_uint32 * 64)(), (C.c_float * 64)(), C.c_uint32(0)
+        self._ck(self._L.b2rt_stage_times(self._h, kinds, ms, 64, C.byref(n)))
+        names = {1: "generate", 2: "trace", 3: "tail", 4: "shade"}
+        return [(names.get(kinds[i], "?"), float(ms[i])) for i in range(n.value)]
 
     def counters(self):
         c = Counters()

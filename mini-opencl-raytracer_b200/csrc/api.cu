@@ -328,16 +328,37 @@ int ensure_wavefront(b2rt_context* ctx, uint64_t paths) {
 // One wavefront over work items [0, n) of `map` on stream `s`, using the queue/state slices that start at path
 // `offset` and the counter block `lane`: generate, then per bounce one persistent traversal launch over the live
 // ray queue and one shade/compact launch. Queue lengths stay on the device.
+// Stage timing (B2RT_OPT_STAGE_TIMES): an event after every stage of wavefront 0 of the launch; read with b2rt_stage_times.
+cudaEvent_t stage_mark(b2rt_context* ctx, bool on, uint32_t kind, cudaStream_t s) {
+    if (!on || ctx->stage_used >= 64) return nullptr;
+    if (ctx->stage_events.size() <= ctx->stage_used) {
+        cudaEvent_t ev = nullptr;
+        if (cudaEventCreate(&ev) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        ctx->stage_events.push_back(ev);
+        ctx->stage_kinds.push_back(0);
+    }
+    ctx->stage_kinds[ctx->stage_used] = kind;
+    return ctx->stage_events[ctx->stage_used++];
+}
+#define STAGE(kind)                                                                    \
+    do {                                                                               \
+        if (cudaEvent_t ev__ = stage_mark(ctx, timed, (kind), s)) CK(cudaEventRecord(ev__, s)); \
+    } while (0)
+
 int wavefront_lane(b2rt_context* ctx, const FrameArgs& a, float* d_result, const GidMap& map, uint32_t n, int lane, uint64_t offset,
                    cudaStream_t s) {
     int st_pol = apply_l2_policy(ctx, s);
     if (st_pol) return st_pol;
+    const bool timed = ctx->opt_stage_times != 0 && lane == 0;
+    if (timed) ctx->stage_used = 0;
+    STAGE(B2RT_STAGE_BEGIN);
     unsigned long long* cnt = ctx->d_wf_count + 8 * lane;           // three rotating queue counters, the trace kernel's ray counter, its tail queue's two
     char* rays[2] = { static_cast<char*>(ctx->d_wf_rays[0]) + offset * sizeof(b2rt_ray), static_cast<char*>(ctx->d_wf_rays[1]) + offset * sizeof(b2rt_ray) };
     char* hits = static_cast<char*>(ctx->d_wf_hits) + offset * sizeof(b2rt_hit);
     char* state = static_cast<char*>(ctx->d_wf_state) + offset * 32;
     CK(launch_wf_generate(a, map, n, rays[0], state, cnt, s));        // also resets the lane's four counters
     ctx->launches += 1;
+    STAGE(B2RT_STAGE_GENERATE);
     int grid = ctx->grid_closest;
     if (ctx->opt_blocks_per_sm > 0) grid = ctx->sm_count * (int)ctx->opt_blocks_per_sm;
     uint64_t blocks_needed = ((uint64_t)n + trace_block_threads() - 1) / trace_block_threads();
@@ -349,13 +370,17 @@ int wavefront_lane(b2rt_context* ctx, const FrameArgs& a, float* d_result, const
         const int in = b & 1, out = in ^ 1;
         unsigned long long *n_in = cnt + (b % 3), *n_out = cnt + ((b + 1) % 3), *n_clear = cnt + ((b + 2) % 3);
         CK(launch_trace_wide(ctx->view, rays[in], n, hits, false, ctx->opt_counters != 0, ctx->stack_bound, grid,
-                             cnt + 3, ctx->d_counters, (uint32_t)ctx->opt_refill_min, (uint32_t)ctx->opt_leaf_bias, s, n_in, &tail, ctx->grid_tail));
+                             cnt + 3, ctx->d_counters, (uint32_t)ctx->opt_refill_min, (uint32_t)ctx->opt_leaf_bias, s, n_in, &tail, ctx->grid_tail,
+                             stage_mark(ctx, timed, B2RT_STAGE_TRACE, s)));
+        STAGE(B2RT_STAGE_TAIL);
         // the shade stage also clears the counter the NEXT shade stage appends to and the traversal kernels' three counters
         CK(launch_wf_shade(ctx->view, a, map, n, rays[in], hits, n_in, rays[out], n_out, state, d_result, b == a.bounces - 1, n_clear, cnt + 3, s));
         ctx->launches += tail.coop_max ? 3 : 2;
+        STAGE(B2RT_STAGE_SHADE);
     }
     return B2RT_SUCCESS;
 }
+#undef STAGE
 
 // KernelEntry for work items [0, n) of `map` as up to WF_LANES independent wavefronts on their own streams. A
 // stage's persistent traversal kernel ends with a tail (a few rays need 10-100x the average number of steps, on
@@ -607,6 +632,7 @@ extern "C" void b2rt_destroy(b2rt_context* ctx) {
     }
     if (ctx->ev_wf_fork) cudaEventDestroy(ctx->ev_wf_fork);
     for (int i = 0; i < 2; ++i) if (ctx->ev_tune[i]) cudaEventDestroy(ctx->ev_tune[i]);
+    for (cudaEvent_t ev : ctx->stage_events) cudaEventDestroy(ev);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->stream_in) cudaStreamDestroy(ctx->stream_in);
     if (ctx->stream_out) cudaStreamDestroy(ctx->stream_out);
@@ -1082,6 +1108,7 @@ static int set_option_one(b2rt_context* ctx, uint32_t option, int64_t value) {
         case B2RT_OPT_LEAF_BIAS: if (value < 1 || value > 512) return fail(ctx, B2RT_INVALID_VALUE, "leaf bias must be 1..512 (sixteenths)"); ctx->opt_leaf_bias = value; break;
         case B2RT_OPT_COOP_MAX: if (value < -1 || value > COOP_MAX_LIMIT) return fail(ctx, B2RT_INVALID_VALUE, "cooperative tail threshold must be -1 (auto), 0 (off) .. 16"); ctx->opt_coop_max = value; break;
         case B2RT_OPT_L2_PERSIST: ctx->opt_l2_persist = value ? 1 : 0; if (!ctx->scene_dirty && use_device(ctx) == B2RT_SUCCESS) { cudaStreamSynchronize(ctx->stream); scene_l2_setup(ctx); } break;
+        case B2RT_OPT_STAGE_TIMES: ctx->opt_stage_times = value ? 1 : 0; ctx->stage_used = 0; break;
         case B2RT_OPT_REFILL_MIN: if (value < 1 || value > 32) return fail(ctx, B2RT_INVALID_VALUE, "refill threshold must be 1..32"); ctx->opt_refill_min = value; break;
         default: return fail(ctx, B2RT_INVALID_VALUE, "unknown option");
     }
@@ -1136,6 +1163,24 @@ extern "C" int b2rt_reset_counters(b2rt_context* ctx) {
     CK(cudaMemsetAsync(ctx->d_counters, 0, 128, ctx->stream));
     return B2RT_SUCCESS;
 }
+extern "C" int b2rt_stage_times(b2rt_context* ctx, uint32_t* kinds, float* ms, uint32_t capacity, uint32_t* n_out) {
+    if (!ctx) return B2RT_INVALID_CONTEXT;
+    if (!kinds || !ms || !n_out) return fail(ctx, B2RT_INVALID_VALUE, "null output");
+    int st = use_device(ctx);
+    if (st) return st;
+    *n_out = 0;
+    if (ctx->stage_used < 2) return B2RT_SUCCESS;
+    CK(cudaEventSynchronize(ctx->stage_events[ctx->stage_used - 1]));
+    for (uint32_t i = 1; i < ctx->stage_used && *n_out < capacity; ++i) {
+        float t = 0.0f;
+        CK(cudaEventElapsedTime(&t, ctx->stage_events[i - 1], ctx->stage_events[i]));
+        kinds[*n_out] = ctx->stage_kinds[i];
+        ms[*n_out] = t;
+        ++*n_out;
+    }
+    return B2RT_SUCCESS;
+}
+
 extern "C" uint64_t b2rt_launch_count(const b2rt_context* ctx) {
     if (!ctx) return 0;
     if (!ctx->group) return ctx->launches;

@@ -35,6 +35,9 @@ static constexpr unsigned FULL = 0xffffffffu;
 #ifndef B2_TOUCH
 #define B2_TOUCH 0
 #endif
+#ifndef B2_TAIL_CODE
+#define B2_TAIL_CODE 1           // 0: compile the hand-over to the cooperative tail kernel out of trace_persistent (A/B of its code-size cost)
+#endif
 #ifndef B2_STREAM_HINTS
 #define B2_STREAM_HINTS 1
 #endif
@@ -171,7 +174,7 @@ trace_persistent(SceneView s, const RayIn* __restrict__ rays, uint64_t n, void* 
         const bool pool_dry = exhausted && pool_left == 0u;
         // tail: nothing left to fetch and only a few rays alive in this warp -> hand them to the cooperative tail kernel
         // (lanes whose stack is empty are about to finish on their own: wait for them)
-        if (pool_dry && tail.coop_max && (vn | vl) != 0u && (unsigned)__popc(vn | vl) <= tail.coop_max &&
+        if (B2_TAIL_CODE && pool_dry && tail.coop_max && (vn | vl) != 0u && (unsigned)__popc(vn | vl) <= tail.coop_max &&
             __ballot_sync(FULL, !L.done() && L.top == REF_EMPTY) == 0u) break;
         if (idle && !pool_dry && ((unsigned)__popc(idle) >= refill_min || (vn | vl) == 0u)) {
             // ---- refill idle lanes from the warp pool -------------------------------------------
@@ -226,7 +229,7 @@ trace_persistent(SceneView s, const RayIn* __restrict__ rays, uint64_t n, void* 
         }
     }
     if (has_out) write_result<ANY>(out, my_index, L.h);       // rays that finished after the last refill
-    if (tail.coop_max && !L.done()) {
+    if (B2_TAIL_CODE && tail.coop_max && !L.done()) {
         // Unfinished ray: its index, best hit so far and pending work (in the reference's depth-first order) go to the tail
         // queue; trace_tail_kernel finishes it with a whole warp. At most coop_max lanes per warp get here, and the queue
         // holds coop_max records per warp of the grid.
@@ -497,7 +500,7 @@ static cudaError_t launch_persistent_cap(int cap, int grid, cudaStream_t st, con
 cudaError_t launch_trace_wide(const SceneView& s, const void* d_rays, uint64_t n, void* d_out, bool any, bool count,
                               uint32_t stack_bound, int grid_blocks, unsigned long long* d_next,
                               unsigned long long* d_counters, uint32_t refill_min, uint32_t leaf_bias, cudaStream_t st,
-                              const unsigned long long* d_n, const TailQueue* tail_in, int tail_grid) {
+                              const unsigned long long* d_n, const TailQueue* tail_in, int tail_grid, cudaEvent_t between) {
     int cap = pick_cap(stack_bound);
     if (!cap) return cudaErrorInvalidValue;
     TailQueue tail = { nullptr, nullptr, nullptr, 0, 0 };
@@ -514,6 +517,7 @@ cudaError_t launch_trace_wide(const SceneView& s, const void* d_rays, uint64_t n
                        : launch_persistent_cap<true, false>(cap, grid_blocks, st, s, d_rays, n, d_out, d_next, d_counters, refill_min, leaf_bias, d_n, tail);
     else e = count ? launch_persistent_cap<false, true>(cap, grid_blocks, st, s, d_rays, n, d_out, d_next, d_counters, refill_min, leaf_bias, d_n, tail)
                    : launch_persistent_cap<false, false>(cap, grid_blocks, st, s, d_rays, n, d_out, d_next, d_counters, refill_min, leaf_bias, d_n, tail);
+    if (e == cudaSuccess && between) e = cudaEventRecord(between, st);
     if (e != cudaSuccess || !tail.coop_max) return e;
     // the tail kernel: frontier capacity per warp and the size up to which four nodes are expanded per round
     const uint32_t fcap = tail_frontier_words(stack_bound), wide_limit = fcap - (stack_bound + 8u) - 32u;

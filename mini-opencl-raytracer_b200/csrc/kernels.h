@@ -26,7 +26,8 @@ cudaError_t launch_trace_wide(const SceneView& s, const void* d_rays, uint64_t n
                               uint32_t stack_bound, int grid_blocks, unsigned long long* d_next,
                               unsigned long long* d_counters, uint32_t refill_min, uint32_t leaf_bias, cudaStream_t st,
                               const unsigned long long* d_n = nullptr,    // d_n != null: ray count read on the device (n = upper bound)
-                              const TailQueue* tail = nullptr, int tail_grid = 0);
+                              const TailQueue* tail = nullptr, int tail_grid = 0,
+                              cudaEvent_t between = nullptr);           // recorded between the persistent and the tail kernel (stage timing)
 // One thread per ray over the reference-layout arrays (baseline / cross-check).
 cudaError_t launch_trace_binary(const SceneView& s, const void* d_rays, uint64_t n, void* d_out, bool any, cudaStream_t st);
 cudaError_t launch_camera_rays(const FrameArgs& a, uint64_t gid0, uint64_t gid1, void* d_rays, cudaStream_t st);

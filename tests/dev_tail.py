@@ -61,6 +61,16 @@ with prod.Context(0) as ctx:
     ctx.set_option(cap.OPT_RENDER_MODE, 1)
     print("megakernel: 1/%d share %.3f ms, full %.3f ms" % (world, frames(lambda: plan.render(ctx, 0)), frames(lambda: ctx.execute(W * H), 3)), flush=True)
     ctx.set_option(cap.OPT_RENDER_MODE, 0)
+    # per-stage device times of the share (events after every stage of the launch's one wavefront)
+    for coop in (0, 8):
+        ctx.set_option(cap.OPT_COOP_MAX, coop)
+        ctx.set_option(cap.OPT_WAVEFRONT_LANES, 1)
+        ctx.set_option(cap.OPT_STAGE_TIMES, 1)
+        for f in (20, 21, 22):
+            ctx.set_frame(f, 4, **cam); plan.render(ctx, 0); ctx.finish()
+        st = ctx.stage_times()
+        ctx.set_option(cap.OPT_STAGE_TIMES, 0)
+        print("coop %d stages (ms): %s  | sum %.3f" % (coop, " ".join("%s %.3f" % (k, v) for k, v in st), sum(v for _, v in st)), flush=True)
     # counted share: how much work goes through the tail kernel, and the worst solo ray
     for coop in (0, 8):
         ctx.set_option(cap.OPT_COOP_MAX, coop)

@@ -9,9 +9,9 @@ out = os.path.join(ROOT, "variants", "libb2rt_%s.so" % name)
 objdir = os.path.join(ROOT, "variants", "obj_" + name)
 os.makedirs(objdir, exist_ok=True)
 objs = []
-for f in ("kernels.cu", "lbvh.cu", "api.cu", "wide_bvh.cpp"):
+for f in ("kernels.cu", "lbvh.cu", "api.cu", "multi.cu", "refit.cu", "wide_bvh.cpp"):
     o = os.path.join(objdir, f + ".o")
     subprocess.check_call([build.NVCC] + build.NVCC_FLAGS + extra + ["-x", "cu", "-c", os.path.join(build.CSRC, f), "-o", o])
     objs.append(o)
-subprocess.check_call([build.NVCC, "-shared", "-o", out] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"])
+subprocess.check_call([build.NVCC, "-shared", "-o", out] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-ldl"])
 print(out)
