@@ -35,8 +35,6 @@ def lib():
         "g3d_scene_load": (vp, [cs, C.c_uint, cs, sz]),
         "g3d_scene_load_cached": (vp, [cs, C.c_uint, cs, C.POINTER(C.c_int), cs, sz]),
         "g3d_engine_load_scene_cached": (C.c_int, [vp, cs, C.c_uint, cs, C.POINTER(C.c_int), cs, sz]),
-        "g3d_parse_numbers": (C.c_int, [cs, vp, C.c_int]),
-        "g3d_scan_triplet": (None, [cs, vp]),
         "g3d_scene_load_triangles": (vp, [cs, cs, sz]),
         "g3d_engine_load_scene_device_bvh": (C.c_int, [vp, cs, cs, sz]),
         "g3d_scene_from_triangles": (vp, [vp, u64, vp, u64, C.c_uint, cs, sz]),
@@ -121,20 +119,6 @@ def load_triangles(obj_path):
         return t, m
     finally:
         L.g3d_scene_free(h)
-
-
-def scan_triplet(token):
-    """One `v/vt/vn` face token as CLOBJloader reads it (sscanf "%d/%d/%d" semantics); test hook."""
-    out = (C.c_uint * 3)(0, 0, 0)
-    lib().g3d_scan_triplet(token.encode(), out)
-    return tuple(int(x) for x in out)
-
-
-def parse_numbers(text, max_count=1 << 20):
-    """The numbers of `text` exactly as CLOBJloader reads them (scanf("%f") semantics); test hook."""
-    out = np.empty(max_count, dtype=np.float32)
-    n = lib().g3d_parse_numbers(text.encode(), out.ctypes.data, max_count)
-    return out[:n].copy()
 
 
 def build_scene(tris, mats, max_prims=4):

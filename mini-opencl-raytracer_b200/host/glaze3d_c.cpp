@@ -22,10 +22,6 @@ namespace
     } catch (const std::exception& e) { setError(err, errLen, e.what()); return failValue; } \
       catch (...) { setError(err, errLen, "unknown exception"); return failValue; }
 
-namespace Glaze3D { int ParseNumbersForTest(const char* text, float* out, int maxCount); }
-namespace Glaze3D { void ScanTripletForTest(const char* token, unsigned int out[3]); }
-extern "C" void g3d_scan_triplet(const char* token, unsigned int* out) { ScanTripletForTest(token, out); }
-extern "C" int g3d_parse_numbers(const char* text, float* out, int maxCount) { return ParseNumbersForTest(text, out, maxCount); }
 
 // ---- scenes without a device: CLOBJloader + CLBVHScene::BuildOnly ---------------------------------
 extern "C" void* g3d_scene_load(const char* objPath, unsigned maxPrims, char* err, size_t errLen)

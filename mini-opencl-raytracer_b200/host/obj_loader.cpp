@@ -205,6 +205,9 @@ namespace Glaze3D
         }
     }
 
+#ifdef G3D_TEST_HOOKS
+    // TEST BUILD ONLY (the test harness compiles this file with -DG3D_TEST_HOOKS into a library of its own): the scanners
+    // behind the loader, reachable one token at a time. The product library does not contain them.
     // Test hook: one face-vertex token through the triplet scanner.
     void ScanTripletForTest(const char* token, unsigned int out[3])
     {
@@ -222,6 +225,7 @@ namespace Glaze3D
         while (n < maxCount && c.number(out[n])) ++n;
         return n;
     }
+#endif
 
     void CLOBJloader::LoadInto(CLBVHScene& scene, const char* filename)
     {
@@ -309,3 +313,8 @@ namespace Glaze3D
         LoadInto(*eng->render->m_Scene, filename);
     }
 }
+
+#ifdef G3D_TEST_HOOKS
+extern "C" void g3d_scan_triplet(const char* token, unsigned int* out) { Glaze3D::ScanTripletForTest(token, out); }
+extern "C" int g3d_parse_numbers(const char* text, float* out, int maxCount) { return Glaze3D::ParseNumbersForTest(text, out, maxCount); }
+#endif

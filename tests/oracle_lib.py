@@ -73,6 +73,39 @@ def build_emu():
     return out
 
 
+def build_loader_hooks():
+    """tests/emu/libloaderhooks.so: the product's OBJ loader source compiled with -DG3D_TEST_HOOKS, which exposes its number
+    and face-token scanners one token at a time (the product library itself does not export them)."""
+    out = os.path.join(EMU_DIR, "libloaderhooks.so")
+    pkg = os.path.join(ROOT, "mini-opencl-raytracer_b200")
+    src = os.path.join(pkg, "host", "obj_loader.cpp")
+    if _stale(out, [src, os.path.join(pkg, "host", "glaze3d.h")]):
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-DG3D_TEST_HOOKS", "-I", os.path.join(ROOT, "include"),
+                               "-I", os.path.join(pkg, "host"), src, "-L", pkg, "-lglaze3d", "-lb2rt", "-Wl,-rpath," + pkg, "-o", out])
+    return out
+
+
+def scan_triplet(token):
+    """One `v/vt/vn` face token as the product's CLOBJloader reads it (sscanf "%d/%d/%d" semantics)."""
+    if "hooks" not in _cache:
+        _cache["hooks"] = C.CDLL(build_loader_hooks())
+    out = (C.c_uint * 3)(0, 0, 0)
+    _cache["hooks"].g3d_scan_triplet(token.encode(), out)
+    return tuple(int(x) for x in out)
+
+
+def parse_numbers(text, max_count=1 << 20):
+    """The numbers of `text` exactly as the product's CLOBJloader reads them (scanf("%f") semantics)."""
+    if "hooks" not in _cache:
+        _cache["hooks"] = C.CDLL(build_loader_hooks())
+    L = _cache["hooks"]
+    L.g3d_parse_numbers.restype = C.c_int
+    L.g3d_parse_numbers.argtypes = [C.c_char_p, C.c_void_p, C.c_int]
+    out = np.empty(max_count, dtype=np.float32)
+    n = L.g3d_parse_numbers(text.encode(), out.ctypes.data, max_count)
+    return out[:n].copy()
+
+
 _cache = {}
 
 

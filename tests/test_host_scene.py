@@ -181,12 +181,12 @@ def test_number_parsing_equals_strtof():
             words.append("%.17g" % np.nextafter(mid, np.inf))
         else:
             words.append("%d.%0*d" % (rng.integers(0, 1000), int(rng.integers(1, 12)), rng.integers(0, 10 ** 9)))
-    got = prod.host.parse_numbers(" ".join(w for w in words if w not in ("1e", "2e+")), len(words) + 8)
+    got = ol.parse_numbers(" ".join(w for w in words if w not in ("1e", "2e+")), len(words) + 8)
     want = np.array([libc.strtof(w.encode(), None) for w in words if w not in ("1e", "2e+")], dtype=np.float32)
     assert got.shape == want.shape
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
     # a number with a dangling exponent marker stops where strtof stops: "1e" is 1, then the word "e" is not a number
-    assert np.array_equal(prod.host.parse_numbers("1e 7"), np.array([1.0], dtype=np.float32))
+    assert np.array_equal(ol.parse_numbers("1e 7"), np.array([1.0], dtype=np.float32))
 
 
 def test_face_token_scanner_equals_sscanf():
@@ -205,4 +205,4 @@ def test_face_token_scanner_equals_sscanf():
         a, b, c = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_int(0)
         libc.sscanf(tok.encode(), b"%d/%d/%d", ctypes.byref(a), ctypes.byref(b), ctypes.byref(c))
         want = tuple(v.value & 0xFFFFFFFF for v in (a, b, c))
-        assert prod.host.scan_triplet(tok) == want, tok
+        assert ol.scan_triplet(tok) == want, tok
