@@ -116,6 +116,8 @@ def lib():
                                        C.POINTER(u64), C.POINTER(u64)]),
     }
     for name, (res, args) in sig.items():
+        if not hasattr(L, name) and os.environ.get("B2RT_LIB"):
+            continue                          # an older build of the library under A/B: newer entry points are simply absent
         fn = getattr(L, name)
         fn.restype, fn.argtypes = res, args
     _LIB = L

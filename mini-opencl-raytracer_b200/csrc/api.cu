@@ -1142,6 +1142,9 @@ extern "C" int b2rt_get_counters(b2rt_context* ctx, b2rt_counters* out) {
     unsigned long long v[16];
     CK(cudaDeviceSynchronize());     // counted launches may sit on caller-provided streams
     CK(cudaMemcpy(v, ctx->d_counters, sizeof(v), cudaMemcpyDeviceToHost));
+    unsigned long long ovf = 0;
+    CK(stack_overflow_count(&ovf, false));
+    v[13] += ovf;
     out->rays = v[0]; out->wide_nodes = v[1]; out->leaf_blocks = v[2]; out->leaf_gate_pass = v[3]; out->tri_tests = v[4];
     out->bytes_fetched = v[5] * 16ull - v[1] * 28ull;     // a node visit REQUESTS 84 of the record's 112 bytes: five 16-byte words + one of the eight order words
     out->node_phases = v[6]; out->node_phase_lanes = v[7]; out->leaf_phases = v[8]; out->leaf_phase_lanes = v[9];
@@ -1153,6 +1156,7 @@ static int reset_counters_each(b2rt_context* ctx, void*) {
     int st = use_device(ctx);
     if (st) return st;
     CK(cudaMemsetAsync(ctx->d_counters, 0, 128, ctx->stream));
+    CK(stack_overflow_count(nullptr, true));
     return B2RT_SUCCESS;
 }
 extern "C" int b2rt_reset_counters(b2rt_context* ctx) {

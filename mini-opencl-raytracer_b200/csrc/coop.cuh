@@ -67,18 +67,19 @@ B2_HD bool coop_child_test(const U4& w0, const U4& w2, const U4& w3, const U4& w
 // Lays out a solo lane's pending work as a frontier, back to front: the short stack (oldest first), its register-held
 // top, the current node (or leaf waiting for a queue slot), then the queued leaves -- the reverse of the order in which
 // the solo walk would get to them. Returns the number of entries.
+B2_HD uint32_t coop_dump_fields(int sp, uint32_t top, uint32_t cur, uint32_t leaf1, uint32_t leaf0, const uint32_t* stack, uint32_t* F) {
+    uint32_t k = 0;
+    for (int i = 0; i < sp; ++i) F[k++] = stack[i];
+    if (top != REF_EMPTY) F[k++] = top;
+    if (cur != REF_EMPTY) F[k++] = cur;
+    if (leaf1 != REF_EMPTY) F[k++] = leaf1;
+    if (leaf0 != REF_EMPTY) F[k++] = leaf0;
+    return k;
+}
 template <class LaneT>
 B2_HD uint32_t coop_dump(const LaneT& L, const uint32_t* stack, uint32_t* F) {
-    uint32_t k = 0;
-    for (int i = 0; i < L.sp; ++i) F[k++] = stack[i];
-    if (L.top != REF_EMPTY) F[k++] = L.top;
-    if (L.cur != REF_EMPTY) F[k++] = L.cur;
-#if B2_LEAF_QUEUE == 3
-    if (L.leaf2 != REF_EMPTY) F[k++] = L.leaf2;
-#endif
-    if (L.leaf1 != REF_EMPTY) F[k++] = L.leaf1;
-    if (L.leaf0 != REF_EMPTY) F[k++] = L.leaf0;
-    return k;
+    static_assert(B2_LEAF_QUEUE == 2, "the hand-over lays out a two-leaf queue");
+    return coop_dump_fields(L.sp, L.top, L.cur, L.leaf1, L.leaf0, stack, F);
 }
 
 // Finishes the ray whose frontier F[0..n) (front = F[n-1]) and state (r, h) every lane holds identically.

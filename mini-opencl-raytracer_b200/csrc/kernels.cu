@@ -117,7 +117,7 @@ trace_tail_kernel(SceneView s, const RayIn* __restrict__ rays, void* __restrict_
         __syncwarp();
     }
     if (lane == 0) {
-        if (overflow) atomicAdd(&counters[13], 1ull);
+        if (overflow) report_stack_overflow();
         if (COUNT && done) {
             atomicAdd(&counters[0], done);
             atomicAdd(&counters[1], (unsigned long long)tc.wide_nodes); atomicAdd(&counters[2], (unsigned long long)tc.leaf_blocks);
@@ -127,6 +127,26 @@ trace_tail_kernel(SceneView s, const RayIn* __restrict__ rays, void* __restrict_
             atomicAdd(&counters[15], (unsigned long long)tc.wide_nodes + tc.leaf_blocks);   // ... and their node + leaf visits
         }
     }
+}
+
+#ifndef B2_TAIL_NOINLINE
+#define B2_TAIL_NOINLINE 0
+#endif
+// The hand-over of one unfinished ray: index, best hit so far and pending work (in the reference's depth-first order) go to
+// the tail queue; trace_tail_kernel finishes it with a whole warp.
+#if B2_TAIL_NOINLINE
+__device__ __noinline__
+#else
+__device__ __forceinline__
+#endif
+void tail_handover(const TailQueue& tail, uint64_t index, float t, float u, float v, uint32_t tri, uint32_t cur, uint32_t leaf0,
+                   uint32_t leaf1, uint32_t top, int sp, const uint32_t* stack) {
+    const unsigned long long slot = atomicAdd(tail.count, 1ull);
+    uint32_t* rec = tail.records + slot * tail.rec_words;
+    rec[0] = (uint32_t)index; rec[1] = (uint32_t)(index >> 32);
+    rec[2] = __float_as_uint(t); rec[3] = __float_as_uint(u); rec[4] = __float_as_uint(v); rec[5] = tri;
+    rec[6] = coop_dump_fields(sp, top, cur, leaf1, leaf0, stack, rec + TAIL_HEADER_WORDS);      // the frontier, back to front
+    rec[7] = 0u;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -155,7 +175,6 @@ trace_persistent(SceneView s, const RayIn* __restrict__ rays, uint64_t n, void* 
     Lane<ANY, COUNT, CAP> L;
     uint32_t stack[CAP];
     L.clear();
-    L.overflow = false;
     L.tc.wide_nodes = L.tc.leaf_blocks = L.tc.leaf_pass = L.tc.tri_tests = L.tc.words = L.tc.max_stack = 0;
     uint64_t my_index = 0;
     bool has_out = false;                    // this lane's finished ray still has to be written (done together with the next refill)
@@ -229,18 +248,9 @@ trace_persistent(SceneView s, const RayIn* __restrict__ rays, uint64_t n, void* 
         }
     }
     if (has_out) write_result<ANY>(out, my_index, L.h);       // rays that finished after the last refill
-    if (B2_TAIL_CODE && tail.coop_max && !L.done()) {
-        // Unfinished ray: its index, best hit so far and pending work (in the reference's depth-first order) go to the tail
-        // queue; trace_tail_kernel finishes it with a whole warp. At most coop_max lanes per warp get here, and the queue
-        // holds coop_max records per warp of the grid.
-        const unsigned long long slot = atomicAdd(tail.count, 1ull);
-        uint32_t* rec = tail.records + slot * tail.rec_words;
-        rec[0] = (uint32_t)my_index; rec[1] = (uint32_t)(my_index >> 32);
-        rec[2] = __float_as_uint(L.h.t); rec[3] = __float_as_uint(L.h.u); rec[4] = __float_as_uint(L.h.v); rec[5] = L.h.tri;
-        rec[6] = coop_dump(L, stack, rec + TAIL_HEADER_WORDS);
-        rec[7] = 0u;
-    }
-    if (L.overflow) atomicAdd(&counters[13], 1ull);            // never expected: the stack capacity is the tree's exact bound
+    // at most coop_max lanes per warp get here, and the queue holds coop_max records per warp of the grid
+    if (B2_TAIL_CODE && tail.coop_max && !L.done())
+        tail_handover(tail, my_index, L.h.t, L.h.u, L.h.v, L.h.tri, L.cur, L.leaf0, L.leaf1, L.top, L.sp, stack);
 
     if (COUNT) {
         // one atomic per counter per warp
@@ -593,6 +603,13 @@ cudaError_t launch_tonemap_rgba8(const void* d_image, void* d_out, uint64_t n, c
 }
 
 int trace_block_threads() { return TRACE_BLOCK; }
+
+cudaError_t stack_overflow_count(unsigned long long* out, bool reset) {
+    cudaError_t e = cudaSuccess;
+    if (out) e = cudaMemcpyFromSymbol(out, g_stack_overflows, sizeof(unsigned long long));
+    if (e == cudaSuccess && reset) { const unsigned long long zero = 0; e = cudaMemcpyToSymbol(g_stack_overflows, &zero, sizeof(zero)); }
+    return e;
+}
 
 cudaError_t tail_occupancy(uint32_t stack_bound, int* blocks_per_sm) {
     const size_t smem = (size_t)(TAIL_BLOCK / 32) * tail_frontier_words(stack_bound) * sizeof(uint32_t);

@@ -44,6 +44,8 @@ cudaError_t launch_wf_shade(const SceneView& s, const FrameArgs& a, const GidMap
 // float4 accumulation image -> clamped 8-bit RGBA (alpha 255), n pixels.
 cudaError_t launch_tonemap_rgba8(const void* d_image, void* d_out, uint64_t n, cudaStream_t st);
 int trace_block_threads();
+// Stack / frontier overflows seen by the traversal kernels on the current device since the last reset (never expected).
+cudaError_t stack_overflow_count(unsigned long long* out, bool reset);
 cudaError_t tail_occupancy(uint32_t stack_bound, int* blocks_per_sm);
 cudaError_t trace_occupancy(bool any, uint32_t stack_bound, int* blocks_per_sm);
 

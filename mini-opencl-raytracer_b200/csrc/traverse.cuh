@@ -78,6 +78,8 @@ B2_HD uint32_t w_redor(uint32_t v) { return __reduce_or_sync(0xffffffffu, v); }
 B2_HD void w_sync() { __syncwarp(); }
 B2_HD uint32_t ctz32(uint32_t v) { return (uint32_t)__ffs((int)v) - 1u; }     // v != 0
 B2_HD void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
+__device__ unsigned long long g_stack_overflows;      // per device; read + cleared by b2rt_get_counters / b2rt_reset_counters
+B2_HD void report_stack_overflow() { atomicAdd(&g_stack_overflows, 1ull); }
 #else
 // Host emulation (tests only). Built with -ffp-contract=off -frounding-math.
 B2_HD float xadd(float a, float b) { volatile float r = a + b; return r; }
@@ -124,6 +126,8 @@ B2_HD uint32_t w_redor(uint32_t v) { return b2rt_emu::exchange(v, 3, 0); }
 B2_HD void w_sync() { (void)b2rt_emu::exchange(0, 4, 0); }
 B2_HD uint32_t ctz32(uint32_t v) { return (uint32_t)__builtin_ctz(v); }
 B2_HD void prefetch_l2(const void*) {}
+extern unsigned long long g_emu_stack_overflows;
+B2_HD void report_stack_overflow() { ++g_emu_stack_overflows; }
 #endif
 
 // OpenCL max()/min() as worded by the spec ("y if x < y, otherwise x"), the
@@ -348,13 +352,12 @@ struct Lane {
 #endif
     uint32_t top;          // most recently pushed child reference, kept in a register (REF_EMPTY = stack empty)
     int sp;                // entries below `top`, in the caller's local array
-    bool overflow;
     TravCounters tc;
 
     B2_HD void start(const RayX& ray, float tmax) {
         r = ray;
         h.t = tmax; h.u = 0.0f; h.v = 0.0f; h.tri = 0xFFFFFFFFu;
-        cur = 0; leaf0 = leaf1 = top = REF_EMPTY; sp = 0; overflow = false;
+        cur = 0; leaf0 = leaf1 = top = REF_EMPTY; sp = 0;
 #if B2_LEAF_QUEUE == 3
         leaf2 = REF_EMPTY;
 #endif
@@ -372,7 +375,9 @@ struct Lane {
     // The top of the stack sits in a register: a pop answers at once and the load that refills the
     // register from local memory is only waited for by the NEXT pop.
     B2_HD void push(uint32_t* stack, uint32_t ref) {
-        if (top != REF_EMPTY) { if (sp < CAP) stack[sp++] = top; else overflow = true; }
+        // CAP is at least the tree's exact bound (wide_stack_bound), so the else branch never runs; it must not cost the
+        // loop a live register either: the report goes straight to a global counter (b2rt_counters::stack_overflows)
+        if (top != REF_EMPTY) { if (sp < CAP) stack[sp++] = top; else report_stack_overflow(); }
         top = ref;
         if (COUNT && (uint32_t)sp + 1u > tc.max_stack) tc.max_stack = (uint32_t)sp + 1u;
     }
@@ -445,7 +450,7 @@ B2_HD HitX trace_wide(const U4* wide, const U4* leaf, const RayX& r, float tmax,
         else L.node_step(wide, stack, one);
     }
     if (COUNT && c) *c = L.tc;
-    if (overflow) *overflow = L.overflow;
+    if (overflow) *overflow = false;      // reported through report_stack_overflow()
     return L.h;
 }
 

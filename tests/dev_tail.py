@@ -71,6 +71,15 @@ with prod.Context(0) as ctx:
         st = ctx.stage_times()
         ctx.set_option(cap.OPT_STAGE_TIMES, 0)
         print("coop %d stages (ms): %s  | sum %.3f" % (coop, " ".join("%s %.3f" % (k, v) for k, v in st), sum(v for _, v in st)), flush=True)
+    for coop in (0, 8):
+        ctx.set_option(cap.OPT_COOP_MAX, coop)
+        ctx.set_option(cap.OPT_WAVEFRONT_LANES, 1)
+        ctx.set_option(cap.OPT_STAGE_TIMES, 1)
+        for f in (30, 31, 32):
+            ctx.set_frame(f, 4, **cam); ctx.execute(W * H); ctx.finish()
+        st = ctx.stage_times()
+        ctx.set_option(cap.OPT_STAGE_TIMES, 0)
+        print("FULL frame coop %d stages (ms): %s  | sum %.3f" % (coop, " ".join("%s %.3f" % (k, v) for k, v in st), sum(v for _, v in st)), flush=True)
     # counted share: how much work goes through the tail kernel, and the worst solo ray
     for coop in (0, 8):
         ctx.set_option(cap.OPT_COOP_MAX, coop)

@@ -21,6 +21,7 @@ struct EmuStats {
     uint64_t wide_visits, leaf_blocks, leaf_pass, tri_tests, words, overflow, max_stack;
 };
 
+namespace b2rt { unsigned long long g_emu_stack_overflows = 0; }     // bumped by traverse.cuh's report_stack_overflow() in the host build
 static WideBVH g_bvh;
 static std::string g_err;
 
@@ -51,6 +52,7 @@ extern "C" void emu_trace(const EmuRay* rays, uint64_t n, EmuHit* hits, uint32_t
         HitX h = any ? trace_wide<true, true, 256>(wide, leaf, r, rays[i].tmax, &c, &overflow, 0x3F800000u, sched)
                      : trace_wide<false, true, 256>(wide, leaf, r, rays[i].tmax, &c, &overflow, 0x3F800000u, sched);
         if (overflow) st->overflow++;
+        if (g_emu_stack_overflows) { st->overflow += g_emu_stack_overflows; g_emu_stack_overflows = 0; }
         if (any) occluded[i] = h.tri != 0xFFFFFFFFu;
         else { hits[i].t = h.t; hits[i].u = h.u; hits[i].v = h.v; hits[i].tri = h.tri; }
         if (c.max_stack > st->max_stack) st->max_stack = c.max_stack;
