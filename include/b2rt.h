@@ -98,8 +98,8 @@ typedef struct {
     /* warp scheduling of the persistent kernels: phases run and lanes that took part in them */
     uint64_t node_phases, node_phase_lanes, leaf_phases, leaf_phase_lanes, refills, refill_lanes;
     uint64_t max_steps_per_ray; /* node + leaf steps of the most expensive ray (tail detector; solo steps only) */
-    uint64_t stack_overflows;   /* lanes whose traversal stack or cooperative frontier overflowed: always 0 for trees that
-                                   passed upload validation (counted by every build, not only the counting one)          */
+    uint64_t stack_overflows;   /* lanes whose traversal stack (counting build) or cooperative frontier (every build) overflowed:
+                                   always 0 for trees that passed upload validation, whose exact bound sizes the stack      */
     uint64_t coop_rays;         /* rays finished by the warp-cooperative tail mode ...                                   */
     uint64_t coop_steps;        /* ... and the node + leaf visits done for them                                          */
 } b2rt_counters;

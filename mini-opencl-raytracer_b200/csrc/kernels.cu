@@ -129,8 +129,11 @@ trace_tail_kernel(SceneView s, const RayIn* __restrict__ rays, void* __restrict_
     }
 }
 
+#ifndef B2_TAIL_CHECK_POS
+#define B2_TAIL_CHECK_POS 0      // where the loop tests for the hand-over: 0 = after the refill branch, 1 = at the top (A/B of code generation)
+#endif
 #ifndef B2_TAIL_NOINLINE
-#define B2_TAIL_NOINLINE 0
+#define B2_TAIL_NOINLINE 1      // measured (r2 A/B, 10^8-ray stream): inlined 2 840 Mrays/s, not inlined 2 885 = the kernel without any hand-over code
 #endif
 // The hand-over of one unfinished ray: index, best hit so far and pending work (in the reference's depth-first order) go to
 // the tail queue; trace_tail_kernel finishes it with a whole warp.
@@ -175,6 +178,7 @@ trace_persistent(SceneView s, const RayIn* __restrict__ rays, uint64_t n, void* 
     Lane<ANY, COUNT, CAP> L;
     uint32_t stack[CAP];
     L.clear();
+    L.overflow = false;
     L.tc.wide_nodes = L.tc.leaf_blocks = L.tc.leaf_pass = L.tc.tri_tests = L.tc.words = L.tc.max_stack = 0;
     uint64_t my_index = 0;
     bool has_out = false;                    // this lane's finished ray still has to be written (done together with the next refill)
@@ -191,10 +195,9 @@ trace_persistent(SceneView s, const RayIn* __restrict__ rays, uint64_t n, void* 
         const unsigned vl = __ballot_sync(FULL, L.wants_leaf());
         const unsigned idle = ~(vn | vl);
         const bool pool_dry = exhausted && pool_left == 0u;
-        // tail: nothing left to fetch and only a few rays alive in this warp -> hand them to the cooperative tail kernel
-        // (lanes whose stack is empty are about to finish on their own: wait for them)
-        if (B2_TAIL_CODE && pool_dry && tail.coop_max && (vn | vl) != 0u && (unsigned)__popc(vn | vl) <= tail.coop_max &&
-            __ballot_sync(FULL, !L.done() && L.top == REF_EMPTY) == 0u) break;
+#if B2_TAIL_CHECK_POS == 1
+        if (B2_TAIL_CODE && pool_dry && (unsigned)__popc(vn | vl) <= tail.coop_max && (vn | vl) != 0u) break;
+#endif
         if (idle && !pool_dry && ((unsigned)__popc(idle) >= refill_min || (vn | vl) == 0u)) {
             // ---- refill idle lanes from the warp pool -------------------------------------------
             // Finished rays are written here, several lanes at a time, instead of one lane at a time when they finish.
@@ -223,6 +226,11 @@ trace_persistent(SceneView s, const RayIn* __restrict__ rays, uint64_t n, void* 
             continue;
         }
         if ((vn | vl) == 0u) break;          // nothing in flight and nothing left to fetch
+        // tail: nothing left to fetch and only a few rays alive in this warp -> leave; they are handed to the cooperative
+        // tail kernel below
+#if B2_TAIL_CHECK_POS == 0
+        if (B2_TAIL_CODE && pool_dry && (unsigned)__popc(idle) >= 32u - tail.coop_max) break;
+#endif
 
         // leaf_bias/16 weighs the leaf vote: > 1 consumes queued leaves earlier (less speculation)
         bool stepped;
@@ -253,6 +261,7 @@ trace_persistent(SceneView s, const RayIn* __restrict__ rays, uint64_t n, void* 
         tail_handover(tail, my_index, L.h.t, L.h.u, L.h.v, L.h.tri, L.cur, L.leaf0, L.leaf1, L.top, L.sp, stack);
 
     if (COUNT) {
+        if (L.overflow) report_stack_overflow();             // counting build only, see Lane::push
         // one atomic per counter per warp
         unsigned long long v[6] = { traced, L.tc.wide_nodes, L.tc.leaf_blocks, L.tc.leaf_pass, L.tc.tri_tests, L.tc.words };
 #pragma unroll

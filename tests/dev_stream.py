@@ -35,7 +35,7 @@ with prod.Context(0) as ctx:
         torch.cuda.synchronize()
         return n * reps / (e0.elapsed_time(e1) * 1e-3) / 1e6
 
-    for l2 in (1, 0):
+    for l2 in (1,):
         for coop in (8, 0):
             try:
                 ctx.set_option(cap.OPT_L2_PERSIST, l2)

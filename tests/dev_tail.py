@@ -61,6 +61,13 @@ with prod.Context(0) as ctx:
     ctx.set_option(cap.OPT_RENDER_MODE, 1)
     print("megakernel: 1/%d share %.3f ms, full %.3f ms" % (world, frames(lambda: plan.render(ctx, 0)), frames(lambda: ctx.execute(W * H), 3)), flush=True)
     ctx.set_option(cap.OPT_RENDER_MODE, 0)
+    # coarser bands: a rank's rays touch a smaller part of the BVH (L2 / DRAM locality) at the price of load balance
+    ctx.set_option(cap.OPT_COOP_MAX, 8)
+    ctx.set_option(cap.OPT_WAVEFRONT_LANES, 1)
+    for rows in (8, 30, 90, 270):
+        p2 = prod.sharding.BandPlan(W, H, world, band_rows=rows)
+        ts = [frames(lambda: p2.render(ctx, r), 4) for r in (0, world // 2, world - 1)]
+        print("band_rows %3d: 1/%d share of ranks 0 / %d / %d: %s ms" % (rows, world, world // 2, world - 1, " ".join("%.3f" % t for t in ts)), flush=True)
     # per-stage device times of the share (events after every stage of the launch's one wavefront)
     for coop in (0, 8):
         ctx.set_option(cap.OPT_COOP_MAX, coop)
