@@ -119,6 +119,10 @@ enum {
                                    Results do not depend on it. */
     B2RT_OPT_STAGE_TIMES = 9,   /* 1: the wavefront frame path records a CUDA event after every stage of the launch's first wavefront;
                                    read the durations with b2rt_stage_times (profiling aid, default 0) */
+    B2RT_OPT_WAVEFRONT_GRID_SPLIT = 10, /* wavefront frame path with several wavefronts in flight: 1 = each one's persistent grids take an
+                                   equal part of the device's CTA slots, so that one wavefront's latency-bound stage tails run next to
+                                   another's bulk traversal instead of queueing behind a full-device grid; 0 = every grid sized for the
+                                   whole device. Results do not depend on it. */
     B2RT_OPT_COOP_MAX = 7       /* tail mode of the persistent kernels: a warp whose ray pool is dry and that has at most this many
                                    rays alive hands them to the cooperative tail kernel, 32 lanes per ray (0 = off .. 16; default -1 = 8, but off for scenes
                                    of fewer than ~1000 nodes, whose rays are too short to gain). Results do not

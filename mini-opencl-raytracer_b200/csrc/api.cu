@@ -346,7 +346,7 @@ cudaEvent_t stage_mark(b2rt_context* ctx, bool on, uint32_t kind, cudaStream_t s
     } while (0)
 
 int wavefront_lane(b2rt_context* ctx, const FrameArgs& a, float* d_result, const GidMap& map, uint32_t n, int lane, uint64_t offset,
-                   cudaStream_t s) {
+                   cudaStream_t s, int share = 1) {
     int st_pol = apply_l2_policy(ctx, s);
     if (st_pol) return st_pol;
     const bool timed = ctx->opt_stage_times != 0 && lane == 0;
@@ -361,6 +361,12 @@ int wavefront_lane(b2rt_context* ctx, const FrameArgs& a, float* d_result, const
     STAGE(B2RT_STAGE_GENERATE);
     int grid = ctx->grid_closest;
     if (ctx->opt_blocks_per_sm > 0) grid = ctx->sm_count * (int)ctx->opt_blocks_per_sm;
+    // `share` wavefronts run side by side: each takes its part of the CTA slots (whole CTAs per SM)
+    int tail_grid = ctx->grid_tail;
+    if (share > 1) {
+        grid = ctx->sm_count * std::max(1, grid / ctx->sm_count / share);
+        tail_grid = ctx->sm_count * std::max(1, tail_grid / ctx->sm_count / share);
+    }
     uint64_t blocks_needed = ((uint64_t)n + trace_block_threads() - 1) / trace_block_threads();
     if ((uint64_t)grid > blocks_needed) grid = (int)blocks_needed;
     TailQueue tail;
@@ -370,7 +376,7 @@ int wavefront_lane(b2rt_context* ctx, const FrameArgs& a, float* d_result, const
         const int in = b & 1, out = in ^ 1;
         unsigned long long *n_in = cnt + (b % 3), *n_out = cnt + ((b + 1) % 3), *n_clear = cnt + ((b + 2) % 3);
         CK(launch_trace_wide(ctx->view, rays[in], n, hits, false, ctx->opt_counters != 0, ctx->stack_bound, grid,
-                             cnt + 3, ctx->d_counters, (uint32_t)ctx->opt_refill_min, (uint32_t)ctx->opt_leaf_bias, s, n_in, &tail, ctx->grid_tail,
+                             cnt + 3, ctx->d_counters, (uint32_t)ctx->opt_refill_min, (uint32_t)ctx->opt_leaf_bias, s, n_in, &tail, tail_grid,
                              stage_mark(ctx, timed, B2RT_STAGE_TRACE, s)));
         STAGE(B2RT_STAGE_TAIL);
         // the shade stage also clears the counter the NEXT shade stage appends to and the traversal kernels' three counters
@@ -410,7 +416,7 @@ int render_wavefront(b2rt_context* ctx, const FrameArgs& a, float* d_result, con
         if (contiguous) { sub.begin = map.begin + off; sub.band = sub.stride = (uint32_t)m; }
         else sub.begin = map.begin + (off / map.band) * map.stride;
         CK(cudaStreamWaitEvent(ctx->wf_stream[l], ctx->ev_wf_fork, 0));
-        st = wavefront_lane(ctx, a, d_result, sub, (uint32_t)m, l, off, ctx->wf_stream[l]);
+        st = wavefront_lane(ctx, a, d_result, sub, (uint32_t)m, l, off, ctx->wf_stream[l], ctx->opt_wf_grid_split ? lanes : 1);
         if (st) return st;
         CK(cudaEventRecord(ctx->ev_wf_join[l], ctx->wf_stream[l]));
         CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_wf_join[l], 0));
@@ -1108,6 +1114,7 @@ static int set_option_one(b2rt_context* ctx, uint32_t option, int64_t value) {
         case B2RT_OPT_LEAF_BIAS: if (value < 1 || value > 512) return fail(ctx, B2RT_INVALID_VALUE, "leaf bias must be 1..512 (sixteenths)"); ctx->opt_leaf_bias = value; break;
         case B2RT_OPT_COOP_MAX: if (value < -1 || value > COOP_MAX_LIMIT) return fail(ctx, B2RT_INVALID_VALUE, "cooperative tail threshold must be -1 (auto), 0 (off) .. 16"); ctx->opt_coop_max = value; break;
         case B2RT_OPT_L2_PERSIST: ctx->opt_l2_persist = value ? 1 : 0; if (!ctx->scene_dirty && use_device(ctx) == B2RT_SUCCESS) { cudaStreamSynchronize(ctx->stream); scene_l2_setup(ctx); } break;
+        case B2RT_OPT_WAVEFRONT_GRID_SPLIT: ctx->opt_wf_grid_split = value ? 1 : 0; break;
         case B2RT_OPT_STAGE_TIMES: ctx->opt_stage_times = value ? 1 : 0; ctx->stage_used = 0; break;
         case B2RT_OPT_REFILL_MIN: if (value < 1 || value > 32) return fail(ctx, B2RT_INVALID_VALUE, "refill threshold must be 1..32"); ctx->opt_refill_min = value; break;
         default: return fail(ctx, B2RT_INVALID_VALUE, "unknown option");
