@@ -102,6 +102,8 @@ typedef struct {
                                    always 0 for trees that passed upload validation, whose exact bound sizes the stack      */
     uint64_t coop_rays;         /* rays finished by the warp-cooperative tail mode ...                                   */
     uint64_t coop_steps;        /* ... and the node + leaf visits done for them                                          */
+    uint64_t coop_max_steps;    /* node + leaf visits of the most expensive ray of the cooperative tail mode ...         */
+    uint64_t coop_max_rounds;   /* ... and the most rounds (memory round trips) one ray took there                       */
 } b2rt_counters;
 
 enum {

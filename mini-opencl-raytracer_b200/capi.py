@@ -42,7 +42,7 @@ class Counters(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("rays", "wide_nodes", "leaf_blocks", "leaf_gate_pass", "tri_tests",
                                           "bytes_fetched", "node_phases", "node_phase_lanes", "leaf_phases",
                                           "leaf_phase_lanes", "refills", "refill_lanes", "max_steps_per_ray",
-                                          "stack_overflows", "coop_rays", "coop_steps")]
+                                          "stack_overflows", "coop_rays", "coop_steps", "coop_max_steps", "coop_max_rounds")]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}

@@ -600,8 +600,8 @@ extern "C" int b2rt_create(int device_id, b2rt_context** out) {
         cudaGetLastError();
     }
     if ((e = cudaMalloc(&ctx->d_next, NEXT_RING * 4 * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMalloc");
-    if ((e = cudaMalloc(&ctx->d_counters, 128)) != cudaSuccess) return bail(e, "cudaMalloc");
-    if ((e = cudaMemset(ctx->d_counters, 0, 128)) != cudaSuccess) return bail(e, "cudaMemset");
+    if ((e = cudaMalloc(&ctx->d_counters, 192)) != cudaSuccess) return bail(e, "cudaMalloc");
+    if ((e = cudaMemset(ctx->d_counters, 0, 192)) != cudaSuccess) return bail(e, "cudaMemset");
     { std::lock_guard<std::mutex> lk(g_live_mutex); g_live.insert(ctx); }
     *out = ctx;
     return B2RT_SUCCESS;
@@ -1140,13 +1140,15 @@ extern "C" int b2rt_get_counters(b2rt_context* ctx, b2rt_counters* out) {
             uint64_t* b = reinterpret_cast<uint64_t*>(&sum);
             for (size_t i = 0; i < sizeof(c) / 8; ++i) b[i] += a[i];
             sum.max_steps_per_ray = std::max(sum.max_steps_per_ray - c.max_steps_per_ray, c.max_steps_per_ray);
+            sum.coop_max_steps = std::max(sum.coop_max_steps - c.coop_max_steps, c.coop_max_steps);
+            sum.coop_max_rounds = std::max(sum.coop_max_rounds - c.coop_max_rounds, c.coop_max_rounds);
         }
         *out = sum;
         return B2RT_SUCCESS;
     }
     int st = use_device(ctx);
     if (st) return st;
-    unsigned long long v[16];
+    unsigned long long v[24];
     CK(cudaDeviceSynchronize());     // counted launches may sit on caller-provided streams
     CK(cudaMemcpy(v, ctx->d_counters, sizeof(v), cudaMemcpyDeviceToHost));
     unsigned long long ovf = 0;
@@ -1157,12 +1159,13 @@ extern "C" int b2rt_get_counters(b2rt_context* ctx, b2rt_counters* out) {
     out->node_phases = v[6]; out->node_phase_lanes = v[7]; out->leaf_phases = v[8]; out->leaf_phase_lanes = v[9];
     out->refills = v[10]; out->refill_lanes = v[11]; out->max_steps_per_ray = v[12];
     out->stack_overflows = v[13]; out->coop_rays = v[14]; out->coop_steps = v[15];
+    out->coop_max_steps = v[16]; out->coop_max_rounds = v[17];
     return B2RT_SUCCESS;
 }
 static int reset_counters_each(b2rt_context* ctx, void*) {
     int st = use_device(ctx);
     if (st) return st;
-    CK(cudaMemsetAsync(ctx->d_counters, 0, 128, ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_counters, 0, 192, ctx->stream));
     CK(stack_overflow_count(nullptr, true));
     return B2RT_SUCCESS;
 }
@@ -1171,7 +1174,7 @@ extern "C" int b2rt_reset_counters(b2rt_context* ctx) {
     if (ctx->group) return group_each(ctx, reset_counters_each, nullptr, false);
     int st = use_device(ctx);
     if (st) return st;
-    CK(cudaMemsetAsync(ctx->d_counters, 0, 128, ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_counters, 0, 192, ctx->stream));
     return B2RT_SUCCESS;
 }
 extern "C" int b2rt_stage_times(b2rt_context* ctx, uint32_t* kinds, float* ms, uint32_t capacity, uint32_t* n_out) {

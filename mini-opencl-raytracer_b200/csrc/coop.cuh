@@ -44,6 +44,19 @@ B2_HD bool coop_child_test(const U4& w0, const U4& w2, const U4& w3, const U4& w
     const float base[3] = { bits2f(w0.x), bits2f(w0.y), bits2f(w0.z) };
     const uint32_t qlo_a[3] = { w2.x, w2.z, w3.x }, qlo_b[3] = { w2.y, w2.w, w3.y };
     const uint32_t qhi_a[3] = { w3.z, w4.x, w4.z }, qhi_b[3] = { w3.w, w4.y, w4.w };
+    if (r.sign & RAY_DEGENERATE) {          // see test_wide_node_robust (warp-uniform: every lane holds the same ray)
+        float N = 0.0f, F = best;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const float S = bits2f(((w0.w >> (8 * a)) & 0xffu) << 23);
+            const float lo = fma_rd(u2f(prmt(qlo_a[a], qlo_b[a], slot) & 0xffu), S, base[a]);
+            const float hi = fma_ru(u2f(prmt(qhi_a[a], qhi_b[a], slot) & 0xffu), S, base[a]);
+            const bool neg = (r.sign >> a) & 1u;
+            N = max_nn(N, xmul(xsub(neg ? hi : lo, o[a]), inv[a]));
+            F = min_nn(F, xmul(xsub(neg ? lo : hi, o[a]), inv[a]));
+        }
+        return F >= N;
+    }
     float nn[3], ff[3];
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
@@ -96,6 +109,7 @@ B2_HD void coop_trace(const U4* wide, const U4* leaf, uint32_t* F, uint32_t n, u
                       const RayX& r, HitX& h, TravCounters& tc, bool& overflow) {
     const uint32_t lane = w_lane();
     while (n) {
+        if (COUNT) tc.rounds++;
         const uint32_t win = n < 32u ? n : 32u;
         const uint32_t e = lane < win ? F[n - 1u - lane] : REF_EMPTY;
         const bool is_node = lane < win && !(e & REF_LEAF_BIT);
@@ -136,7 +150,7 @@ B2_HD void coop_trace(const U4* wide, const U4* leaf, uint32_t* F, uint32_t n, u
         if (gact) {
             const U4* p = wide + (uint32_t)WIDE_NODE_WORDS * node;
             w0 = ld128(p); w1 = ld128(p + 1); w2 = ld128(p + 2); w3 = ld128(p + 3); w4 = ld128(p + 4);
-            order = ld32(reinterpret_cast<const uint32_t*>(p + 5) + r.sign);
+            order = ld32(reinterpret_cast<const uint32_t*>(p + 5) + (r.sign & 7u));
         }
 
         // ---- leaves: blocks of more than two records leave the fast path -------------------------------------------------

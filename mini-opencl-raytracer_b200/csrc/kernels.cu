@@ -22,6 +22,7 @@
 // parity-critical arithmetic additionally uses explicit *_rn intrinsics.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 #include "kernels.h"
 #include "shade.cuh"
 #include "coop.cuh"
@@ -92,8 +93,9 @@ trace_tail_kernel(SceneView s, const RayIn* __restrict__ rays, void* __restrict_
     uint32_t* F = tail_frontiers + (threadIdx.x >> 5) * fcap;
     const unsigned lane = threadIdx.x & 31u;
     const unsigned long long total = *tail.count;
-    TravCounters tc = { 0, 0, 0, 0, 0, 0 };
+    TravCounters tc = { 0, 0, 0, 0, 0, 0, 0 };
     unsigned long long done = 0;
+    uint32_t worst_steps = 0, worst_rounds = 0;                         // COUNT only
     bool overflow = false;
     for (;;) {
         unsigned long long slot = 0;
@@ -111,7 +113,15 @@ trace_tail_kernel(SceneView s, const RayIn* __restrict__ rays, void* __restrict_
         RayX r; float tmax;
         load_ray(rays, index, r, tmax);                                 // every lane: the same 32 bytes, the same arithmetic
         __syncwarp();
+        const uint32_t steps0 = tc.wide_nodes + tc.leaf_blocks, rounds0 = tc.rounds;
         coop_trace<ANY, COUNT>(s.wide, s.leaf, F, n, fcap, wide_limit, r, h, tc, overflow);
+        if (COUNT) {
+            const uint32_t ds = tc.wide_nodes + tc.leaf_blocks - steps0, dr = tc.rounds - rounds0;
+            worst_steps = worst_steps > ds ? worst_steps : ds; worst_rounds = worst_rounds > dr ? worst_rounds : dr;
+#ifdef B2_DEBUG_LONG_RAYS
+            if (dr > 300 && lane == 0) printf("LONGRAY idx %llu steps %u rounds %u o %.9g %.9g %.9g d %.9g %.9g %.9g inv %g %g %g t %g tri %u\n", (unsigned long long)index, ds, dr, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, r.ix, r.iy, r.iz, h.t, h.tri);
+#endif
+        }
         if (lane == 0) write_result<ANY>(out, index, h);
         ++done;
         __syncwarp();
@@ -125,6 +135,7 @@ trace_tail_kernel(SceneView s, const RayIn* __restrict__ rays, void* __restrict_
             atomicAdd(&counters[5], (unsigned long long)tc.words);
             atomicAdd(&counters[14], done);                                              // rays finished cooperatively ...
             atomicAdd(&counters[15], (unsigned long long)tc.wide_nodes + tc.leaf_blocks);   // ... and their node + leaf visits
+            atomicMax(&counters[16], (unsigned long long)worst_steps); atomicMax(&counters[17], (unsigned long long)worst_rounds);
         }
     }
 }
@@ -179,7 +190,7 @@ trace_persistent(SceneView s, const RayIn* __restrict__ rays, uint64_t n, void* 
     uint32_t stack[CAP];
     L.clear();
     L.overflow = false;
-    L.tc.wide_nodes = L.tc.leaf_blocks = L.tc.leaf_pass = L.tc.tri_tests = L.tc.words = L.tc.max_stack = 0;
+    L.tc.wide_nodes = L.tc.leaf_blocks = L.tc.leaf_pass = L.tc.tri_tests = L.tc.words = L.tc.max_stack = L.tc.rounds = 0;
     uint64_t my_index = 0;
     bool has_out = false;                    // this lane's finished ray still has to be written (done together with the next refill)
     uint64_t pool_next = 0;                  // warp-uniform: next ray of the warp's pool ...

@@ -20,7 +20,7 @@ uint32_t tail_record_words(uint32_t stack_bound);
 // Persistent while-while traversal of the compressed wide BVH over a device-resident ray
 // stream. d_out is b2rt_hit[n] (closest) or uint32_t[n] (any). d_next points at three 64-bit scratch
 // counters (ray counter, tail-queue length, tail-queue read position; reset by the wrapper unless d_n is given),
-// d_counters sixteen 64-bit accumulators (used when count; [13] = stack/frontier overflows, always). With a tail
+// d_counters twenty-four 64-bit accumulators (used when count; [13] = stack/frontier overflows, always). With a tail
 // queue the cooperative tail kernel is launched right behind the persistent one (tail_grid blocks).
 cudaError_t launch_trace_wide(const SceneView& s, const void* d_rays, uint64_t n, void* d_out, bool any, bool count,
                               uint32_t stack_bound, int grid_blocks, unsigned long long* d_next,

@@ -140,8 +140,9 @@ struct RayX {
     float ox, oy, oz;
     float dx, dy, dz;      // normalised exactly like InitRay
     float ix, iy, iz;      // 1/d, may be +-inf
-    uint32_t sign;         // bit a: inv[a] < 0
+    uint32_t sign;         // bit a: inv[a] < 0; bit 3 (RAY_DEGENERATE): some inv[a] is infinite or beyond 2^100
 };
+enum : uint32_t { RAY_DEGENERATE = 8u };
 
 // InitRay, kernel_bvh.cl:42-55, with normalize(v) = v / sqrt(dot(v,v)).
 B2_HD RayX make_ray(float ox, float oy, float oz, float dx, float dy, float dz) {
@@ -151,6 +152,10 @@ B2_HD RayX make_ray(float ox, float oy, float oz, float dx, float dy, float dz) 
     r.dx = xdiv(dx, len); r.dy = xdiv(dy, len); r.dz = xdiv(dz, len);
     r.ix = xdiv(1.0f, r.dx); r.iy = xdiv(1.0f, r.dy); r.iz = xdiv(1.0f, r.dz);
     r.sign = (r.ix < 0 ? 1u : 0u) | (r.iy < 0 ? 2u : 0u) | (r.iz < 0 ? 4u : 0u);
+    // a direction component that is exactly (or all but) zero: 1/d is +-inf, the one-FMA plane evaluation of test_wide_node
+    // then yields NaN on that axis (inf - inf) and stops culling there; such rays take test_wide_node_robust instead
+    const float big = 1.2676506e30f;                       // 2^100
+    if (!(fabsf(r.ix) <= big) || !(fabsf(r.iy) <= big) || !(fabsf(r.iz) <= big)) r.sign |= RAY_DEGENERATE;
     return r;
 }
 
@@ -159,7 +164,7 @@ struct HitX {
     uint32_t tri;          // B2RT_MISS (0xFFFFFFFF) until a triangle is accepted
 };
 
-struct TravCounters { uint32_t wide_nodes, leaf_blocks, leaf_pass, tri_tests, words, max_stack; };   // max_stack: most deferred references at once (incl. the register-held top)
+struct TravCounters { uint32_t wide_nodes, leaf_blocks, leaf_pass, tri_tests, words, max_stack, rounds; };   // max_stack: most deferred references at once (incl. the register-held top)
 
 // RayBounds, kernel_bvh.cl:156-169, on an exact fp32 box.
 B2_HD bool box_gate_exact(const RayX& r, float lox, float loy, float loz, float hix, float hiy, float hiz, float best) {
@@ -334,6 +339,48 @@ B2_HD WideHits test_wide_node(const U4* wide, uint32_t index, const RayX& r, flo
     return out;
 }
 
+// The same decision for rays whose reciprocal direction has an infinite (or NaN, or > 2^100) component (RAY_DEGENERATE):
+// a direction component of exactly zero is not rare in rendered frames (a few rays per million: central camera rows,
+// BRDF frames of axis-aligned normals), and with one FMA per plane such an axis evaluates to inf - inf = NaN and no longer
+// culls -- the ray then walks every node its projection onto the other axes overlaps (measured: 26 000 steps instead of
+// ~40, a 5 ms tail on a 4 ms frame share). Here the planes are decoded to fp32 (rounded outwards: lo_q <= base + q*S <=
+// child's exact lo as real numbers, wide_bvh.cpp) and the reference's own two operations fl(fl(P - o) * inv) are applied:
+// they are monotone in P, so near(lo_q) <= near(exact box of any leaf below) and far(hi_q) >= far(...); (P - o) * inf is
+// +-inf on the correct side and 0 * inf = NaN drops out of fmaxf/fminf like out of the reference's max()/min().
+B2_HD WideHits test_wide_node_robust(const U4* wide, uint32_t index, const RayX& r, float best) {
+    const U4* p = wide + (uint32_t)WIDE_NODE_WORDS * index;
+    U4 w0 = ld128(p), w1 = ld128(p + 1), w2 = ld128(p + 2), w3 = ld128(p + 3), w4 = ld128(p + 4);
+    const uint32_t order = ld32(reinterpret_cast<const uint32_t*>(p + 5) + (r.sign & 7u));
+    WideHits out;
+    out.add_interior = w1.x - (uint32_t)META_INTERIOR;
+    out.add_leaf = REF_LEAF_BIT | w1.y;
+    out.meta_lo = prmt(w1.z, w1.w, order);
+    out.meta_hi = prmt(w1.z, w1.w, order >> 16);
+    const float o[3] = { r.ox, r.oy, r.oz };
+    const float inv[3] = { r.ix, r.iy, r.iz };
+    const float base[3] = { bits2f(w0.x), bits2f(w0.y), bits2f(w0.z) };
+    const uint32_t qlo_a[3] = { w2.x, w2.z, w3.x }, qlo_b[3] = { w2.y, w2.w, w3.y };
+    const uint32_t qhi_a[3] = { w3.z, w4.x, w4.z }, qhi_b[3] = { w3.w, w4.y, w4.w };
+    uint32_t mask = 0;
+    const uint32_t n_children = w0.w >> 24;
+    for (uint32_t k = 0; k < n_children; ++k) {
+        const uint32_t slot = (order >> (4u * k)) & 7u;
+        float N = 0.0f, F = best;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const float S = bits2f(((w0.w >> (8 * a)) & 0xffu) << 23);
+            const float lo = fma_rd(u2f(prmt(qlo_a[a], qlo_b[a], slot) & 0xffu), S, base[a]);
+            const float hi = fma_ru(u2f(prmt(qhi_a[a], qhi_b[a], slot) & 0xffu), S, base[a]);
+            const bool neg = (r.sign >> a) & 1u;
+            N = max_nn(N, xmul(xsub(neg ? hi : lo, o[a]), inv[a]));
+            F = min_nn(F, xmul(xsub(neg ? lo : hi, o[a]), inv[a]));
+        }
+        if (F >= N) mask |= 1u << k;
+    }
+    out.mask = mask;
+    return out;
+}
+
 // ---- one ray's traversal state ------------------------------------------------------------
 // node_step() tests the current wide node and walks on; leaves met on the way are queued (two
 // slots, FIFO) and consumed in order by leaf_step(). Any interleaving of the two calls that the
@@ -405,7 +452,7 @@ struct Lane {
     // `one` must be 0x3F800000, passed as run-time data: held in one register it lets the constant
     // byte selectors of B2_PLANE_V be instruction immediates (ptxas otherwise keeps four selector registers).
     B2_HD void node_step(const U4* wide, uint32_t* stack, uint32_t one) {
-        WideHits w = test_wide_node(wide, cur, r, h.t, one);
+        WideHits w = (r.sign & RAY_DEGENERATE) ? test_wide_node_robust(wide, cur, r, h.t) : test_wide_node(wide, cur, r, h.t, one);
         if (COUNT) { tc.wide_nodes++; tc.words += WIDE_NODE_WORDS; }
         uint32_t m = w.mask;
         if (m == 0) { cur = pop(stack); }
@@ -442,7 +489,7 @@ B2_HD HitX trace_wide(const U4* wide, const U4* leaf, const RayX& r, float tmax,
                       uint32_t one, uint32_t schedule = 0) {
     Lane<ANY, COUNT, CAP> L;
     uint32_t stack[CAP];
-    L.tc.wide_nodes = L.tc.leaf_blocks = L.tc.leaf_pass = L.tc.tri_tests = L.tc.words = L.tc.max_stack = 0;
+    L.tc.wide_nodes = L.tc.leaf_blocks = L.tc.leaf_pass = L.tc.tri_tests = L.tc.words = L.tc.max_stack = L.tc.rounds = 0;
     L.start(r, tmax);
     while (!L.done()) {
         const bool node = L.wants_node(), lf = L.wants_leaf();

@@ -36,7 +36,7 @@ with prod.Context(0) as ctx:
         return n * reps / (e0.elapsed_time(e1) * 1e-3) / 1e6
 
     for l2 in (1,):
-        for coop in (8, 0):
+        for coop in (8, 0, 8, 0, 4):
             try:
                 ctx.set_option(cap.OPT_L2_PERSIST, l2)
                 ctx.set_option(cap.OPT_COOP_MAX, coop)
