@@ -104,6 +104,7 @@ typedef struct {
     uint64_t coop_steps;        /* ... and the node + leaf visits done for them                                          */
     uint64_t coop_max_steps;    /* node + leaf visits of the most expensive ray of the cooperative tail mode ...         */
     uint64_t coop_max_rounds;   /* ... and the most rounds (memory round trips) one ray took there                       */
+    uint64_t resumed_rays;      /* suspended rays picked up again by the second persistent pass of the two-step tail     */
 } b2rt_counters;
 
 enum {
@@ -125,6 +126,10 @@ enum {
                                    equal part of the device's CTA slots, so that one wavefront's latency-bound stage tails run next to
                                    another's bulk traversal instead of queueing behind a full-device grid; 0 = every grid sized for the
                                    whole device. Results do not depend on it. */
+    B2RT_OPT_RESUME_MAX = 11,   /* two-step tail: a dry warp with at most this many live rays suspends them; a second persistent launch
+                                   re-packs all suspended rays 32 to a warp and walks on at full width, and only what that pass
+                                   leaves (B2RT_OPT_COOP_MAX per warp) goes to the cooperative kernel. 0 = off (default, also -1) .. 16.
+                                   Only used while larger than the cooperative threshold. Results do not depend on it. */
     B2RT_OPT_COOP_MAX = 7       /* tail mode of the persistent kernels: a warp whose ray pool is dry and that has at most this many
                                    rays alive hands them to the cooperative tail kernel, 32 lanes per ray (0 = off .. 16; default -1 = 8, but off for scenes
                                    of fewer than ~1000 nodes, whose rays are too short to gain). Results do not

@@ -202,13 +202,18 @@ int apply_l2_policy(b2rt_context* ctx, cudaStream_t st) {
 // The tail queue in slot `which` (allocated on first use), wired to the given device counters. coop_max = 0 when the
 // tail mode is off or the launch runs the reference-layout walk.
 int tail_queue(b2rt_context* ctx, int which, unsigned long long* count, unsigned long long* next, TailQueue& q) {
-    q = TailQueue{ count, next, nullptr, ctx->tail_rec_words, 0u };
+    q = TailQueue{ count, next, nullptr, ctx->tail_rec_words, 0u, 0u, count + 2, next + 2, nullptr };
     // auto (-1): on; but a tree this small has no long rays -- a hand-over would cost more than the few steps it saves
     const int64_t coop = ctx->opt_coop_max >= 0 ? ctx->opt_coop_max : (ctx->info.n_wide_nodes + ctx->info.n_leaf_blocks > 1000 ? 8 : 0);
     if (coop <= 0 || ctx->opt_traversal == 1 || ctx->tail_capacity_records == 0) return B2RT_SUCCESS;
-    if (!ctx->d_tail[which]) CK(cudaMalloc(&ctx->d_tail[which], ctx->tail_capacity_records * ctx->tail_rec_words * sizeof(uint32_t)));
+    // two queues of the same capacity: what the first pass suspends, and what the re-packed second pass leaves for the cooperative kernel
+    const size_t queue_words = (size_t)ctx->tail_capacity_records * ctx->tail_rec_words;
+    if (!ctx->d_tail[which]) CK(cudaMalloc(&ctx->d_tail[which], 2 * queue_words * sizeof(uint32_t)));
     q.records = static_cast<uint32_t*>(ctx->d_tail[which]);
+    q.records2 = q.records + queue_words;
     q.coop_max = (uint32_t)coop;
+    const int64_t resume = ctx->opt_resume_max >= 0 ? ctx->opt_resume_max : 0;     // measured (r2, 10 M-face frame shares): no gain, see DESIGN.md
+    q.resume_max = resume > coop ? (uint32_t)resume : 0u;       // a second pass only pays when it suspends earlier than the cooperative threshold
     return B2RT_SUCCESS;
 }
 
@@ -229,7 +234,7 @@ int trace_device(b2rt_context* ctx, const void* d_rays, uint64_t n, void* d_out,
     int st_pol = apply_l2_policy(ctx, st);
     if (st_pol) return st_pol;
     const uint64_t seq = ctx->next_seq++;
-    unsigned long long* next = ctx->d_next + 4 * (seq % NEXT_RING);
+    unsigned long long* next = ctx->d_next + 8 * (seq % NEXT_RING);
     // Tail queues are shared round robin: launches on the context's own stream are ordered anyway, and up to TAIL_RING
     // launches on different caller streams may overlap (documented in b2rt.h).
     TailQueue tail;
@@ -237,7 +242,7 @@ int trace_device(b2rt_context* ctx, const void* d_rays, uint64_t n, void* d_out,
     if (st_tail) return st_tail;
     CK(launch_trace_wide(ctx->view, d_rays, n, d_out, any, ctx->opt_counters != 0, ctx->stack_bound, grid, next,
                          ctx->d_counters, (uint32_t)ctx->opt_refill_min, (uint32_t)ctx->opt_leaf_bias, st, nullptr, &tail, ctx->grid_tail));
-    ctx->launches += tail.coop_max ? 2 : 1;
+    ctx->launches += tail.coop_max ? (tail.resume_max ? 3 : 2) : 1;
     return B2RT_SUCCESS;
 }
 
@@ -381,7 +386,7 @@ int wavefront_lane(b2rt_context* ctx, const FrameArgs& a, float* d_result, const
         STAGE(B2RT_STAGE_TAIL);
         // the shade stage also clears the counter the NEXT shade stage appends to and the traversal kernels' three counters
         CK(launch_wf_shade(ctx->view, a, map, n, rays[in], hits, n_in, rays[out], n_out, state, d_result, b == a.bounces - 1, n_clear, cnt + 3, s));
-        ctx->launches += tail.coop_max ? 3 : 2;
+        ctx->launches += tail.coop_max ? (tail.resume_max ? 4 : 3) : 2;
         STAGE(B2RT_STAGE_SHADE);
     }
     return B2RT_SUCCESS;
@@ -599,7 +604,7 @@ extern "C" int b2rt_create(int device_id, b2rt_context** out) {
         }
         cudaGetLastError();
     }
-    if ((e = cudaMalloc(&ctx->d_next, NEXT_RING * 4 * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMalloc");
+    if ((e = cudaMalloc(&ctx->d_next, NEXT_RING * 8 * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMalloc");
     if ((e = cudaMalloc(&ctx->d_counters, 192)) != cudaSuccess) return bail(e, "cudaMalloc");
     if ((e = cudaMemset(ctx->d_counters, 0, 192)) != cudaSuccess) return bail(e, "cudaMemset");
     { std::lock_guard<std::mutex> lk(g_live_mutex); g_live.insert(ctx); }
@@ -1114,6 +1119,7 @@ static int set_option_one(b2rt_context* ctx, uint32_t option, int64_t value) {
         case B2RT_OPT_LEAF_BIAS: if (value < 1 || value > 512) return fail(ctx, B2RT_INVALID_VALUE, "leaf bias must be 1..512 (sixteenths)"); ctx->opt_leaf_bias = value; break;
         case B2RT_OPT_COOP_MAX: if (value < -1 || value > COOP_MAX_LIMIT) return fail(ctx, B2RT_INVALID_VALUE, "cooperative tail threshold must be -1 (auto), 0 (off) .. 16"); ctx->opt_coop_max = value; break;
         case B2RT_OPT_L2_PERSIST: ctx->opt_l2_persist = value ? 1 : 0; if (!ctx->scene_dirty && use_device(ctx) == B2RT_SUCCESS) { cudaStreamSynchronize(ctx->stream); scene_l2_setup(ctx); } break;
+        case B2RT_OPT_RESUME_MAX: if (value < -1 || value > COOP_MAX_LIMIT) return fail(ctx, B2RT_INVALID_VALUE, "resume threshold must be -1 (auto), 0 (off) .. 16"); ctx->opt_resume_max = value; break;
         case B2RT_OPT_WAVEFRONT_GRID_SPLIT: ctx->opt_wf_grid_split = value ? 1 : 0; break;
         case B2RT_OPT_STAGE_TIMES: ctx->opt_stage_times = value ? 1 : 0; ctx->stage_used = 0; break;
         case B2RT_OPT_REFILL_MIN: if (value < 1 || value > 32) return fail(ctx, B2RT_INVALID_VALUE, "refill threshold must be 1..32"); ctx->opt_refill_min = value; break;
@@ -1159,7 +1165,7 @@ extern "C" int b2rt_get_counters(b2rt_context* ctx, b2rt_counters* out) {
     out->node_phases = v[6]; out->node_phase_lanes = v[7]; out->leaf_phases = v[8]; out->leaf_phase_lanes = v[9];
     out->refills = v[10]; out->refill_lanes = v[11]; out->max_steps_per_ray = v[12];
     out->stack_overflows = v[13]; out->coop_rays = v[14]; out->coop_steps = v[15];
-    out->coop_max_steps = v[16]; out->coop_max_rounds = v[17];
+    out->coop_max_steps = v[16]; out->coop_max_rounds = v[17]; out->resumed_rays = v[18];
     return B2RT_SUCCESS;
 }
 static int reset_counters_each(b2rt_context* ctx, void*) {

@@ -163,6 +163,20 @@ void tail_handover(const TailQueue& tail, uint64_t index, float t, float u, floa
     rec[7] = 0u;
 }
 
+// A suspended ray comes back: best hit so far and the frontier of the record, see Lane::resume. Not inlined (the refill
+// path runs once per ray) and handed back by value: a Lane whose address escaped would live in local memory for good.
+struct ResumeState { float t, u, v; uint32_t tri, cur, leaf0, leaf1, top; int sp; };
+template <class LaneT>
+__device__ __noinline__ ResumeState resume_fetch(uint32_t* stack, const uint32_t* __restrict__ rec) {
+    static_assert(B2_LEAF_QUEUE == 2, "Lane::resume deals out a two-leaf queue");
+    LaneT T;
+    T.resume(stack, rec + TAIL_HEADER_WORDS, rec[6]);
+    ResumeState o;
+    o.t = __uint_as_float(rec[2]); o.u = __uint_as_float(rec[3]); o.v = __uint_as_float(rec[4]); o.tri = rec[5];
+    o.cur = T.cur; o.leaf0 = T.leaf0; o.leaf1 = T.leaf1; o.top = T.top; o.sp = T.sp;
+    return o;
+}
+
 // ---------------------------------------------------------------------------------------
 // Persistent speculative while-while traversal.
 //
@@ -177,7 +191,10 @@ template <bool ANY, bool COUNT, int CAP>
 __global__ void __launch_bounds__(TRACE_BLOCK, B2_MIN_BLOCKS)
 trace_persistent(SceneView s, const RayIn* __restrict__ rays, uint64_t n, void* __restrict__ out,
                  unsigned long long* __restrict__ next, unsigned long long* __restrict__ counters, uint32_t chunk,
-                 uint32_t refill_min, uint32_t leaf_bias, const unsigned long long* __restrict__ n_dev, TailQueue tail) {
+                 uint32_t refill_min, uint32_t leaf_bias, const unsigned long long* __restrict__ n_dev, TailQueue tail,
+                 const uint32_t* __restrict__ resume) {
+    // resume != null: the "rays" of this launch are the hand-over records of a previous one (n_dev = their count): every
+    // lane picks a suspended ray up where its first owner left it
     const unsigned lane = threadIdx.x & 31u;
     if (n_dev) {
         // wavefront stages: the ray count is the previous stage's queue counter, never seen by the host
@@ -225,12 +242,22 @@ trace_persistent(SceneView s, const RayIn* __restrict__ rays, uint64_t n, void* 
                 const unsigned rank = __popc(idle & ((1u << lane) - 1u));
                 if (((idle >> lane) & 1u) && rank < avail) {
                     my_index = pool_next + rank;
+                    const uint32_t* rec = nullptr;
+                    if (resume) {
+                        rec = resume + my_index * tail.rec_words;
+                        my_index = (uint64_t)rec[0] | ((uint64_t)rec[1] << 32);
+                    }
                     RayX r; float tmax;
                     load_ray(rays, my_index, r, tmax);
                     L.start(r, tmax);
+                    if (resume) {
+                        const ResumeState o = resume_fetch<Lane<ANY, COUNT, CAP>>(stack, rec);
+                        L.h.t = o.t; L.h.u = o.u; L.h.v = o.v; L.h.tri = o.tri;
+                        L.cur = o.cur; L.leaf0 = o.leaf0; L.leaf1 = o.leaf1; L.top = o.top; L.sp = o.sp;
+                    }
                 }
                 const unsigned taken = __popc(idle), used = (taken < avail) ? taken : avail;
-                if (COUNT) { ph_refill++; ph_refill_lanes += used; }
+                if (COUNT) { ph_refill++; ph_refill_lanes += used; if (resume && lane == 0) atomicAdd(&counters[18], (unsigned long long)used); }
                 pool_next += used;
                 pool_left -= used;
             }
@@ -422,8 +449,8 @@ __global__ void __launch_bounds__(256)
 wf_generate_kernel(FrameArgs a, GidMap map, uint32_t n, RayIn* __restrict__ rays, float4* __restrict__ state,
                    unsigned long long* __restrict__ queue_count) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    // counter block of this wavefront: [0..2] rotating queue lengths, [3] the traversal kernel's ray counter, [4] [5] its tail queue's length and read position
-    if (i == 0) { queue_count[0] = n; queue_count[1] = 0; queue_count[2] = 0; queue_count[3] = 0; queue_count[4] = 0; queue_count[5] = 0; }
+    // counter block of this wavefront: [0..2] rotating queue lengths, [3] the traversal kernel's ray counter, [4] [5] its tail queue's length and read position, [6] [7] the second tail queue's
+    if (i == 0) { queue_count[0] = n; for (int k = 1; k < 8; ++k) queue_count[k] = 0; }
     if (i >= n) return;
     uint32_t gid = (uint32_t)map.gid(i);
     uint32_t seed = gid + hash_u32(a.frame_count);                        // kernel_bvh.cl:445
@@ -444,7 +471,7 @@ wf_shade_kernel(SceneView s, FrameArgs a, GidMap map, const RayIn* __restrict__ 
     const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     // reset what the NEXT stages start from: the traversal kernel's ray counter and the queue length the next
     // shade stage appends to (neither is read or written by anything in flight now)
-    if (j == 0) { *clear_a = 0; clear_b[0] = 0; clear_b[1] = 0; clear_b[2] = 0; }
+    if (j == 0) { *clear_a = 0; for (int k = 0; k < 5; ++k) clear_b[k] = 0; }
     if ((j & ~31ull) >= n) return;                      // whole warp beyond the queue
     const unsigned lane = threadIdx.x & 31u;
     bool go_on = false;
@@ -511,17 +538,18 @@ static int pick_cap(uint32_t bound) { return bound <= 32 ? 32 : (bound <= 64 ? 6
 template <bool ANY, bool COUNT>
 static cudaError_t launch_persistent_cap(int cap, int grid, cudaStream_t st, const SceneView& s, const void* rays,
                                          uint64_t n, void* out, unsigned long long* next, unsigned long long* counters,
-                                         uint32_t refill_min, uint32_t leaf_bias, const unsigned long long* n_dev, const TailQueue& tail) {
+                                         uint32_t refill_min, uint32_t leaf_bias, const unsigned long long* n_dev, const TailQueue& tail,
+                                         const uint32_t* resume = nullptr) {
     const RayIn* r = static_cast<const RayIn*>(rays);
     // rays per pool top-up: about 1/8 of a warp's fair share, a multiple of 32 in [32, 512]
     uint64_t warps = (uint64_t)grid * (TRACE_BLOCK / 32);
     uint64_t c = n / (warps * 8u + 1u);
     uint32_t chunk = (uint32_t)(c < 32 ? 32 : (c > 512 ? 512 : (c & ~31ull)));
     switch (cap) {
-        case 32: trace_persistent<ANY, COUNT, 32><<<grid, TRACE_BLOCK, 0, st>>>(s, r, n, out, next, counters, chunk, refill_min, leaf_bias, n_dev, tail); break;
-        case 64: trace_persistent<ANY, COUNT, 64><<<grid, TRACE_BLOCK, 0, st>>>(s, r, n, out, next, counters, chunk, refill_min, leaf_bias, n_dev, tail); break;
-        case 128: trace_persistent<ANY, COUNT, 128><<<grid, TRACE_BLOCK, 0, st>>>(s, r, n, out, next, counters, chunk, refill_min, leaf_bias, n_dev, tail); break;
-        case 256: trace_persistent<ANY, COUNT, 256><<<grid, TRACE_BLOCK, 0, st>>>(s, r, n, out, next, counters, chunk, refill_min, leaf_bias, n_dev, tail); break;
+        case 32: trace_persistent<ANY, COUNT, 32><<<grid, TRACE_BLOCK, 0, st>>>(s, r, n, out, next, counters, chunk, refill_min, leaf_bias, n_dev, tail, resume); break;
+        case 64: trace_persistent<ANY, COUNT, 64><<<grid, TRACE_BLOCK, 0, st>>>(s, r, n, out, next, counters, chunk, refill_min, leaf_bias, n_dev, tail, resume); break;
+        case 128: trace_persistent<ANY, COUNT, 128><<<grid, TRACE_BLOCK, 0, st>>>(s, r, n, out, next, counters, chunk, refill_min, leaf_bias, n_dev, tail, resume); break;
+        case 256: trace_persistent<ANY, COUNT, 256><<<grid, TRACE_BLOCK, 0, st>>>(s, r, n, out, next, counters, chunk, refill_min, leaf_bias, n_dev, tail, resume); break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
@@ -533,30 +561,40 @@ cudaError_t launch_trace_wide(const SceneView& s, const void* d_rays, uint64_t n
                               const unsigned long long* d_n, const TailQueue* tail_in, int tail_grid, cudaEvent_t between) {
     int cap = pick_cap(stack_bound);
     if (!cap) return cudaErrorInvalidValue;
-    TailQueue tail = { nullptr, nullptr, nullptr, 0, 0 };
+    TailQueue tail = { nullptr, nullptr, nullptr, 0, 0, 0, nullptr, nullptr, nullptr };
     if (tail_in && tail_in->coop_max && tail_in->records) tail = *tail_in;
+    const bool two_step = tail.coop_max && tail.resume_max && tail.records2;
     if (!d_n) {     // wavefront stages (d_n given) get their counters reset by the preceding stage's kernel
-        // [0] the ray counter, [1] tail-queue length, [2] tail-queue read position
-        cudaError_t e = cudaMemsetAsync(d_next, 0, 3 * sizeof(unsigned long long), st);
+        // [0] the ray counter, [1] [2] tail-queue length and read position, [3] [4] the second tail queue's
+        cudaError_t e = cudaMemsetAsync(d_next, 0, 5 * sizeof(unsigned long long), st);
         if (e != cudaSuccess) return e;
     }
     if (refill_min < 1 || refill_min > 32) refill_min = 8;
     if (leaf_bias < 1 || leaf_bias > 512) leaf_bias = 16;
-    cudaError_t e;
-    if (any) e = count ? launch_persistent_cap<true, true>(cap, grid_blocks, st, s, d_rays, n, d_out, d_next, d_counters, refill_min, leaf_bias, d_n, tail)
-                       : launch_persistent_cap<true, false>(cap, grid_blocks, st, s, d_rays, n, d_out, d_next, d_counters, refill_min, leaf_bias, d_n, tail);
-    else e = count ? launch_persistent_cap<false, true>(cap, grid_blocks, st, s, d_rays, n, d_out, d_next, d_counters, refill_min, leaf_bias, d_n, tail)
-                   : launch_persistent_cap<false, false>(cap, grid_blocks, st, s, d_rays, n, d_out, d_next, d_counters, refill_min, leaf_bias, d_n, tail);
+    // what each pass hands over to: the first pass suspends into queue 1 (at resume_max live rays when a second pass follows)
+    TailQueue q1 = tail;
+    if (two_step) q1.coop_max = tail.resume_max;
+    TailQueue q2 = tail;
+    if (two_step) { q2.count = tail.count2; q2.next = tail.next2; q2.records = tail.records2; }
+    auto pass = [&](const unsigned long long* n_dev, unsigned long long* next, const TailQueue& q, const uint32_t* resume) -> cudaError_t {
+        if (any) return count ? launch_persistent_cap<true, true>(cap, grid_blocks, st, s, d_rays, n, d_out, next, d_counters, refill_min, leaf_bias, n_dev, q, resume)
+                              : launch_persistent_cap<true, false>(cap, grid_blocks, st, s, d_rays, n, d_out, next, d_counters, refill_min, leaf_bias, n_dev, q, resume);
+        return count ? launch_persistent_cap<false, true>(cap, grid_blocks, st, s, d_rays, n, d_out, next, d_counters, refill_min, leaf_bias, n_dev, q, resume)
+                     : launch_persistent_cap<false, false>(cap, grid_blocks, st, s, d_rays, n, d_out, next, d_counters, refill_min, leaf_bias, n_dev, q, resume);
+    };
+    cudaError_t e = pass(d_n, d_next, q1, nullptr);
+    // second pass: the suspended rays are its ray stream (count and read position = queue 1's counters)
+    if (e == cudaSuccess && two_step) e = pass(tail.count, tail.next, q2, tail.records);
     if (e == cudaSuccess && between) e = cudaEventRecord(between, st);
     if (e != cudaSuccess || !tail.coop_max) return e;
     // the tail kernel: frontier capacity per warp and the size up to which four nodes are expanded per round
     const uint32_t fcap = tail_frontier_words(stack_bound), wide_limit = fcap - (stack_bound + 8u) - 32u;
     const size_t smem = (size_t)(TAIL_BLOCK / 32) * fcap * sizeof(uint32_t);
     const RayIn* r = static_cast<const RayIn*>(d_rays);
-    if (any) { if (count) trace_tail_kernel<true, true><<<tail_grid, TAIL_BLOCK, smem, st>>>(s, r, d_out, tail, d_counters, fcap, wide_limit);
-               else trace_tail_kernel<true, false><<<tail_grid, TAIL_BLOCK, smem, st>>>(s, r, d_out, tail, d_counters, fcap, wide_limit); }
-    else { if (count) trace_tail_kernel<false, true><<<tail_grid, TAIL_BLOCK, smem, st>>>(s, r, d_out, tail, d_counters, fcap, wide_limit);
-           else trace_tail_kernel<false, false><<<tail_grid, TAIL_BLOCK, smem, st>>>(s, r, d_out, tail, d_counters, fcap, wide_limit); }
+    if (any) { if (count) trace_tail_kernel<true, true><<<tail_grid, TAIL_BLOCK, smem, st>>>(s, r, d_out, q2, d_counters, fcap, wide_limit);
+               else trace_tail_kernel<true, false><<<tail_grid, TAIL_BLOCK, smem, st>>>(s, r, d_out, q2, d_counters, fcap, wide_limit); }
+    else { if (count) trace_tail_kernel<false, true><<<tail_grid, TAIL_BLOCK, smem, st>>>(s, r, d_out, q2, d_counters, fcap, wide_limit);
+           else trace_tail_kernel<false, false><<<tail_grid, TAIL_BLOCK, smem, st>>>(s, r, d_out, q2, d_counters, fcap, wide_limit); }
     return cudaGetLastError();
 }
 

@@ -13,13 +13,20 @@ struct TailQueue {
     uint32_t* records;             // capacity: coop_max records per warp of the persistent grid
     uint32_t rec_words;            // tail_record_words(stack_bound)
     uint32_t coop_max;             // a dry warp with at most this many live rays hands them over
+    // Two-step tail (resume_max > 0): the persistent launch suspends at resume_max live rays per dry warp into THIS queue,
+    // a second persistent launch re-packs the suspended rays 32 to a warp and walks on (full SIMT width again), hands what
+    // is left at coop_max live rays per warp to the second queue below, and the cooperative kernel finishes those.
+    uint32_t resume_max;
+    unsigned long long* count2;
+    unsigned long long* next2;
+    uint32_t* records2;
 };
 uint32_t tail_frontier_words(uint32_t stack_bound);   // shared-memory words per warp of the tail kernel
 uint32_t tail_record_words(uint32_t stack_bound);
 
 // Persistent while-while traversal of the compressed wide BVH over a device-resident ray
-// stream. d_out is b2rt_hit[n] (closest) or uint32_t[n] (any). d_next points at three 64-bit scratch
-// counters (ray counter, tail-queue length, tail-queue read position; reset by the wrapper unless d_n is given),
+// stream. d_out is b2rt_hit[n] (closest) or uint32_t[n] (any). d_next points at five 64-bit scratch
+// counters (ray counter, tail-queue length and read position, second tail queue's likewise; reset by the wrapper unless d_n is given),
 // d_counters twenty-four 64-bit accumulators (used when count; [13] = stack/frontier overflows, always). With a tail
 // queue the cooperative tail kernel is launched right behind the persistent one (tail_grid blocks).
 cudaError_t launch_trace_wide(const SceneView& s, const void* d_rays, uint64_t n, void* d_out, bool any, bool count,

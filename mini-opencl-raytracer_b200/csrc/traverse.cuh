@@ -449,6 +449,21 @@ struct Lane {
         }
 #endif
     }
+    // A suspended ray comes back (two-step tail, kernels.cu): F[0..n) is its frontier as coop_dump laid it out (front =
+    // F[n-1]); the entries are dealt out again the way settle() would have left them -- queued leaves, current node,
+    // register-held top, the rest on the short stack (never more entries there than the first owner had). The caller has
+    // called start() and restored h.
+    B2_HD void resume(uint32_t* stack, const uint32_t* F, uint32_t n) {
+        leaf0 = leaf1 = REF_EMPTY;
+        cur = n ? F[--n] : REF_EMPTY;
+        while (cur != REF_EMPTY && (cur & REF_LEAF_BIT) && leaf1 == REF_EMPTY) {
+            if (leaf0 == REF_EMPTY) leaf0 = cur; else leaf1 = cur;
+            cur = n ? F[--n] : REF_EMPTY;
+        }
+        top = n ? F[--n] : REF_EMPTY;
+        sp = (int)n;
+        for (uint32_t i = 0; i < n; ++i) stack[i] = F[i];
+    }
     // `one` must be 0x3F800000, passed as run-time data: held in one register it lets the constant
     // byte selectors of B2_PLANE_V be instruction immediates (ptxas otherwise keeps four selector registers).
     B2_HD void node_step(const U4* wide, uint32_t* stack, uint32_t one) {

@@ -27,8 +27,9 @@ with prod.Context(0) as ctx:
     ctx.set_option(cap.OPT_RENDER_MODE, 0)
     ctx.set_option(cap.OPT_WAVEFRONT_LANES, 1)
     plan = prod.sharding.BandPlan(W, H, world, band_rows=8)
-    for coop in [int(x) for x in os.environ.get("COOPS", "8,0").split(",")]:
+    for coop, resume in [tuple(int(y) for y in x.split(":")) for x in os.environ.get("COOPS", "8:0,8:16,4:16,4:12,2:16").split(",")]:
         ctx.set_option(cap.OPT_COOP_MAX, coop)
+        ctx.set_option(cap.OPT_RESUME_MAX, resume)
         for r in ranks:
             ctx.set_option(cap.OPT_STAGE_TIMES, 1)
             for f in (1, 2, 3):
@@ -40,5 +41,5 @@ with prod.Context(0) as ctx:
             ctx.set_frame(3, 4, **cam); plan.render(ctx, r); ctx.finish()
             c = ctx.counters()
             ctx.set_option(cap.OPT_COUNTERS, 0)
-            print("coop %d rank %d stages (ms): %s | sum %.3f" % (coop, r, " ".join("%s %.3f" % (k[:2], v) for k, v in st), sum(v for _, v in st)))
-            print("      ", {k: c[k] for k in c if k in ("rays", "wide_nodes", "leaf_blocks", "max_steps_per_ray", "coop_rays", "coop_steps", "coop_max_rounds", "coop_max_steps")}, flush=True)
+            print("coop %d resume %d rank %d stages (ms): %s | sum %.3f" % (coop, resume, r, " ".join("%s %.3f" % (k[:2], v) for k, v in st), sum(v for _, v in st)))
+            print("      ", {k: c[k] for k in c if k in ("rays", "wide_nodes", "leaf_blocks", "max_steps_per_ray", "coop_rays", "coop_steps", "coop_max_rounds", "coop_max_steps", "resumed_rays")}, flush=True)

@@ -73,7 +73,7 @@ namespace b2rt_emu { void run_warp(const std::function<void(uint32_t)>& body); }
 
 template <bool ANY>
 static void coop_one(const U4* wide, const U4* leaf, const EmuRay& in, uint32_t handoff, uint32_t wide_limit, uint32_t fcap,
-                     uint32_t seed, HitX& out, EmuStats* st) {
+                     uint32_t seed, HitX& out, EmuStats* st, uint32_t resume) {
     const RayX r = make_ray(in.ox, in.oy, in.oz, in.dx, in.dy, in.dz);
     Lane<ANY, true, 256> L;
     uint32_t stack[256];
@@ -91,7 +91,28 @@ static void coop_one(const U4* wide, const U4* leaf, const EmuRay& in, uint32_t 
     }
     if (L.done()) { out = L.h; return; }
     std::vector<uint32_t> F(fcap + 64);
-    const uint32_t n = coop_dump(L, stack, F.data());
+    uint32_t n = coop_dump(L, stack, F.data());
+    if (resume) {
+        // two-step tail: another lane picks the suspended ray up from the record (Lane::resume), walks on alone for a
+        // random number of steps and suspends it again for the cooperative finish
+        Lane<ANY, true, 256> L2;
+        uint32_t stack2[256];
+        L2.tc = L.tc;
+        L2.start(r, in.tmax);
+        L2.h = L.h;
+        L2.resume(stack2, F.data(), n);
+        steps = (seed >> 8) % resume;
+        while (steps-- && !L2.done()) {
+            const bool node = L2.wants_node(), lf = L2.wants_leaf();
+            bool do_leaf = lf;
+            if (node && lf) { sched = sched * 1664525u + 1013904223u; do_leaf = (sched >> 16) & 1u; }
+            if (do_leaf) { if (L2.leaf_step(leaf, stack2)) break; }
+            else L2.node_step(wide, stack2, 0x3F800000u);
+        }
+        if (L2.done()) { out = L2.h; return; }
+        n = coop_dump(L2, stack2, F.data());
+        L.h = L2.h;
+    }
     HitX res[32];
     bool ovf[32];
     b2rt_emu::run_warp([&](uint32_t lane) {
@@ -110,7 +131,7 @@ static void coop_one(const U4* wide, const U4* leaf, const EmuRay& in, uint32_t 
 }
 
 extern "C" void emu_trace_coop(const EmuRay* rays, uint64_t n, EmuHit* hits, uint32_t* occluded, int any, EmuStats* st,
-                               uint32_t handoff, uint32_t wide_limit, uint32_t fcap) {
+                               uint32_t handoff, uint32_t wide_limit, uint32_t fcap, uint32_t resume) {
     const U4* wide = reinterpret_cast<const U4*>(g_bvh.nodes.data());
     const U4* leaf = g_bvh.leaf.data();
     unsigned nt = std::thread::hardware_concurrency();
@@ -124,8 +145,8 @@ extern "C" void emu_trace_coop(const EmuRay* rays, uint64_t n, EmuHit* hits, uin
             for (uint64_t i = n * w / nt; i < n * (w + 1) / nt; ++i) {
                 HitX h;
                 const uint32_t seed = (uint32_t)i * 2654435761u + 12345u;
-                if (any) coop_one<true>(wide, leaf, rays[i], handoff, wide_limit, fcap, seed, h, &part[w]);
-                else coop_one<false>(wide, leaf, rays[i], handoff, wide_limit, fcap, seed, h, &part[w]);
+                if (any) coop_one<true>(wide, leaf, rays[i], handoff, wide_limit, fcap, seed, h, &part[w], resume);
+                else coop_one<false>(wide, leaf, rays[i], handoff, wide_limit, fcap, seed, h, &part[w], resume);
                 if (any) occluded[i] = h.tri != 0xFFFFFFFFu;
                 else { hits[i].t = h.t; hits[i].u = h.u; hits[i].v = h.v; hits[i].tri = h.tri; }
             }

@@ -272,21 +272,22 @@ def emu_build(tris, nodes):
     return st
 
 
-def emu_trace_coop(rays, any_hit=False, stats=None, handoff=0, wide_limit=192, fcap=256):
+def emu_trace_coop(rays, any_hit=False, stats=None, handoff=0, wide_limit=192, fcap=256, resume=0):
     """The warp-cooperative tail mode (csrc/coop.cuh) on 32 emulated lanes (tests/emu/warp_emu.cpp). handoff = 0: the
     whole ray runs cooperatively from the root; > 0: a pseudo-random number (< handoff) of solo steps first, then the
-    solo lane's state is handed over like trace_persistent does when its ray pool runs dry."""
+    solo lane's state is handed over like trace_persistent does when its ray pool runs dry. resume > 0: the two-step
+    tail -- another lane restores the suspended state (Lane::resume), walks on alone (< resume steps) and suspends again."""
     rays = np.ascontiguousarray(rays)
     st = stats if stats is not None else EmuStats()
     L = emu()
     L.emu_trace_coop.restype = None
-    L.emu_trace_coop.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]
+    L.emu_trace_coop.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
     if any_hit:
         occ = np.empty(rays.shape[0], dtype=np.uint32)
-        L.emu_trace_coop(_p(rays), rays.shape[0], None, _p(occ), 1, C.addressof(st), handoff, wide_limit, fcap)
+        L.emu_trace_coop(_p(rays), rays.shape[0], None, _p(occ), 1, C.addressof(st), handoff, wide_limit, fcap, resume)
         return occ
     hits = np.empty(rays.shape[0], dtype=HIT)
-    L.emu_trace_coop(_p(rays), rays.shape[0], _p(hits), None, 0, C.addressof(st), handoff, wide_limit, fcap)
+    L.emu_trace_coop(_p(rays), rays.shape[0], _p(hits), None, 0, C.addressof(st), handoff, wide_limit, fcap, resume)
     return hits
 
 

@@ -150,13 +150,13 @@ def test_random_scenes_fuzz(tmp_scene_dir):
 def _coop_same(rays, want, occluded=None):
     """Whole rays cooperatively from the root, hand-overs after a few / many solo steps, one node per round (the
     depth-first fallback) and four: all must give the oracle's hit, bit for bit."""
-    for handoff, wide_limit in ((0, 192), (6, 192), (60, 192), (0, 0), (9, 0)):
+    for handoff, wide_limit, resume in ((0, 192, 0), (6, 192, 0), (60, 192, 0), (0, 0, 0), (9, 0, 0), (5, 192, 7), (30, 192, 40), (1, 0, 3)):
         st = ol.EmuStats()
-        _same(ol.emu_trace_coop(rays, stats=st, handoff=handoff, wide_limit=wide_limit), want)
+        _same(ol.emu_trace_coop(rays, stats=st, handoff=handoff, wide_limit=wide_limit, resume=resume), want)   # resume: two-step tail (Lane::resume)
         assert st.overflow == 0
     if occluded is not None:
-        for handoff in (0, 7):
-            assert np.array_equal(ol.emu_trace_coop(rays, any_hit=True, handoff=handoff) != 0, occluded != 0)
+        for handoff, resume in ((0, 0), (7, 0), (7, 9)):
+            assert np.array_equal(ol.emu_trace_coop(rays, any_hit=True, handoff=handoff, resume=resume) != 0, occluded != 0)
 
 
 def test_coop_cornell(cornell_ref):
@@ -251,6 +251,7 @@ def test_rays_with_zero_direction_components_are_culled_like_any_other_ray(bumpy
     _same(ol.emu_trace(rays, schedule=9), want)
     _same(ol.emu_trace_coop(rays), want)
     _same(ol.emu_trace_coop(rays, handoff=12), want)
+    _same(ol.emu_trace_coop(rays, handoff=12, resume=9), want)
     assert np.array_equal(ol.emu_trace(rays, any_hit=True) != 0, ol.oracle_any(tris, nodes, rays) != 0)
     tilted = scenes.pack_rays(o, d + 1e-4 * rng.normal(size=(n, 3)), 100000.0)
     st2 = ol.EmuStats()

@@ -70,6 +70,47 @@ def test_cooperative_tail_is_result_neutral(product, bumpy_ref, tmp_scene_dir):
             _check_hits(np.concatenate([ctx.trace_closest(tr[i:i + 16]) for i in range(0, 1600, 16)]), tw[:1600])
 
 
+def test_two_step_tail_is_result_neutral(product, bumpy_ref, cornell_ref):
+    """B2RT_OPT_RESUME_MAX: dry warps suspend their last rays early, a second persistent launch re-packs the suspended rays
+    and walks on (Lane::resume), the cooperative kernel finishes what that pass leaves. Hits and frames must not depend on
+    either threshold, and the counting build must show that rays really were resumed."""
+    cap = product.capi
+    tris, nodes, mats = bumpy_ref
+    rays = scenes.shell_rays(120000, 10.0, seed=171)
+    want = ol.oracle_closest(tris, nodes, rays)
+    b = scenes.bounce_rays(rays, want, scenes.tri_normals(tris, want), seed=172)
+    wb = ol.oracle_closest(tris, nodes, b)
+    occ_want = ol.oracle_any(tris, nodes, b)
+    W, H = 301, 203
+    cam = dict(pos=(0.0, -14.0, 2.0), front=(0.0, 1.0, -0.1), up=(0.0, 0.0, 1.0))
+    frames = []
+    with product.Context(0) as ctx:
+        ctx.upload_scene(tris, nodes, mats)
+        ctx.resize(W, H)
+        ctx.set_option(cap.OPT_RENDER_MODE, 0)
+        for coop, resume in ((8, 0), (8, 16), (1, 16), (4, 9), (2, 3)):
+            ctx.set_option(cap.OPT_COOP_MAX, coop)
+            ctx.set_option(cap.OPT_RESUME_MAX, resume)
+            got, c = _counted(product, ctx, lambda: ctx.trace_closest(rays))
+            _check_hits(got, want)
+            assert c["rays"] == rays.shape[0] and c["stack_overflows"] == 0
+            assert (c["resumed_rays"] > 0) == (resume > coop), (coop, resume, c)
+            _check_hits(ctx.trace_closest(b), wb)
+            assert np.array_equal(ctx.trace_any(b) != 0, occ_want != 0)
+            for n in (1, 31, 33, 1000):
+                _check_hits(ctx.trace_closest(b[:n]), wb[:n])
+            got = np.concatenate([ctx.trace_closest(b[i:i + 16]) for i in range(0, 1600, 16)])     # every ray is suspended at once
+            _check_hits(got, wb[:1600])
+            for fc in (0, 1, 2):                                   # frameCount 0 overwrites the image, 1 and 2 accumulate
+                ctx.set_frame(fc, 4, **cam)
+                ctx.execute(W * H)
+            frames.append(ctx.read_pixels().copy())
+        with pytest.raises(product.B2RTError):
+            ctx.set_option(cap.OPT_RESUME_MAX, 17)
+    for f in frames[1:]:
+        assert np.array_equal(f.view(np.uint32), frames[0].view(np.uint32))
+
+
 def test_cuda_path_against_the_verbatim_reference_build(product, bumpy_ref):
     """no port in between -- CUDA hits and a CUDA frame compared directly with the reference's own
     Intersect() / KernelEntry compiled from /root/reference (oracle/_ref)."""
