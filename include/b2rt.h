@@ -94,7 +94,8 @@ typedef struct {
     uint64_t leaf_gate_pass;    /* ... of which passed the exact fp32 leaf box             */
     uint64_t tri_tests;         /* Moller-Trumbore evaluations                             */
     uint64_t bytes_fetched;     /* algorithmic (requested) bytes: 84 B per wide-node visit (5 x 16 B + one 4-byte order word of
-                                   the 112-byte record) + 32 B header + 48 B per record of every leaf block fetched */
+                                   the 112-byte record) + 48 B per record of every leaf block fetched (+ 32 B for the few blocks
+                                   that carry an explicit box) */
     /* warp scheduling of the persistent kernels: phases run and lanes that took part in them */
     uint64_t node_phases, node_phase_lanes, leaf_phases, leaf_phase_lanes, refills, refill_lanes;
     uint64_t max_steps_per_ray; /* node + leaf steps of the most expensive ray (tail detector; solo steps only) */

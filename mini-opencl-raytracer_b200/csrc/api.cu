@@ -111,7 +111,7 @@ int ensure_scene(b2rt_context* ctx) {
     free_scene(ctx);
     size_t wb = w.nodes.size() * sizeof(WideNode), lb = w.leaf.size() * sizeof(U4), sb = w.shade.size() * sizeof(ShadeTri);
     CK(cudaMalloc(&ctx->d_wide, std::max<size_t>(wb, sizeof(WideNode))));
-    CK(cudaMalloc(&ctx->d_leaf, std::max<size_t>(lb, 16) + 64));   // +64: visit_leaf prefetches one record past the header
+    CK(cudaMalloc(&ctx->d_leaf, std::max<size_t>(lb, 16) + 64));   // +64: slack behind the last block
     CK(cudaMalloc(&ctx->d_shade, std::max<size_t>(sb, 48)));
     CK(cudaMemsetAsync(static_cast<char*>(ctx->d_leaf) + std::max<size_t>(lb, 16), 0, 64, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_wide, w.nodes.data(), wb, cudaMemcpyHostToDevice, ctx->stream));

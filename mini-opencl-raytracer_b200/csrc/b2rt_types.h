@@ -61,17 +61,24 @@ struct alignas(16) WideNode {
 static_assert(sizeof(WideNode) == 112, "WideNode must be 112 B (seven 16-byte words)");
 enum { WIDE_NODE_WORDS = 7, META_INTERIOR = 0x80, META_MAX_LEAF_OFFSET = 0x7f };
 
-// Leaf block header, two 16-byte words followed by n_records * 3 words.
-//   word0 = { bmin.x, bmin.y, bmin.z, first_tri }
-//   word1 = { bmax.x, bmax.y, bmax.z, n_records }
-//   record = { v1.xyz, flags } { v2.xyz, 0 } { v3.xyz, 0 }
+// Leaf block: n_records * 3 sixteen-byte words, optionally followed by two words holding the leaf's box.
+//   record = { v1.xyz, w0 } { v2.xyz, w1 } { v3.xyz, 0 }
+//   w0 = flags (bits 0-1); in the block's FIRST record additionally n_records << 8 and LEAF_HAS_BOX (bit 31)
+//   w1 = (first record only) index of the block's first reference triangle
+//   [ { bmin.xyz, 0 } { bmax.xyz, 0 } ]   only when LEAF_HAS_BOX is set
 // flags: 0 = one reference triangle (v1,v2,v3);
 //        1 = two reference triangles: (v1,v2,v3) then its rotation (v2,v3,v1);
 //        2 = two reference triangles: (v1,v2,v3) then its rotation (v3,v1,v2).
 // The reference's loader emits every OBJ triangle twice, the second copy
 // rotated (CLOBJloader.cpp:102-126), and both copies always share a leaf, so a
 // record usually stands for two consecutive reference triangles.
-enum { LEAF_HEADER_WORDS = 2, LEAF_RECORD_WORDS = 3 };
+// The reference's builder gives a leaf the union of its triangles' bounds (CLBVHnode.cpp:18-23), i.e. the exact
+// component-wise min / max of the vertex positions. A one-record block whose node box equals that min / max (checked when
+// the block is written) therefore carries no box at all: the kernels recompute it from the three vertices they load
+// anyway (min / max are exact), 48 bytes per leaf instead of 80. Any other block (several records, or a caller-supplied
+// tree whose leaf box is something else) keeps its box behind the records and is fetched with one more round trip.
+enum { LEAF_RECORD_WORDS = 3, LEAF_BOX_WORDS = 2 };
+enum : uint32_t { LEAF_HAS_BOX = 0x80000000u, LEAF_NREC_SHIFT = 8, LEAF_NREC_MASK = 0xffffu, REC_FLAG_MASK = 3u };
 enum : uint32_t { REC_SINGLE = 0, REC_ROT_LEFT = 1, REC_ROT_RIGHT = 2 };
 
 struct ShadeTri { float n1[3]; uint32_t mtl; float n2[3]; uint32_t pad0; float n3[3]; uint32_t pad1; }; // 48 B

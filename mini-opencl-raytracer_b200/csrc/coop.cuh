@@ -8,7 +8,7 @@
 //  * the ray's pending work -- its queued leaves, current node and short stack -- is laid out as one
 //    FRONTIER in shared memory, in the reference's depth-first order (kernel_bvh.cl:182-216), front at the
 //    highest index;
-//  * leaves at the front are resolved in parallel: one lane per (leaf record, loader copy) evaluates the
+//  * leaves at the front are resolved in parallel: one lane per (one-record leaf block, loader copy) evaluates the
 //    reference's exact Moller-Trumbore sequence; results are committed leaf by leaf in frontier order,
 //    every leaf gated by its exact fp32 box against the `best` of that moment -- the reference's own
 //    sequence of decisions, so ties and negative t resolve as in the solo walk (traverse.cuh);
@@ -100,7 +100,7 @@ B2_HD uint32_t coop_dump(const LaneT& L, const uint32_t* stack, uint32_t* F) {
 // (depth-first: the frontier then grows by at most the solo walk's stack bound). On return h is the final hit on
 // every lane; `overflow` is set if F would have overflowed (the ray is then abandoned: the caller reports it).
 //
-// One round = one memory round trip: the (up to 8) leaves at the front of the frontier and the first Q interior
+// One round = one memory round trip: the (up to 16) leaves at the front of the frontier and the first Q interior
 // entries of the 32-entry window are fetched together; the leaves are resolved and committed in order, then the nodes
 // are tested against the `best` just updated, and the window is rewritten in place (leaves consumed, nodes replaced by
 // their passing children). Children just found are prefetched towards L2 for the next round.
@@ -116,18 +116,14 @@ B2_HD void coop_trace(const U4* wide, const U4* leaf, uint32_t* F, uint32_t n, u
         const uint32_t mnode = w_ballot(is_node);
         const uint32_t lead = mnode ? ctz32(mnode) : win;
 
-        // ---- fetch: leaves at the front, four lanes each = (record 0 | record 1) x (the loader's two copies) -----------
-        const uint32_t lg = lane >> 2, rec = (lane >> 1) & 1u, copy = lane & 1u;
-        uint32_t nl = lead < 8u ? lead : 8u;
+        // ---- fetch: leaves at the front, two lanes each = the loader's two copies of a one-record block -------------------
+        const uint32_t lg = lane >> 1, copy = lane & 1u;
+        uint32_t nl = lead < 16u ? lead : 16u;
         const uint32_t lref = w_shfl(e, lg);
-        U4 g0 = { 0, 0, 0, 0 }, g1 = g0, va = g0, vb = g0, vc = g0;
+        U4 va = { 0, 0, 0, 0 }, vb = va, vc = va;
         if (lg < nl) {
             const U4* p = leaf + (lref & ~REF_LEAF_BIT);
-            g0 = ld128(p); g1 = ld128(p + 1);
-            // record 1 is fetched before the record count is known: a one-record block is followed by another block or
-            // by the buffer's 64 bytes of padding, and the lanes are switched off below when the record does not exist
-            const U4* q = p + LEAF_HEADER_WORDS + LEAF_RECORD_WORDS * rec;
-            va = ld128(q); vb = ld128(q + 1); vc = ld128(q + 2);
+            va = ld128(p); vb = ld128(p + 1); vc = ld128(p + 2);
         }
         // ---- fetch: the first Q interior entries of the window, eight lanes each = one lane per child ---------------------
         uint32_t Q = n <= wide_limit ? (uint32_t)B2_COOP_NODES : 1u;
@@ -153,26 +149,28 @@ B2_HD void coop_trace(const U4* wide, const U4* leaf, uint32_t* F, uint32_t n, u
             order = ld32(reinterpret_cast<const uint32_t*>(p + 5) + (r.sign & 7u));
         }
 
-        // ---- leaves: blocks of more than two records leave the fast path -------------------------------------------------
+        // ---- leaves: blocks with several records or an explicit box leave the fast path ----------------------------------
         if (nl) {
-            const uint32_t big = w_ballot(lg < nl && g1.w > 2u);           // all four lanes of a group agree
+            const uint32_t big = w_ballot(lg < nl && ((va.w & LEAF_HAS_BOX) || ((va.w >> LEAF_NREC_SHIFT) & LEAF_NREC_MASK) != 1u));   // both lanes of a pair agree
             if (big & 1u) {
-                // the first leaf is a big block: every lane walks it like the solo path (same result on every lane)
+                // the first leaf is such a block: every lane walks it like the solo path (same result on every lane)
                 const bool got = visit_leaf<COUNT>(leaf, w_shfl(e, 0) & ~REF_LEAF_BIT, r, h, &tc);
                 n -= 1u;
                 if ((ANY && got) || h.t < 0.0f) { n = 0; break; }
                 continue;
             }
-            if (big) nl = ctz32(big) >> 2;                                   // stop before the first big block
+            if (big) nl = ctz32(big) >> 1;                                   // stop before the first such block
         }
         bool finished = false;
         if (nl) {
-            const bool active = lg < nl && rec < g1.w;
-            const uint32_t flags = va.w;
-            const uint32_t dup0 = w_ballot(active && rec == 0u && copy == 0u && flags != 0u);    // bit 4*lg: record 0 of leaf lg is doubled
-            // triangle id: first id of the block + one per earlier record + one more per earlier doubled record
-            const uint32_t id = g0.w + rec + (rec ? ((dup0 >> (4u * lg)) & 1u) : 0u) + copy;
+            const bool active = lg < nl;
+            const uint32_t flags = va.w & REC_FLAG_MASK;
+            const uint32_t id = vb.w + copy;
             const bool valid = active && (copy == 0u || flags != 0u);
+            // the block's exact box: min / max of the record's vertices (b2rt_types.h)
+            const float lox = min3_nn(bits2f(va.x), bits2f(vb.x), bits2f(vc.x)), hix = max3_nn(bits2f(va.x), bits2f(vb.x), bits2f(vc.x));
+            const float loy = min3_nn(bits2f(va.y), bits2f(vb.y), bits2f(vc.y)), hiy = max3_nn(bits2f(va.y), bits2f(vb.y), bits2f(vc.y));
+            const float loz = min3_nn(bits2f(va.z), bits2f(vb.z), bits2f(vc.z)), hiz = max3_nn(bits2f(va.z), bits2f(vb.z), bits2f(vc.z));
             float t = 0.0f, u = 0.0f, v = 0.0f;
             bool ok = false;
             if (valid) {
@@ -183,21 +181,21 @@ B2_HD void coop_trace(const U4* wide, const U4* leaf, uint32_t* F, uint32_t n, u
                                     bits2f(p3.x), bits2f(p3.y), bits2f(p3.z), t, u, v);
             }
             if (COUNT) {
-                const bool g = lg < nl && box_gate_exact(r, bits2f(g0.x), bits2f(g0.y), bits2f(g0.z), bits2f(g1.x), bits2f(g1.y), bits2f(g1.z), h.t);
+                const bool g = active && box_gate_exact(r, lox, loy, loz, hix, hiy, hiz, h.t);
                 tc.leaf_blocks += nl;
-                tc.leaf_pass += popc32(w_ballot(g) & 0x11111111u);
+                tc.leaf_pass += popc32(w_ballot(g) & 0x55555555u);
                 tc.tri_tests += popc32(w_ballot(valid));                     // evaluations actually made (some behind a gate that fails later)
-                tc.words += LEAF_HEADER_WORDS * nl + LEAF_RECORD_WORDS * popc32(w_ballot(active && copy == 0u));
+                tc.words += LEAF_RECORD_WORDS * nl;
             }
             // Commit in frontier order. Only a leaf holding a candidate under the current `best` can change it, and
             // `best` only shrinks: jump from one such leaf to the next, re-evaluating gates and candidates in between.
             uint32_t lo = 0;
             for (;;) {
-                const bool gate = lg < nl && box_gate_exact(r, bits2f(g0.x), bits2f(g0.y), bits2f(g0.z), bits2f(g1.x), bits2f(g1.y), bits2f(g1.z), h.t);
+                const bool gate = active && box_gate_exact(r, lox, loy, loz, hix, hiy, hiz, h.t);
                 const bool cand = valid && ok && t < h.t && gate && lg >= lo;
                 const uint32_t cm = w_ballot(cand);
                 if (!cm) break;
-                const uint32_t first = ctz32(cm) >> 2;                        // the first leaf (frontier order) with a candidate
+                const uint32_t first = ctz32(cm) >> 1;                        // the first leaf (frontier order) with a candidate
                 const bool mine = cand && lg == first;
                 const uint32_t key = mine ? order_key(t) : 0xffffffffu;
                 const uint32_t kmin = w_redmin(key);

@@ -22,7 +22,7 @@ using namespace b2rt_detail;
 
 namespace {
 
-enum : unsigned { REFIT_ERR_NONFINITE = 1u, REFIT_ERR_DUPLICATE = 2u, REFIT_ERR_RANGE = 4u };
+enum : unsigned { REFIT_ERR_NONFINITE = 1u, REFIT_ERR_DUPLICATE = 2u, REFIT_ERR_RANGE = 4u, REFIT_ERR_LEAF_BOX = 8u };
 
 __global__ void refit_leaf_kernel(RefNode* __restrict__ nodes, uint32_t n_nodes, const RefTriangle* __restrict__ tris, int* __restrict__ parent,
                                   unsigned* __restrict__ arrivals) {
@@ -122,13 +122,12 @@ __global__ void refit_block_kernel(U4* __restrict__ leaf, const uint32_t* __rest
     if (i >= n_blocks) return;
     const RefNode& nd = nodes[leaf_dir[2 * (size_t)i]];
     U4* p = leaf + leaf_dir[2 * (size_t)i + 1];
-    const uint32_t nrec = p[1].w;
-    uint32_t id = p[0].w;
-    p[0] = U4{ __float_as_uint(nd.bmin.x), __float_as_uint(nd.bmin.y), __float_as_uint(nd.bmin.z), id };
-    p[1] = U4{ __float_as_uint(nd.bmax.x), __float_as_uint(nd.bmax.y), __float_as_uint(nd.bmax.z), nrec };
+    const uint32_t head = p[0].w, nrec = (head >> LEAF_NREC_SHIFT) & LEAF_NREC_MASK;
+    uint32_t id = p[1].w;
+    const uint32_t first = id;
     for (uint32_t k = 0; k < nrec; ++k) {
-        U4* q = p + LEAF_HEADER_WORDS + LEAF_RECORD_WORDS * k;
-        const uint32_t flags = q[0].w;
+        U4* q = p + LEAF_RECORD_WORDS * k;
+        const uint32_t w0 = q[0].w, flags = w0 & REC_FLAG_MASK;
         const RefTriangle& t = tris[id];
         if (flags) {
             // the record stands for triangle id AND its rotated copy id + 1: the new data must keep them bit-identical
@@ -137,10 +136,25 @@ __global__ void refit_block_kernel(U4* __restrict__ leaf, const uint32_t* __rest
                                                   : (same_bits(s.v1.position, t.v3.position) && same_bits(s.v2.position, t.v1.position) && same_bits(s.v3.position, t.v2.position));
             if (!ok) atomicOr(error, REFIT_ERR_DUPLICATE);
         }
-        q[0] = U4{ __float_as_uint(t.v1.position.x), __float_as_uint(t.v1.position.y), __float_as_uint(t.v1.position.z), flags };
-        q[1] = U4{ __float_as_uint(t.v2.position.x), __float_as_uint(t.v2.position.y), __float_as_uint(t.v2.position.z), 0u };
+        q[0] = U4{ __float_as_uint(t.v1.position.x), __float_as_uint(t.v1.position.y), __float_as_uint(t.v1.position.z), w0 };
+        q[1] = U4{ __float_as_uint(t.v2.position.x), __float_as_uint(t.v2.position.y), __float_as_uint(t.v2.position.z), k == 0 ? first : 0u };
         q[2] = U4{ __float_as_uint(t.v3.position.x), __float_as_uint(t.v3.position.y), __float_as_uint(t.v3.position.z), 0u };
         id += flags ? 2u : 1u;
+    }
+    // A block without a stored box relies on box == min / max of its vertices; refit_leaf_kernel has just recomputed the
+    // node's box as exactly that (a NaN vertex would break the equality: reported, the scene must be uploaded afresh).
+    if (head & LEAF_HAS_BOX) {
+        U4* q = p + LEAF_RECORD_WORDS * nrec;
+        q[0] = U4{ __float_as_uint(nd.bmin.x), __float_as_uint(nd.bmin.y), __float_as_uint(nd.bmin.z), 0u };
+        q[1] = U4{ __float_as_uint(nd.bmax.x), __float_as_uint(nd.bmax.y), __float_as_uint(nd.bmax.z), 0u };
+    } else {
+        const RefTriangle& t = tris[first];
+        const float lo[3] = { fminf(fminf(t.v1.position.x, t.v2.position.x), t.v3.position.x), fminf(fminf(t.v1.position.y, t.v2.position.y), t.v3.position.y),
+                              fminf(fminf(t.v1.position.z, t.v2.position.z), t.v3.position.z) };
+        const float hi[3] = { fmaxf(fmaxf(t.v1.position.x, t.v2.position.x), t.v3.position.x), fmaxf(fmaxf(t.v1.position.y, t.v2.position.y), t.v3.position.y),
+                              fmaxf(fmaxf(t.v1.position.z, t.v2.position.z), t.v3.position.z) };
+        if (!(lo[0] == nd.bmin.x && lo[1] == nd.bmin.y && lo[2] == nd.bmin.z && hi[0] == nd.bmax.x && hi[1] == nd.bmax.y && hi[2] == nd.bmax.z))
+            atomicOr(error, REFIT_ERR_LEAF_BOX);
     }
 }
 
@@ -194,6 +208,7 @@ int refit_one(b2rt_context* ctx, const void* triangles, uint64_t n_triangles) {
     bn->shadow.clear();
     if (err & REFIT_ERR_NONFINITE) return fail(ctx, B2RT_INVALID_ARG_VALUE, "refit: non-finite vertex positions; the scene must be uploaded again");
     if (err & REFIT_ERR_RANGE) return fail(ctx, B2RT_INVALID_ARG_VALUE, "refit: bounds too large to quantise; the scene must be uploaded again");
+    if (err & REFIT_ERR_LEAF_BOX) return fail(ctx, B2RT_INVALID_ARG_VALUE, "refit: a leaf's box is not the min / max of its vertices; the scene must be uploaded again");
     if (err & REFIT_ERR_DUPLICATE)
         return fail(ctx, B2RT_INVALID_ARG_VALUE, "refit: two triangles that were the loader's copies of one face no longer are; rebuild the scene instead");
     return B2RT_SUCCESS;

@@ -214,25 +214,38 @@ B2_HD void tri_test_exact(const RayX& r, float ax, float ay, float az, float bx,
 }
 
 // ---- leaf block ----------------------------------------------------------------------
+// The exact fp32 box of a one-record block: component-wise min / max of its vertices (exact operations; see b2rt_types.h).
+B2_HD float min3_nn(float a, float b, float c) { return min_nn(min_nn(a, b), c); }
+B2_HD float max3_nn(float a, float b, float c) { return max_nn(max_nn(a, b), c); }
+
 // Returns true when at least one triangle was accepted by this call.
 template <bool COUNT>
 B2_HD bool visit_leaf(const U4* leaf, uint32_t offset, const RayX& r, HitX& h, TravCounters* c) {
     const U4* p = leaf + offset;
-    U4 h0 = ld128(p), h1 = ld128(p + 1);
-    U4 a = ld128(p + 2), b = ld128(p + 3), cc = ld128(p + 4);   // every block has >= 1 record
-    uint32_t nrec = h1.w;
-    if (COUNT) { c->leaf_blocks++; c->words += LEAF_HEADER_WORDS + LEAF_RECORD_WORDS * nrec; }
-    if (!box_gate_exact(r, bits2f(h0.x), bits2f(h0.y), bits2f(h0.z), bits2f(h1.x), bits2f(h1.y), bits2f(h1.z), h.t))
+    U4 a = ld128(p), b = ld128(p + 1), cc = ld128(p + 2);       // every block has >= 1 record
+    const uint32_t nrec = (a.w >> LEAF_NREC_SHIFT) & LEAF_NREC_MASK;
+    float lox, loy, loz, hix, hiy, hiz;
+    if (a.w & LEAF_HAS_BOX) {                                   // rare: several records, or a box that is not the vertices' min / max
+        const U4 b0 = ld128(p + LEAF_RECORD_WORDS * nrec), b1 = ld128(p + LEAF_RECORD_WORDS * nrec + 1);
+        lox = bits2f(b0.x); loy = bits2f(b0.y); loz = bits2f(b0.z); hix = bits2f(b1.x); hiy = bits2f(b1.y); hiz = bits2f(b1.z);
+        if (COUNT) c->words += LEAF_BOX_WORDS;
+    } else {
+        lox = min3_nn(bits2f(a.x), bits2f(b.x), bits2f(cc.x)); hix = max3_nn(bits2f(a.x), bits2f(b.x), bits2f(cc.x));
+        loy = min3_nn(bits2f(a.y), bits2f(b.y), bits2f(cc.y)); hiy = max3_nn(bits2f(a.y), bits2f(b.y), bits2f(cc.y));
+        loz = min3_nn(bits2f(a.z), bits2f(b.z), bits2f(cc.z)); hiz = max3_nn(bits2f(a.z), bits2f(b.z), bits2f(cc.z));
+    }
+    if (COUNT) { c->leaf_blocks++; c->words += LEAF_RECORD_WORDS * nrec; }
+    if (!box_gate_exact(r, lox, loy, loz, hix, hiy, hiz, h.t))
         return false;
     if (COUNT) c->leaf_pass++;
     uint32_t before = h.tri;
     float t_before = h.t;
-    uint32_t id = h0.w;
+    uint32_t id = b.w;
     for (uint32_t k = 0;;) {
         float v1x = bits2f(a.x), v1y = bits2f(a.y), v1z = bits2f(a.z);
         float v2x = bits2f(b.x), v2y = bits2f(b.y), v2z = bits2f(b.z);
         float v3x = bits2f(cc.x), v3y = bits2f(cc.y), v3z = bits2f(cc.z);
-        uint32_t flags = a.w;
+        uint32_t flags = a.w & REC_FLAG_MASK;
         tri_test_exact(r, v1x, v1y, v1z, v2x, v2y, v2z, v3x, v3y, v3z, id, h);
         if (COUNT) c->tri_tests++;
         if (flags) {
@@ -245,7 +258,7 @@ B2_HD bool visit_leaf(const U4* leaf, uint32_t offset, const RayX& r, HitX& h, T
         }
         id += flags ? 2u : 1u;
         if (++k >= nrec) break;
-        const U4* q = p + LEAF_HEADER_WORDS + LEAF_RECORD_WORDS * k;
+        const U4* q = p + LEAF_RECORD_WORDS * k;
         a = ld128(q); b = ld128(q + 1); cc = ld128(q + 2);
     }
     return h.tri != before || h.t != t_before;

@@ -27,13 +27,15 @@ inline bool same_pos(const RefVec& a, const RefVec& b) {
 }
 inline uint32_t fbits(float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; }
 
+// min / max the way the kernels evaluate them (fminf / fmaxf of three); only used where no operand is NaN
+inline float min3(float a, float b, float c) { return std::fmin(std::fmin(a, b), c); }
+inline float max3(float a, float b, float c) { return std::fmax(std::fmax(a, b), c); }
+
 // Append the leaf block of binary leaf `n`; returns the number of 16-byte words written.
 uint32_t emit_leaf(const RefNode& n, uint32_t bin, const RefTriangle* tris, WideBVH& out) {
     size_t head = out.leaf.size();
     out.leaf_dir.push_back(bin);
     out.leaf_dir.push_back((uint32_t)head);
-    out.leaf.push_back(U4{ fbits(n.bmin.x), fbits(n.bmin.y), fbits(n.bmin.z), n.offset });
-    out.leaf.push_back(U4{ fbits(n.bmax.x), fbits(n.bmax.y), fbits(n.bmax.z), 0u });
     uint32_t nrec = 0;
     uint32_t end = n.offset + n.nPrimitives;
     for (uint32_t i = n.offset; i < end;) {
@@ -54,7 +56,26 @@ uint32_t emit_leaf(const RefNode& n, uint32_t bin, const RefTriangle* tris, Wide
         ++nrec;
         i += flags ? 2u : 1u;
     }
-    out.leaf[head + 1].w = nrec;
+    // one record whose node box is exactly the min / max of its three vertices (what the reference's builder produces):
+    // the kernels recompute that box, none is stored. Comparison by value: the sign of a zero never changes RayBounds.
+    bool implied = nrec == 1;
+    if (implied) {
+        const RefTriangle& t = tris[n.offset];
+        const float* a = &t.v1.position.x; const float* b = &t.v2.position.x; const float* c = &t.v3.position.x;
+        const float* lo = &n.bmin.x; const float* hi = &n.bmax.x;
+        for (int k = 0; k < 3 && implied; ++k) {
+            if (std::isnan(a[k]) || std::isnan(b[k]) || std::isnan(c[k])) implied = false;
+            else implied = min3(a[k], b[k], c[k]) == lo[k] && max3(a[k], b[k], c[k]) == hi[k];
+        }
+    }
+    if (nrec > LEAF_NREC_MASK) nrec = LEAF_NREC_MASK;       // cannot happen: nPrimitives is 16 bits
+    out.leaf[head].w |= (nrec << LEAF_NREC_SHIFT) | (implied ? 0u : LEAF_HAS_BOX);
+    out.leaf[head + 1].w = n.offset;
+    if (!implied) {
+        out.leaf.push_back(U4{ fbits(n.bmin.x), fbits(n.bmin.y), fbits(n.bmin.z), 0u });
+        out.leaf.push_back(U4{ fbits(n.bmax.x), fbits(n.bmax.y), fbits(n.bmax.z), 0u });
+        out.n_boxed_blocks++;
+    }
     out.n_leaf_blocks++;
     out.max_leaf_records = std::max(out.max_leaf_records, nrec);
     return (uint32_t)(out.leaf.size() - head);

@@ -18,6 +18,7 @@ struct WideBVH {
     uint32_t max_depth_binary = 0;    // deepest binary node (root = 0)
     uint32_t max_depth_wide = 0;      // deepest wide node (root = 0)
     uint32_t max_leaf_records = 0;
+    uint64_t n_boxed_blocks = 0;         // leaf blocks that carry an explicit box (LEAF_HAS_BOX)
     uint64_t n_children = 0;          // occupied child slots, for fill statistics
     uint32_t stack_entries = 0;       // most child references any walk can have deferred at once (exact, see build_wide_bvh)
     // refit support (refit.cu): where every child box and leaf block came from in the binary tree

@@ -257,3 +257,35 @@ def test_rays_with_zero_direction_components_are_culled_like_any_other_ray(bumpy
     st2 = ol.EmuStats()
     ol.emu_trace(tilted, stats=st2)
     assert st.wide_visits < 1.25 * st2.wide_visits, (st.wide_visits, st2.wide_visits)
+
+
+def test_leaf_blocks_with_explicit_boxes(tmp_scene_dir):
+    """Leaf blocks normally carry no box: the kernels recompute the min / max of the record's vertices, which is what the
+    reference's builder stores (CLBVHnode.cpp:18-23). Blocks of several records, and leaves of a caller-supplied tree whose
+    box is something else, keep an explicit box -- here leaf boxes SHRUNK below their triangles (a valid tree: children
+    stay inside parents), so a walk that used the vertices' box instead would accept hits the reference culls."""
+    import os
+    p, n, f = scenes.displaced_sphere(4)
+    path = scenes.write_obj(os.path.join(tmp_scene_dir, "boxed.obj"), p, n, f)
+    rays = scenes.shell_rays(30000, 10.0, seed=91)
+    for max_prims in (4, 16):
+        tris, nodes, _ = _reference_scene(path, max_prims)
+        st = ol.emu_build(tris, nodes)
+        words_plain = st.leaf_words
+        _same(ol.emu_trace(rays), ol.oracle_closest(tris, nodes, rays))
+        nodes = nodes.copy()
+        raw = nodes.view(np.uint8).reshape(-1, 48)
+        box = raw[:, :32].view(np.float32).reshape(-1, 8)          # bmin.xyzw, bmax.xyzw
+        nprim = raw[:, 36:38].view(np.uint16).reshape(-1)
+        leaf = nprim > 0
+        centre = 0.5 * (box[leaf, 0:3] + box[leaf, 4:7])
+        box[leaf, 0:3] = centre + 0.35 * (box[leaf, 0:3] - centre)
+        box[leaf, 4:7] = centre + 0.35 * (box[leaf, 4:7] - centre)
+        st = ol.emu_build(tris, nodes)
+        assert st.leaf_words > words_plain + 1.8 * leaf.sum()      # (nearly) every block went without a box before and carries two box words now
+        want = ol.oracle_closest(tris, nodes, rays)
+        assert (want["tri"] != MISS).mean() < 0.8 * (ol.oracle_closest(*_reference_scene(path, max_prims)[:2], rays)["tri"] != MISS).mean()
+        _same(ol.emu_trace(rays), want)
+        _same(ol.emu_trace(rays, schedule=5), want)
+        _same(ol.emu_trace_coop(rays[:6000], handoff=5), want[:6000])
+        _same(ol.emu_trace_coop(rays[:6000]), want[:6000])

@@ -350,3 +350,31 @@ def test_refit_scene_matches_the_oracle_on_the_refitted_tree(product, bumpy_ref)
             ctx.refit_scene(tris[:-2])
         ctx.refit_scene(tris)                                                 # and back
         assert np.array_equal(ctx.trace_closest(rays).view(np.uint32), before.view(np.uint32))
+
+
+def test_leaf_blocks_with_explicit_boxes_on_the_gpu(product, tmp_scene_dir):
+    """The compact leaf block (no stored box: min / max of the record's vertices) against blocks that must keep their box:
+    several records per leaf (max_prims 16) and leaf boxes shrunk below their triangles. Same check as the CPU emulation's
+    (tests/test_emu_traversal.py), through the C ABI, solo and cooperative walks, plus a refit of the compact scene."""
+    cap = product.capi
+    p, n, f = scenes.displaced_sphere(4)
+    path = scenes.write_obj(os.path.join(tmp_scene_dir, "boxed_gpu.obj"), p, n, f)
+    rays = scenes.shell_rays(60000, 10.0, seed=191)
+    for max_prims in (4, 16):
+        tris, nodes, mats = product.host.load_scene(path, max_prims)
+        shrunk = nodes.copy()
+        raw = shrunk.view(np.uint8).reshape(-1, 48)
+        box = raw[:, :32].view(np.float32).reshape(-1, 8)
+        leaf = raw[:, 36:38].view(np.uint16).reshape(-1) > 0
+        centre = 0.5 * (box[leaf, 0:3] + box[leaf, 4:7])
+        box[leaf, 0:3] = centre + 0.35 * (box[leaf, 0:3] - centre)
+        box[leaf, 4:7] = centre + 0.35 * (box[leaf, 4:7] - centre)
+        for nd in (nodes, shrunk):
+            want = ol.oracle_closest(tris, nd, rays)
+            with product.Context(0) as ctx:
+                ctx.upload_scene(tris, nd, mats)
+                for coop in (0, 16):
+                    ctx.set_option(cap.OPT_COOP_MAX, coop)
+                    _check_hits(ctx.trace_closest(rays), want)
+                    _check_hits(np.concatenate([ctx.trace_closest(rays[i:i + 16]) for i in range(0, 800, 16)]), want[:800])
+                assert np.array_equal(ctx.trace_any(rays) != 0, ol.oracle_any(tris, nd, rays) != 0)
