@@ -62,13 +62,23 @@ void free_tail(b2rt_context* ctx) {
 }
 
 void free_scene(b2rt_context* ctx) {
-    if (ctx->d_wide) cudaFree(ctx->d_wide);
-    if (ctx->d_leaf) cudaFree(ctx->d_leaf);
+    if (ctx->d_wide) cudaFree(ctx->d_wide);          // one allocation: wide nodes, then the leaf blocks (alloc_bvh)
     if (ctx->d_shade) cudaFree(ctx->d_shade);
     if (ctx->d_child_bin) cudaFree(ctx->d_child_bin);
     if (ctx->d_leaf_dir) cudaFree(ctx->d_leaf_dir);
     ctx->d_wide = ctx->d_leaf = ctx->d_shade = nullptr;
     ctx->d_child_bin = ctx->d_leaf_dir = nullptr;
+}
+
+// Wide nodes and leaf blocks share ONE allocation (nodes first, leaf blocks behind them at a 256-byte boundary): a stream's
+// L2 access-policy window is a single address range, and on scenes whose whole traversal set fits the persisting carve-out
+// the window covers both (apply_l2_policy).
+int alloc_bvh(b2rt_context* ctx, size_t wide_bytes, size_t leaf_bytes) {
+    const size_t wb = (std::max<size_t>(wide_bytes, sizeof(WideNode)) + 255) & ~(size_t)255, lb = std::max<size_t>(leaf_bytes, 16) + 64;   // +64: slack behind the last block
+    CK(cudaMalloc(&ctx->d_wide, wb + lb));
+    ctx->d_leaf = static_cast<char*>(ctx->d_wide) + wb;
+    ctx->bvh_bytes = wb + lb;
+    return B2RT_SUCCESS;
 }
 
 // Host view of a buffer's contents: the creation-time shadow if still held, else a read-back.
@@ -110,8 +120,8 @@ int ensure_scene(b2rt_context* ctx) {
     if (bound > 256) return fail(ctx, B2RT_OUT_OF_RESOURCES, "BVH too deep for the traversal stack (wide depth " + std::to_string(w.max_depth_wide) + ")");
     free_scene(ctx);
     size_t wb = w.nodes.size() * sizeof(WideNode), lb = w.leaf.size() * sizeof(U4), sb = w.shade.size() * sizeof(ShadeTri);
-    CK(cudaMalloc(&ctx->d_wide, std::max<size_t>(wb, sizeof(WideNode))));
-    CK(cudaMalloc(&ctx->d_leaf, std::max<size_t>(lb, 16) + 64));   // +64: slack behind the last block
+    int st_alloc = alloc_bvh(ctx, wb, lb);
+    if (st_alloc) return st_alloc;
     CK(cudaMalloc(&ctx->d_shade, std::max<size_t>(sb, 48)));
     CK(cudaMemsetAsync(static_cast<char*>(ctx->d_leaf) + std::max<size_t>(lb, 16), 0, 64, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_wide, w.nodes.data(), wb, cudaMemcpyHostToDevice, ctx->stream));
@@ -177,7 +187,11 @@ int ensure_scene(b2rt_context* ctx) {
 void scene_l2_setup(b2rt_context* ctx) {
     ctx->policy_streams.clear();
     if (!ctx->l2_persist_max) return;
-    const size_t want = ((size_t)ctx->info.wide_node_bytes + (4u << 20)) & ~(size_t)((1u << 20) - 1);
+    // what the window covers: the whole traversal set (nodes + leaf blocks, one allocation) when it fits the persisting
+    // carve-out this device allows, else the wide-node array alone (the part every ray re-reads most)
+    const size_t all = ctx->bvh_bytes, nodes_only = (size_t)ctx->info.wide_node_bytes;
+    ctx->l2_window_bytes = (all <= ctx->l2_persist_max && all <= ctx->l2_window_max) ? all : std::min(nodes_only, ctx->l2_window_max);
+    const size_t want = (ctx->l2_window_bytes + (4u << 20)) & ~(size_t)((1u << 20) - 1);
     cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, ctx->opt_l2_persist ? std::min(ctx->l2_persist_max, want) : 0);
     cudaGetLastError();
 }
@@ -189,7 +203,7 @@ int apply_l2_policy(b2rt_context* ctx, cudaStream_t st) {
     memset(&attr, 0, sizeof(attr));
     if (ctx->opt_l2_persist) {
         attr.accessPolicyWindow.base_ptr = ctx->d_wide;
-        attr.accessPolicyWindow.num_bytes = std::min<size_t>(ctx->info.wide_node_bytes, ctx->l2_window_max);
+        attr.accessPolicyWindow.num_bytes = ctx->l2_window_bytes;
         attr.accessPolicyWindow.hitRatio = std::min(1.0f, (float)ctx->l2_persist_max / (float)std::max<size_t>(attr.accessPolicyWindow.num_bytes, 1));
         attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
         attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;

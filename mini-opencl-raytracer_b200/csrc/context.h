@@ -50,7 +50,8 @@ struct b2rt_context {
     float cam_pos[4] = { 0, 0, 0, 0 }, cam_front[4] = { 0, 0, 0, 0 }, cam_up[4] = { 0, 0, 0, 0 };
     // derived scene
     bool scene_dirty = true;
-    void *d_wide = nullptr, *d_leaf = nullptr, *d_shade = nullptr;
+    void *d_wide = nullptr, *d_leaf = nullptr, *d_shade = nullptr;      // d_leaf points into d_wide's allocation (alloc_bvh)
+    size_t bvh_bytes = 0, l2_window_bytes = 0;
     uint32_t *d_child_bin = nullptr, *d_leaf_dir = nullptr;   // refit support: binary node behind every wide child slot / leaf block
     b2rt_scene_info info;
     uint32_t stack_bound = 8;
@@ -107,6 +108,7 @@ int use_device(b2rt_context* ctx);
 Buffer* find(b2rt_context* ctx, b2rt_buffer id);
 int ensure_scene(b2rt_context* ctx);
 void free_scene(b2rt_context* ctx);
+int alloc_bvh(b2rt_context* ctx, size_t wide_bytes, size_t leaf_bytes);   // one allocation for wide nodes + leaf blocks
 void free_tail(b2rt_context* ctx);
 void scene_l2_setup(b2rt_context* ctx);
 int buffer_create_single(b2rt_context* ctx, uint32_t flags, size_t bytes, const void* host_ptr, b2rt_buffer* out, bool zero_fill);

@@ -241,8 +241,8 @@ int group_adopt_scene(b2rt_context* root) {
         CK(cudaSetDevice(ctx->device));
         free_scene(ctx);
         free_tail(ctx);
-        CK(cudaMalloc(&ctx->d_wide, wb));
-        CK(cudaMalloc(&ctx->d_leaf, lb));
+        int st_alloc = alloc_bvh(ctx, root->info.wide_node_bytes, root->info.leaf_bytes);
+        if (st_alloc) return st_alloc;
         CK(cudaMalloc(&ctx->d_shade, sb));
         CK(cudaMalloc(reinterpret_cast<void**>(&ctx->d_child_bin), cb));
         CK(cudaMalloc(reinterpret_cast<void**>(&ctx->d_leaf_dir), db));
