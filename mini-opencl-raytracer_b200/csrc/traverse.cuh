@@ -24,6 +24,9 @@
 #pragma once
 #include "b2rt_types.h"
 
+#ifndef B2_NODE_TEST_H2
+#define B2_NODE_TEST_H2 1      // wide-node test in packed fp16 (two children per instruction); 0 = one fp32 FMA per plane
+#endif
 #ifndef B2_LEAF_QUEUE
 #define B2_LEAF_QUEUE 2        // leaves a lane may hold back while it walks on (speculation depth)
 #endif
@@ -78,6 +81,13 @@ B2_HD uint32_t w_redor(uint32_t v) { return __reduce_or_sync(0xffffffffu, v); }
 B2_HD void w_sync() { __syncwarp(); }
 B2_HD uint32_t ctz32(uint32_t v) { return (uint32_t)__ffs((int)v) - 1u; }     // v != 0
 B2_HD void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
+// packed fp16 arithmetic of test_wide_node_h2, on raw 32-bit patterns (two halves per register)
+B2_HD uint32_t h2_fma(uint32_t a, uint32_t b, uint32_t c) { uint32_t d; asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
+B2_HD uint32_t h2_max(uint32_t a, uint32_t b) { uint32_t d; asm("max.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d; }   // NaN operand: the other one
+B2_HD uint32_t h2_min(uint32_t a, uint32_t b) { uint32_t d; asm("min.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d; }
+B2_HD uint32_t h2_sub(uint32_t a, uint32_t b) { uint32_t d; asm("sub.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d; }
+B2_HD uint32_t h2_both(float v) { uint32_t d; asm("cvt.rn.f16x2.f32 %0, %1, %1;" : "=r"(d) : "f"(v)); return d; }                   // (v, v) rounded to nearest; overflow -> inf
+B2_HD uint32_t dot4(uint32_t a, uint32_t b) { return __dp4a(a, b, 0u); }                                                             // sum of byte products
 __device__ unsigned long long g_stack_overflows;      // per device; read + cleared by b2rt_get_counters / b2rt_reset_counters
 B2_HD void report_stack_overflow() { atomicAdd(&g_stack_overflows, 1ull); }
 #else
@@ -100,10 +110,55 @@ B2_HD float max_nn(float a, float b) { return std::fmax(a, b); }
 B2_HD float min_nn(float a, float b) { return std::fmin(a, b); }
 B2_HD float u2f(uint32_t v) { return (float)v; }
 B2_HD float fma_rn(float a, float b, float c) { return std::fmaf(a, b, c); }
-B2_HD uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {   // PTX prmt.b32, default mode, selector nibbles 0..7
+B2_HD uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {   // PTX prmt.b32, default mode: nibble bits 0-2 pick a byte, bit 3 replicates its sign
     uint64_t src = ((uint64_t)b << 32) | a;
     uint32_t r = 0;
-    for (int i = 0; i < 4; ++i) r |= (uint32_t)((src >> (8 * ((sel >> (4 * i)) & 7u))) & 0xffu) << (8 * i);
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t nib = (sel >> (4 * i)) & 0xfu;
+        uint32_t byte = (uint32_t)((src >> (8 * (nib & 7u))) & 0xffu);
+        if (nib & 8u) byte = (byte & 0x80u) ? 0xffu : 0u;
+        r |= byte << (8 * i);
+    }
+    return r;
+}
+// IEEE binary16 on the host, enough for test_wide_node_h2: decode, round-to-nearest-even encode (subnormals, overflow to inf),
+// and the packed operations with ONE rounding each (products and sums of halves are exact in double).
+B2_HD double h_dec(uint32_t h) {
+    const uint32_t s = (h >> 15) & 1u, e = (h >> 10) & 31u, m = h & 1023u;
+    double v;
+    if (e == 31u) v = m ? std::nan("") : INFINITY;
+    else if (e == 0u) v = std::ldexp((double)m, -24);
+    else v = std::ldexp((double)(m | 1024u), (int)e - 25);
+    return s ? -v : v;
+}
+B2_HD uint32_t h_enc(double v) {
+    if (std::isnan(v)) return 0x7fffu;
+    const uint32_t s = std::signbit(v) ? 0x8000u : 0u;
+    double a = std::fabs(v);
+    if (a >= 65520.0) return s | 0x7c00u;                     // rounds to infinity
+    if (a < std::ldexp(1.0, -14)) {                            // subnormal: multiples of 2^-24
+        const double q = std::nearbyint(std::ldexp(a, 24));    // default rounding mode: to nearest even
+        return s | (uint32_t)q;                                // 1024 -> the smallest normal, encoded correctly by the carry
+    }
+    int e;
+    const double f = std::frexp(a, &e);                        // a = f * 2^e, f in [0.5, 1)
+    double m = std::nearbyint(std::ldexp(f, 11));              // 11 significant bits
+    if (m >= 2048.0) { m = 1024.0; ++e; }
+    const int be = e - 1 + 15;
+    if (be >= 31) return s | 0x7c00u;
+    return s | ((uint32_t)be << 10) | ((uint32_t)m & 1023u);
+}
+template <class F> B2_HD uint32_t h2_map(uint32_t a, uint32_t b, uint32_t c, F f) {
+    return h_enc(f(h_dec(a & 0xffffu), h_dec(b & 0xffffu), h_dec(c & 0xffffu))) | (h_enc(f(h_dec(a >> 16), h_dec(b >> 16), h_dec(c >> 16))) << 16);
+}
+B2_HD uint32_t h2_fma(uint32_t a, uint32_t b, uint32_t c) { return h2_map(a, b, c, [](double x, double y, double z) { return x * y + z; }); }
+B2_HD uint32_t h2_sub(uint32_t a, uint32_t b) { return h2_map(a, b, 0u, [](double x, double y, double) { return x - y; }); }
+B2_HD uint32_t h2_max(uint32_t a, uint32_t b) { return h2_map(a, b, 0u, [](double x, double y, double) { return std::fmax(x, y); }); }
+B2_HD uint32_t h2_min(uint32_t a, uint32_t b) { return h2_map(a, b, 0u, [](double x, double y, double) { return std::fmin(x, y); }); }
+B2_HD uint32_t h2_both(float v) { const uint32_t h = h_enc((double)v); return h | (h << 16); }
+B2_HD uint32_t dot4(uint32_t a, uint32_t b) {
+    uint32_t r = 0;
+    for (int i = 0; i < 4; ++i) r += ((a >> (8 * i)) & 0xffu) * ((b >> (8 * i)) & 0xffu);
     return r;
 }
 B2_HD uint32_t top_bit(uint32_t v) { return 31u - (uint32_t)__builtin_clz(v); }
@@ -127,6 +182,7 @@ B2_HD void w_sync() { (void)b2rt_emu::exchange(0, 4, 0); }
 B2_HD uint32_t ctz32(uint32_t v) { return (uint32_t)__builtin_ctz(v); }
 B2_HD void prefetch_l2(const void*) {}
 extern unsigned long long g_emu_stack_overflows;
+extern unsigned long long g_emu_culling_violations;
 B2_HD void report_stack_overflow() { ++g_emu_stack_overflows; }
 #endif
 
@@ -352,6 +408,101 @@ B2_HD WideHits test_wide_node(const U4* wide, uint32_t index, const RayX& r, flo
     return out;
 }
 
+B2_HD WideHits test_wide_node_robust(const U4* wide, uint32_t index, const RayX& r, float best);
+
+// Packed-fp16 variant of test_wide_node (B2_NODE_TEST_H2): two children per instruction.
+//
+// The slab values are evaluated RELATIVE to t_ref (the ray's entry distance into the node's own box, any fp32 number would
+// do) and SCALED by a power of two chosen per visit, so that they fit binary16: with K1 = S*inv (exact), A = fl(fl(base-o)*inv)
+//     T(q) = ((A - t_ref) + q*K1) * scale            plane q of this axis, real arithmetic
+// and scale = 2^(117 - exponent(max_a |K1|)), the largest |K2| = |K1| * 2^24 * scale lies in [2^14, 2^15) and the node's own
+// extent in T is below 255 * 2^-9.5 < 1. One PRMT turns two plane bytes into two SUBNORMAL halves q * 2^-24 (byte in the
+// low mantissa bits, exponent zero: exact), one fma.f16x2 gives q*2^-24 * K2h + Bh for both children.
+// Error budget per plane, against the reference's R(P) = fl(fl(P - o) * inv) of any exact plane beyond the quantised one:
+//   K2h = K2 (1 + d), |d| <= 2^-11:  q*2^-24*|K2|*2^-11 <= 2^-16 |K2| * 2^-11 * 255/256 ... < 2^-11 * 2^-16 |K2| * 256
+//   Bh rounded to nearest: 2^-11 |B|;   the FMA's own rounding: 2^-11 (|B| + 2^-16 |K2|) (or 2^-25 absolute when subnormal);
+//   fp32 roundings inside A, A - t_ref and R(P): < 2^-21 (|A| + |t_ref|) * scale.
+// Their sum is below 2^-10 (|Bh| + 2^-16 |K2|) + 2^-21 (...) with |Bh| <= |B| + slack, so
+// slack = 1.025 * 2^-10 (|B| + 2^-16 |K2|) + 2^-20 (|A| + |t_ref|) scale + 2^-22 covers it; near planes are lowered and far
+// planes raised by it before the conversion. Overflowing values become +-inf on the side that keeps the test
+// conservative: a near plane beyond the binary16 range is more than 2^5 node extents past the entry point while some far
+// plane of the node is within 255 * max|K1| of it, so the child is truly missed; a far plane below the range lies before the
+// entry point, likewise; inf - inf = NaN has a clear sign bit and lets the child through.
+// 0 and `best` join the same frame (rounded outwards): pass iff min(far..., best) >= max(near..., 0).
+// Children are evaluated in SLOT order; the 8 sign bytes are permuted into visiting order afterwards (two PRMT) and
+// squeezed into the mask with two dot products.
+B2_HD WideHits test_wide_node_h2(const U4* wide, uint32_t index, const RayX& r, float best) {
+    const U4* p = wide + (uint32_t)WIDE_NODE_WORDS * index;
+    U4 w0 = ld128(p), w1 = ld128(p + 1), w2 = ld128(p + 2), w3 = ld128(p + 3), w4 = ld128(p + 4);
+    const uint32_t order = ld32(reinterpret_cast<const uint32_t*>(p + 5) + r.sign);
+    WideHits out;
+    out.add_interior = w1.x - (uint32_t)META_INTERIOR;
+    out.add_leaf = REF_LEAF_BIT | w1.y;
+    const uint32_t sel_lo = order, sel_hi = order >> 16;
+    out.meta_lo = prmt(w1.z, w1.w, sel_lo);
+    out.meta_hi = prmt(w1.z, w1.w, sel_hi);
+
+    const float o[3] = { r.ox, r.oy, r.oz };
+    const float inv[3] = { r.ix, r.iy, r.iz };
+    const float base[3] = { bits2f(w0.x), bits2f(w0.y), bits2f(w0.z) };
+    const uint32_t qlo_a[3] = { w2.x, w2.z, w3.x }, qlo_b[3] = { w2.y, w2.w, w3.y };   // slots 0..3 / 4..7
+    const uint32_t qhi_a[3] = { w3.z, w4.x, w4.z }, qhi_b[3] = { w3.w, w4.y, w4.w };
+    float K1[3], A[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        K1[a] = xmul(bits2f(((w0.w >> (8 * a)) & 0xffu) << 23), inv[a]);
+        A[a] = xmul(xsub(base[a], o[a]), inv[a]);
+    }
+    const float kmax = max_nn(max_nn(fabsf(K1[0]), fabsf(K1[1])), fabsf(K1[2]));
+    // magnitudes this frame cannot hold (overflow of (base - o) * inv or S * inv: coordinates or reciprocals beyond 2^100):
+    // decide in fp32 instead. Written so that NaN takes the branch too.
+    if (!(max_nn(max_nn(fabsf(A[0]), fabsf(A[1])), max_nn(fabsf(A[2]), xmul(kmax, 256.0f))) < 1.2676506e30f))
+        return test_wide_node_robust(wide, index, r, best);
+    // entry distance into the node's box (near plane = q 0 or q 255 by the ray's sign), clamped at 0
+    const float t_ref = max_nn(max_nn(max_nn((r.sign & 1u) ? fma_rn(255.0f, K1[0], A[0]) : A[0], (r.sign & 2u) ? fma_rn(255.0f, K1[1], A[1]) : A[1]),
+                                      (r.sign & 4u) ? fma_rn(255.0f, K1[2], A[2]) : A[2]), 0.0f);
+    uint32_t eb = f2bits(kmax) >> 23;                                   // biased exponent (kmax >= 0, finite: degenerate rays never get here)
+    eb = eb < 15u ? 15u : eb;                                           // |K1| below 2^-112: keep the scale factors representable
+    const float scale = bits2f((244u - eb) << 23);                     // 2^(117 - (eb - 127))
+    const float kscale = bits2f((268u - eb) << 23);                    // scale * 2^24
+    uint32_t Kh[3], Bn[3], Bf[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const float B = xmul(xsub(A[a], t_ref), scale);
+        const float K2 = xmul(K1[a], kscale);
+        const float slack = fma_rn(fma_rn(fabsf(K2), 1.52587890625e-5f, fabsf(B)), 1.0009765625e-3f,
+                                   fma_rn(xmul(xadd(fabsf(A[a]), t_ref), scale), 9.5367431640625e-7f, 2.384185791015625e-7f));
+        Kh[a] = h2_both(K2);
+        Bn[a] = h2_both(xsub(B, slack));
+        Bf[a] = h2_both(xadd(B, slack));
+    }
+    const float z = xmul(-t_ref, scale), b = xmul(xsub(best, t_ref), scale);
+    const uint32_t zero_h = h2_both(xsub(z, fma_rn(fabsf(z), 9.765625e-4f, 2.384185791015625e-7f)));     // 0 and best: one conversion each, 2^-11 relative
+    const uint32_t best_h = h2_both(xadd(b, fma_rn(fabsf(b), 9.765625e-4f, 2.384185791015625e-7f)));
+    uint32_t d[4];
+#pragma unroll
+    for (int pr = 0; pr < 4; ++pr) {
+        // slots 2pr, 2pr+1: bytes (0,1) or (2,3) of the word that holds them, each widened to a subnormal half
+        const uint32_t sel = (pr & 1) ? 0x4342u : 0x4140u;
+        uint32_t N = zero_h, F = best_h;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const bool neg = (r.sign >> a) & 1u;
+            const uint32_t lo_w = pr < 2 ? qlo_a[a] : qlo_b[a], hi_w = pr < 2 ? qhi_a[a] : qhi_b[a];
+            const uint32_t qn = prmt(neg ? hi_w : lo_w, 0u, sel), qf = prmt(neg ? lo_w : hi_w, 0u, sel);
+            N = h2_max(N, h2_fma(qn, Kh[a], Bn[a]));
+            F = h2_min(F, h2_fma(qf, Kh[a], Bf[a]));
+        }
+        d[pr] = h2_sub(F, N);                                           // sign bit set: the child is culled
+    }
+    // sign bytes of the eight differences in slot order (0xff = culled), then in visiting order, then one bit each
+    const uint32_t c_lo = prmt(d[0], d[1], 0xfdb9u), c_hi = prmt(d[2], d[3], 0xfdb9u);
+    const uint32_t v_lo = prmt(c_lo, c_hi, sel_lo), v_hi = prmt(c_lo, c_hi, sel_hi);
+    const uint32_t cull = dot4(v_lo & 0x08040201u, 0x01010101u) | (dot4(v_hi & 0x08040201u, 0x01010101u) << 4);
+    out.mask = ~cull & ((1u << (w0.w >> 24)) - 1u);
+    return out;
+}
+
 // The same decision for rays whose reciprocal direction has an infinite (or NaN, or > 2^100) component (RAY_DEGENERATE):
 // a direction component of exactly zero is not rare in rendered frames (a few rays per million: central camera rows,
 // BRDF frames of axis-aligned normals), and with one FMA per plane such an axis evaluates to inf - inf = NaN and no longer
@@ -480,7 +631,15 @@ struct Lane {
     // `one` must be 0x3F800000, passed as run-time data: held in one register it lets the constant
     // byte selectors of B2_PLANE_V be instruction immediates (ptxas otherwise keeps four selector registers).
     B2_HD void node_step(const U4* wide, uint32_t* stack, uint32_t one) {
+#if B2_NODE_TEST_H2
+        WideHits w = (r.sign & RAY_DEGENERATE) ? test_wide_node_robust(wide, cur, r, h.t) : test_wide_node_h2(wide, cur, r, h.t);
+#else
         WideHits w = (r.sign & RAY_DEGENERATE) ? test_wide_node_robust(wide, cur, r, h.t) : test_wide_node(wide, cur, r, h.t, one);
+#endif
+#if defined(B2_EMU_CHECK_CULLING)
+        // host emulation only: no child that the exact-arithmetic test lets through may be culled by the fast one
+        { const WideHits x = test_wide_node_robust(wide, cur, r, h.t); if (x.mask & ~w.mask) ++g_emu_culling_violations; }
+#endif
         if (COUNT) { tc.wide_nodes++; tc.words += WIDE_NODE_WORDS; }
         uint32_t m = w.mask;
         if (m == 0) { cur = pop(stack); }

@@ -21,7 +21,7 @@ struct EmuStats {
     uint64_t wide_visits, leaf_blocks, leaf_pass, tri_tests, words, overflow, max_stack;
 };
 
-namespace b2rt { unsigned long long g_emu_stack_overflows = 0; }     // bumped by traverse.cuh's report_stack_overflow() in the host build
+namespace b2rt { unsigned long long g_emu_stack_overflows = 0; unsigned long long g_emu_culling_violations = 0; }     // bumped by traverse.cuh's report_stack_overflow() in the host build
 static WideBVH g_bvh;
 static std::string g_err;
 
@@ -61,6 +61,9 @@ extern "C" void emu_trace(const EmuRay* rays, uint64_t n, EmuHit* hits, uint32_t
     (void)total;
     st->wide_visits += sums[0]; st->leaf_blocks += sums[1]; st->leaf_pass += sums[2]; st->tri_tests += sums[3]; st->words += sums[4];
 }
+
+// Children that the exact-arithmetic node test lets through but the fast one culled, over all emulated walks so far (must be 0).
+extern "C" uint64_t emu_culling_violations() { return g_emu_culling_violations; }
 
 // Histogram of children per wide node (index 0..8) of the last emu_build.
 extern "C" void emu_child_histogram(uint64_t* hist9) {

@@ -68,7 +68,7 @@ def build_emu():
            [os.path.join(CSRC, f) for f in ("traverse.cuh", "coop.cuh", "wide_bvh.cpp", "wide_bvh.h", "b2rt_types.h")]
     if _stale(out, srcs):
         subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-frounding-math",
-                               "-fno-fast-math", "-pthread", "-x", "c++", "-I", CSRC, os.path.join(EMU_DIR, "emu.cpp"),
+                               "-fno-fast-math", "-pthread", "-DB2_EMU_CHECK_CULLING", "-x", "c++", "-I", CSRC, os.path.join(EMU_DIR, "emu.cpp"),
                                os.path.join(EMU_DIR, "warp_emu.cpp"), os.path.join(CSRC, "wide_bvh.cpp"), "-o", out])
     return out
 
@@ -264,6 +264,14 @@ def oracle_camera_rays(width, height, frame_count, pos=(0.0, -25.0, 8.5), front=
 
 
 # ---- host emulation of the product's traversal ------------------------------------------------
+def emu_culling_violations():
+    """Children let through by the exact-arithmetic wide-node test (test_wide_node_robust) but culled by the fast one, counted
+    over every emulated walk of this process: the fast test must be conservative, so this stays 0."""
+    L = emu()
+    L.emu_culling_violations.restype = C.c_uint64
+    return int(L.emu_culling_violations())
+
+
 def emu_build(tris, nodes):
     st = EmuStats()
     err = emu().emu_build(_p(nodes), nodes.shape[0], _p(tris), tris.shape[0], C.byref(st))

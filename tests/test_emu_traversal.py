@@ -289,3 +289,10 @@ def test_leaf_blocks_with_explicit_boxes(tmp_scene_dir):
         _same(ol.emu_trace(rays, schedule=5), want)
         _same(ol.emu_trace_coop(rays[:6000], handoff=5), want[:6000])
         _same(ol.emu_trace_coop(rays[:6000]), want[:6000])
+
+
+def test_fast_node_test_never_culls_what_the_exact_one_lets_through():
+    """Runs last in this file: every emulated walk above (all scenes, schedules and the cooperative mode's solo prefixes)
+    compared, node by node, the fast wide-node test with test_wide_node_robust on the same node, ray and `best`
+    (B2_EMU_CHECK_CULLING): the fast test may pass more children, never fewer."""
+    assert ol.emu_culling_violations() == 0
