@@ -62,6 +62,7 @@ B2_HD float fma_rn(float a, float b, float c) { return __fmaf_rn(a, b, c); }
 B2_HD uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) { uint32_t d; asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel)); return d; }
 
 B2_HD uint32_t top_bit(uint32_t v) { return 31u - (uint32_t)__clz((int)v); }
+B2_HD uint32_t low_mask(uint32_t n) { uint32_t d; asm("bmsk.clamp.b32 %0, %1, %2;" : "=r"(d) : "r"(0u), "r"(n)); return d; }   // (1 << n) - 1
 B2_HD uint32_t byte_of(uint32_t w, uint32_t i) { return __byte_perm(w, 0, 0x4440u + i); }
 B2_HD uint32_t popc32(uint32_t v) { return __popc(v); }
 B2_HD uint32_t funnel_l(uint32_t lo, uint32_t hi, uint32_t n) { return __funnelshift_l(lo, hi, n); }
@@ -162,6 +163,7 @@ B2_HD uint32_t dot4(uint32_t a, uint32_t b) {
     return r;
 }
 B2_HD uint32_t top_bit(uint32_t v) { return 31u - (uint32_t)__builtin_clz(v); }
+B2_HD uint32_t low_mask(uint32_t n) { return n >= 32u ? 0xffffffffu : (1u << n) - 1u; }
 B2_HD uint32_t byte_of(uint32_t w, uint32_t i) { return (w >> (8 * i)) & 0xffu; }
 B2_HD uint32_t popc32(uint32_t v) { return (uint32_t)__builtin_popcount(v); }
 B2_HD uint32_t funnel_l(uint32_t lo, uint32_t hi, uint32_t n) { return (uint32_t)(((((uint64_t)hi) << 32) | lo) << (n & 31u) >> 32); }
@@ -423,7 +425,7 @@ B2_HD WideHits test_wide_node_robust(const U4* wide, uint32_t index, const RayX&
 //   Bh rounded to nearest: 2^-11 |B|;   the FMA's own rounding: 2^-11 (|B| + 2^-16 |K2|) (or 2^-25 absolute when subnormal);
 //   fp32 roundings inside A, A - t_ref and R(P): < 2^-21 (|A| + |t_ref|) * scale.
 // Their sum is below 2^-10 (|Bh| + 2^-16 |K2|) + 2^-21 (...) with |Bh| <= |B| + slack, so
-// slack = 1.025 * 2^-10 (|B| + 2^-16 |K2|) + 2^-20 (|A| + |t_ref|) scale + 2^-22 covers it; near planes are lowered and far
+// slack = 1.025 * 2^-10 (|B| + 2^-16 |K2|) + 2^-20 (max_a |A| + |t_ref|) scale + 2^-22 covers it; near planes are lowered and far
 // planes raised by it before the conversion. Overflowing values become +-inf on the side that keeps the test
 // conservative: a near plane beyond the binary16 range is more than 2^5 node extents past the entry point while some far
 // plane of the node is within 255 * max|K1| of it, so the child is truly missed; a far plane below the range lies before the
@@ -456,7 +458,8 @@ B2_HD WideHits test_wide_node_h2(const U4* wide, uint32_t index, const RayX& r, 
     const float kmax = max_nn(max_nn(fabsf(K1[0]), fabsf(K1[1])), fabsf(K1[2]));
     // magnitudes this frame cannot hold (overflow of (base - o) * inv or S * inv: coordinates or reciprocals beyond 2^100):
     // decide in fp32 instead. Written so that NaN takes the branch too.
-    if (!(max_nn(max_nn(fabsf(A[0]), fabsf(A[1])), max_nn(fabsf(A[2]), xmul(kmax, 256.0f))) < 1.2676506e30f))
+    const float amax = max_nn(max_nn(fabsf(A[0]), fabsf(A[1])), fabsf(A[2]));
+    if (!(max_nn(amax, xmul(kmax, 256.0f)) < 1.2676506e30f))
         return test_wide_node_robust(wide, index, r, best);
     // entry distance into the node's box (near plane = q 0 or q 255 by the ray's sign), clamped at 0
     const float t_ref = max_nn(max_nn(max_nn((r.sign & 1u) ? fma_rn(255.0f, K1[0], A[0]) : A[0], (r.sign & 2u) ? fma_rn(255.0f, K1[1], A[1]) : A[1]),
@@ -466,12 +469,12 @@ B2_HD WideHits test_wide_node_h2(const U4* wide, uint32_t index, const RayX& r, 
     const float scale = bits2f((244u - eb) << 23);                     // 2^(117 - (eb - 127))
     const float kscale = bits2f((268u - eb) << 23);                    // scale * 2^24
     uint32_t Kh[3], Bn[3], Bf[3];
+    const float e32 = fma_rn(xmul(xadd(amax, t_ref), scale), 9.5367431640625e-7f, 2.384185791015625e-7f);   // the fp32 roundings' share, one bound for all axes
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
         const float B = xmul(xsub(A[a], t_ref), scale);
         const float K2 = xmul(K1[a], kscale);
-        const float slack = fma_rn(fma_rn(fabsf(K2), 1.52587890625e-5f, fabsf(B)), 1.0009765625e-3f,
-                                   fma_rn(xmul(xadd(fabsf(A[a]), t_ref), scale), 9.5367431640625e-7f, 2.384185791015625e-7f));
+        const float slack = fma_rn(fma_rn(fabsf(K2), 1.52587890625e-5f, fabsf(B)), 1.0009765625e-3f, e32);
         Kh[a] = h2_both(K2);
         Bn[a] = h2_both(xsub(B, slack));
         Bf[a] = h2_both(xadd(B, slack));
@@ -646,7 +649,7 @@ struct Lane {
         else {
             while (m & (m - 1u)) {                       // more than one: push the farthest
                 uint32_t k = top_bit(m);
-                m ^= 1u << k;
+                m &= low_mask(k);
                 push(stack, child_ref(w, k));
             }
             cur = child_ref(w, top_bit(m));
