@@ -3,6 +3,8 @@
 // CLContext / CLKernel (CLutils.cpp:9-77). There is no CPU path in this file: a
 // missing CUDA device makes b2rt_create fail and nothing else is reachable.
 #include <cuda_runtime.h>
+#include <atomic>
+#include <thread>
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -937,107 +939,107 @@ extern "C" int b2rt_build_bvh(b2rt_context* ctx, const void* triangles, uint64_t
     const bool trace = getenv("B2RT_TRACE_BUILD") != nullptr;        // developer aid: phase times on stderr
     auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double t_start = now();
-    // 1. groups: runs of consecutive triangles with bit-identical centroids (the loader's copies of one face)
+    // 1. groups: runs of consecutive triangles with bit-identical centroids (the loader's copies of one face). One streaming
+    //    pass over the 256-byte triangles at host memory bandwidth, cut into fixed chunks that a team of threads scans
+    //    independently (a run that straddles a chunk boundary becomes two groups: same centroid, adjacent Morton codes,
+    //    still valid leaves; the cut points do not depend on the number of threads, so the result is deterministic).
+    constexpr uint64_t CHUNK = 1u << 16;
+    const uint64_t n_chunks = (n_triangles + CHUNK - 1) / CHUNK;
+    struct Part { std::vector<uint32_t> first; std::vector<float> gb; float clo[3], chi[3]; };
+    std::vector<Part> parts;
     std::vector<uint32_t> first;
     std::vector<float> gb;
     float clo[3] = { INFINITY, INFINITY, INFINITY }, chi[3] = { -INFINITY, -INFINITY, -INFINITY };
     try {
-        first.reserve(n_triangles / 2 + 2);
-        gb.reserve(3 * n_triangles + 6);
-        float prev[3] = { 0, 0, 0 };
-        for (uint64_t i = 0; i < n_triangles; ++i) {
-            const RefVec &a = tris[i].v1.position, &b = tris[i].v2.position, &c = tris[i].v3.position;
-            float lo[3] = { std::min(a.x, std::min(b.x, c.x)), std::min(a.y, std::min(b.y, c.y)), std::min(a.z, std::min(b.z, c.z)) };
-            float hi[3] = { std::max(a.x, std::max(b.x, c.x)), std::max(a.y, std::max(b.y, c.y)), std::max(a.z, std::max(b.z, c.z)) };
-            float cen[3] = { lo[0] * 0.5f + hi[0] * 0.5f, lo[1] * 0.5f + hi[1] * 0.5f, lo[2] * 0.5f + hi[2] * 0.5f };   // CLBVHnode.cpp:190-193
-            const bool fresh = first.empty() || memcmp(cen, prev, 12) != 0 || i - first.back() >= 255;
-            if (fresh) {
-                first.push_back((uint32_t)i);
-                gb.insert(gb.end(), { lo[0], lo[1], lo[2], hi[0], hi[1], hi[2] });
-                memcpy(prev, cen, 12);
-                for (int k = 0; k < 3; ++k) { clo[k] = std::min(clo[k], cen[k]); chi[k] = std::max(chi[k], cen[k]); }
-            } else {
-                float* g = &gb[gb.size() - 6];
-                for (int k = 0; k < 3; ++k) { g[k] = std::min(g[k], lo[k]); g[3 + k] = std::max(g[3 + k], hi[k]); }
+        parts.resize(n_chunks);
+        auto scan_chunk = [&](uint64_t c) {
+            Part& P = parts[c];
+            const uint64_t lo_i = c * CHUNK, hi_i = std::min<uint64_t>(n_triangles, lo_i + CHUNK);
+            P.first.reserve((hi_i - lo_i) / 2 + 2);
+            P.gb.reserve(3 * (hi_i - lo_i) + 6);
+            for (int k = 0; k < 3; ++k) { P.clo[k] = INFINITY; P.chi[k] = -INFINITY; }
+            float prev[3] = { 0, 0, 0 };
+            for (uint64_t i = lo_i; i < hi_i; ++i) {
+                const RefVec &a = tris[i].v1.position, &b = tris[i].v2.position, &c3 = tris[i].v3.position;
+                float lo[3] = { std::min(a.x, std::min(b.x, c3.x)), std::min(a.y, std::min(b.y, c3.y)), std::min(a.z, std::min(b.z, c3.z)) };
+                float hi[3] = { std::max(a.x, std::max(b.x, c3.x)), std::max(a.y, std::max(b.y, c3.y)), std::max(a.z, std::max(b.z, c3.z)) };
+                float cen[3] = { lo[0] * 0.5f + hi[0] * 0.5f, lo[1] * 0.5f + hi[1] * 0.5f, lo[2] * 0.5f + hi[2] * 0.5f };   // CLBVHnode.cpp:190-193
+                const bool fresh = P.first.empty() || memcmp(cen, prev, 12) != 0 || i - P.first.back() >= 255;
+                if (fresh) {
+                    P.first.push_back((uint32_t)i);
+                    P.gb.insert(P.gb.end(), { lo[0], lo[1], lo[2], hi[0], hi[1], hi[2] });
+                    memcpy(prev, cen, 12);
+                    for (int k = 0; k < 3; ++k) { P.clo[k] = std::min(P.clo[k], cen[k]); P.chi[k] = std::max(P.chi[k], cen[k]); }
+                } else {
+                    float* g = &P.gb[P.gb.size() - 6];
+                    for (int k = 0; k < 3; ++k) { g[k] = std::min(g[k], lo[k]); g[3 + k] = std::max(g[3 + k], hi[k]); }
+                }
             }
+        };
+        const unsigned team = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>({ (uint64_t)std::thread::hardware_concurrency(), n_chunks, 16 }));
+        if (team <= 1) { for (uint64_t c = 0; c < n_chunks; ++c) scan_chunk(c); }
+        else {
+            std::atomic<uint64_t> next_chunk{ 0 };
+            std::atomic<bool> oom{ false };
+            std::vector<std::thread> pool;
+            for (unsigned w = 0; w < team; ++w)
+                pool.emplace_back([&]() {
+                    try { for (uint64_t c; (c = next_chunk.fetch_add(1)) < n_chunks;) scan_chunk(c); }
+                    catch (const std::bad_alloc&) { oom = true; }
+                });
+            for (auto& t : pool) t.join();
+            if (oom) throw std::bad_alloc();
+        }
+        size_t total_groups = 0;
+        for (const Part& P : parts) total_groups += P.first.size();
+        first.reserve(total_groups + 1);
+        gb.reserve(6 * total_groups);
+        for (const Part& P : parts) {
+            first.insert(first.end(), P.first.begin(), P.first.end());
+            gb.insert(gb.end(), P.gb.begin(), P.gb.end());
+            for (int k = 0; k < 3; ++k) { clo[k] = std::min(clo[k], P.clo[k]); chi[k] = std::max(chi[k], P.chi[k]); }
         }
         first.push_back((uint32_t)n_triangles);
+        parts.clear();
     } catch (const std::bad_alloc&) {
         return fail(ctx, B2RT_OUT_OF_HOST_MEMORY, "BVH build ran out of host memory");
     }
     const uint32_t m = (uint32_t)first.size() - 1;
     if (nodes_capacity < 2ull * m - 1) return fail(ctx, B2RT_INVALID_VALUE, "node buffer too small: " + std::to_string(2ull * m - 1) + " nodes needed");
     RefNode* out = static_cast<RefNode*>(nodes_out);
-    auto leaf_node = [&](RefNode& nd, uint32_t group, uint32_t first_tri) {
-        memset(&nd, 0, sizeof(nd));
-        const float* g = &gb[6 * (size_t)group];
-        nd.bmin.x = g[0]; nd.bmin.y = g[1]; nd.bmin.z = g[2]; nd.bmax.x = g[3]; nd.bmax.y = g[4]; nd.bmax.z = g[5];
-        nd.offset = first_tri;
-        nd.nPrimitives = (uint16_t)(first[group + 1] - first[group]);
-    };
     if (m == 1) {
-        leaf_node(out[0], 0, 0);
+        RefNode& nd = out[0];
+        memset(&nd, 0, sizeof(nd));
+        nd.bmin.x = gb[0]; nd.bmin.y = gb[1]; nd.bmin.z = gb[2]; nd.bmax.x = gb[3]; nd.bmax.y = gb[4]; nd.bmax.z = gb[5];
+        nd.offset = 0;
+        nd.nPrimitives = (uint16_t)n_triangles;
         for (uint64_t i = 0; i < n_triangles; ++i) order_out[i] = (uint32_t)i;
         *n_nodes_out = 1;
         return B2RT_SUCCESS;
     }
     const double t_grouped = now();
-    // 2. Morton order, hierarchy and boxes on the device
+    // 2. Morton order, hierarchy, boxes AND the reference's flattened format on the device (lbvh.cu): 24 bytes + one index per
+    //    group go up, the CLLinearBVHNode array and the triangle order come back.
     // one stream-ordered allocation for everything (the pool keeps it mapped between builds)
     auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
-    const size_t o_gb = 0, o_children = o_gb + up((size_t)m * 24), o_bounds = o_children + up((size_t)(m - 1) * sizeof(int2)),
-                 o_axis = o_bounds + up((size_t)(m - 1) * 24), o_sorted = o_axis + up(m), o_scratch = o_sorted + up((size_t)m * 4),
-                 total = o_scratch + up(lbvh_scratch_bytes(m));
-    std::vector<int2> children;
-    std::vector<float> nb;
-    std::vector<uint8_t> axis;
-    std::vector<uint32_t> sorted;
-    try { children.resize(m - 1); nb.resize(6 * (size_t)(m - 1)); axis.resize(m - 1); sorted.resize(m); }
-    catch (const std::bad_alloc&) { return fail(ctx, B2RT_OUT_OF_HOST_MEMORY, "BVH build ran out of host memory"); }
+    const uint64_t n_nodes = 2ull * m - 1;
+    const size_t o_gb = 0, o_first = o_gb + up((size_t)m * 24), o_nodes = o_first + up((size_t)(m + 1) * 4), o_order = o_nodes + up(n_nodes * sizeof(RefNode)),
+                 o_scratch = o_order + up((size_t)n_triangles * 4), total = o_scratch + up(lbvh_scratch_bytes(m));
     char* d_all = nullptr;
     cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&d_all), total, ctx->stream);
     if (e != cudaSuccess) return cuda_fail(ctx, e, "device BVH build allocation");
     if ((e = cudaMemcpyAsync(d_all + o_gb, gb.data(), (size_t)m * 24, cudaMemcpyHostToDevice, ctx->stream)) == cudaSuccess &&
-        (e = lbvh_build(reinterpret_cast<const float*>(d_all + o_gb), m, clo, chi, d_all + o_scratch, reinterpret_cast<int2*>(d_all + o_children),
-                        reinterpret_cast<float*>(d_all + o_bounds), reinterpret_cast<uint8_t*>(d_all + o_axis),
-                        reinterpret_cast<uint32_t*>(d_all + o_sorted), &ctx->launches, ctx->stream)) == cudaSuccess &&
-        (e = cudaMemcpyAsync(children.data(), d_all + o_children, (size_t)(m - 1) * sizeof(int2), cudaMemcpyDeviceToHost, ctx->stream)) == cudaSuccess &&
-        (e = cudaMemcpyAsync(nb.data(), d_all + o_bounds, (size_t)(m - 1) * 24, cudaMemcpyDeviceToHost, ctx->stream)) == cudaSuccess &&
-        (e = cudaMemcpyAsync(axis.data(), d_all + o_axis, m - 1, cudaMemcpyDeviceToHost, ctx->stream)) == cudaSuccess &&
-        (e = cudaMemcpyAsync(sorted.data(), d_all + o_sorted, (size_t)m * 4, cudaMemcpyDeviceToHost, ctx->stream)) == cudaSuccess)
+        (e = cudaMemcpyAsync(d_all + o_first, first.data(), (size_t)(m + 1) * 4, cudaMemcpyHostToDevice, ctx->stream)) == cudaSuccess &&
+        (e = lbvh_build(reinterpret_cast<const float*>(d_all + o_gb), reinterpret_cast<const uint32_t*>(d_all + o_first), m, clo, chi, d_all + o_scratch,
+                        reinterpret_cast<RefNode*>(d_all + o_nodes), reinterpret_cast<uint32_t*>(d_all + o_order), &ctx->launches, ctx->stream)) == cudaSuccess &&
+        (e = cudaMemcpyAsync(out, d_all + o_nodes, n_nodes * sizeof(RefNode), cudaMemcpyDeviceToHost, ctx->stream)) == cudaSuccess &&
+        (e = cudaMemcpyAsync(order_out, d_all + o_order, (size_t)n_triangles * 4, cudaMemcpyDeviceToHost, ctx->stream)) == cudaSuccess)
         e = cudaStreamSynchronize(ctx->stream);
     cudaFreeAsync(d_all, ctx->stream);
     if (e != cudaSuccess) return cuda_fail(ctx, e, "device BVH build");
-    const double t_device = now();
-    // 3. the reference's format: pre-order numbering, first child at index + 1, `offset` = second child (interior) or
-    //    first triangle (leaf); triangles re-ordered leaf by leaf (FlattenBVHTree, CLBVHnode.cpp:161-183)
-    struct Visit { int ref; int64_t parent; };
-    std::vector<Visit> todo;
-    todo.push_back(Visit{ 0, -1 });
-    uint64_t next = 0, tri_out = 0;
-    while (!todo.empty()) {
-        const Visit v = todo.back();
-        todo.pop_back();
-        const uint64_t me = next++;
-        if (v.parent >= 0) out[v.parent].offset = (uint32_t)me;
-        if (v.ref < 0) {
-            const uint32_t g = sorted[~v.ref];
-            leaf_node(out[me], g, (uint32_t)tri_out);
-            for (uint32_t t = first[g]; t < first[g + 1]; ++t) order_out[tri_out++] = t;
-        } else {
-            RefNode& nd = out[me];
-            memset(&nd, 0, sizeof(nd));
-            const float* b = &nb[6 * (size_t)v.ref];
-            nd.bmin.x = b[0]; nd.bmin.y = b[1]; nd.bmin.z = b[2]; nd.bmax.x = b[3]; nd.bmax.y = b[4]; nd.bmax.z = b[5];
-            nd.axis = axis[v.ref];
-            todo.push_back(Visit{ children[v.ref].y, (int64_t)me });    // numbered after the whole first subtree
-            todo.push_back(Visit{ children[v.ref].x, -1 });             // numbered next: index me + 1
-        }
-    }
-    if (next != 2ull * m - 1 || tri_out != n_triangles) return fail(ctx, B2RT_OUT_OF_RESOURCES, "device BVH build produced an inconsistent tree");
-    if (trace) fprintf(stderr, "[b2rt_build_bvh] %llu triangles, %u groups: grouping %.1f ms, device (alloc + copies + 93 launches) %.1f ms, flatten %.1f ms\n",
-                       (unsigned long long)n_triangles, m, (t_grouped - t_start) * 1e3, (t_device - t_grouped) * 1e3, (now() - t_device) * 1e3);
-    *n_nodes_out = next;
+    if (trace) fprintf(stderr, "[b2rt_build_bvh] %llu triangles, %u groups: grouping %.1f ms, device (alloc + copies + 20 launches, flattened there) %.1f ms\n",
+                       (unsigned long long)n_triangles, m, (t_grouped - t_start) * 1e3, (now() - t_grouped) * 1e3);
+    *n_nodes_out = n_nodes;
     return B2RT_SUCCESS;
 }
 
