@@ -94,13 +94,20 @@ class BandPlan:
 def gather_frame(plan, frame, rank, group=None):
     """All ranks end up with the complete frame. `frame` is this rank's (W*H, C) buffer in which only its own
     bands are valid. One collective: all_gather of equal contiguous shards. The returned tensor is a buffer owned by
-    `plan` and is overwritten by the next gather."""
+    `plan` and is overwritten by the next gather. `frame` is usually a zero-copy view of the library's output image, which the
+    next frame's kernels (on the context's own stream) overwrite: the torch stream is therefore drained before returning, so
+    that the pack copy has read `frame` and the result is complete when the caller goes on. (Harness utility: the product's
+    multi-GPU path is b2rt_execute_shard / b2rt_create_multi, which need no gather.)"""
     shard = plan.pack(frame, rank)
     if plan.world == 1:
-        return plan.unpack(shard)
-    out = plan._buffer("gathered", (plan.world * shard.shape[0], shard.shape[1]), shard)
-    dist.all_gather_into_tensor(out, shard, group=group)
-    return plan.unpack(out)
+        out = plan.unpack(shard)
+    else:
+        gathered = plan._buffer("gathered", (plan.world * shard.shape[0], shard.shape[1]), shard)
+        dist.all_gather_into_tensor(gathered, shard, group=group)
+        out = plan.unpack(gathered)
+    if out.is_cuda:
+        torch.cuda.current_stream(out.device).synchronize()
+    return out
 
 
 class DeviceBuffer:
