@@ -291,6 +291,31 @@ def test_leaf_blocks_with_explicit_boxes(tmp_scene_dir):
         _same(ol.emu_trace_coop(rays[:6000]), want[:6000])
 
 
+def test_scaled_and_offset_scenes(tmp_scene_dir):
+    """The packed-fp16 node test works in a per-visit frame (entry distance, power-of-two scale): tiny scenes, huge scenes
+    and scenes far from the origin (coordinates ~1e5 with metre-sized triangles, where fp32 itself leaves only ~7 bits
+    inside a leaf) must still give the oracle's hits, with tmax left at its default and tightened to scene size."""
+    import os
+    p, n, f = scenes.displaced_sphere(4)
+    for k, (scale, centre) in enumerate(((1.0e-4, (0.0, 0.0, 0.0)), (1.0e4, (0.0, 0.0, 0.0)), (1.0, (1.0e5, -2.0e5, 5.0e4)),
+                                         (1.0e-3, (-300.0, 700.0, 90.0)), (3.0e5, (1.0e7, 1.0e7, -1.0e7)))):
+        q = (p.astype(np.float64) * scale + np.asarray(centre)).astype(np.float32)
+        path = scenes.write_obj(os.path.join(tmp_scene_dir, "scaled%d.obj" % k), q, n, f)
+        tris, nodes, _ = _reference_scene(path)
+        ol.emu_build(tris, nodes)
+        radius = 10.0 * scale
+        for tmax in (max(100000.0, 40.0 * radius), 3.5 * radius):      # the default (or beyond the scene), and one that cuts rays short
+            rays = np.concatenate([scenes.shell_rays(6000, radius, seed=61 + k, centre=centre, tmax=tmax),
+                                   scenes.box_rays(3000, np.asarray(centre) - 1.5 * radius, np.asarray(centre) + 1.5 * radius, seed=71 + k, tmax=tmax)])
+            want = ol.oracle_closest(tris, nodes, rays)
+            if scale >= 1.0:                                      # (tiny triangles fall under the reference's det < 1e-8 cull: all misses)
+                assert (want["tri"] != MISS).mean() > 0.25
+            _same(ol.emu_trace(rays), want)
+            _same(ol.emu_trace(rays, schedule=3), want)
+            _same(ol.emu_trace_coop(rays[:3000], handoff=7), want[:3000])
+            assert np.array_equal(ol.emu_trace(rays, any_hit=True) != 0, ol.oracle_any(tris, nodes, rays) != 0)
+
+
 def test_fast_node_test_never_culls_what_the_exact_one_lets_through():
     """Runs last in this file: every emulated walk above (all scenes, schedules and the cooperative mode's solo prefixes)
     compared, node by node, the fast wide-node test with test_wide_node_robust on the same node, ray and `best`

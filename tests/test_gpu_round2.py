@@ -378,3 +378,27 @@ def test_leaf_blocks_with_explicit_boxes_on_the_gpu(product, tmp_scene_dir):
                     _check_hits(ctx.trace_closest(rays), want)
                     _check_hits(np.concatenate([ctx.trace_closest(rays[i:i + 16]) for i in range(0, 800, 16)]), want[:800])
                 assert np.array_equal(ctx.trace_any(rays) != 0, ol.oracle_any(tris, nd, rays) != 0)
+
+
+def test_scaled_and_offset_scenes_on_the_gpu(product, tmp_scene_dir):
+    """The packed-fp16 wide-node test evaluates slabs in a per-visit frame (relative to the entry distance, scaled by a
+    power of two): scenes of very different size and scenes far from the origin must give the oracle's hits bit for bit
+    (the same cases run through the CPU emulation with the node-by-node culling check, tests/test_emu_traversal.py)."""
+    cap = product.capi
+    p, n, f = scenes.displaced_sphere(4)
+    for k, (scale, centre) in enumerate(((1.0e4, (0.0, 0.0, 0.0)), (1.0, (1.0e5, -2.0e5, 5.0e4)), (1.0e-3, (-300.0, 700.0, 90.0)),
+                                         (3.0e5, (1.0e7, 1.0e7, -1.0e7)))):
+        q = (p.astype(np.float64) * scale + np.asarray(centre)).astype(np.float32)
+        path = scenes.write_obj(os.path.join(tmp_scene_dir, "scaled_gpu%d.obj" % k), q, n, f)
+        tris, nodes, mats = product.host.load_scene(path, 4)
+        radius = 10.0 * scale
+        with product.Context(0) as ctx:
+            ctx.upload_scene(tris, nodes, mats)
+            for tmax in (max(100000.0, 40.0 * radius), 3.5 * radius):
+                rays = np.concatenate([scenes.shell_rays(40000, radius, seed=61 + k, centre=centre, tmax=tmax),
+                                       scenes.box_rays(20000, np.asarray(centre) - 1.5 * radius, np.asarray(centre) + 1.5 * radius, seed=71 + k, tmax=tmax)])
+                want = ol.oracle_closest(tris, nodes, rays)
+                for coop in (8, 0):
+                    ctx.set_option(cap.OPT_COOP_MAX, coop)
+                    _check_hits(ctx.trace_closest(rays), want)
+                assert np.array_equal(ctx.trace_any(rays) != 0, ol.oracle_any(tris, nodes, rays) != 0)
