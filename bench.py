@@ -325,17 +325,19 @@ def run_b200(args, rank, world, local_rank):
             d_camhits = torch.empty((W4 * H4, 4), dtype=torch.float32, device="cuda")
             sc.camera_rays_device(0, W4 * H4, d_cam.data_ptr(), stream.cuda_stream)
 
+            reps_sc = max(args.steps, 20)            # launches of 2-3 ms: enough of them for a steady figure
+
             def timed_sc(fn):
                 with torch.cuda.stream(stream):
-                    for _ in range(args.warmup):
+                    for _ in range(max(args.warmup, 3)):
                         fn()
                     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     e0.record()
-                    for _ in range(args.steps):
+                    for _ in range(reps_sc):
                         fn()
                     e1.record()
                 torch.cuda.synchronize()
-                return e0.elapsed_time(e1)
+                return e0.elapsed_time(e1) * args.steps / reps_sc      # scaled to args.steps launches, which the rates below divide by
             prim_ms = timed_sc(lambda: sc.trace_closest_device(d_cam.data_ptr(), W4 * H4, d_camhits.data_ptr(), stream.cuda_stream))
             cam_np = d_cam.cpu().numpy().view(prod.RAY_DTYPE).reshape(-1)
             camhits_np = d_camhits.cpu().numpy().view(prod.HIT_DTYPE).reshape(-1)
