@@ -701,7 +701,10 @@ def run_b200(args, rank, world, local_rank):
             "cpu_baseline": cpu,
             "clocks": clocks,
         }
-        out["parity_full_step_vs_reference_layout_walk"] = {"rays": n, "ids_and_t_bit_identical": same_bits}
+        out["parity_full_step_vs_reference_layout_walk"] = {"rays": n, "ids_and_t_bit_identical": same_bits,
+                                                            "kind": "self-comparison: the wide-BVH kernel against the product's own one-thread-per-ray walk over the reference's "
+                                                                    "48 B / 256 B arrays in the reference's order (itself oracle-checked at test sizes); the oracle comparison of "
+                                                                    "this run is parity_ids_identical_frac_100k"}
         out.update(extra)
         emit(out)
     eng.close()
