@@ -346,9 +346,17 @@ namespace Glaze3D
         int st = b2rt_build_bvh(ctx, m_Triangles.data(), m_Triangles.size(), nodes.data(), nodes.size(), &n_nodes, order.data());
         if (st) throw CLException(std::string("Failed to build the BVH on the device: ") + b2rt_last_error(ctx), st);
         nodes.resize(n_nodes);
-        std::vector<CLTriangle> ordered;
-        ordered.reserve(order.size());
-        for (uint32_t src : order) ordered.push_back(m_Triangles[src]);
+        // re-order m_Triangles like CreateBVHTrees does (CLBVHnode.cpp:197): a 256-byte gather per triangle, split over a team
+        std::vector<CLTriangle> ordered(order.size());
+        const size_t n = order.size();
+        const unsigned team = (unsigned)std::max<size_t>(1, std::min<size_t>({ (size_t)std::thread::hardware_concurrency(), n / 65536 + 1, 16 }));
+        auto gather = [&](size_t lo, size_t hi) { for (size_t k = lo; k < hi; ++k) ordered[k] = m_Triangles[order[k]]; };
+        if (team <= 1) gather(0, n);
+        else {
+            std::vector<std::thread> pool;
+            for (unsigned w = 0; w < team; ++w) pool.emplace_back(gather, n * w / team, n * (w + 1) / team);
+            for (auto& t : pool) t.join();
+        }
         m_Triangles.swap(ordered);
         m_Nodes.swap(nodes);
         SetupBuffers();
