@@ -12,8 +12,8 @@
 //    reference's exact Moller-Trumbore sequence; results are committed leaf by leaf in frontier order,
 //    every leaf gated by its exact fp32 box against the `best` of that moment -- the reference's own
 //    sequence of decisions, so ties and negative t resolve as in the solo walk (traverse.cuh);
-//  * the first B2_COOP_NODES interior entries of the frontier are expanded in one round, 8 lanes per
-//    node, one lane per child in the reference's visiting order (same conservative quantised slab test
+//  * the first B2_COOP_NODES (8) interior entries of the frontier are expanded in one round, four lanes per
+//    node, two children per lane in the reference's visiting order (same conservative quantised slab test
 //    as test_wide_node); passing children replace their parent in place, keeping the order. Interior
 //    nodes behind unresolved leaves are thereby tested with a stale (larger) `best`, which can only let
 //    more children through -- allowed for the same reason as the solo walk's speculation.
@@ -23,8 +23,10 @@
 #include "traverse.cuh"
 
 #ifndef B2_COOP_NODES
-#define B2_COOP_NODES 4
+#define B2_COOP_NODES 8         // interior entries expanded per round: 4 (eight lanes per node, one child per lane) or 8 (four lanes, two children)
 #endif
+#define COOP_LPN (32 / B2_COOP_NODES)      // lanes per expanded node
+#define COOP_CPL (B2_COOP_NODES / 4)       // children per lane
 
 namespace b2rt {
 
@@ -125,21 +127,21 @@ B2_HD void coop_trace(const U4* wide, const U4* leaf, uint32_t* F, uint32_t n, u
             const U4* p = leaf + (lref & ~REF_LEAF_BIT);
             va = ld128(p); vb = ld128(p + 1); vc = ld128(p + 2);
         }
-        // ---- fetch: the first Q interior entries of the window, eight lanes each = one lane per child ---------------------
+        // ---- fetch: the first Q interior entries of the window, COOP_LPN lanes each, every lane COOP_CPL children -------------
         uint32_t Q = n <= wide_limit ? (uint32_t)B2_COOP_NODES : 1u;
         const uint32_t have = popc32(mnode);
         if (Q > have) Q = have;
-        uint32_t pos0 = 32, pos1 = 32, pos2 = 32, pos3 = 32;
+        // window positions of those Q entries: mexp has their bits, gpos is the one this lane's group expands
+        const uint32_t grp = lane / COOP_LPN, jj = lane % COOP_LPN;
+        uint32_t mexp = 0, gpos = 0;
         {
             uint32_t mm = mnode;
-            if (Q > 0u) { pos0 = ctz32(mm); mm &= mm - 1u; }
-            if (Q > 1u) { pos1 = ctz32(mm); mm &= mm - 1u; }
-            if (Q > 2u) { pos2 = ctz32(mm); mm &= mm - 1u; }
-            if (Q > 3u) { pos3 = ctz32(mm); }
+#pragma unroll
+            for (uint32_t g = 0; g < (uint32_t)B2_COOP_NODES; ++g) {
+                if (g < Q) { const uint32_t pos = ctz32(mm); mm &= mm - 1u; mexp |= 1u << pos; if (g == grp) gpos = pos; }
+            }
         }
-        const uint32_t grp = lane >> 3, j = lane & 7u;
         const bool gact = grp < Q;
-        const uint32_t gpos = grp == 0u ? pos0 : (grp == 1u ? pos1 : (grp == 2u ? pos2 : pos3));
         const uint32_t node = w_shfl(e, gact ? gpos : 0u);
         U4 w0 = { 0, 0, 0, 0 }, w1 = w0, w2 = w0, w3 = w0, w4 = w0;
         uint32_t order = 0;
@@ -209,35 +211,58 @@ B2_HD void coop_trace(const U4* wide, const U4* leaf, uint32_t* F, uint32_t n, u
         }
 
         // ---- nodes, against the `best` the leaves of this round left ---------------------------------------------------------
-        bool pass = false;
-        uint32_t ref = REF_EMPTY;
-        if (gact) {
-            const uint32_t slot = (order >> (4u * j)) & 7u;                   // child visited j-th (reference order)
-            if (j < (w0.w >> 24) && coop_child_test(w0, w2, w3, w4, slot, r, h.t)) {
-                pass = true;
-                const uint32_t mb = prmt(w1.z, w1.w, slot) & 0xffu;
-                ref = mb + ((mb & META_INTERIOR) ? w1.x - (uint32_t)META_INTERIOR : (REF_LEAF_BIT | w1.y));
-                // towards L2 for the next round: the child's node record or leaf block (either may straddle two lines)
-                const U4* c = (ref & REF_LEAF_BIT) ? leaf + (ref & ~REF_LEAF_BIT) : wide + (uint32_t)WIDE_NODE_WORDS * ref;
-                prefetch_l2(c); prefetch_l2(c + 6);
+        bool pass[COOP_CPL];
+        uint32_t ref[COOP_CPL], pm[COOP_CPL];
+#pragma unroll
+        for (uint32_t t = 0; t < (uint32_t)COOP_CPL; ++t) {
+            pass[t] = false; ref[t] = REF_EMPTY;
+            const uint32_t j = jj + COOP_LPN * t;                              // child visited j-th (reference order)
+            if (gact) {
+                const uint32_t slot = (order >> (4u * j)) & 7u;
+                if (j < (w0.w >> 24) && coop_child_test(w0, w2, w3, w4, slot, r, h.t)) {
+                    pass[t] = true;
+                    const uint32_t mb = prmt(w1.z, w1.w, slot) & 0xffu;
+                    ref[t] = mb + ((mb & META_INTERIOR) ? w1.x - (uint32_t)META_INTERIOR : (REF_LEAF_BIT | w1.y));
+                    // towards L2 for the next round: the child's node record or leaf block (either may straddle two lines)
+                    const U4* c = (ref[t] & REF_LEAF_BIT) ? leaf + (ref[t] & ~REF_LEAF_BIT) : wide + (uint32_t)WIDE_NODE_WORDS * ref[t];
+                    prefetch_l2(c); prefetch_l2(c + 6);
+                }
             }
+            pm[t] = w_ballot(pass[t]);
         }
-        const uint32_t hm = w_ballot(pass);
-        const int c0 = Q > 0u ? (int)popc32(hm & 0xffu) - 1 : 0, c1 = Q > 1u ? (int)popc32((hm >> 8) & 0xffu) - 1 : 0,
-                  c2 = Q > 2u ? (int)popc32((hm >> 16) & 0xffu) - 1 : 0, c3 = Q > 3u ? (int)popc32(hm >> 24) - 1 : 0;
-        // window entries [0, K) are rewritten: the nl leaves at the front are consumed, every expanded node is replaced by
-        // its passing children, leaves in between keep their place
-        const uint32_t lastpos = Q > 3u ? pos3 : (Q > 2u ? pos2 : (Q > 1u ? pos1 : (Q > 0u ? pos0 : 0u)));
-        const uint32_t K = Q ? lastpos + 1u : nl;
-        // position (front first) of window entry p >= nl after the rewrite
-        #define B2_COOP_FP(p) ((int)(p) - (int)nl + (pos0 < (p) ? c0 : 0) + (pos1 < (p) ? c1 : 0) + (pos2 < (p) ? c2 : 0) + (pos3 < (p) ? c3 : 0))
-        const uint32_t newn = (uint32_t)((int)(n - nl) + c0 + c1 + c2 + c3);
+        // Window entries are rewritten in place: the nl leaves at the front are consumed, every expanded node is replaced by
+        // its passing children (in visiting order), everything else keeps its place. What window position `lane` puts out:
+        const uint32_t gmask = (1u << COOP_LPN) - 1u;
+        uint32_t mine = 0;                                                      // entries this window position contributes
+        if (lane >= nl && lane < win) {
+            if ((mexp >> lane) & 1u) {
+                const uint32_t g = popc32(mexp & lanes_below(lane));           // which group expanded the node at this position
+#pragma unroll
+                for (uint32_t t = 0; t < (uint32_t)COOP_CPL; ++t) mine += popc32((pm[t] >> (COOP_LPN * g)) & gmask);
+            } else mine = 1u;
+        }
+        // exclusive prefix sum of `mine` over the window (counts are at most 8: four ballots)
+        uint32_t before_me = 0, total = 0;
+#pragma unroll
+        for (uint32_t bit = 0; bit < 4u; ++bit) {
+            const uint32_t bm = w_ballot((mine >> bit) & 1u);
+            before_me += popc32(bm & lanes_below(lane)) << bit;
+            total += popc32(bm) << bit;
+        }
+        const uint32_t newn = n - win + total;
         if (COUNT) { tc.wide_nodes += Q; tc.words += WIDE_NODE_WORDS * Q; if (newn > tc.max_stack) tc.max_stack = newn; }
         if (newn > fcap) { overflow = true; n = 0; break; }
+        const uint32_t K = Q ? top_bit(mexp) + 1u : nl;   // beyond the last expanded entry nothing moves
+        const uint32_t node_first = w_shfl(before_me, gact ? gpos : 0u);      // where this group's children start
         w_sync();                                                    // every lane holds its window entry
-        if (lane >= nl && lane < K && !is_node) F[newn - 1u - (uint32_t)B2_COOP_FP(lane)] = e;
-        if (pass) F[newn - 1u - (uint32_t)(B2_COOP_FP(gpos) + (int)popc32((hm >> (8u * grp)) & 0xffu & lanes_below(j)))] = ref;
-        #undef B2_COOP_FP
+        if (lane >= nl && lane < K && !((mexp >> lane) & 1u)) F[newn - 1u - before_me] = e;
+        uint32_t earlier = 0;                                                   // passing children of this node before child j
+#pragma unroll
+        for (uint32_t t = 0; t < (uint32_t)COOP_CPL; ++t) {
+            const uint32_t gb = (pm[t] >> (COOP_LPN * grp)) & gmask;
+            if (pass[t]) F[newn - 1u - (node_first + earlier + popc32(gb & lanes_below(jj)))] = ref[t];
+            earlier += popc32(gb);
+        }
         w_sync();
         n = newn;
     }

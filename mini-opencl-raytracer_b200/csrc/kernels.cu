@@ -609,7 +609,7 @@ cudaError_t launch_trace_wide(const SceneView& s, const void* d_rays, uint64_t n
     if (e == cudaSuccess && between) e = cudaEventRecord(between, st);
     if (e != cudaSuccess || !tail.coop_max) return e;
     // the tail kernel: frontier capacity per warp and the size up to which four nodes are expanded per round
-    const uint32_t fcap = tail_frontier_words(stack_bound), wide_limit = fcap - (stack_bound + 8u) - 32u;
+    const uint32_t fcap = tail_frontier_words(stack_bound), wide_limit = fcap - (stack_bound + 8u) - (7u * B2_COOP_NODES + 4u);   // a round adds at most 7 entries per expanded node
     const size_t smem = (size_t)(TAIL_BLOCK / 32) * fcap * sizeof(uint32_t);
     const RayIn* r = static_cast<const RayIn*>(d_rays);
     if (any) { if (count) trace_tail_kernel<true, true><<<tail_grid, TAIL_BLOCK, smem, st>>>(s, r, d_out, q2, d_counters, fcap, wide_limit);
