@@ -115,8 +115,8 @@ enum {
     B2RT_OPT_RENDER_MODE = 3,   /* frame path: 0 = wavefront (generate, then trace + shade/compact per bounce), 1 = megakernel
                                    (one thread per pixel, like KernelEntry), 2 = whichever of the two measures faster for the
                                    launch shape at hand (default). Frames are bit-identical in every mode. */
-    B2RT_OPT_REFILL_MIN = 4,    /* idle lanes of a warp that trigger a ray refill (1..32, default 8) */
-    B2RT_OPT_LEAF_BIAS = 5,     /* weight of the leaf vote in sixteenths (16 = plain majority, default 32) */
+    B2RT_OPT_REFILL_MIN = 4,    /* idle lanes of a warp that trigger a ray refill (1..32, default 6) */
+    B2RT_OPT_LEAF_BIAS = 5,     /* weight of the leaf vote in sixteenths (16 = plain majority; 0 = default: 32 closest-hit and frames, 48 any-hit) */
     B2RT_OPT_WAVEFRONT_LANES = 6, /* wavefront frame path: independent wavefronts in flight per launch, 1..4 (0 = by size) */
     B2RT_OPT_L2_PERSIST = 8,    /* 1 (default): the wide-node array is kept resident in L2 by an access-policy window (persisting
                                    carve-out sized to it) on every stream that runs traversal kernels; 0 = plain caching.

@@ -257,7 +257,7 @@ int trace_device(b2rt_context* ctx, const void* d_rays, uint64_t n, void* d_out,
     int st_tail = tail_queue(ctx, (int)(seq % TAIL_RING), next + 1, next + 2, tail);
     if (st_tail) return st_tail;
     CK(launch_trace_wide(ctx->view, d_rays, n, d_out, any, ctx->opt_counters != 0, ctx->stack_bound, grid, next,
-                         ctx->d_counters, (uint32_t)ctx->opt_refill_min, (uint32_t)ctx->opt_leaf_bias, st, nullptr, &tail, ctx->grid_tail));
+                         ctx->d_counters, (uint32_t)ctx->opt_refill_min, (uint32_t)(ctx->opt_leaf_bias ? ctx->opt_leaf_bias : (any ? 48 : 32)), st, nullptr, &tail, ctx->grid_tail));
     ctx->launches += tail.coop_max ? (tail.resume_max ? 3 : 2) : 1;
     return B2RT_SUCCESS;
 }
@@ -397,7 +397,7 @@ int wavefront_lane(b2rt_context* ctx, const FrameArgs& a, float* d_result, const
         const int in = b & 1, out = in ^ 1;
         unsigned long long *n_in = cnt + (b % 3), *n_out = cnt + ((b + 1) % 3), *n_clear = cnt + ((b + 2) % 3);
         CK(launch_trace_wide(ctx->view, rays[in], n, hits, false, ctx->opt_counters != 0, ctx->stack_bound, grid,
-                             cnt + 3, ctx->d_counters, (uint32_t)ctx->opt_refill_min, (uint32_t)ctx->opt_leaf_bias, s, n_in, &tail, tail_grid,
+                             cnt + 3, ctx->d_counters, (uint32_t)ctx->opt_refill_min, (uint32_t)(ctx->opt_leaf_bias ? ctx->opt_leaf_bias : 32), s, n_in, &tail, tail_grid,
                              stage_mark(ctx, timed, B2RT_STAGE_TRACE, s)));
         STAGE(B2RT_STAGE_TAIL);
         // the shade stage also clears the counter the NEXT shade stage appends to and the traversal kernels' three counters
@@ -1132,7 +1132,7 @@ static int set_option_one(b2rt_context* ctx, uint32_t option, int64_t value) {
         case B2RT_OPT_BLOCKS_PER_SM: if (value < 0 || value > 32) return fail(ctx, B2RT_INVALID_VALUE, "blocks per SM out of range"); ctx->opt_blocks_per_sm = value; break;
         case B2RT_OPT_RENDER_MODE: if (value < 0 || value > 2) return fail(ctx, B2RT_INVALID_VALUE, "render mode must be 0 (wavefront), 1 (megakernel) or 2 (measured choice)"); ctx->opt_render_mode = value; break;
         case B2RT_OPT_WAVEFRONT_LANES: if (value < 0 || value > 4) return fail(ctx, B2RT_INVALID_VALUE, "wavefront lanes must be 0 (auto) .. 4"); ctx->opt_wf_lanes = value; break;
-        case B2RT_OPT_LEAF_BIAS: if (value < 1 || value > 512) return fail(ctx, B2RT_INVALID_VALUE, "leaf bias must be 1..512 (sixteenths)"); ctx->opt_leaf_bias = value; break;
+        case B2RT_OPT_LEAF_BIAS: if (value < 0 || value > 512) return fail(ctx, B2RT_INVALID_VALUE, "leaf bias must be 0 (default) or 1..512 (sixteenths)"); ctx->opt_leaf_bias = value; break;
         case B2RT_OPT_COOP_MAX: if (value < -1 || value > COOP_MAX_LIMIT) return fail(ctx, B2RT_INVALID_VALUE, "cooperative tail threshold must be -1 (auto), 0 (off) .. 16"); ctx->opt_coop_max = value; break;
         case B2RT_OPT_L2_PERSIST: ctx->opt_l2_persist = value ? 1 : 0; if (!ctx->scene_dirty && use_device(ctx) == B2RT_SUCCESS) { cudaStreamSynchronize(ctx->stream); scene_l2_setup(ctx); } break;
         case B2RT_OPT_RESUME_MAX: if (value < -1 || value > COOP_MAX_LIMIT) return fail(ctx, B2RT_INVALID_VALUE, "resume threshold must be -1 (auto), 0 (off) .. 16"); ctx->opt_resume_max = value; break;

@@ -42,8 +42,11 @@ static constexpr unsigned FULL = 0xffffffffu;
 #ifndef B2_STREAM_HINTS
 #define B2_STREAM_HINTS 1
 #endif
+#ifndef B2_NODE_STAY_ANY
+#define B2_NODE_STAY_ANY 16      // the same threshold in the any-hit kernel (r2 A/B: 16 is +2.5 % over 20 there, and -5 % for closest-hit)
+#endif
 #ifndef B2_NODE_STAY
-#define B2_NODE_STAY 20          // (0 = off; r2 A/B: +0.9 % closest-hit at 20, +1.2 % at 24 with -0.5 % any-hit, -1.2 % at 28) > 0: consecutive node phases without a scheduling round while this many lanes want one
+#define B2_NODE_STAY 24          // (0 = off; r2 A/B: +0.9 % closest-hit at 20, +1.2 % at 24 with -0.5 % any-hit, -1.2 % at 28) > 0: consecutive node phases without a scheduling round while this many lanes want one
 #endif
 // "Touch" prefetch: an ordinary cached load whose result is never read, issued as soon as the next
 // node / leaf of a lane is known so that the line is (on its way) in L1 when the step runs.
@@ -51,6 +54,7 @@ __device__ __forceinline__ void touch(const void* p) { unsigned d; asm volatile(
 static constexpr int TRACE_BLOCK = 128;
 
 struct RayIn { float ox, oy, oz, tmin, dx, dy, dz, tmax; };
+enum { STAGE_WORDS = 11 };
 
 __device__ __forceinline__ void load_ray(const RayIn* rays, uint64_t i, RayX& r, float& tmax) {
     // rays are read once and hits written once: streaming (evict-first) accesses keep them from displacing the
@@ -143,8 +147,11 @@ trace_tail_kernel(SceneView s, const RayIn* __restrict__ rays, void* __restrict_
     }
 }
 
-#ifndef B2_TAIL_CHECK_POS
-#define B2_TAIL_CHECK_POS 0      // where the loop tests for the hand-over: 0 = after the refill branch, 1 = at the top (A/B of code generation)
+#ifndef B2_STAGE_RAYS
+#define B2_STAGE_RAYS 1          // ray set-up (InitRay: one square root, six divisions) done by all 32 lanes for the next 32 rays of the warp's pool and parked in shared memory; a refill is then ten shared-memory loads
+#endif
+#ifndef B2_SMEM_STACK
+#define B2_SMEM_STACK 12         // entries of every lane's traversal stack kept in shared memory (HybridStack, traverse.cuh); 0 = all in local memory
 #endif
 #ifndef B2_TAIL_NOINLINE
 #define B2_TAIL_NOINLINE 1      // measured (r2 A/B, 10^8-ray stream): inlined 2 840 Mrays/s, not inlined 2 885 = the kernel without any hand-over code
@@ -207,15 +214,34 @@ trace_persistent(SceneView s, const RayIn* __restrict__ rays, uint64_t n, void* 
         chunk = (uint32_t)(c < 32 ? 32 : (c > 512 ? 512 : (c & ~31ull)));
     }
     Lane<ANY, COUNT, CAP> L;
-    uint32_t stack[CAP];
+    uint32_t local_stack[CAP];
+#if B2_SMEM_STACK
+    __shared__ uint32_t smem_stack[B2_SMEM_STACK * TRACE_BLOCK];
+    const HybridStack<B2_SMEM_STACK, TRACE_BLOCK> stack = { smem_stack + threadIdx.x, local_stack };
+#else
+    uint32_t* const stack = local_stack;
+#endif
+#if B2_STAGE_RAYS
+    // [word][slot] per warp: o, d (normalised), 1/d, tmax, sign -- the slot of ray i is i mod 32 (the staged rays are the
+    // next <= 32 of the warp's contiguous pool, so the slots are distinct)
+    __shared__ uint32_t smem_rays[(TRACE_BLOCK / 32) * STAGE_WORDS * 32];
+    uint32_t* const stage = smem_rays + (threadIdx.x >> 5) * (STAGE_WORDS * 32);
+    // Staged at any time: the rays of the pool that share pool_next's block of 32 indices (pool chunks start at multiples of
+    // 32), set up when pool_next enters the block -- no extra state.
+#endif
     L.clear();
     L.overflow = false;
     L.tc.wide_nodes = L.tc.leaf_blocks = L.tc.leaf_pass = L.tc.tri_tests = L.tc.words = L.tc.max_stack = L.tc.rounds = 0;
     uint64_t my_index = 0;
-    bool has_out = false;                    // this lane's finished ray still has to be written (done together with the next refill)
+    uint32_t has_out = 0;                    // this lane's finished ray still has to be written (done together with the next refill)
     uint64_t pool_next = 0;                  // warp-uniform: next ray of the warp's pool ...
     uint32_t pool_left = 0;                  // ... and how many it still holds
     bool exhausted = false;                  // warp-uniform: the global counter ran past n
+    // warp-uniform: the number of idle lanes at which the warp leaves the step loop -- refill_min while the pool can still be
+    // topped up, 32 - coop_max (hand-over to the cooperative tail; 32 = only when every lane is idle) once it has run dry.
+    // One compare per scheduling round instead of the refill / finished / hand-over conditions one by one.
+    uint32_t leave_at = refill_min;
+    bool dry = false;
     uint32_t traced = 0;
     uint32_t ray_steps = 0, max_ray_steps = 0;   // COUNT only: node + leaf steps of the current ray / the worst ray of this lane
     uint32_t ph_node = 0, ph_node_lanes = 0, ph_leaf = 0, ph_leaf_lanes = 0, ph_refill = 0, ph_refill_lanes = 0;   // COUNT only, warp-uniform
@@ -224,15 +250,15 @@ trace_persistent(SceneView s, const RayIn* __restrict__ rays, uint64_t n, void* 
     for (;;) {
         const unsigned vn = __ballot_sync(FULL, L.wants_node());
         const unsigned vl = __ballot_sync(FULL, L.wants_leaf());
-        const unsigned idle = ~(vn | vl);
-        const bool pool_dry = exhausted && pool_left == 0u;
-#if B2_TAIL_CHECK_POS == 1
-        if (B2_TAIL_CODE && pool_dry && (unsigned)__popc(vn | vl) <= tail.coop_max && (vn | vl) != 0u) break;
-#endif
-        if (idle && !pool_dry && ((unsigned)__popc(idle) >= refill_min || (vn | vl) == 0u)) {
+        const unsigned busy = vn | vl;
+        if (32u - (unsigned)__popc(busy) >= leave_at) {
+            // nothing in flight and nothing left to fetch, or (tail) nothing left to fetch and only a few rays alive in this
+            // warp: leave; those rays are handed to the cooperative tail kernel below
+            if (dry) break;
             // ---- refill idle lanes from the warp pool -------------------------------------------
             // Finished rays are written here, several lanes at a time, instead of one lane at a time when they finish.
-            if (has_out) { write_result<ANY>(out, my_index, L.h); has_out = false; }
+            const unsigned idle = ~busy;
+            if (has_out) { write_result<ANY>(out, my_index, L.h); has_out = 0; }
             if (pool_left == 0u) {
                 unsigned long long base = 0;
                 if (lane == 0) base = atomicAdd(next, (unsigned long long)chunk);
@@ -240,38 +266,75 @@ trace_persistent(SceneView s, const RayIn* __restrict__ rays, uint64_t n, void* 
                 if (base >= n) exhausted = true;
                 else { pool_next = base; pool_left = (base + chunk < n) ? chunk : (uint32_t)(n - base); }
             }
-            const uint32_t avail = pool_left;
-            if (avail) {
-                const unsigned rank = __popc(idle & ((1u << lane) - 1u));
-                if (((idle >> lane) & 1u) && rank < avail) {
-                    my_index = pool_next + rank;
-                    const uint32_t* rec = nullptr;
-                    if (resume) {
-                        rec = resume + my_index * tail.rec_words;
-                        my_index = (uint64_t)rec[0] | ((uint64_t)rec[1] << 32);
+#if B2_STAGE_RAYS
+            if (!resume) {
+                const uint32_t in_block = 32u - ((uint32_t)pool_next & 31u);
+                const uint32_t staged = pool_left < in_block ? pool_left : in_block;
+                if (in_block == 32u && pool_left) {
+                    // set-up of the next rays of the pool on all lanes at once, busy ones included: 1/32 of InitRay per ray
+                    // instead of 1/(refilled lanes), and one wait for HBM per 32 rays
+                    if (lane < staged) {
+                        const uint64_t i = pool_next + lane;
+                        RayX r; float tmax;
+                        load_ray(rays, i, r, tmax);
+                        uint32_t* q = stage + ((uint32_t)i & 31u);
+                        q[0 * 32] = __float_as_uint(r.ox); q[1 * 32] = __float_as_uint(r.oy); q[2 * 32] = __float_as_uint(r.oz);
+                        q[3 * 32] = __float_as_uint(r.dx); q[4 * 32] = __float_as_uint(r.dy); q[5 * 32] = __float_as_uint(r.dz);
+                        q[6 * 32] = __float_as_uint(r.ix); q[7 * 32] = __float_as_uint(r.iy); q[8 * 32] = __float_as_uint(r.iz);
+                        q[9 * 32] = __float_as_uint(tmax); q[10 * 32] = r.sign;
                     }
-                    RayX r; float tmax;
-                    load_ray(rays, my_index, r, tmax);
-                    L.start(r, tmax);
-                    if (resume) {
-                        const ResumeState o = resume_fetch<Lane<ANY, COUNT, CAP>>(stack, rec);
-                        L.h.t = o.t; L.h.u = o.u; L.h.v = o.v; L.h.tri = o.tri;
-                        L.cur = o.cur; L.leaf0 = o.leaf0; L.leaf1 = o.leaf1; L.top = o.top; L.sp = o.sp;
-                    }
+                    __syncwarp();
                 }
-                const unsigned taken = __popc(idle), used = (taken < avail) ? taken : avail;
-                if (COUNT) { ph_refill++; ph_refill_lanes += used; if (resume && lane == 0) atomicAdd(&counters[18], (unsigned long long)used); }
+                const unsigned rank = __popc(idle & ((1u << lane) - 1u));
+                if (((idle >> lane) & 1u) && rank < staged) {
+                    my_index = pool_next + rank;
+                    const uint32_t* q = stage + ((uint32_t)my_index & 31u);
+                    RayX r;
+                    r.ox = __uint_as_float(q[0 * 32]); r.oy = __uint_as_float(q[1 * 32]); r.oz = __uint_as_float(q[2 * 32]);
+                    r.dx = __uint_as_float(q[3 * 32]); r.dy = __uint_as_float(q[4 * 32]); r.dz = __uint_as_float(q[5 * 32]);
+                    r.ix = __uint_as_float(q[6 * 32]); r.iy = __uint_as_float(q[7 * 32]); r.iz = __uint_as_float(q[8 * 32]);
+                    r.sign = q[10 * 32];
+                    L.start(r, __uint_as_float(q[9 * 32]));
+                }
+                const unsigned taken = __popc(idle), used = (taken < staged) ? taken : staged;
+                if (COUNT && used) { ph_refill++; ph_refill_lanes += used; }
+                __syncwarp();                                      // the slots are read before the next staging overwrites them
                 pool_next += used;
                 pool_left -= used;
+            } else
+#endif
+            {
+                const uint32_t avail = pool_left;
+                if (avail) {
+                    const unsigned rank = __popc(idle & ((1u << lane) - 1u));
+                    if (((idle >> lane) & 1u) && rank < avail) {
+                        my_index = pool_next + rank;
+                        const uint32_t* rec = nullptr;
+                        if (resume) {
+                            rec = resume + my_index * tail.rec_words;
+                            my_index = (uint64_t)rec[0] | ((uint64_t)rec[1] << 32);
+                        }
+                        RayX r; float tmax;
+                        load_ray(rays, my_index, r, tmax);
+                        L.start(r, tmax);
+                        if (resume) {
+                            const ResumeState o = resume_fetch<Lane<ANY, COUNT, CAP>>(local_stack, rec);
+                            L.h.t = o.t; L.h.u = o.u; L.h.v = o.v; L.h.tri = o.tri;
+                            L.cur = o.cur; L.leaf0 = o.leaf0; L.leaf1 = o.leaf1; L.top = o.top; L.sp = o.sp;
+#if B2_SMEM_STACK
+                            for (int i = 0; i < L.sp && i < B2_SMEM_STACK; ++i) stk_set(stack, i, local_stack[i]);
+#endif
+                        }
+                    }
+                    const unsigned taken = __popc(idle), used = (taken < avail) ? taken : avail;
+                    if (COUNT) { ph_refill++; ph_refill_lanes += used; if (resume && lane == 0) atomicAdd(&counters[18], (unsigned long long)used); }
+                    pool_next += used;
+                    pool_left -= used;
+                }
             }
+            if (exhausted && pool_left == 0u) { dry = true; leave_at = B2_TAIL_CODE ? 32u - (tail.coop_max < 31u ? tail.coop_max : 31u) : 32u; }
             continue;
         }
-        if ((vn | vl) == 0u) break;          // nothing in flight and nothing left to fetch
-        // tail: nothing left to fetch and only a few rays alive in this warp -> leave; they are handed to the cooperative
-        // tail kernel below
-#if B2_TAIL_CHECK_POS == 0
-        if (B2_TAIL_CODE && pool_dry && (unsigned)__popc(idle) >= 32u - tail.coop_max) break;
-#endif
 
         // leaf_bias/16 weighs the leaf vote: > 1 consumes queued leaves earlier (less speculation)
         bool stepped;
@@ -286,11 +349,11 @@ trace_persistent(SceneView s, const RayIn* __restrict__ rays, uint64_t n, void* 
                 if (stepped) L.node_step(s.wide, stack, s.one_bits);
                 if (COUNT && stepped) ray_steps++;
                 if (stepped && L.done()) {
-                    has_out = true;
+                    has_out = 1;
                     if (COUNT) { traced++; max_ray_steps = max_ray_steps > ray_steps ? max_ray_steps : ray_steps; ray_steps = 0; }
                 }
                 want = __ballot_sync(FULL, L.wants_node());
-            } while ((unsigned)__popc(want) >= (unsigned)B2_NODE_STAY);
+            } while ((unsigned)__popc(want) >= (unsigned)(ANY ? B2_NODE_STAY_ANY : B2_NODE_STAY));
             continue;
 #else
             if (COUNT) { ph_node++; ph_node_lanes += __popc(vn); }
@@ -310,14 +373,18 @@ trace_persistent(SceneView s, const RayIn* __restrict__ rays, uint64_t n, void* 
 #endif
         if (COUNT && stepped) ray_steps++;
         if (stepped && L.done()) {
-            has_out = true;
+            has_out = 1;
             if (COUNT) { traced++; max_ray_steps = max_ray_steps > ray_steps ? max_ray_steps : ray_steps; ray_steps = 0; }
         }
     }
     if (has_out) write_result<ANY>(out, my_index, L.h);       // rays that finished after the last refill
     // at most coop_max lanes per warp get here, and the queue holds coop_max records per warp of the grid
-    if (B2_TAIL_CODE && tail.coop_max && !L.done())
-        tail_handover(tail, my_index, L.h.t, L.h.u, L.h.v, L.h.tri, L.cur, L.leaf0, L.leaf1, L.top, L.sp, stack);
+    if (B2_TAIL_CODE && tail.coop_max && !L.done()) {
+#if B2_SMEM_STACK
+        for (int i = 0; i < L.sp && i < B2_SMEM_STACK; ++i) local_stack[i] = stk_get(stack, i);      // the record wants one plain array
+#endif
+        tail_handover(tail, my_index, L.h.t, L.h.u, L.h.v, L.h.tri, L.cur, L.leaf0, L.leaf1, L.top, L.sp, local_stack);
+    }
 
     if (COUNT) {
         if (L.overflow) report_stack_overflow();             // counting build only, see Lane::push

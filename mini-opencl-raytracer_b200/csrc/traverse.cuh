@@ -548,6 +548,25 @@ B2_HD WideHits test_wide_node_robust(const U4* wide, uint32_t index, const RayX&
     return out;
 }
 
+// ---- the short stack -------------------------------------------------------------------------
+// Lane<> reaches its stack of deferred child references only through stk_get / stk_set, so that the caller chooses where
+// the entries live: a plain local array (the per-ray driver below, the frame megakernel, the host emulation), or
+// HybridStack -- the first B2_SMEM_STACK entries in shared memory, one 4-byte column per thread (conflict-free), the rest in
+// the local array at the same indices. Measured on the bench stream (host emulation, depth histogram at pop time): 26 % of
+// the pops find the stack empty, 69 % read one of the first six entries, 4.5 % a deeper one -- while ncu saw 38 % of the
+// local-memory pops miss L1 (the lines are evicted by the node / leaf traffic between a push and its pop) and local memory
+// make up a quarter of the kernel's L2 sectors. Six entries x 128 threads x 8 CTAs = 24 KB per SM, inside the 32 KB
+// shared-memory carve-out the kernel already ran with: L1 keeps its size.
+B2_HD uint32_t stk_get(const uint32_t* s, int i) { return s[i]; }
+B2_HD void stk_set(uint32_t* s, int i, uint32_t v) { s[i] = v; }
+template <int DEPTH, int STRIDE>
+struct HybridStack {
+    uint32_t* sh;          // this thread's column: entry i at sh[i * STRIDE]
+    uint32_t* loc;         // entries DEPTH.. (indices as in a plain array)
+};
+template <int DEPTH, int STRIDE> B2_HD uint32_t stk_get(HybridStack<DEPTH, STRIDE> s, int i) { return i < DEPTH ? s.sh[i * STRIDE] : s.loc[i]; }
+template <int DEPTH, int STRIDE> B2_HD void stk_set(HybridStack<DEPTH, STRIDE> s, int i, uint32_t v) { if (i < DEPTH) s.sh[i * STRIDE] = v; else s.loc[i] = v; }
+
 // ---- one ray's traversal state ------------------------------------------------------------
 // node_step() tests the current wide node and walks on; leaves met on the way are queued (two
 // slots, FIFO) and consumed in order by leaf_step(). Any interleaving of the two calls that the
@@ -589,21 +608,27 @@ struct Lane {
 
     // The top of the stack sits in a register: a pop answers at once and the load that refills the
     // register from local memory is only waited for by the NEXT pop.
-    B2_HD void push(uint32_t* stack, uint32_t ref) {
+    template <class S> B2_HD void push(S stack, uint32_t ref) {
         // CAP is at least the tree's exact bound (wide_stack_bound, checked at upload), so the else branch never runs. The
         // flag is only READ by the counting build (-> b2rt_counters::stack_overflows): in the production build it is dead
         // and costs nothing -- an atomic or a live flag here measurably slows the loop (r2 A/B: -4 %).
-        if (top != REF_EMPTY) { if (sp < CAP) stack[sp++] = top; else overflow = true; }
+        if (COUNT) { if (top != REF_EMPTY) { if (sp < CAP) stk_set(stack, sp++, top); else overflow = true; } }
+        else {
+            // branch-free: the slot at sp is free by construction (sp < CAP, see above), so the old top is stored
+            // unconditionally and only kept (sp advanced) when there was one
+            stk_set(stack, sp, top);
+            sp += top != REF_EMPTY ? 1 : 0;
+        }
         top = ref;
         if (COUNT && (uint32_t)sp + 1u > tc.max_stack) tc.max_stack = (uint32_t)sp + 1u;
     }
-    B2_HD uint32_t pop(const uint32_t* stack) {
+    template <class S> B2_HD uint32_t pop(S stack) {
         uint32_t ref = top;
-        top = sp > 0 ? stack[--sp] : REF_EMPTY;
+        if (sp > 0) { --sp; top = stk_get(stack, sp); } else top = REF_EMPTY;
         return ref;
     }
     // Move leaves from `cur` into the queue while there is room.
-    B2_HD void settle(const uint32_t* stack) {
+    template <class S> B2_HD void settle(S stack) {
 #if B2_LEAF_QUEUE == 3
         while (cur != REF_EMPTY && (cur & REF_LEAF_BIT) && leaf2 == REF_EMPTY) {
             if (leaf0 == REF_EMPTY) leaf0 = cur; else if (leaf1 == REF_EMPTY) leaf1 = cur; else leaf2 = cur;
@@ -633,7 +658,7 @@ struct Lane {
     }
     // `one` must be 0x3F800000, passed as run-time data: held in one register it lets the constant
     // byte selectors of B2_PLANE_V be instruction immediates (ptxas otherwise keeps four selector registers).
-    B2_HD void node_step(const U4* wide, uint32_t* stack, uint32_t one) {
+    template <class S> B2_HD void node_step(const U4* wide, S stack, uint32_t one) {
 #if B2_NODE_TEST_H2
         WideHits w = (r.sign & RAY_DEGENERATE) ? test_wide_node_robust(wide, cur, r, h.t) : test_wide_node_h2(wide, cur, r, h.t);
 #else
@@ -658,7 +683,7 @@ struct Lane {
     }
     // Returns true when the ray is finished by this leaf (any-hit accept, or best < 0: every later
     // box test of the reference fails).
-    B2_HD bool leaf_step(const U4* leaf, const uint32_t* stack) {
+    template <class S> B2_HD bool leaf_step(const U4* leaf, S stack) {
         bool got = visit_leaf<COUNT>(leaf, leaf0 & ~REF_LEAF_BIT, r, h, COUNT ? &tc : nullptr);
 #if B2_LEAF_QUEUE == 3
         leaf0 = leaf1; leaf1 = leaf2; leaf2 = REF_EMPTY;

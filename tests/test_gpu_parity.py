@@ -380,7 +380,7 @@ def test_context_lifecycle_and_error_paths(product, cornell_ref, bumpy_ref):
         a.set_frame(1, 2)
         a.execute(32 * 16)
         assert np.array_equal(a.read_pixels().view(np.uint32), first.view(np.uint32))
-        for opt, bad in ((cap.OPT_TRAVERSAL, 7), (cap.OPT_RENDER_MODE, 9), (cap.OPT_REFILL_MIN, 0), (cap.OPT_LEAF_BIAS, 0),
+        for opt, bad in ((cap.OPT_TRAVERSAL, 7), (cap.OPT_RENDER_MODE, 9), (cap.OPT_REFILL_MIN, 0), (cap.OPT_LEAF_BIAS, -1),
                          (cap.OPT_WAVEFRONT_LANES, 5), (99, 1)):
             with pytest.raises(product.B2RTError) as e:
                 a.set_option(opt, bad)
