@@ -235,13 +235,12 @@ trace_persistent(SceneView s, const RayIn* __restrict__ rays, uint64_t n, void* 
     uint64_t my_index = 0;
     uint32_t has_out = 0;                    // this lane's finished ray still has to be written (done together with the next refill)
     uint64_t pool_next = 0;                  // warp-uniform: next ray of the warp's pool ...
-    uint32_t pool_left = 0;                  // ... and how many it still holds
-    bool exhausted = false;                  // warp-uniform: the global counter ran past n
+    uint32_t pool_left = 0;                  // ... and how many it still holds; POOL_DRY once the global counter has run past n
     // warp-uniform: the number of idle lanes at which the warp leaves the step loop -- refill_min while the pool can still be
     // topped up, 32 - coop_max (hand-over to the cooperative tail; 32 = only when every lane is idle) once it has run dry.
     // One compare per scheduling round instead of the refill / finished / hand-over conditions one by one.
     uint32_t leave_at = refill_min;
-    bool dry = false;
+    const uint32_t POOL_DRY = 0xffffffffu;   // pools are only topped up when empty, so "the counter ran past n" and "nothing left to hand out" coincide
     uint32_t traced = 0;
     uint32_t ray_steps = 0, max_ray_steps = 0;   // COUNT only: node + leaf steps of the current ray / the worst ray of this lane
     uint32_t ph_node = 0, ph_node_lanes = 0, ph_leaf = 0, ph_leaf_lanes = 0, ph_refill = 0, ph_refill_lanes = 0;   // COUNT only, warp-uniform
@@ -254,7 +253,7 @@ trace_persistent(SceneView s, const RayIn* __restrict__ rays, uint64_t n, void* 
         if (32u - (unsigned)__popc(busy) >= leave_at) {
             // nothing in flight and nothing left to fetch, or (tail) nothing left to fetch and only a few rays alive in this
             // warp: leave; those rays are handed to the cooperative tail kernel below
-            if (dry) break;
+            if (pool_left == POOL_DRY) break;
             // ---- refill idle lanes from the warp pool -------------------------------------------
             // Finished rays are written here, several lanes at a time, instead of one lane at a time when they finish.
             const unsigned idle = ~busy;
@@ -263,8 +262,9 @@ trace_persistent(SceneView s, const RayIn* __restrict__ rays, uint64_t n, void* 
                 unsigned long long base = 0;
                 if (lane == 0) base = atomicAdd(next, (unsigned long long)chunk);
                 base = __shfl_sync(FULL, base, 0);
-                if (base >= n) exhausted = true;
-                else { pool_next = base; pool_left = (base + chunk < n) ? chunk : (uint32_t)(n - base); }
+                if (base >= n) { pool_left = POOL_DRY; leave_at = B2_TAIL_CODE ? 32u - (tail.coop_max < 31u ? tail.coop_max : 31u) : 32u; continue; }
+                pool_next = base;
+                pool_left = (base + chunk < n) ? chunk : (uint32_t)(n - base);
             }
 #if B2_STAGE_RAYS
             if (!resume) {
@@ -332,7 +332,6 @@ trace_persistent(SceneView s, const RayIn* __restrict__ rays, uint64_t n, void* 
                     pool_left -= used;
                 }
             }
-            if (exhausted && pool_left == 0u) { dry = true; leave_at = B2_TAIL_CODE ? 32u - (tail.coop_max < 31u ? tail.coop_max : 31u) : 32u; }
             continue;
         }
 
