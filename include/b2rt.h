@@ -131,6 +131,10 @@ enum {
                                    re-packs all suspended rays 32 to a warp and walks on at full width, and only what that pass
                                    leaves (B2RT_OPT_COOP_MAX per warp) goes to the cooperative kernel. 0 = off (default, also -1) .. 16.
                                    Only used while larger than the cooperative threshold. Results do not depend on it. */
+    B2RT_OPT_TAIL_HELP = 12,    /* 1 (default) / 0: in a library built with -DB2_TAIL_HELP=1, warps of a persistent traversal launch that have
+                                   finished or handed over their own rays serve the cooperative tail queue inside the same launch; the
+                                   tail kernel takes what is left. The default build compiles this out (measured slower on frame shares,
+                                   DESIGN.md 4c), the option is then accepted and ignored. Results do not depend on it. */
     B2RT_OPT_COOP_MAX = 7       /* tail mode of the persistent kernels: a warp whose ray pool is dry and that has at most this many
                                    rays alive hands them to the cooperative tail kernel, 32 lanes per ray (0 = off .. 16; default -1 = 8, but off for scenes
                                    of fewer than ~1000 nodes, whose rays are too short to gain). Results do not

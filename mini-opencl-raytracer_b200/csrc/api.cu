@@ -217,19 +217,27 @@ int apply_l2_policy(b2rt_context* ctx, cudaStream_t st) {
 
 // The tail queue in slot `which` (allocated on first use), wired to the given device counters. coop_max = 0 when the
 // tail mode is off or the launch runs the reference-layout walk.
+// Every persistent launch marks the records it writes with its own tag (never 0).
+uint32_t tail_tag(b2rt_context* ctx) { if (++ctx->tail_tag_seq == 0u) ctx->tail_tag_seq = 1u; return ctx->tail_tag_seq; }
+
 int tail_queue(b2rt_context* ctx, int which, unsigned long long* count, unsigned long long* next, TailQueue& q) {
-    q = TailQueue{ count, next, nullptr, ctx->tail_rec_words, 0u, 0u, count + 2, next + 2, nullptr };
+    q = TailQueue{ count, next, nullptr, ctx->tail_rec_words, 0u, 0u, count + 2, next + 2, nullptr, count + 4, nullptr, 0u, 0u, 0u };
     // auto (-1): on; but a tree this small has no long rays -- a hand-over would cost more than the few steps it saves
     const int64_t coop = ctx->opt_coop_max >= 0 ? ctx->opt_coop_max : (ctx->info.n_wide_nodes + ctx->info.n_leaf_blocks > 1000 ? 8 : 0);
     if (coop <= 0 || ctx->opt_traversal == 1 || ctx->tail_capacity_records == 0) return B2RT_SUCCESS;
     // two queues of the same capacity: what the first pass suspends, and what the re-packed second pass leaves for the cooperative kernel
     const size_t queue_words = (size_t)ctx->tail_capacity_records * ctx->tail_rec_words;
-    if (!ctx->d_tail[which]) CK(cudaMalloc(&ctx->d_tail[which], 2 * queue_words * sizeof(uint32_t)));
+    // ... and, behind them, one ticket slot per warp of the largest grid (helping warps that give a ticket back)
+    const size_t orphan_slots = (size_t)ctx->tail_capacity_records / COOP_MAX_LIMIT;
+    if (!ctx->d_tail[which]) CK(cudaMalloc(&ctx->d_tail[which], 2 * queue_words * sizeof(uint32_t) + orphan_slots * sizeof(unsigned long long)));
     q.records = static_cast<uint32_t*>(ctx->d_tail[which]);
     q.records2 = q.records + queue_words;
+    q.orphans = reinterpret_cast<unsigned long long*>(q.records2 + queue_words);
     q.coop_max = (uint32_t)coop;
     const int64_t resume = ctx->opt_resume_max >= 0 ? ctx->opt_resume_max : 0;     // measured (r2, 10 M-face frame shares): no gain, see DESIGN.md
     q.resume_max = resume > coop ? (uint32_t)resume : 0u;       // a second pass only pays when it suspends earlier than the cooperative threshold
+    q.tag = tail_tag(ctx);
+    q.help_fcap = ctx->opt_tail_help ? 1u : 0u;                 // launch_trace_wide sizes it (or switches it off)
     return B2RT_SUCCESS;
 }
 
@@ -335,7 +343,7 @@ void free_wavefront(b2rt_context* ctx) {
 }
 
 int ensure_wavefront(b2rt_context* ctx, uint64_t paths) {
-    if (!ctx->d_wf_count) CK(cudaMalloc(&ctx->d_wf_count, WF_LANES * 8 * sizeof(unsigned long long)));
+    if (!ctx->d_wf_count) CK(cudaMalloc(&ctx->d_wf_count, WF_LANES * 16 * sizeof(unsigned long long)));
     if (ctx->wf_capacity >= paths) return B2RT_SUCCESS;
     CK(cudaStreamSynchronize(ctx->stream));
     free_wavefront(ctx);
@@ -373,7 +381,7 @@ int wavefront_lane(b2rt_context* ctx, const FrameArgs& a, float* d_result, const
     const bool timed = ctx->opt_stage_times != 0 && lane == 0;
     if (timed) ctx->stage_used = 0;
     STAGE(B2RT_STAGE_BEGIN);
-    unsigned long long* cnt = ctx->d_wf_count + 8 * lane;           // three rotating queue counters, the trace kernel's ray counter, its tail queue's two
+    unsigned long long* cnt = ctx->d_wf_count + 16 * lane;          // three rotating queue counters, the trace kernel's ray counter, its tail queues' four, the hand-over count
     char* rays[2] = { static_cast<char*>(ctx->d_wf_rays[0]) + offset * sizeof(b2rt_ray), static_cast<char*>(ctx->d_wf_rays[1]) + offset * sizeof(b2rt_ray) };
     char* hits = static_cast<char*>(ctx->d_wf_hits) + offset * sizeof(b2rt_hit);
     char* state = static_cast<char*>(ctx->d_wf_state) + offset * 32;
@@ -396,6 +404,7 @@ int wavefront_lane(b2rt_context* ctx, const FrameArgs& a, float* d_result, const
     for (int b = 0; b < a.bounces; ++b) {
         const int in = b & 1, out = in ^ 1;
         unsigned long long *n_in = cnt + (b % 3), *n_out = cnt + ((b + 1) % 3), *n_clear = cnt + ((b + 2) % 3);
+        if (b) tail.tag = tail_tag(ctx);
         CK(launch_trace_wide(ctx->view, rays[in], n, hits, false, ctx->opt_counters != 0, ctx->stack_bound, grid,
                              cnt + 3, ctx->d_counters, (uint32_t)ctx->opt_refill_min, (uint32_t)(ctx->opt_leaf_bias ? ctx->opt_leaf_bias : 32), s, n_in, &tail, tail_grid,
                              stage_mark(ctx, timed, B2RT_STAGE_TRACE, s)));
@@ -1137,6 +1146,7 @@ static int set_option_one(b2rt_context* ctx, uint32_t option, int64_t value) {
         case B2RT_OPT_L2_PERSIST: ctx->opt_l2_persist = value ? 1 : 0; if (!ctx->scene_dirty && use_device(ctx) == B2RT_SUCCESS) { cudaStreamSynchronize(ctx->stream); scene_l2_setup(ctx); } break;
         case B2RT_OPT_RESUME_MAX: if (value < -1 || value > COOP_MAX_LIMIT) return fail(ctx, B2RT_INVALID_VALUE, "resume threshold must be -1 (auto), 0 (off) .. 16"); ctx->opt_resume_max = value; break;
         case B2RT_OPT_WAVEFRONT_GRID_SPLIT: ctx->opt_wf_grid_split = value ? 1 : 0; break;
+        case B2RT_OPT_TAIL_HELP: ctx->opt_tail_help = value ? 1 : 0; break;
         case B2RT_OPT_STAGE_TIMES: ctx->opt_stage_times = value ? 1 : 0; ctx->stage_used = 0; break;
         case B2RT_OPT_REFILL_MIN: if (value < 1 || value > 32) return fail(ctx, B2RT_INVALID_VALUE, "refill threshold must be 1..32"); ctx->opt_refill_min = value; break;
         default: return fail(ctx, B2RT_INVALID_VALUE, "unknown option");

@@ -92,6 +92,62 @@ static constexpr int TAIL_BLOCK = 128;
 #define B2_TAIL_MIN_BLOCKS 8      // 64 registers: as many rays in flight as possible (the tail is latency-bound)
 #endif
 
+// What a warp serving the tail queue accumulates (the counters only in the COUNT build).
+struct TailStats {
+    TravCounters tc;
+    unsigned long long done;
+    uint32_t worst_steps, worst_rounds;
+    bool overflow;
+};
+__device__ __forceinline__ void tail_stats_clear(TailStats& ts) {
+    ts.tc = TravCounters{ 0, 0, 0, 0, 0, 0, 0 };
+    ts.done = 0; ts.worst_steps = ts.worst_rounds = 0; ts.overflow = false;
+}
+template <bool COUNT>
+__device__ __forceinline__ void tail_stats_flush(const TailStats& ts, unsigned long long* __restrict__ counters, unsigned lane) {
+    if (lane != 0) return;
+    if (ts.overflow) report_stack_overflow();
+    if (COUNT && ts.done) {
+        atomicAdd(&counters[0], ts.done);
+        atomicAdd(&counters[1], (unsigned long long)ts.tc.wide_nodes); atomicAdd(&counters[2], (unsigned long long)ts.tc.leaf_blocks);
+        atomicAdd(&counters[3], (unsigned long long)ts.tc.leaf_pass); atomicAdd(&counters[4], (unsigned long long)ts.tc.tri_tests);
+        atomicAdd(&counters[5], (unsigned long long)ts.tc.words);
+        atomicAdd(&counters[14], ts.done);                                                     // rays finished cooperatively ...
+        atomicAdd(&counters[15], (unsigned long long)ts.tc.wide_nodes + ts.tc.leaf_blocks);   // ... and their node + leaf visits
+        atomicMax(&counters[16], (unsigned long long)ts.worst_steps); atomicMax(&counters[17], (unsigned long long)ts.worst_rounds);
+    }
+}
+
+// One record of the tail queue, finished by the whole warp. F: fcap words of this warp's shared memory. The record is read
+// around L1 (ld.global.cg): a helping warp of the persistent launch reads records other SMs wrote during the same launch.
+template <bool ANY, bool COUNT>
+__device__ __forceinline__ void tail_process(const SceneView& s, const RayIn* __restrict__ rays, void* __restrict__ out, const uint32_t* rec,
+                                             uint32_t* F, uint32_t fcap, uint32_t wide_limit, TailStats& ts) {
+    const unsigned lane = threadIdx.x & 31u;
+    const uint32_t head = lane < TAIL_HEADER_WORDS ? __ldcg(rec + lane) : 0u;
+    const uint64_t index = (uint64_t)__shfl_sync(FULL, head, 0) | ((uint64_t)__shfl_sync(FULL, head, 1) << 32);
+    HitX h;
+    h.t = __uint_as_float(__shfl_sync(FULL, head, 2)); h.u = __uint_as_float(__shfl_sync(FULL, head, 3));
+    h.v = __uint_as_float(__shfl_sync(FULL, head, 4)); h.tri = __shfl_sync(FULL, head, 5);
+    const uint32_t n = __shfl_sync(FULL, head, 6);
+    for (uint32_t i = lane; i < n; i += 32u) F[i] = __ldcg(rec + TAIL_HEADER_WORDS + i);
+    RayX r; float tmax;
+    load_ray(rays, index, r, tmax);                                 // every lane: the same 32 bytes, the same arithmetic
+    __syncwarp();
+    const uint32_t steps0 = ts.tc.wide_nodes + ts.tc.leaf_blocks, rounds0 = ts.tc.rounds;
+    coop_trace<ANY, COUNT>(s.wide, s.leaf, F, n, fcap, wide_limit, r, h, ts.tc, ts.overflow);
+    if (COUNT) {
+        const uint32_t ds = ts.tc.wide_nodes + ts.tc.leaf_blocks - steps0, dr = ts.tc.rounds - rounds0;
+        ts.worst_steps = ts.worst_steps > ds ? ts.worst_steps : ds; ts.worst_rounds = ts.worst_rounds > dr ? ts.worst_rounds : dr;
+#ifdef B2_DEBUG_LONG_RAYS
+        if (dr > 300 && lane == 0) printf("LONGRAY idx %llu steps %u rounds %u o %.9g %.9g %.9g d %.9g %.9g %.9g inv %g %g %g t %g tri %u\n", (unsigned long long)index, ds, dr, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, r.ix, r.iy, r.iz, h.t, h.tri);
+#endif
+    }
+    if (lane == 0) write_result<ANY>(out, index, h);
+    ++ts.done;
+    __syncwarp();
+}
+
 template <bool ANY, bool COUNT>
 __global__ void __launch_bounds__(TAIL_BLOCK, B2_TAIL_MIN_BLOCKS)
 trace_tail_kernel(SceneView s, const RayIn* __restrict__ rays, void* __restrict__ out, TailQueue tail,
@@ -100,64 +156,32 @@ trace_tail_kernel(SceneView s, const RayIn* __restrict__ rays, void* __restrict_
     uint32_t* F = tail_frontiers + (threadIdx.x >> 5) * fcap;
     const unsigned lane = threadIdx.x & 31u;
     const unsigned long long total = *tail.count;
-    TravCounters tc = { 0, 0, 0, 0, 0, 0, 0 };
-    unsigned long long done = 0;
-    uint32_t worst_steps = 0, worst_rounds = 0;                         // COUNT only
-    bool overflow = false;
+    TailStats ts;
+    tail_stats_clear(ts);
+    // tickets that helping warps of the persistent launch drew and gave back (their records were not written in time)
+    if (tail.help_fcap) {
+        const unsigned long long n_orphans = tail.handed[2], warps = (unsigned long long)gridDim.x * (TAIL_BLOCK / 32);
+        for (unsigned long long i = (unsigned long long)blockIdx.x * (TAIL_BLOCK / 32) + (threadIdx.x >> 5); i < n_orphans; i += warps) {
+            const unsigned long long slot = tail.orphans[i];
+            if (slot < total) tail_process<ANY, COUNT>(s, rays, out, tail.records + slot * tail.rec_words, F, fcap, wide_limit, ts);
+        }
+    }
     for (;;) {
         unsigned long long slot = 0;
         if (lane == 0) slot = atomicAdd(tail.next, 1ull);
         slot = __shfl_sync(FULL, slot, 0);
         if (slot >= total) break;
-        const uint32_t* rec = tail.records + slot * tail.rec_words;
-        const uint32_t head = lane < TAIL_HEADER_WORDS ? rec[lane] : 0u;
-        const uint64_t index = (uint64_t)__shfl_sync(FULL, head, 0) | ((uint64_t)__shfl_sync(FULL, head, 1) << 32);
-        HitX h;
-        h.t = __uint_as_float(__shfl_sync(FULL, head, 2)); h.u = __uint_as_float(__shfl_sync(FULL, head, 3));
-        h.v = __uint_as_float(__shfl_sync(FULL, head, 4)); h.tri = __shfl_sync(FULL, head, 5);
-        const uint32_t n = __shfl_sync(FULL, head, 6);
-        for (uint32_t i = lane; i < n; i += 32u) F[i] = rec[TAIL_HEADER_WORDS + i];
-        RayX r; float tmax;
-        load_ray(rays, index, r, tmax);                                 // every lane: the same 32 bytes, the same arithmetic
-        __syncwarp();
-        const uint32_t steps0 = tc.wide_nodes + tc.leaf_blocks, rounds0 = tc.rounds;
-        coop_trace<ANY, COUNT>(s.wide, s.leaf, F, n, fcap, wide_limit, r, h, tc, overflow);
-        if (COUNT) {
-            const uint32_t ds = tc.wide_nodes + tc.leaf_blocks - steps0, dr = tc.rounds - rounds0;
-            worst_steps = worst_steps > ds ? worst_steps : ds; worst_rounds = worst_rounds > dr ? worst_rounds : dr;
-#ifdef B2_DEBUG_LONG_RAYS
-            if (dr > 300 && lane == 0) printf("LONGRAY idx %llu steps %u rounds %u o %.9g %.9g %.9g d %.9g %.9g %.9g inv %g %g %g t %g tri %u\n", (unsigned long long)index, ds, dr, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, r.ix, r.iy, r.iz, h.t, h.tri);
-#endif
-        }
-        if (lane == 0) write_result<ANY>(out, index, h);
-        ++done;
-        __syncwarp();
+        tail_process<ANY, COUNT>(s, rays, out, tail.records + slot * tail.rec_words, F, fcap, wide_limit, ts);
     }
-    if (lane == 0) {
-        if (overflow) report_stack_overflow();
-        if (COUNT && done) {
-            atomicAdd(&counters[0], done);
-            atomicAdd(&counters[1], (unsigned long long)tc.wide_nodes); atomicAdd(&counters[2], (unsigned long long)tc.leaf_blocks);
-            atomicAdd(&counters[3], (unsigned long long)tc.leaf_pass); atomicAdd(&counters[4], (unsigned long long)tc.tri_tests);
-            atomicAdd(&counters[5], (unsigned long long)tc.words);
-            atomicAdd(&counters[14], done);                                              // rays finished cooperatively ...
-            atomicAdd(&counters[15], (unsigned long long)tc.wide_nodes + tc.leaf_blocks);   // ... and their node + leaf visits
-            atomicMax(&counters[16], (unsigned long long)worst_steps); atomicMax(&counters[17], (unsigned long long)worst_rounds);
-        }
-    }
+    tail_stats_flush<COUNT>(ts, counters, lane);
 }
 
-#ifndef B2_STAGE_RAYS
-#define B2_STAGE_RAYS 1          // ray set-up (InitRay: one square root, six divisions) done by all 32 lanes for the next 32 rays of the warp's pool and parked in shared memory; a refill is then ten shared-memory loads
-#endif
-#ifndef B2_SMEM_STACK
-#define B2_SMEM_STACK 12         // entries of every lane's traversal stack kept in shared memory (HybridStack, traverse.cuh); 0 = all in local memory
-#endif
 #ifndef B2_TAIL_NOINLINE
 #define B2_TAIL_NOINLINE 1      // measured (r2 A/B, 10^8-ray stream): inlined 2 840 Mrays/s, not inlined 2 885 = the kernel without any hand-over code
 #endif
 // The hand-over of one unfinished ray: index, best hit so far and pending work (in the reference's depth-first order) go to
-// the tail queue; trace_tail_kernel finishes it with a whole warp.
+// the tail queue; a whole warp finishes it (a helping warp of this launch, or trace_tail_kernel). The tag goes in last,
+// behind a fence: whoever sees it sees the record.
 #if B2_TAIL_NOINLINE
 __device__ __noinline__
 #else
@@ -170,7 +194,8 @@ void tail_handover(const TailQueue& tail, uint64_t index, float t, float u, floa
     rec[0] = (uint32_t)index; rec[1] = (uint32_t)(index >> 32);
     rec[2] = __float_as_uint(t); rec[3] = __float_as_uint(u); rec[4] = __float_as_uint(v); rec[5] = tri;
     rec[6] = coop_dump_fields(sp, top, cur, leaf1, leaf0, stack, rec + TAIL_HEADER_WORDS);      // the frontier, back to front
-    rec[7] = 0u;
+    __threadfence();
+    *reinterpret_cast<volatile uint32_t*>(rec + 7) = tail.tag;
 }
 
 // A suspended ray comes back: best hit so far and the frontier of the record, see Lane::resume. Not inlined (the refill
@@ -186,6 +211,23 @@ __device__ __noinline__ ResumeState resume_fetch(uint32_t* stack, const uint32_t
     o.cur = T.cur; o.leaf0 = T.leaf0; o.leaf1 = T.leaf1; o.top = T.top; o.sp = T.sp;
     return o;
 }
+
+#ifndef B2_STAGE_RAYS
+#define B2_STAGE_RAYS 1          // ray set-up (InitRay: one square root, six divisions) done by all 32 lanes for the next 32 rays of the warp's pool and parked in shared memory; a refill is then eleven shared-memory loads
+#endif
+#ifndef B2_SMEM_STACK
+#define B2_SMEM_STACK 12         // entries of every lane's traversal stack kept in shared memory (HybridStack, traverse.cuh); 0 = all in local memory
+#endif
+#ifndef B2_TAIL_HELP
+#define B2_TAIL_HELP 0           // 1: warps that are past their hand-over serve the tail queue inside the persistent launch (epilogue of trace_persistent). Measured on a
+                                 // rank's eighth of the 10 M-face 4K frame: 4.23-4.30 ms against 3.86-3.93 with the separate tail kernel -- the warps of a stage reach their hand-over
+                                 // within ~0.1 ms of each other, so there is nobody free to help early, and the queue is then served less evenly than by a fresh grid. Off; kept for scenes
+                                 // whose stages end less abruptly (B2RT_OPT_TAIL_HELP has an effect only in a build with 1).
+#endif
+#ifndef B2_HELP_POLLS
+#define B2_HELP_POLLS 64         // empty polls (~0.5 us apart) a helping warp makes before it gives up: never an unbounded wait on CTAs that may not be resident
+#endif
+enum { WARP_SMEM_WORDS = (B2_SMEM_STACK + (B2_STAGE_RAYS ? STAGE_WORDS : 0)) * 32 };   // shared memory of one warp of trace_persistent: stack columns, then the staged rays
 
 // ---------------------------------------------------------------------------------------
 // Persistent speculative while-while traversal.
@@ -213,19 +255,26 @@ trace_persistent(SceneView s, const RayIn* __restrict__ rays, uint64_t n, void* 
         const uint64_t c = n / ((uint64_t)gridDim.x * (TRACE_BLOCK / 32) * 8u + 1u);
         chunk = (uint32_t)(c < 32 ? 32 : (c > 512 ? 512 : (c & ~31ull)));
     }
+#if B2_TAIL_CODE && B2_TAIL_HELP
+    if (tail.help_fcap && lane == 0) atomicAdd(tail.handed + 1, 1ull);           // "started", see the helping epilogue
+#endif
     Lane<ANY, COUNT, CAP> L;
     uint32_t local_stack[CAP];
+    // One contiguous piece of shared memory per warp: [stack entry][lane] columns, then the staged rays; the whole piece is
+    // the frontier of a helping warp once its own rays are done (epilogue).
+#if B2_SMEM_STACK || B2_STAGE_RAYS
+    __shared__ uint32_t smem_warps[(TRACE_BLOCK / 32) * WARP_SMEM_WORDS];
+    uint32_t* const smem_warp = smem_warps + (threadIdx.x >> 5) * WARP_SMEM_WORDS;
+#endif
 #if B2_SMEM_STACK
-    __shared__ uint32_t smem_stack[B2_SMEM_STACK * TRACE_BLOCK];
-    const HybridStack<B2_SMEM_STACK, TRACE_BLOCK> stack = { smem_stack + threadIdx.x, local_stack };
+    const HybridStack<B2_SMEM_STACK, 32> stack = { smem_warp + lane, local_stack };
 #else
     uint32_t* const stack = local_stack;
 #endif
 #if B2_STAGE_RAYS
     // [word][slot] per warp: o, d (normalised), 1/d, tmax, sign -- the slot of ray i is i mod 32 (the staged rays are the
     // next <= 32 of the warp's contiguous pool, so the slots are distinct)
-    __shared__ uint32_t smem_rays[(TRACE_BLOCK / 32) * STAGE_WORDS * 32];
-    uint32_t* const stage = smem_rays + (threadIdx.x >> 5) * (STAGE_WORDS * 32);
+    uint32_t* const stage = smem_warp + B2_SMEM_STACK * 32;
     // Staged at any time: the rays of the pool that share pool_next's block of 32 indices (pool chunks start at multiples of
     // 32), set up when pool_next enters the block -- no extra state.
 #endif
@@ -384,6 +433,61 @@ trace_persistent(SceneView s, const RayIn* __restrict__ rays, uint64_t n, void* 
 #endif
         tail_handover(tail, my_index, L.h.t, L.h.u, L.h.v, L.h.tri, L.cur, L.leaf0, L.leaf1, L.top, L.sp, local_stack);
     }
+#if B2_TAIL_CODE && B2_TAIL_HELP && (B2_SMEM_STACK || B2_STAGE_RAYS)
+    // ---- helping -----------------------------------------------------------------------------------------------------------
+    // This warp's rays are finished or handed over, while other warps of the launch may walk on for a long time (a stage of a
+    // frame share is a few rays per lane: its end is most of it). Instead of leaving, the warp serves the tail queue: it takes
+    // the records that are completely written (tag), in queue order, and finishes each with all 32 lanes -- the tail kernel's
+    // work, started while the queue is still filling. It leaves when every warp of the grid is past its hand-over and the
+    // queue is empty, or after B2_HELP_POLLS empty polls: no unbounded wait, so nothing depends on the whole grid being
+    // resident; whatever is left in the queue is the tail kernel's, as before.
+    if (tail.coop_max && tail.help_fcap) {
+        __syncwarp();
+        TailStats ts;
+        tail_stats_clear(ts);
+        const unsigned long long total_warps = (unsigned long long)gridDim.x * (TRACE_BLOCK / 32);
+        volatile unsigned long long* const v_handed = tail.handed;            // warps past their hand-over
+        volatile unsigned long long* const v_started = tail.handed + 1;       // warps that have begun (all of them: the whole grid is resident)
+        volatile unsigned long long* const v_next = tail.next;
+        volatile unsigned long long* const v_count = tail.count;
+        if (lane == 0) { __threadfence(); atomicAdd(tail.handed, 1ull); }
+        const uint32_t fcap = tail.help_fcap, wide_limit = tail.help_wide_limit;
+        for (;;) {
+            // Lane 0 looks (plain reads) and, if there may be a record, draws a ticket: one atomic per claim, and a ticket
+            // beyond the records written so far simply waits for ITS record -- no herd of failing compare-and-swaps on one
+            // word (measured: 4 700 warps retrying a CAS per record made a 0.7 ms stage take 120 ms).
+            uint32_t take = 0;
+            unsigned long long slot = 0;
+            if (lane == 0) {
+                uint32_t polls = 0;
+                bool ticket = false;
+                for (;;) {
+                    const bool all_here = *v_started >= total_warps, all_handed = *v_handed >= total_warps;
+                    if (!ticket) {
+                        if (*v_next < *v_count) { slot = atomicAdd(tail.next, 1ull); ticket = true; continue; }
+                        // nothing to claim: wait for more only if every producer is resident and some are still walking
+                        if (all_handed || !all_here || ++polls > (uint32_t)B2_HELP_POLLS) break;
+                    } else {
+                        if (*reinterpret_cast<volatile uint32_t*>(tail.records + slot * tail.rec_words + 7) == tail.tag) { take = 1; break; }
+                        if (all_handed && slot >= *v_count) break;            // a ticket past the final count: there is no such record
+                        if (!all_here || ++polls > (uint32_t)B2_HELP_POLLS) {
+                            // not waiting on CTAs that may not be resident: the ticket goes to the tail kernel's list
+                            tail.orphans[atomicAdd(tail.handed + 2, 1ull)] = slot;
+                            break;
+                        }
+                    }
+                    __nanosleep(polls < 8u ? 500u : 4000u);
+                }
+            }
+            take = __shfl_sync(FULL, take, 0);
+            if (!take) break;
+            slot = __shfl_sync(FULL, slot, 0);
+            __threadfence();
+            tail_process<ANY, COUNT>(s, rays, out, tail.records + slot * tail.rec_words, smem_warp, fcap, wide_limit, ts);
+        }
+        tail_stats_flush<COUNT>(ts, counters, lane);
+    }
+#endif
 
     if (COUNT) {
         if (L.overflow) report_stack_overflow();             // counting build only, see Lane::push
@@ -536,8 +640,8 @@ __global__ void __launch_bounds__(256)
 wf_generate_kernel(FrameArgs a, GidMap map, uint32_t n, RayIn* __restrict__ rays, float4* __restrict__ state,
                    unsigned long long* __restrict__ queue_count) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    // counter block of this wavefront: [0..2] rotating queue lengths, [3] the traversal kernel's ray counter, [4] [5] its tail queue's length and read position, [6] [7] the second tail queue's
-    if (i == 0) { queue_count[0] = n; for (int k = 1; k < 8; ++k) queue_count[k] = 0; }
+    // counter block of this wavefront: [0..2] rotating queue lengths, [3] the traversal kernel's ray counter, [4] [5] its tail queue's length and read position, [6] [7] the second tail queue's, [8] [9] [10] helping: warps past their hand-over, warps started, tickets given back
+    if (i == 0) { queue_count[0] = n; for (int k = 1; k < 16; ++k) queue_count[k] = 0; }
     if (i >= n) return;
     uint32_t gid = (uint32_t)map.gid(i);
     uint32_t seed = gid + hash_u32(a.frame_count);                        // kernel_bvh.cl:445
@@ -558,7 +662,7 @@ wf_shade_kernel(SceneView s, FrameArgs a, GidMap map, const RayIn* __restrict__ 
     const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     // reset what the NEXT stages start from: the traversal kernel's ray counter and the queue length the next
     // shade stage appends to (neither is read or written by anything in flight now)
-    if (j == 0) { *clear_a = 0; for (int k = 0; k < 5; ++k) clear_b[k] = 0; }
+    if (j == 0) { *clear_a = 0; for (int k = 0; k < 8; ++k) clear_b[k] = 0; }
     if ((j & ~31ull) >= n) return;                      // whole warp beyond the queue
     const unsigned lane = threadIdx.x & 31u;
     bool go_on = false;
@@ -648,17 +752,22 @@ cudaError_t launch_trace_wide(const SceneView& s, const void* d_rays, uint64_t n
                               const unsigned long long* d_n, const TailQueue* tail_in, int tail_grid, cudaEvent_t between) {
     int cap = pick_cap(stack_bound);
     if (!cap) return cudaErrorInvalidValue;
-    TailQueue tail = { nullptr, nullptr, nullptr, 0, 0, 0, nullptr, nullptr, nullptr };
+    TailQueue tail = { nullptr, nullptr, nullptr, 0, 0, 0, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0 };
     if (tail_in && tail_in->coop_max && tail_in->records) tail = *tail_in;
     const bool two_step = tail.coop_max && tail.resume_max && tail.records2;
     if (!d_n) {     // wavefront stages (d_n given) get their counters reset by the preceding stage's kernel
-        // [0] the ray counter, [1] [2] tail-queue length and read position, [3] [4] the second tail queue's
-        cudaError_t e = cudaMemsetAsync(d_next, 0, 5 * sizeof(unsigned long long), st);
+        // [0] the ray counter, [1] [2] tail-queue length and read position, [3] [4] the second tail queue's, [5] [6] [7] helping: warps past their hand-over, warps started, tickets given back
+        cudaError_t e = cudaMemsetAsync(d_next, 0, 8 * sizeof(unsigned long long), st);
         if (e != cudaSuccess) return e;
     }
     if (refill_min < 1 || refill_min > 32) refill_min = 8;
     if (leaf_bias < 1 || leaf_bias > 512) leaf_bias = 16;
     // what each pass hands over to: the first pass suspends into queue 1 (at resume_max live rays when a second pass follows)
+    // helping: only when the helping warp's shared memory holds the tail kernel's frontier, and not in the two-step mode (its
+    // first queue is the second pass's ray stream)
+    const uint32_t fcap_tail = tail_frontier_words(stack_bound);
+    if (two_step || !tail.help_fcap || !tail.handed || !tail.orphans || !tail.tag || fcap_tail > trace_warp_smem_words()) tail.help_fcap = 0;
+    else { tail.help_fcap = fcap_tail; tail.help_wide_limit = fcap_tail - (stack_bound + 8u) - (7u * B2_COOP_NODES + 4u); }
     TailQueue q1 = tail;
     if (two_step) q1.coop_max = tail.resume_max;
     TailQueue q2 = tail;
@@ -685,6 +794,7 @@ cudaError_t launch_trace_wide(const SceneView& s, const void* d_rays, uint64_t n
     return cudaGetLastError();
 }
 
+uint32_t trace_warp_smem_words() { return (B2_TAIL_HELP && B2_TAIL_CODE) ? (uint32_t)WARP_SMEM_WORDS : 0u; }
 uint32_t tail_frontier_words(uint32_t stack_bound) { uint32_t w = 4u * (stack_bound + 8u); return w < 256u ? 256u : w; }
 uint32_t tail_record_words(uint32_t stack_bound) { return TAIL_HEADER_WORDS + ((stack_bound + 8u + 3u) & ~3u); }
 

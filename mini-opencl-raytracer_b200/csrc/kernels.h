@@ -20,7 +20,17 @@ struct TailQueue {
     unsigned long long* count2;
     unsigned long long* next2;
     uint32_t* records2;
+    // Helping (help_fcap > 0): a warp of the persistent launch that has handed its last rays over serves the queue itself
+    // (trace_persistent's epilogue) while other warps are still walking; what is left when the launch ends goes to the tail
+    // kernel as before. `handed` counts the warps that are past their hand-over (zeroed with the other counters), `tag`
+    // (unique per launch, never 0) marks a record as completely written.
+    unsigned long long* handed;    // [0] warps past their hand-over, [1] warps started, [2] tickets in `orphans`
+    unsigned long long* orphans;   // tickets (queue positions) that helping warps drew and gave back: one per warp of the grid at most
+    uint32_t tag;
+    uint32_t help_fcap;            // frontier words a helping warp has (its own shared-memory columns); 0 = no helping
+    uint32_t help_wide_limit;      // frontier size up to which a helping warp expands several nodes per round (as in the tail kernel)
 };
+uint32_t trace_warp_smem_words();                     // shared-memory words each warp of trace_persistent owns
 uint32_t tail_frontier_words(uint32_t stack_bound);   // shared-memory words per warp of the tail kernel
 uint32_t tail_record_words(uint32_t stack_bound);
 

@@ -27,9 +27,11 @@ with prod.Context(0) as ctx:
     ctx.set_option(cap.OPT_RENDER_MODE, 0)
     ctx.set_option(cap.OPT_WAVEFRONT_LANES, 1)
     plan = prod.sharding.BandPlan(W, H, world, band_rows=8)
-    for coop, resume in [tuple(int(y) for y in x.split(":")) for x in os.environ.get("COOPS", "8:0,8:16,4:16,4:12,2:16").split(",")]:
+    for coop, resume, help_ in [tuple(int(y) for y in (x.split(":") + ["1"])[:3]) for x in os.environ.get("COOPS", "8:0:1,8:0:0,8:16,4:16,4:12,2:16").split(",")]:
         ctx.set_option(cap.OPT_COOP_MAX, coop)
         ctx.set_option(cap.OPT_RESUME_MAX, resume)
+        ctx.set_option(cap.OPT_TAIL_HELP, help_)
+        print("== coop %d resume %d help %d" % (coop, resume, help_))
         for r in ranks:
             ctx.set_option(cap.OPT_STAGE_TIMES, 1)
             for f in (1, 2, 3):
