@@ -62,6 +62,50 @@ extern "C" void emu_trace(const EmuRay* rays, uint64_t n, EmuHit* hits, uint32_t
     st->wide_visits += sums[0]; st->leaf_blocks += sums[1]; st->leaf_pass += sums[2]; st->tri_tests += sums[3]; st->words += sums[4];
 }
 
+// The kernels' stack placement (HybridStack, traverse.cuh) and the production build's branch-free push (COUNT = false), which
+// emu_trace (plain array, counting build) does not run: the first `depth` entries live in a strided "shared" array, the
+// rest in the local one. depth: 1, 2, 3 or 12.
+template <bool ANY, int DEPTH>
+static HitX hybrid_one(const U4* wide, const U4* leaf, const RayX& r, float tmax, uint32_t schedule) {
+    Lane<ANY, false, 256> L;
+    uint32_t local_stack[256];
+    uint32_t shared_cols[DEPTH * 4 + 4];                       // stride 4: this "thread" is column 1 of four
+    for (uint32_t& v : shared_cols) v = 0xDEADBEEFu;
+    const HybridStack<DEPTH, 4> stack = { shared_cols + 1, local_stack };
+    L.start(r, tmax);
+    L.overflow = false;
+    while (!L.done()) {
+        const bool node = L.wants_node(), lf = L.wants_leaf();
+        bool do_leaf = lf;
+        if (node && lf && schedule) { schedule = schedule * 1664525u + 1013904223u; do_leaf = (schedule >> 16) & 1u; }
+        if (do_leaf) { if (L.leaf_step(leaf, stack)) break; }
+        else L.node_step(wide, stack, 0x3F800000u);
+    }
+    for (int i = 0; i < DEPTH * 4 + 4; ++i)                    // the neighbouring columns are untouched
+        if ((i & 3) != 1 && shared_cols[i] != 0xDEADBEEFu) { HitX bad; bad.t = -1.0f; bad.u = bad.v = 0.0f; bad.tri = 0xBADBADu; return bad; }
+    return L.h;
+}
+template <bool ANY>
+static HitX hybrid_depth(int depth, const U4* wide, const U4* leaf, const RayX& r, float tmax, uint32_t schedule) {
+    switch (depth) {
+        case 1: return hybrid_one<ANY, 1>(wide, leaf, r, tmax, schedule);
+        case 2: return hybrid_one<ANY, 2>(wide, leaf, r, tmax, schedule);
+        case 3: return hybrid_one<ANY, 3>(wide, leaf, r, tmax, schedule);
+        default: return hybrid_one<ANY, 12>(wide, leaf, r, tmax, schedule);
+    }
+}
+extern "C" void emu_trace_hybrid(const EmuRay* rays, uint64_t n, EmuHit* hits, uint32_t* occluded, int any, int depth, uint32_t schedule) {
+    const U4* wide = reinterpret_cast<const U4*>(g_bvh.nodes.data());
+    const U4* leaf = g_bvh.leaf.data();
+    for (uint64_t i = 0; i < n; ++i) {
+        const RayX r = make_ray(rays[i].ox, rays[i].oy, rays[i].oz, rays[i].dx, rays[i].dy, rays[i].dz);
+        const uint32_t sched = schedule ? schedule + (uint32_t)i * 2654435761u : 0u;
+        const HitX h = any ? hybrid_depth<true>(depth, wide, leaf, r, rays[i].tmax, sched) : hybrid_depth<false>(depth, wide, leaf, r, rays[i].tmax, sched);
+        if (any) occluded[i] = h.tri != 0xFFFFFFFFu;
+        else { hits[i].t = h.t; hits[i].u = h.u; hits[i].v = h.v; hits[i].tri = h.tri; }
+    }
+}
+
 // Children that the exact-arithmetic node test lets through but the fast one culled, over all emulated walks so far (must be 0).
 extern "C" uint64_t emu_culling_violations() { return g_emu_culling_violations; }
 

@@ -299,6 +299,22 @@ def emu_trace_coop(rays, any_hit=False, stats=None, handoff=0, wide_limit=192, f
     return hits
 
 
+def emu_trace_hybrid(rays, any_hit=False, depth=2, schedule=0):
+    """The walk with the kernels' stack placement (first `depth` entries in a strided 'shared' column, the rest local) and
+    the production build's branch-free push."""
+    rays = np.ascontiguousarray(rays)
+    L = emu()
+    L.emu_trace_hybrid.restype = None
+    L.emu_trace_hybrid.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint32]
+    if any_hit:
+        occ = np.empty(rays.shape[0], dtype=np.uint32)
+        L.emu_trace_hybrid(_p(rays), rays.shape[0], None, _p(occ), 1, depth, schedule)
+        return occ
+    hits = np.empty(rays.shape[0], dtype=HIT)
+    L.emu_trace_hybrid(_p(rays), rays.shape[0], _p(hits), None, 0, depth, schedule)
+    return hits
+
+
 def emu_trace(rays, any_hit=False, stats=None, schedule=0):
     """schedule = 0: leaves are consumed as soon as they are queued; != 0: node and leaf steps are
     interleaved pseudo-randomly per ray (what the warp-vote scheduling of the kernels can produce)."""

@@ -52,6 +52,26 @@ def test_bumpy_primary_bounce_and_any(bumpy_ref):
     _same(ol.emu_trace(inside), ol.oracle_closest(tris, nodes, inside))
 
 
+def test_stack_in_shared_columns_and_branch_free_push(bumpy_ref):
+    """The kernels keep the first entries of a lane's stack in a strided shared-memory column (HybridStack) and, outside the
+    counting build, push without a branch: same hits for every split between 'shared' and local entries, under any
+    interleaving of node and leaf steps."""
+    tris, nodes, _ = bumpy_ref
+    ol.emu_build(tris, nodes)
+    rays = scenes.shell_rays(20000, 10.0, seed=71)
+    h = ol.oracle_closest(tris, nodes, rays)
+    b = scenes.bounce_rays(rays, h, scenes.tri_normals(tris, h), seed=72)
+    hb = ol.oracle_closest(tris, nodes, b)
+    short = b.copy()
+    short["tmax"] = 3.0
+    occ = ol.oracle_any(tris, nodes, short) != 0
+    for depth in (1, 2, 3, 12):
+        for schedule in (0, 977 + depth):
+            _same(ol.emu_trace_hybrid(rays, depth=depth, schedule=schedule), h)
+            _same(ol.emu_trace_hybrid(b, depth=depth, schedule=schedule), hb)
+            assert np.array_equal(ol.emu_trace_hybrid(short, any_hit=True, depth=depth, schedule=schedule) != 0, occ)
+
+
 def test_wide_nodes_fetch_fewer_bytes_than_reference_layout(bumpy_ref):
     tris, nodes, _ = bumpy_ref
     ol.emu_build(tris, nodes)
