@@ -532,7 +532,7 @@ def run_b200(args, rank, world, local_rank):
                 def frame(k):
                     fc.set_frame(k, 4, **cam_t)
                     if world > 1:
-                        fc.execute_shard()                              # this rank's bands + store-through + completion barrier
+                        fc.execute_shard()                              # entry fence + this rank's bands + store-through + completion barrier
                     else:
                         fc.execute(W * H)
                     fc.finish()                                         # the frame is complete in rank 0's HBM
@@ -552,7 +552,7 @@ def run_b200(args, rank, world, local_rank):
                          "api": "b2rt_execute_shard + b2rt_finish per frame" if world > 1 else "b2rt_execute + b2rt_finish per frame",
                          "partition": "8-row bands of gid = y*W + x round robin over %d ranks" % world}
                 if world > 1:
-                    entry["gather"] = dict(fc.group_info(), how="kernels store finished pixels into rank 0's image (CUDA IPC mapping over NVLink); 4-byte ncclAllReduce as completion barrier")
+                    entry["gather"] = dict(fc.group_info(), how="kernels store finished pixels into rank 0's image (CUDA IPC mapping over NVLink); one 4-byte ncclAllReduce as entry fence (orders the stores behind rank 0's reads of the previous frame) and one as completion barrier")
                 if rank == 0:
                     img = fc.read_pixels().copy()
                     tiled_checks[key] = (img, tris_c, nodes_c, mats_c, cam_t, 5 + frames)

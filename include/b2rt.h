@@ -135,6 +135,10 @@ enum {
                                    finished or handed over their own rays serve the cooperative tail queue inside the same launch; the
                                    tail kernel takes what is left. The default build compiles this out (measured slower on frame shares,
                                    DESIGN.md 4c), the option is then accepted and ignored. Results do not depend on it. */
+    B2RT_OPT_SHARD_FENCE = 13,  /* 1 (default) / 0: b2rt_execute_shard with a mapped root image starts with a 4-byte ncclAllReduce, so that no
+                                   rank's kernels store pixels of the new frame into rank 0's image while rank 0 is still reading the
+                                   previous one (b2rt_read_pixels is asynchronous). A job that never reads between two frames may set 0 on
+                                   EVERY rank (the fence is a collective). Results do not depend on it. */
     B2RT_OPT_COOP_MAX = 7       /* tail mode of the persistent kernels: a warp whose ray pool is dry and that has at most this many
                                    rays alive hands them to the cooperative tail kernel, 32 lanes per ray (0 = off .. 16; default -1 = 8, but off for scenes
                                    of fewer than ~1000 nodes, whose rays are too short to gain). Results do not
@@ -254,7 +258,10 @@ int b2rt_group_info(const b2rt_context* ctx, int* peer_store, int* nccl_loaded);
  * store-through target. b2rt_execute_shard: KernelEntry for this rank's bands of the WIDTH x HEIGHT frame, then the
  * gather on rank 0 -- a 4-byte ncclAllReduce as completion barrier when the image is mapped (pixels were stored through
  * by the kernels), else grouped ncclSend/ncclRecv of the bands straight into place. Asynchronous: rank 0 reads the
- * complete frame with b2rt_read_pixels + b2rt_finish. */
+ * complete frame with b2rt_read_pixels + b2rt_finish. Rank 0's stream is the reference point of the image: the next
+ * b2rt_execute_shard on any rank starts storing only after rank 0's stream has reached ITS next b2rt_execute_shard, i.e.
+ * after the reads rank 0 enqueued in between (entry fence, B2RT_OPT_SHARD_FENCE). A device-group handle
+ * (b2rt_create_multi) orders its peers behind the root's stream the same way, with an event. */
 int b2rt_comm_unique_id(void* id_out, size_t bytes);
 int b2rt_comm_init(b2rt_context* ctx, const void* id, size_t bytes, int rank, int world);
 int b2rt_comm_share_output(b2rt_context* ctx);

@@ -16,7 +16,7 @@ ARG_BUFFER_OUT, ARG_BUFFER_SCENE, ARG_BUFFER_NODE, ARG_BUFFER_MATERIAL = 0, 1, 2
 ARG_WIDTH, ARG_HEIGHT, ARG_FRAME_COUNT, ARG_FRAME_SEED = 4, 5, 6, 7
 ARG_LIGHT_BOUNCES, ARG_LIGHT_TYPE, ARG_SKYBOX_INTENSITY = 8, 9, 10
 ARG_CAMERA_POS, ARG_CAMERA_FRONT, ARG_CAMERA_UP = 11, 12, 13
-OPT_TRAVERSAL, OPT_COUNTERS, OPT_BLOCKS_PER_SM, OPT_RENDER_MODE, OPT_REFILL_MIN, OPT_LEAF_BIAS, OPT_WAVEFRONT_LANES, OPT_COOP_MAX, OPT_L2_PERSIST, OPT_STAGE_TIMES, OPT_WAVEFRONT_GRID_SPLIT, OPT_RESUME_MAX, OPT_TAIL_HELP = 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12
+OPT_TRAVERSAL, OPT_COUNTERS, OPT_BLOCKS_PER_SM, OPT_RENDER_MODE, OPT_REFILL_MIN, OPT_LEAF_BIAS, OPT_WAVEFRONT_LANES, OPT_COOP_MAX, OPT_L2_PERSIST, OPT_STAGE_TIMES, OPT_WAVEFRONT_GRID_SPLIT, OPT_RESUME_MAX, OPT_TAIL_HELP, OPT_SHARD_FENCE = 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13
 MEM_WRITE_ONLY, MEM_READ_ONLY, MEM_COPY_HOST_PTR = 1 << 1, 1 << 2, 1 << 5
 
 # every symbol include/b2rt.h declares (tests/test_abi.py checks the header against this list)
@@ -315,6 +315,11 @@ class Context:
         self._ck(self._L.b2rt_read_pixels(self._h, _ptr(out), out.nbytes))
         self.finish()
         return out
+
+    def read_pixels_async(self, out):
+        """b2rt_read_pixels without the finish: the copy is only enqueued (asynchronous for real when `out` is pinned,
+        see host_register); the caller calls finish() before looking at `out`."""
+        self._ck(self._L.b2rt_read_pixels(self._h, _ptr(out), out.nbytes))
 
     def read_pixels_rgba8(self, out=None):
         """Clamped 8-bit RGBA view of the accumulation image, quantised on the device (4 B/pixel read-back)."""

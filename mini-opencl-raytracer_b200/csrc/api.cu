@@ -1147,6 +1147,7 @@ static int set_option_one(b2rt_context* ctx, uint32_t option, int64_t value) {
         case B2RT_OPT_RESUME_MAX: if (value < -1 || value > COOP_MAX_LIMIT) return fail(ctx, B2RT_INVALID_VALUE, "resume threshold must be -1 (auto), 0 (off) .. 16"); ctx->opt_resume_max = value; break;
         case B2RT_OPT_WAVEFRONT_GRID_SPLIT: ctx->opt_wf_grid_split = value ? 1 : 0; break;
         case B2RT_OPT_TAIL_HELP: ctx->opt_tail_help = value ? 1 : 0; break;
+        case B2RT_OPT_SHARD_FENCE: ctx->opt_shard_fence = value ? 1 : 0; break;
         case B2RT_OPT_STAGE_TIMES: ctx->opt_stage_times = value ? 1 : 0; ctx->stage_used = 0; break;
         case B2RT_OPT_REFILL_MIN: if (value < 1 || value > 32) return fail(ctx, B2RT_INVALID_VALUE, "refill threshold must be 1..32"); ctx->opt_refill_min = value; break;
         default: return fail(ctx, B2RT_INVALID_VALUE, "unknown option");

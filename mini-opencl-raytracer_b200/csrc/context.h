@@ -83,7 +83,7 @@ struct b2rt_context {
     uint64_t rgba8_capacity = 0;
     cudaEvent_t ev_in[2] = { nullptr, nullptr }, ev_comp[2] = { nullptr, nullptr }, ev_out[2] = { nullptr, nullptr };
     // options
-    int64_t opt_traversal = 0, opt_counters = 0, opt_blocks_per_sm = 0, opt_render_mode = 2, opt_refill_min = 6, opt_leaf_bias = 0, opt_wf_lanes = 0, opt_coop_max = -1, opt_l2_persist = 1, opt_stage_times = 0, opt_wf_grid_split = 0, opt_resume_max = 0, opt_tail_help = 1;
+    int64_t opt_traversal = 0, opt_counters = 0, opt_blocks_per_sm = 0, opt_render_mode = 2, opt_refill_min = 6, opt_leaf_bias = 0, opt_wf_lanes = 0, opt_coop_max = -1, opt_l2_persist = 1, opt_stage_times = 0, opt_wf_grid_split = 0, opt_resume_max = 0, opt_tail_help = 1, opt_shard_fence = 1;
     uint32_t tail_tag_seq = 0;                 // tag of the last persistent launch's tail records (kernels.h)
     int grid_closest = 0, grid_any = 0;
     uint64_t launches = 0;

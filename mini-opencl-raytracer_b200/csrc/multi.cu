@@ -150,6 +150,7 @@ struct Group {
     std::vector<std::unique_ptr<Worker>> workers;       // [k-1] issues member k's work
     std::vector<ncclComm_t> comms;                       // empty when NCCL could not be loaded
     std::vector<cudaEvent_t> done;                       // member k's share of the frame has been rendered
+    cudaEvent_t root_free = nullptr;                     // the root's stream has reached this frame: earlier reads of its image are done
     bool peer_store = false;                             // every member can store into the root's memory
 };
 
@@ -294,9 +295,14 @@ int group_execute(b2rt_context* ctx, size_t gid_begin, size_t gid_end) {
     if (st) return st;
     const int world = (int)g->members.size();
     const uint64_t band = band_items(ctx);
+    // The peers write into the root's image (store-through or band copies). Whatever the root's stream still has to do with
+    // that image -- an asynchronous b2rt_read_buffer of the previous frame above all -- must come first: without this
+    // edge a peer's pixels of frame f+1 could land in the middle of the read of frame f.
+    CK(cudaEventRecord(g->root_free, ctx->stream));
     st = run_members(ctx, [&](b2rt_context* m, int k) {
         int s = use_device(m);
         if (s) return s;
+        if (k) { b2rt_context* ctx = m; CK(cudaStreamWaitEvent(m->stream, g->root_free, 0)); }
         s = render_share(m, band_share(gid_begin, gid_end, band, k, world));
         if (s || k == 0) return s;
         b2rt_context* ctx = m;
@@ -356,6 +362,7 @@ void group_destroy(b2rt_context* ctx) {
     Nccl* nc = nccl();
     for (size_t k = 0; k < g->comms.size(); ++k) if (nc && g->comms[k]) nc->CommDestroy(g->comms[k]);
     for (size_t k = 0; k < g->done.size(); ++k) if (g->done[k]) { cudaSetDevice(g->members[k]->device); cudaEventDestroy(g->done[k]); }
+    if (g->root_free) { cudaSetDevice(ctx->device); cudaEventDestroy(g->root_free); }
     for (size_t k = 1; k < g->members.size(); ++k) { g->members[k]->parent = nullptr; b2rt_destroy(g->members[k]); }
     ctx->group = nullptr;
     delete g;
@@ -432,6 +439,8 @@ extern "C" int b2rt_create_multi(const int* device_ids, int n_devices, b2rt_cont
         cudaSetDevice(device_ids[k]);
         if (cudaEventCreateWithFlags(&g->done[k], cudaEventDisableTiming) != cudaSuccess) return bail(B2RT_OUT_OF_RESOURCES, "cudaEventCreate (device group)");
     }
+    cudaSetDevice(device_ids[0]);
+    if (cudaEventCreateWithFlags(&g->root_free, cudaEventDisableTiming) != cudaSuccess) return bail(B2RT_OUT_OF_RESOURCES, "cudaEventCreate (device group)");
     if (Nccl* nc = nccl()) {
         g->comms.assign(n_devices, nullptr);
         ncclResult_t r = nc->CommInitAll(g->comms.data(), n_devices, device_ids);
@@ -573,6 +582,12 @@ extern "C" int b2rt_execute_shard(b2rt_context* ctx) {
     if (st) return st;
     if (!ctx->width || !ctx->height) return fail(ctx, B2RT_INVALID_KERNEL_ARGS, "WIDTH/HEIGHT must be non-zero");
     const uint64_t n = (uint64_t)ctx->width * ctx->height, band = band_items(ctx);
+    if (c->world > 1 && c->shared && ctx->opt_shard_fence) {
+        // Entry fence: nobody's kernels of THIS frame may store into rank 0's image before rank 0's stream has got here,
+        // i.e. before whatever rank 0 enqueued after the previous frame's completion barrier -- its read of that frame --
+        // is done. (The completion barrier alone does not give that: a rank leaves it as soon as everybody has joined.)
+        NK(nc->AllReduce(c->d_flag + 16, c->d_flag + 16, 1, ncclInt, ncclSum, c->comm, ctx->stream));
+    }
     st = render_share(ctx, band_share(0, n, band, c->rank, c->world));
     if (st) return st;
     if (c->world == 1) return B2RT_SUCCESS;

@@ -267,6 +267,42 @@ def test_device_group_frame_and_streams(product, bumpy_ref, cornell_ref):
             grp.execute_bands(0, 64, 128, 2)                        # addresses one device
 
 
+def test_device_group_orders_peer_stores_behind_the_roots_reads(product, cornell_ref):
+    """b2rt_read_pixels is asynchronous (clEnqueueReadBuffer, non-blocking): a frame enqueued right behind it must not
+    change what the read returns, although the peers' kernels write the root's image from their own streams."""
+    tris, nodes, mats = cornell_ref
+    W, H, frames = 1024, 768, (1, 2, 3, 4, 5)
+    with product.Context(0) as one:
+        one.upload_scene(tris, nodes, mats)
+        one.resize(W, H)
+        want = []
+        for fc in frames:
+            one.set_frame(fc, 4)
+            one.execute(W * H)
+            want.append(one.read_pixels().copy())
+    with product.Context(_device_list(product, 3)) as grp:
+        grp.upload_scene(tris, nodes, mats)
+        grp.resize(W, H)
+        got = [np.zeros((W * H, 4), dtype=np.float32) for _ in frames]
+        for g in got:
+            grp.host_register(g)
+        try:
+            for rep in range(2):                                # frame 1 ignores the image's old content; the second pass runs with the render-mode choice settled
+                for fc, g in zip(frames, got):
+                    grp.set_frame(fc, 4)
+                    grp.execute(W * H)
+                    grp.read_pixels_async(g)                    # no finish: the next frame is enqueued behind the copy
+                grp.finish()
+                if rep == 0:
+                    continue
+                for fc, g, w in zip(frames, got, want):
+                    assert np.array_equal(g.view(np.uint32), w.view(np.uint32)), fc
+        finally:
+            grp.finish()
+            for g in got:
+                grp.host_unregister(g)
+
+
 def test_cpp_program_drives_a_device_group(product, tmp_scene_dir, cornell_ref):
     """VERDICT r1 #2: a C++ program written against CLRaytracer renders a multi-GPU frame with no Python in the path."""
     from test_cpp_host import _build
