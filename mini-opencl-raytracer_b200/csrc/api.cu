@@ -457,10 +457,15 @@ int render_wavefront(b2rt_context* ctx, const FrameArgs& a, float* d_result, con
 int render_with_mode(b2rt_context* ctx, const FrameArgs& a, float* result, const GidMap& map, uint64_t n, int mode);
 int render_tuned(b2rt_context* ctx, const FrameArgs& a, float* result, const GidMap& map, uint64_t n);
 
-// Folds a finished timing into the tuner table (waits for the timed launch if it is still running).
-int tuner_resolve(b2rt_context* ctx) {
+// Folds a finished timing into the tuner table. Never waits: while the timed launch is still running `*busy` is set and the
+// caller simply runs another (untimed) frame in the same mode -- the host thread of an asynchronous frame loop is not
+// stalled by the measurement (r1: a cudaEventSynchronize here made the first four frames of every new launch shape blocking).
+int tuner_resolve(b2rt_context* ctx, bool* busy) {
+    *busy = false;
     if (ctx->tune_pending_mode < 0) return B2RT_SUCCESS;
-    CK(cudaEventSynchronize(ctx->ev_tune[1]));
+    const cudaError_t q = cudaEventQuery(ctx->ev_tune[1]);
+    if (q == cudaErrorNotReady) { cudaGetLastError(); *busy = true; return B2RT_SUCCESS; }
+    if (q != cudaSuccess) return cuda_fail(ctx, q, "cudaEventQuery (render-mode trial)");
     float ms = 0.0f;
     CK(cudaEventElapsedTime(&ms, ctx->ev_tune[0], ctx->ev_tune[1]));
     ModeTrial& t = ctx->tuner[ctx->tune_pending_key];
@@ -472,16 +477,20 @@ int tuner_resolve(b2rt_context* ctx) {
 
 // B2RT_OPT_RENDER_MODE = 2: the wavefront and the megakernel produce bit-identical frames, so the faster one for
 // THIS launch shape (work items, bounces) on THIS scene can simply be measured. Calls 1-2 of a shape run the
-// wavefront, calls 3-4 the megakernel, the second of each pair between two CUDA events; from call 5 on the winner
-// runs. The wavefront wins on large launches and incoherent scenes, the megakernel on a rank's small share of a
-// multi-GPU frame, where the per-bounce stage tails of the wavefront add up.
+// wavefront, calls 3-4 the megakernel, the second of each pair between two CUDA events; once both timings have been
+// read back (without waiting: cudaEventQuery at the start of a later call) the winner runs. The wavefront wins on large
+// launches and incoherent scenes, the megakernel on a rank's small share of a multi-GPU frame, where the per-bounce
+// stage tails of the wavefront add up.
 int render_tuned(b2rt_context* ctx, const FrameArgs& a, float* result, const GidMap& map, uint64_t n) {
-    int st = tuner_resolve(ctx);
+    bool busy = false;
+    int st = tuner_resolve(ctx, &busy);
     if (st) return st;
     if (n >= WF_MAX_PATHS) return render_with_mode(ctx, a, result, map, n, 0);
     const std::pair<uint64_t, int> key(n, a.bounces);
     ModeTrial& t = ctx->tuner[key];
     if (t.choice >= 0) return render_with_mode(ctx, a, result, map, n, t.choice);
+    // a trial (of this shape or another) is still in flight and owns the two events: no new measurement now
+    if (busy) return render_with_mode(ctx, a, result, map, n, ctx->tune_pending_key == key ? ctx->tune_pending_mode : 0);
     const int phase = t.calls++;
     const int mode = phase < 2 ? 0 : 1;
     const bool timed = (phase & 1) != 0;

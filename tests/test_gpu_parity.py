@@ -206,13 +206,21 @@ def test_wavefront_and_megakernel_frames_are_bit_identical(product, cornell_ctx,
             ctx.set_option(product.capi.OPT_RENDER_MODE, mode)
             imgs.append(_render(ctx, W, H, (1, 2, 3), bounces, **cam))
         assert np.array_equal(imgs[0].view(np.uint32), imgs[1].view(np.uint32)), bounces
-        # mode 2 (default): calls 1-2 wavefront, 3-4 megakernel, then whichever measured faster -- 7 accumulated frames
-        # cross every phase of that choice and must equal 7 frames of one fixed mode
-        seven = []
+        # mode 2 (default): calls 1-2 wavefront, 3-4 megakernel, then whichever measured faster; the timings are picked up
+        # without waiting, so a trial still in flight makes the next frames run untimed in its mode. 12 accumulated frames
+        # with a finish after every third cross every phase of that choice (trial pending / resolved) and must equal 12
+        # frames of one fixed mode
+        twelve = []
         for mode in (2, 1):
             ctx.set_option(product.capi.OPT_RENDER_MODE, mode)
-            seven.append(_render(ctx, W, H, range(1, 8), bounces, **cam))
-        assert np.array_equal(seven[0].view(np.uint32), seven[1].view(np.uint32)), bounces
+            ctx.resize(W, H)
+            for fc in range(1, 13):
+                ctx.set_frame(fc, bounces, **cam)
+                ctx.execute(W * H)
+                if fc % 3 == 0:
+                    ctx.finish()
+            twelve.append(ctx.read_pixels())
+        assert np.array_equal(twelve[0].view(np.uint32), twelve[1].view(np.uint32)), bounces
         ctx.set_option(product.capi.OPT_RENDER_MODE, 0)
         for lanes in (2, 3, 4):                                  # several wavefronts in flight on their own streams
             ctx.set_option(product.capi.OPT_WAVEFRONT_LANES, lanes)
