@@ -64,6 +64,8 @@ void free_tail(b2rt_context* ctx) {
 }
 
 void free_scene(b2rt_context* ctx) {
+    // the tree's lines must not keep their place in the persisting part of L2 once nobody traverses it (scene_l2_setup)
+    if (ctx->d_wide && ctx->l2_persist_max && ctx->opt_l2_persist) { cudaCtxResetPersistingL2Cache(); cudaGetLastError(); }
     if (ctx->d_wide) cudaFree(ctx->d_wide);          // one allocation: wide nodes, then the leaf blocks (alloc_bvh)
     if (ctx->d_shade) cudaFree(ctx->d_shade);
     if (ctx->d_child_bin) cudaFree(ctx->d_child_bin);
@@ -187,23 +189,50 @@ int ensure_scene(b2rt_context* ctx) {
 // Once per scene and device: size the persisting part of L2 to the wide-node array; the window itself is (re)applied per
 // stream on first use (apply_l2_policy).
 void scene_l2_setup(b2rt_context* ctx) {
-    ctx->policy_streams.clear();
     if (!ctx->l2_persist_max) return;
     // what the window covers: the whole traversal set (nodes + leaf blocks, one allocation) when it fits the persisting
     // carve-out this device allows, else the wide-node array alone (the part every ray re-reads most)
     const size_t all = ctx->bvh_bytes, nodes_only = (size_t)ctx->info.wide_node_bytes;
     ctx->l2_window_bytes = (all <= ctx->l2_persist_max && all <= ctx->l2_window_max) ? all : std::min(nodes_only, ctx->l2_window_max);
     const size_t want = (ctx->l2_window_bytes + (4u << 20)) & ~(size_t)((1u << 20) - 1);
-    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, ctx->opt_l2_persist ? std::min(ctx->l2_persist_max, want) : 0);
+    // the carve-out is a property of the DEVICE: it only grows here (another handle on this device may need what it has), and a
+    // handle that switches its window off leaves it alone
+    if (ctx->opt_l2_persist) {
+        size_t have = 0;
+        if (cudaDeviceGetLimit(&have, cudaLimitPersistingL2CacheSize) != cudaSuccess) { cudaGetLastError(); have = 0; }
+        const size_t need = std::min(ctx->l2_persist_max, want);
+        if (need > have) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, need);
+    }
+    // Lines that an EARLIER scene (of this handle or of another handle on the same device) marked persisting stay in the
+    // carve-out until they are reset -- a new scene would share it with a tree nobody traverses any more (seen in bench.py:
+    // a second handle's 16 M-ray launches at 2 016 instead of 3 110 Mrays/s, depending on what the first had left behind).
+    cudaCtxResetPersistingL2Cache();
     cudaGetLastError();
 }
 
+// Which window a stream carries is a property of the STREAM, and caller streams may be shared by several handles (bench.py
+// traces two scenes on one torch stream): the table is process-wide, keyed by the stream's unique id, and a launch whose
+// stream carries another scene's window (or a stale one) sets its own.
+struct StreamWindow { const void* base; size_t bytes; bool persist; };
+static std::mutex g_window_mutex;
+static std::unordered_map<unsigned long long, StreamWindow> g_stream_windows;
+
 int apply_l2_policy(b2rt_context* ctx, cudaStream_t st) {
     if (ctx->l2_persist_max == 0 || ctx->l2_window_max == 0 || !ctx->d_wide) return B2RT_SUCCESS;
-    for (cudaStream_t s : ctx->policy_streams) if (s == st) return B2RT_SUCCESS;
+    unsigned long long id = 0;
+    if (cudaStreamGetId(st, &id) != cudaSuccess) { cudaGetLastError(); id = (unsigned long long)(uintptr_t)st; }
+    id = id * 64u + (unsigned long long)(ctx->device & 63);          // stream ids are unique per process; keep devices apart anyway
+    const StreamWindow want = { ctx->d_wide, ctx->l2_window_bytes, ctx->opt_l2_persist != 0 };
+    {
+        std::lock_guard<std::mutex> lk(g_window_mutex);
+        auto it = g_stream_windows.find(id);
+        // a window is an address range with properties: whoever set exactly this one, it is the right one
+        if (it != g_stream_windows.end() && it->second.base == want.base && it->second.bytes == want.bytes && it->second.persist == want.persist)
+            return B2RT_SUCCESS;
+    }
     cudaStreamAttrValue attr;
     memset(&attr, 0, sizeof(attr));
-    if (ctx->opt_l2_persist) {
+    if (want.persist) {
         attr.accessPolicyWindow.base_ptr = ctx->d_wide;
         attr.accessPolicyWindow.num_bytes = ctx->l2_window_bytes;
         attr.accessPolicyWindow.hitRatio = std::min(1.0f, (float)ctx->l2_persist_max / (float)std::max<size_t>(attr.accessPolicyWindow.num_bytes, 1));
@@ -211,7 +240,11 @@ int apply_l2_policy(b2rt_context* ctx, cudaStream_t st) {
         attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
     }
     CK(cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr));
-    ctx->policy_streams.push_back(st);
+    {
+        std::lock_guard<std::mutex> lk(g_window_mutex);
+        g_stream_windows[id] = want;
+        if (g_stream_windows.size() > 4096) g_stream_windows.clear();  // ids of streams long gone: start over (costs one attribute call per live stream)
+    }
     return B2RT_SUCCESS;
 }
 

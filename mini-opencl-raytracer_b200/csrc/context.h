@@ -38,7 +38,6 @@ struct b2rt_context {
     int device = 0;
     int sm_count = 0;
     size_t l2_persist_max = 0, l2_window_max = 0;   // cudaDeviceProp persistingL2CacheMaxSize / accessPolicyMaxWindowSize
-    std::vector<cudaStream_t> policy_streams;       // streams that carry the wide-node access-policy window of the current scene
     cudaStream_t stream = nullptr, stream_in = nullptr, stream_out = nullptr;
     std::unordered_map<uint64_t, Buffer> buffers;
     uint64_t next_id = 1;
