@@ -224,8 +224,10 @@ int b2rt_trace_closest(b2rt_context* ctx, const b2rt_ray* rays, uint64_t n, b2rt
 int b2rt_trace_any(b2rt_context* ctx, const b2rt_ray* rays, uint64_t n, uint32_t* occluded);
 /* Device-resident buffers (plain device pointers, e.g. torch tensor data_ptr()); enqueued on
  * `cuda_stream` (a cudaStream_t passed as void*; NULL = the context's own stream). Asynchronous.
- * Every launch has its own work counter, so launches on different streams may overlap; at most 4
- * of them at a time while the cooperative tail mode is on (B2RT_OPT_COOP_MAX > 0: they share 4 tail queues). */
+ * Every launch has its own work counter, so launches on different streams may overlap; on at most 4
+ * DIFFERENT streams at a time while the cooperative tail mode is on (B2RT_OPT_COOP_MAX > 0): a tail queue belongs to
+ * the stream whose launches use it (allocated by that stream's first launch), and a fifth stream takes over the
+ * queue of the stream that has not launched for longest. */
 int b2rt_trace_closest_device(b2rt_context* ctx, const b2rt_ray* d_rays, uint64_t n, b2rt_hit* d_hits, void* cuda_stream);
 int b2rt_trace_any_device(b2rt_context* ctx, const b2rt_ray* d_rays, uint64_t n, uint32_t* d_occluded, void* cuda_stream);
 /* CreateRay (kernel_bvh.cl:386-403) for gid in [gid_begin, gid_end) with the currently bound

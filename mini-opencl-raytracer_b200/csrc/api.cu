@@ -61,6 +61,8 @@ Buffer* find(b2rt_context* ctx, b2rt_buffer id) {
 
 void free_tail(b2rt_context* ctx) {
     for (void*& p : ctx->d_tail) { if (p) cudaFree(p); p = nullptr; }
+    for (int i = 0; i < TAIL_RING + 4; ++i) ctx->tail_two_step[i] = false;
+    for (int i = 0; i < TAIL_RING; ++i) { ctx->tail_slot_stream[i] = 0; ctx->tail_slot_used[i] = 0; }
 }
 
 void free_scene(b2rt_context* ctx) {
@@ -195,17 +197,11 @@ void scene_l2_setup(b2rt_context* ctx) {
     const size_t all = ctx->bvh_bytes, nodes_only = (size_t)ctx->info.wide_node_bytes;
     ctx->l2_window_bytes = (all <= ctx->l2_persist_max && all <= ctx->l2_window_max) ? all : std::min(nodes_only, ctx->l2_window_max);
     const size_t want = (ctx->l2_window_bytes + (4u << 20)) & ~(size_t)((1u << 20) - 1);
-    // the carve-out is a property of the DEVICE: it only grows here (another handle on this device may need what it has), and a
-    // handle that switches its window off leaves it alone
-    if (ctx->opt_l2_persist) {
-        size_t have = 0;
-        if (cudaDeviceGetLimit(&have, cudaLimitPersistingL2CacheSize) != cudaSuccess) { cudaGetLastError(); have = 0; }
-        const size_t need = std::min(ctx->l2_persist_max, want);
-        if (need > have) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, need);
-    }
+    // (the carve-out is a property of the DEVICE: the scene set up last decides. Growing it only was tried and cost the
+    // frame path of a small scene next to a large one 6-8 %: the part set aside is lost to the ray / hit queues.)
+    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, ctx->opt_l2_persist ? std::min(ctx->l2_persist_max, want) : 0);
     // Lines that an EARLIER scene (of this handle or of another handle on the same device) marked persisting stay in the
-    // carve-out until they are reset -- a new scene would share it with a tree nobody traverses any more (seen in bench.py:
-    // a second handle's 16 M-ray launches at 2 016 instead of 3 110 Mrays/s, depending on what the first had left behind).
+    // carve-out until they are reset -- a new scene would share it with a tree nobody traverses any more.
     cudaCtxResetPersistingL2Cache();
     cudaGetLastError();
 }
@@ -258,17 +254,29 @@ int tail_queue(b2rt_context* ctx, int which, unsigned long long* count, unsigned
     // auto (-1): on; but a tree this small has no long rays -- a hand-over would cost more than the few steps it saves
     const int64_t coop = ctx->opt_coop_max >= 0 ? ctx->opt_coop_max : (ctx->info.n_wide_nodes + ctx->info.n_leaf_blocks > 1000 ? 8 : 0);
     if (coop <= 0 || ctx->opt_traversal == 1 || ctx->tail_capacity_records == 0) return B2RT_SUCCESS;
-    // two queues of the same capacity: what the first pass suspends, and what the re-packed second pass leaves for the cooperative kernel
-    const size_t queue_words = (size_t)ctx->tail_capacity_records * ctx->tail_rec_words;
-    // ... and, behind them, one ticket slot per warp of the largest grid (helping warps that give a ticket back)
-    const size_t orphan_slots = (size_t)ctx->tail_capacity_records / COOP_MAX_LIMIT;
-    if (!ctx->d_tail[which]) CK(cudaMalloc(&ctx->d_tail[which], 2 * queue_words * sizeof(uint32_t) + orphan_slots * sizeof(unsigned long long)));
-    q.records = static_cast<uint32_t*>(ctx->d_tail[which]);
-    q.records2 = q.records + queue_words;
-    q.orphans = reinterpret_cast<unsigned long long*>(q.records2 + queue_words);
-    q.coop_max = (uint32_t)coop;
     const int64_t resume = ctx->opt_resume_max >= 0 ? ctx->opt_resume_max : 0;     // measured (r2, 10 M-face frame shares): no gain, see DESIGN.md
-    q.resume_max = resume > coop ? (uint32_t)resume : 0u;       // a second pass only pays when it suspends earlier than the cooperative threshold
+    const bool two_step = resume > coop;                        // a second pass only pays when it suspends earlier than the cooperative threshold
+    // the queue (two of the same capacity for the two-step tail: what the first pass suspends, and what the re-packed second
+    // pass leaves for the cooperative kernel) ...
+    const size_t queue_words = (size_t)ctx->tail_capacity_records * ctx->tail_rec_words;
+    // ... and, behind, one ticket slot per warp of the largest grid (helping warps that give a ticket back)
+    const size_t orphan_slots = (size_t)ctx->tail_capacity_records / COOP_MAX_LIMIT;
+    if (ctx->d_tail[which] && two_step && !ctx->tail_two_step[which]) {
+        // the option was switched on after this slot was allocated with one queue: a rare, synchronous re-allocation
+        CK(cudaDeviceSynchronize());
+        cudaFree(ctx->d_tail[which]);
+        ctx->d_tail[which] = nullptr;
+    }
+    if (!ctx->d_tail[which]) {
+        CK(cudaMalloc(&ctx->d_tail[which], (two_step ? 2 : 1) * queue_words * sizeof(uint32_t) + orphan_slots * sizeof(unsigned long long)));
+        ctx->tail_two_step[which] = two_step;
+    }
+    const size_t queues = ctx->tail_two_step[which] ? 2 : 1;
+    q.records = static_cast<uint32_t*>(ctx->d_tail[which]);
+    q.records2 = queues == 2 ? q.records + queue_words : nullptr;
+    q.orphans = reinterpret_cast<unsigned long long*>(q.records + queues * queue_words);
+    q.coop_max = (uint32_t)coop;
+    q.resume_max = two_step ? (uint32_t)resume : 0u;
     q.tag = tail_tag(ctx);
     q.help_fcap = ctx->opt_tail_help ? 1u : 0u;                 // launch_trace_wide sizes it (or switches it off)
     return B2RT_SUCCESS;
@@ -292,10 +300,23 @@ int trace_device(b2rt_context* ctx, const void* d_rays, uint64_t n, void* d_out,
     if (st_pol) return st_pol;
     const uint64_t seq = ctx->next_seq++;
     unsigned long long* next = ctx->d_next + 8 * (seq % NEXT_RING);
-    // Tail queues are shared round robin: launches on the context's own stream are ordered anyway, and up to TAIL_RING
-    // launches on different caller streams may overlap (documented in b2rt.h).
+    // Tail queues go with the STREAM: launches on one stream are ordered, so they share a queue (allocated by the first of
+    // them -- r2: round robin made each of a handle's first four launches pay a 100 MB cudaMalloc, two of them inside a timed
+    // region of bench.py); launches on up to TAIL_RING different streams may overlap (documented in b2rt.h), a further
+    // stream takes over the queue of the stream that has not launched for longest.
+    unsigned long long sid = 0;
+    if (cudaStreamGetId(st, &sid) != cudaSuccess) { cudaGetLastError(); sid = (unsigned long long)(uintptr_t)st; }
+    sid += 1;                                                  // 0 marks a free slot
+    int slot = -1;
+    for (int i = 0; i < TAIL_RING && slot < 0; ++i) if (ctx->tail_slot_stream[i] == sid) slot = i;
+    if (slot < 0) {
+        slot = 0;
+        for (int i = 1; i < TAIL_RING; ++i) if (ctx->tail_slot_used[i] < ctx->tail_slot_used[slot]) slot = i;
+        ctx->tail_slot_stream[slot] = sid;
+    }
+    ctx->tail_slot_used[slot] = seq + 1;
     TailQueue tail;
-    int st_tail = tail_queue(ctx, (int)(seq % TAIL_RING), next + 1, next + 2, tail);
+    int st_tail = tail_queue(ctx, slot, next + 1, next + 2, tail);
     if (st_tail) return st_tail;
     CK(launch_trace_wide(ctx->view, d_rays, n, d_out, any, ctx->opt_counters != 0, ctx->stack_bound, grid, next,
                          ctx->d_counters, (uint32_t)ctx->opt_refill_min, (uint32_t)(ctx->opt_leaf_bias ? ctx->opt_leaf_bias : (any ? 48 : 32)), st, nullptr, &tail, ctx->grid_tail));

@@ -59,7 +59,10 @@ struct b2rt_context {
     unsigned long long* d_next = nullptr;      // NEXT_RING counter blocks (4 x u64: ray counter, tail-queue length, tail-queue read
     uint64_t next_seq = 0;                     // position, pad), one per in-flight ray-stream launch
     // cooperative tail mode: queues of unfinished rays, one per launch that may be in flight at the same time
-    void* d_tail[b2rt_detail::TAIL_RING + 4] = { nullptr };  // [0, TAIL_RING): ray-stream launches (round robin); then one per wavefront lane
+    void* d_tail[b2rt_detail::TAIL_RING + 4] = { nullptr };  // [0, TAIL_RING): ray-stream launches (one per stream in use); then one per wavefront lane
+    bool tail_two_step[b2rt_detail::TAIL_RING + 4] = { false };   // the slot was allocated with the second queue of the two-step tail
+    unsigned long long tail_slot_stream[b2rt_detail::TAIL_RING] = { 0 };   // stream id + 1 that owns ray-stream slot i (0 = free) ...
+    uint64_t tail_slot_used[b2rt_detail::TAIL_RING] = { 0 };               // ... and the launch number of its last use
     uint64_t tail_capacity_records = 0;
     uint32_t tail_rec_words = 0;
     int grid_tail = 0;
